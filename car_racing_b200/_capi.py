@@ -1,0 +1,181 @@
+"""ctypes binding of libb200mpc.so (include/b200mpc.h).
+
+There is no CPU fallback: importing this module without the built shared library, or creating
+a handle without a CUDA device, raises.  Build with `python __graft_entry__.py` (or
+`__graft_entry__.build()`), which runs nvcc for sm_100a.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200mpc.so")
+NMAX, MMAX = 64, 4
+
+
+class CbfParams(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("M", C.c_int32), ("xt_per_stage", C.c_int32), ("reserved", C.c_int32),
+        ("A", C.c_double * 36), ("B", C.c_double * 12), ("Q", C.c_double * 36), ("R", C.c_double * 4),
+        ("umax", C.c_double * 2), ("vmin", C.c_double), ("vmax", C.c_double), ("width", C.c_double),
+        ("alpha", C.c_double), ("margin", C.c_double), ("L", C.c_double), ("W", C.c_double),
+        ("slack_w", C.c_double),
+    ]
+
+
+class IpmOptions(C.Structure):
+    _fields_ = [
+        ("tol", C.c_double), ("max_iter", C.c_int32), ("acceptable_iter", C.c_int32),
+        ("acceptable_tol", C.c_double), ("mu_init", C.c_double), ("rho", C.c_double),
+        ("bound_push", C.c_double), ("bound_frac", C.c_double), ("max_grad", C.c_double),
+    ]
+
+
+class IlqrParams(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("max_iter", C.c_int32),
+        ("A", C.c_double * 36), ("B", C.c_double * 12), ("Q", C.c_double * 36), ("R", C.c_double * 4),
+        ("L", C.c_double), ("W", C.c_double),
+    ]
+
+
+RECORD_DTYPE = np.dtype([("cost", "<f8"), ("u0", "<f8", (2,)), ("status", "<i4"), ("iters", "<i4")])
+assert RECORD_DTYPE.itemsize == 32
+
+EXPORTS = [
+    "b200mpc_version", "b200mpc_default_ipm_options", "b200mpc_create", "b200mpc_destroy", "b200mpc_last_error",
+    "b200mpc_stream", "b200mpc_launch_count", "b200mpc_cbf_record_doubles", "b200mpc_cbf_solve",
+    "b200mpc_cbf_solve_device", "b200mpc_ilqr_record_doubles", "b200mpc_ilqr_solve", "b200mpc_ilqr_solve_device",
+    "b200mpc_argmin_cost_device",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libb200mpc.so (once).  Raises ImportError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is not built (run `python __graft_entry__.py`). "
+            "car_racing_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip = C.c_void_p, C.c_void_p, C.c_int
+    L.b200mpc_version.restype = C.c_int
+    L.b200mpc_default_ipm_options.argtypes = [C.POINTER(IpmOptions)]
+    L.b200mpc_default_ipm_options.restype = None
+    L.b200mpc_create.argtypes = [ip, ip, C.POINTER(vp)]
+    L.b200mpc_destroy.argtypes = [vp]
+    L.b200mpc_destroy.restype = None
+    L.b200mpc_last_error.argtypes = [vp]
+    L.b200mpc_last_error.restype = C.c_char_p
+    L.b200mpc_stream.argtypes = [vp]
+    L.b200mpc_stream.restype = C.c_uint64
+    L.b200mpc_launch_count.argtypes = [vp]
+    L.b200mpc_launch_count.restype = C.c_uint64
+    L.b200mpc_cbf_record_doubles.argtypes = [ip, ip, ip]
+    L.b200mpc_ilqr_record_doubles.argtypes = [ip]
+    cbf_args = [vp, C.POINTER(CbfParams), C.POINTER(IpmOptions), ip, dp, dp, dp, dp, dp, dp]
+    L.b200mpc_cbf_solve.argtypes = cbf_args
+    L.b200mpc_cbf_solve_device.argtypes = cbf_args
+    ilqr_args = [vp, C.POINTER(IlqrParams), ip, dp, dp, dp, dp]
+    L.b200mpc_ilqr_solve.argtypes = ilqr_args
+    L.b200mpc_ilqr_solve_device.argtypes = ilqr_args
+    L.b200mpc_argmin_cost_device.argtypes = [vp, dp, ip, ip, dp]
+    _lib = L
+    return L
+
+
+class B200MPCError(RuntimeError):
+    pass
+
+
+class Handle:
+    """Opaque solver handle (device buffers + stream).  Not fork-safe; pickles without the
+    native handle and re-creates it lazily (controller objects are pickled with the simulator,
+    car_racing/tests/mpccbf_test.py:45-46)."""
+
+    def __init__(self, device=-1, max_batch=1024):
+        self.device, self.max_batch = device, max_batch
+        self._h = None
+
+    def _ensure(self):
+        if self._h is None:
+            h = C.c_void_p()
+            rc = lib().b200mpc_create(self.device, self.max_batch, C.byref(h))
+            if rc != 0:
+                raise B200MPCError(f"b200mpc_create failed ({rc}): {lib().b200mpc_last_error(None).decode()}")
+            self._h = h
+        return self._h
+
+    @property
+    def ptr(self):
+        return self._ensure()
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise B200MPCError(f"{what} failed ({rc}): {lib().b200mpc_last_error(self._h).decode()}")
+
+    @property
+    def stream(self):
+        return int(lib().b200mpc_stream(self.ptr))
+
+    @property
+    def launch_count(self):
+        return int(lib().b200mpc_launch_count(self.ptr))
+
+    def close(self):
+        if self._h is not None:
+            lib().b200mpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __getstate__(self):
+        return {"device": self.device, "max_batch": self.max_batch}
+
+    def __setstate__(self, st):
+        self.device, self.max_batch = st["device"], st["max_batch"]
+        self._h = None
+
+
+def default_options(**kw):
+    o = IpmOptions()
+    lib().b200mpc_default_ipm_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(f"unknown IPM option {k!r}")
+        setattr(o, k, v)
+    return o
+
+
+def _fill(dst, src, n):
+    a = np.ascontiguousarray(src, dtype=np.float64).ravel()
+    if a.size != n:
+        raise ValueError(f"expected {n} values, got {a.size}")
+    C.memmove(dst, a.ctypes.data, a.nbytes)
+
+
+def make_cbf_params(prm, M, xt_per_stage):
+    p = CbfParams()
+    p.N, p.M, p.xt_per_stage = int(prm["N"]), int(M), int(bool(xt_per_stage))
+    _fill(p.A, prm["A"], 36); _fill(p.B, prm["B"], 12); _fill(p.Q, prm["Q"], 36); _fill(p.R, prm["R"], 4)
+    _fill(p.umax, prm["umax"], 2)
+    for k in ("vmin", "vmax", "width", "alpha", "margin", "L", "W", "slack_w"):
+        setattr(p, k, float(prm[k]))
+    return p
+
+
+def make_ilqr_params(prm):
+    p = IlqrParams()
+    p.N, p.max_iter = int(prm["N"]), int(prm["max_iter"])
+    _fill(p.A, prm["A"], 36); _fill(p.B, prm["B"], 12); _fill(p.Q, prm["Q"], 36); _fill(p.R, prm["R"], 4)
+    p.L, p.W = float(prm["L"]), float(prm["W"])
+    return p

@@ -1,0 +1,134 @@
+"""Explicit batch API: stacked numpy arrays in, stacked numpy arrays out, one kernel launch.
+
+The packers lay each instance out as ONE contiguous record (the warp that solves the instance
+pulls it with a single TMA bulk copy); see include/b200mpc.h for the layout.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+_default_handle = None
+
+
+def default_handle():
+    global _default_handle
+    if _default_handle is None:
+        _default_handle = _capi.Handle()
+    return _default_handle
+
+
+def cbf_record_doubles(N, M, xt_per_stage):
+    hdr = (6 + M + 1) & ~1
+    n = hdr + (6 * (N + 1) if xt_per_stage else 6) + 2 * M * (N + 1)
+    return (n + 1) & ~1
+
+
+def ilqr_record_doubles(N):
+    return (14 + 2 * (N + 1) + 1) & ~1
+
+
+def pack_cbf(x0, xt, obs, lap_off, N, out=None):
+    """x0 (B,6); xt (6,), (B,6) or (B,N+1,6); obs (B,M,2,N+1) = rows 4,5 of each rival's predicted
+    trajectory (control.py:509-511); lap_off (B,M) or None.  Returns (records (B,stride), M, xt_per_stage)."""
+    x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)))
+    B = x0.shape[0]
+    obs = np.asarray(obs, dtype=np.float64)
+    obs = obs.reshape(B, -1, 2, N + 1) if obs.size else np.zeros((B, 0, 2, N + 1))
+    M = obs.shape[1]
+    if M > _capi.MMAX:
+        raise ValueError(f"at most {_capi.MMAX} rivals per instance are supported, got {M}")
+    xt = np.asarray(xt, dtype=np.float64)
+    per_stage = xt.ndim == 3
+    stride = cbf_record_doubles(N, M, per_stage)
+    rec = np.zeros((B, stride)) if out is None else out
+    hdr = (6 + M + 1) & ~1
+    rec[:, 0:6] = x0
+    if M and lap_off is not None:
+        rec[:, 6:6 + M] = np.asarray(lap_off, dtype=np.float64).reshape(B, M)
+    if per_stage:
+        rec[:, hdr:hdr + 6 * (N + 1)] = xt.reshape(B, 6 * (N + 1))
+        o = hdr + 6 * (N + 1)
+    else:
+        rec[:, hdr:hdr + 6] = xt.reshape(-1, 6)
+        o = hdr + 6
+    if M:
+        rec[:, o:o + 2 * M * (N + 1)] = obs.reshape(B, 2 * M * (N + 1))
+    return rec, M, per_stage
+
+
+def pack_ilqr(x0, xt, obs, lap_off, N):
+    """x0 (B,6); xt (6,)|(B,6); obs (B,2,N+1) = rows 4,5 of the rival's prediction; lap_off (B,)|None."""
+    x0 = np.atleast_2d(np.asarray(x0, dtype=np.float64))
+    B = x0.shape[0]
+    stride = ilqr_record_doubles(N)
+    rec = np.zeros((B, stride))
+    rec[:, 0:6] = x0
+    rec[:, 6:12] = np.asarray(xt, dtype=np.float64).reshape(-1, 6)
+    if lap_off is not None:
+        rec[:, 12] = np.asarray(lap_off, dtype=np.float64).reshape(B)
+    rec[:, 14:14 + 2 * (N + 1)] = np.asarray(obs, dtype=np.float64).reshape(B, 2 * (N + 1))
+    return rec
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def solve_cbf_packed(records, prm, M, xt_per_stage, want=("aux", "x", "u", "sigma"), handle=None, **opt):
+    """Host-pointer call: H2D + kernel + D2H inside b200mpc_cbf_solve."""
+    h = handle or default_handle()
+    records = np.ascontiguousarray(records, dtype=np.float64)
+    B, N = records.shape[0], int(prm["N"])
+    if records.shape[1] != cbf_record_doubles(N, M, xt_per_stage):
+        raise ValueError("record stride does not match (N, M, xt_per_stage)")
+    p = _capi.make_cbf_params(prm, M, xt_per_stage)
+    o = _capi.default_options(**opt)
+    rec = np.zeros(B, dtype=_capi.RECORD_DTYPE)
+    aux = np.zeros((B, 4)) if "aux" in want else None
+    x = np.zeros((B, N + 1, 6)) if "x" in want else None
+    u = np.zeros((B, N, 2)) if "u" in want else None
+    sg = np.zeros((B, M, N + 1)) if ("sigma" in want and M > 0) else None
+    rc = _capi.lib().b200mpc_cbf_solve(h.ptr, C.byref(p), C.byref(o), B, _ptr(records), _ptr(rec), _ptr(aux), _ptr(x),
+                                       _ptr(u), _ptr(sg))
+    h.check(rc, "b200mpc_cbf_solve")
+    out = dict(u0=rec["u0"].copy(), cost=rec["cost"].copy(), status=rec["status"].copy(), iters=rec["iters"].copy(),
+               record=rec)
+    if aux is not None:
+        out.update(kkt_err=aux[:, 0], elastic_max=aux[:, 1], n_refactor=aux[:, 2].astype(int),
+                   n_backtrack=aux[:, 3].astype(int))
+    if x is not None:
+        out["x"] = x
+    if u is not None:
+        out["u"] = u
+    if "sigma" in want:
+        out["sigma"] = sg if sg is not None else np.zeros((B, 0, N + 1))
+    return out
+
+
+def solve_cbf_batch(x0, xt, obs, lap_off, prm, want=("aux", "x", "u", "sigma"), handle=None, **opt):
+    """Batched control.mpccbf / mpc_lti / mpc_multi_agents solve (control.py:476-607,198-248,251-473)."""
+    records, M, per_stage = pack_cbf(x0, xt, obs, lap_off, int(prm["N"]))
+    return solve_cbf_packed(records, prm, M, per_stage, want=want, handle=handle, **opt)
+
+
+def solve_ilqr_batch(x0, xt, obs, lap_off, prm, want=("x", "u"), handle=None):
+    """Batched control.ilqr (control.py:64-195).  prm: A,B,Q,R,N,max_iter,L,W."""
+    h = handle or default_handle()
+    N = int(prm["N"])
+    records = pack_ilqr(x0, xt, obs, lap_off, N)
+    B = records.shape[0]
+    p = _capi.make_ilqr_params(prm)
+    rec = np.zeros(B, dtype=_capi.RECORD_DTYPE)
+    x = np.zeros((B, N + 1, 6)) if "x" in want else None
+    u = np.zeros((B, N, 2)) if "u" in want else None
+    rc = _capi.lib().b200mpc_ilqr_solve(h.ptr, C.byref(p), B, _ptr(records), _ptr(rec), _ptr(x), _ptr(u))
+    h.check(rc, "b200mpc_ilqr_solve")
+    out = dict(u0=rec["u0"].copy(), cost=rec["cost"].copy(), converged=(rec["status"] == 0), iters=rec["iters"].copy(),
+               record=rec)
+    if x is not None:
+        out["x"] = x
+    if u is not None:
+        out["u"] = u
+    return out

@@ -1,0 +1,174 @@
+"""Drop-in replacements for the reference's solve functions (car_racing/control/control.py).
+
+Same names, positional signatures, return shapes and error behaviour as the reference, so
+`car_racing/utils/base.py` -- which calls `control.mpc_lti / mpccbf / mpc_multi_agents / ilqr`
+through the module object (base.py:199,256,307,558) -- runs unchanged after
+
+    import car_racing_b200
+    car_racing_b200.install()          # patches the reference's control.control module in place
+
+Each shim does the reference's host-side packing in numpy (proximity filter, lap offsets,
+per-stage targets) and calls the C-ABI with a batch of one.  The solve itself always runs on
+the GPU: there is no CasADi/IPOPT and no CPU fallback here.
+"""
+import numpy as np
+from scipy.interpolate import interp1d
+
+from . import batch
+
+X_DIM, U_DIM = 6, 2
+_SLACK_W = 10000.0          # control.py:560
+_DEGREE = 6                 # control.py:528 (hard-coded in the reference, and in the kernel)
+
+
+def _model(param, N):
+    return dict(A=np.asarray(param.matrix_A, float), B=np.asarray(param.matrix_B, float),
+                Q=np.asarray(param.matrix_Q, float), R=np.asarray(param.matrix_R, float), N=int(N))
+
+
+def _limits(prm, system_param, width):
+    prm.update(umax=[system_param.delta_max, system_param.a_max], vmin=system_param.v_min, vmax=system_param.v_max,
+               width=width, slack_w=_SLACK_W)
+    return prm
+
+
+def _nearby_rivals(xcurv, names, vehicles, agent_name, lap_length, time, timestep, realtime_flag, n_pred):
+    """Proximity filter of control.py:499-523 / :284-309.  Returns [(name, obs_traj (6,n_pred))]."""
+    margin = xcurv[0] * 2.0                      # safety_time = 2.0 (control.py:499-501)
+    num_cycle_ego = int(xcurv[4] / lap_length)
+    dist_ego = xcurv[4] - num_cycle_ego * lap_length
+    kept = []
+    for name in names:
+        if name == agent_name:
+            continue
+        if realtime_flag == False:  # noqa: E712  (the reference compares with ==, None falls through)
+            obs_traj, _ = vehicles[name].get_trajectory_nsteps(time, timestep, n_pred)
+        elif realtime_flag == True:  # noqa: E712
+            obs_traj, _ = vehicles[name].get_trajectory_nsteps(n_pred)
+        else:
+            continue
+        num_cycle_obs = int(obs_traj[4, 0] / lap_length)
+        dist_obs = obs_traj[4, 0] - num_cycle_obs * lap_length
+        if (dist_ego > dist_obs - margin) & (dist_ego < dist_obs + margin):
+            kept.append((name, np.asarray(obs_traj, float)))
+    return kept, num_cycle_ego
+
+
+def _rival_block(kept, num_cycle_ego, lap_length, N):
+    M = len(kept)
+    obs = np.zeros((1, M, 2, N + 1))
+    lap_off = np.zeros((1, M))
+    for j, (_, traj) in enumerate(kept):
+        obs[0, j, 0] = traj[4, :N + 1]
+        obs[0, j, 1] = traj[5, :N + 1]
+        # control.py:538-540: the offset enters h (diffs) but not h_next (diffs_next)
+        lap_off[0, j] = (num_cycle_ego - int(traj[4, 0] / lap_length)) * lap_length
+    return obs, lap_off
+
+
+def _common_size(pairs):
+    L = {round(p[0], 12) for p in pairs}
+    W = {round(p[1], 12) for p in pairs}
+    if len(L) > 1 or len(W) > 1:
+        raise NotImplementedError("rivals of different size inside one solve are not supported by the batched kernel")
+    return (L.pop(), W.pop()) if pairs else (0.4, 0.2)
+
+
+def pid(xcurv, xtarget):
+    """control.py:15-25 (two scalar gains; stays on the host)."""
+    xtarget = np.asarray(xtarget, float).reshape(-1)
+    u = np.zeros(U_DIM)
+    u[0] = -0.6 * (xcurv[5] - xtarget[5]) - 0.9 * xcurv[3]
+    u[1] = 1.5 * (xtarget[0] - xcurv[0])
+    return u
+
+
+def mpc_lti(xcurv, xtarget, mpc_lti_param, system_param, track):
+    """control.py:198-248.  Raises RuntimeError on non-convergence, as the uncaught IPOPT failure does (:242)."""
+    N = mpc_lti_param.num_horizon
+    prm = _limits(_model(mpc_lti_param, N), system_param, track.width)
+    prm.update(alpha=0.8, margin=0.2, L=0.4, W=0.2)
+    xt = np.asarray(xtarget, float).reshape(X_DIM)
+    r = batch.solve_cbf_batch(np.asarray(xcurv, float).reshape(1, 6), xt, np.zeros((1, 0, 2, N + 1)), None, prm,
+                              want=("u",))
+    if r["status"][0] != 0:
+        raise RuntimeError("b200mpc: mpc_lti did not converge (status %d)" % r["status"][0])
+    return r["u"][0, 0, :]
+
+
+def mpccbf(xcurv, xtarget, mpc_cbf_param, vehicles, agent_name, lap_length, time, timestep, realtime_flag, track,
+           system_param, return_details=False):
+    """control.py:476-607.  Returns u_pred[0,:]; never raises on non-convergence (:600-603)."""
+    N = mpc_cbf_param.num_horizon
+    xcurv = np.asarray(xcurv, float).reshape(X_DIM)
+    kept, num_cycle_ego = _nearby_rivals(xcurv, list(vehicles), vehicles, agent_name, lap_length, time, timestep,
+                                         realtime_flag, N + 1)
+    obs, lap_off = _rival_block(kept, num_cycle_ego, lap_length, N)
+    ego = vehicles[agent_name].param
+    L, W = _common_size([(ego.length / 2 + vehicles[n].param.length / 2, ego.width / 2 + vehicles[n].param.width / 2)
+                         for n, _ in kept])
+    prm = _limits(_model(mpc_cbf_param, N), system_param, track.width)
+    prm.update(alpha=mpc_cbf_param.alpha, margin=0.2, L=L, W=W)
+    xt = np.asarray(xtarget, float).reshape(X_DIM)
+    r = batch.solve_cbf_batch(xcurv.reshape(1, 6), xt, obs, lap_off, prm)
+    if return_details:
+        return r["u"][0, 0, :], r
+    return r["u"][0, 0, :]
+
+
+def mpc_multi_agents(xcurv, mpc_lti_param, track, matrix_Atv, matrix_Btv, matrix_Ctv, system_param,
+                     target_traj_xcurv=None, vehicles=None, agent_name=None, direction_flag=None,
+                     target_traj_xglob=None, sorted_vehicles=None, time=None):
+    """control.py:251-473 (the CBF_Flag=True path; lines 383-445 are dead in the reference).
+    Returns (u_pred[0,:], x_pred (N+1,6))."""
+    N = mpc_lti_param.num_horizon_ctrl
+    xcurv = np.asarray(xcurv, float).reshape(X_DIM)
+    vx = xcurv[0]
+    f_traj = interp1d(target_traj_xcurv[:, 4], target_traj_xcurv[:, 5])
+    veh_len, veh_width = vehicles["ego"].param.length, vehicles["ego"].param.width
+    kept, num_cycle_ego = _nearby_rivals(xcurv, sorted_vehicles, vehicles, agent_name, track.lap_length, time, 0.1,
+                                         False, N + 1)
+    obs, lap_off = _rival_block(kept, num_cycle_ego, track.lap_length, N)
+    xt = np.zeros((1, N + 1, 6))
+    for i in range(N + 1):                        # control.py:373-378
+        s_tmp = vx * 0.1 * i + xcurv[4]
+        s_tmp = max(s_tmp, target_traj_xcurv[0, 4])
+        if s_tmp >= target_traj_xcurv[-1, 4]:
+            s_tmp = target_traj_xcurv[-1, 4]
+        xt[0, i] = [vx, 0, 0, 0, 0, float(f_traj(s_tmp))]
+    prm = _limits(_model(mpc_lti_param, N), system_param, track.width)
+    prm.update(alpha=0.6, margin=0.15, L=veh_len, W=veh_width)   # control.py:285,311,316-319
+    r = batch.solve_cbf_batch(xcurv.reshape(1, 6), xt, obs, lap_off, prm)
+    return r["u"][0, 0, :], r["x"][0]
+
+
+def ilqr(xcurv, xtarget, ilqr_param, vehicles, agent_name, lap_length, time, timestep, track, system_param):
+    """control.py:64-195.  Only the last non-ego vehicle's prediction is used (:100-105) and the rival
+    size is read from vehicles["car1"] (:109-110), as in the reference."""
+    N = ilqr_param.num_horizon
+    xcurv = np.asarray(xcurv, float).reshape(X_DIM)
+    obs_traj = None
+    for name in list(vehicles):
+        if name != agent_name:
+            obs_traj, _ = vehicles[name].get_trajectory_nsteps(time, timestep, N + 1)
+    if obs_traj is None:
+        raise NameError("obs_traj")               # the reference fails the same way without a rival
+    l_sum = vehicles[agent_name].param.length / 2 + vehicles["car1"].param.length / 2
+    w_sum = vehicles[agent_name].param.width / 2 + vehicles["car1"].param.width / 2
+    num_cycle_ego = int(xcurv[4] / lap_length)
+    lap_off = (num_cycle_ego - int(obs_traj[4, 0] / lap_length)) * lap_length
+    prm = _model(ilqr_param, N)
+    prm.update(max_iter=ilqr_param.max_iter, L=l_sum, W=w_sum)
+    r = batch.solve_ilqr_batch(xcurv.reshape(1, 6), np.asarray(xtarget, float).reshape(6),
+                               np.asarray(obs_traj, float)[4:6, :N + 1].reshape(1, 2, N + 1), [lap_off], prm, want=("u",))
+    return r["u"][0, 0, :]
+
+
+def install(control_module=None):
+    """Swap the reference's solve functions for the GPU ones (module-level monkey patch).
+    `control_module` defaults to the reference's `control.control` if it is importable."""
+    if control_module is None:
+        from control import control as control_module  # the reference's own package layout (setup.cfg:16-17)
+    for name in ("mpc_lti", "mpccbf", "mpc_multi_agents", "ilqr"):
+        setattr(control_module, name, globals()[name])
+    return control_module

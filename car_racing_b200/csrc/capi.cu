@@ -1,0 +1,271 @@
+// b200mpc: C-ABI (include/b200mpc.h) over the sm_100a kernels.  No torch types, no CPU
+// fallback: every entry point either launches the CUDA kernels or fails with an error code.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/b200mpc.h"
+#include "ilqr.cuh"
+#include "ocp_ipm.cuh"
+
+using namespace b200mpc;
+
+struct b200mpc_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int max_batch = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    // staging buffers for the host-pointer API (grown on demand)
+    void *d_in = nullptr, *d_rec = nullptr, *d_aux = nullptr, *d_x = nullptr, *d_u = nullptr, *d_sig = nullptr;
+    size_t c_in = 0, c_rec = 0, c_aux = 0, c_x = 0, c_u = 0, c_sig = 0;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(b200mpc_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    else g_create_err = msg;
+    return code;
+}
+#define CK(h, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(h, B200MPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+static int grow(b200mpc_handle *h, void **p, size_t *cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) return fail(h, B200MPC_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    *cap = need;
+    return 0;
+}
+
+extern "C" {
+
+int b200mpc_version(void) { return B200MPC_VERSION; }
+
+void b200mpc_default_ipm_options(b200mpc_ipm_options *o) {
+    o->tol = 1e-8;
+    o->max_iter = 200;
+    o->acceptable_iter = 15;
+    o->acceptable_tol = 1e-6;
+    o->mu_init = 0.1;
+    o->rho = 1e3;
+    o->bound_push = 1e-2;
+    o->bound_frac = 1e-2;
+    o->max_grad = 100.0;
+}
+
+int b200mpc_create(int device, int max_batch, b200mpc_handle **out) {
+    if (!out || max_batch < 1) return fail(nullptr, B200MPC_ERR_ARG, "b200mpc_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, B200MPC_ERR_NODEVICE,
+                    std::string("b200mpc_create: no CUDA device (") + cudaGetErrorString(e) + ") -- there is no CPU fallback");
+    if (device < 0) {
+        e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return fail(nullptr, B200MPC_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (device >= ndev) return fail(nullptr, B200MPC_ERR_ARG, "b200mpc_create: device index out of range");
+    b200mpc_handle *h = new (std::nothrow) b200mpc_handle();
+    if (!h) return fail(nullptr, B200MPC_ERR_NOMEM, "out of host memory");
+    h->device = device;
+    h->max_batch = max_batch;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        std::string m = cudaGetErrorString(e);
+        delete h;
+        return fail(nullptr, B200MPC_ERR_CUDA, "b200mpc_create: " + m);
+    }
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    *out = h;
+    return B200MPC_OK;
+}
+
+void b200mpc_destroy(b200mpc_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void *bufs[] = {h->d_in, h->d_rec, h->d_aux, h->d_x, h->d_u, h->d_sig};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char *b200mpc_last_error(const b200mpc_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+uint64_t b200mpc_stream(const b200mpc_handle *h) { return h ? (uint64_t)(uintptr_t)h->stream : 0; }
+uint64_t b200mpc_launch_count(const b200mpc_handle *h) { return h ? h->launches : 0; }
+
+int b200mpc_cbf_record_doubles(int N, int M, int xt_per_stage) {
+    if (N < 1 || N > B200MPC_NMAX || M < 0 || M > B200MPC_MMAX) return B200MPC_ERR_ARG;
+    return cbf_record_doubles(N, M, xt_per_stage);
+}
+int b200mpc_ilqr_record_doubles(int N) {
+    if (N < 1 || N > B200MPC_NMAX) return B200MPC_ERR_ARG;
+    return ilqr_record_doubles(N);
+}
+
+}  // extern "C"
+
+template <int M>
+static int launch_cbf(b200mpc_handle *h, const KParams &kp, const double *d_in, b200mpc_record *d_rec, double *d_aux,
+                      double *d_x, double *d_u, double *d_sig) {
+    SmemPlan<M> pl(kp.p.N, kp.in_stride);
+    size_t smem = pl.bytes();
+    if ((int)smem > h->max_smem_optin)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: horizon too long for one CTA's shared memory");
+    CK(h, cudaFuncSetAttribute(ocp_ipm_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ocp_ipm_kernel<M><<<kp.B, 32, smem, h->stream>>>(kp, d_in, d_rec, d_aux, d_x, d_u, d_sig);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+static int check_cbf(b200mpc_handle *h, const b200mpc_cbf_params *p, const b200mpc_ipm_options *o, int B, const void *in,
+                     const void *rec) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!p || !o || !in || !rec || B < 1) return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: null argument or B < 1");
+    if (p->N < 1 || p->N > B200MPC_NMAX || p->M < 0 || p->M > B200MPC_MMAX)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: N or M out of range");
+    if (!(p->alpha >= 0.0 && p->alpha <= 1.0) || !(p->L > 0.0) || !(p->W > 0.0) || !(o->tol > 0.0) || o->max_iter < 1)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: bad parameter value");
+    return B200MPC_OK;
+}
+
+static KParams make_kp(const b200mpc_cbf_params *p, const b200mpc_ipm_options *o, int B) {
+    KParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.p = *p;
+    kp.o = *o;
+    kp.B = B;
+    kp.in_stride = cbf_record_doubles(p->N, p->M, p->xt_per_stage);
+    kp.hdr = cbf_hdr_doubles(p->M);
+    kp.obs_off = kp.hdr + (p->xt_per_stage ? 6 * (p->N + 1) : 6);
+    double L2 = p->L * p->L, W2 = p->W * p->W;
+    kp.iL6 = 1.0 / (L2 * L2 * L2);
+    kp.iW6 = 1.0 / (W2 * W2 * W2);
+    return kp;
+}
+
+extern "C" {
+
+int b200mpc_cbf_solve_device(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b200mpc_ipm_options *opt, int B,
+                             const double *d_in, b200mpc_record *d_rec, double *d_aux, double *d_xpred, double *d_upred,
+                             double *d_sigma) {
+    int rc = check_cbf(h, prm, opt, B, d_in, d_rec);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    KParams kp = make_kp(prm, opt, B);
+    switch (prm->M) {
+        case 0: return launch_cbf<0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        case 1: return launch_cbf<1>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        case 2: return launch_cbf<2>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        case 3: return launch_cbf<3>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        case 4: return launch_cbf<4>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+    }
+    return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: M out of range");
+}
+
+int b200mpc_cbf_solve(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b200mpc_ipm_options *opt, int B,
+                      const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *sigma) {
+    int rc = check_cbf(h, prm, opt, B, in, rec);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    const int N = prm->N, M = prm->M;
+    const size_t stride = (size_t)cbf_record_doubles(N, M, prm->xt_per_stage);
+    const size_t b_in = stride * 8 * B, b_rec = sizeof(b200mpc_record) * (size_t)B, b_aux = 32 * (size_t)B;
+    const size_t b_x = 48 * (size_t)(N + 1) * B, b_u = 16 * (size_t)N * B, b_sig = 8 * (size_t)M * (N + 1) * B;
+    if ((rc = grow(h, &h->d_in, &h->c_in, b_in))) return rc;
+    if ((rc = grow(h, &h->d_rec, &h->c_rec, b_rec))) return rc;
+    if (aux && (rc = grow(h, &h->d_aux, &h->c_aux, b_aux))) return rc;
+    if (xpred && (rc = grow(h, &h->d_x, &h->c_x, b_x))) return rc;
+    if (upred && (rc = grow(h, &h->d_u, &h->c_u, b_u))) return rc;
+    if (sigma && M > 0 && (rc = grow(h, &h->d_sig, &h->c_sig, b_sig))) return rc;
+    CK(h, cudaMemcpyAsync(h->d_in, in, b_in, cudaMemcpyHostToDevice, h->stream));
+    rc = b200mpc_cbf_solve_device(h, prm, opt, B, (const double *)h->d_in, (b200mpc_record *)h->d_rec,
+                                  aux ? (double *)h->d_aux : nullptr, xpred ? (double *)h->d_x : nullptr,
+                                  upred ? (double *)h->d_u : nullptr, (sigma && M > 0) ? (double *)h->d_sig : nullptr);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(rec, h->d_rec, b_rec, cudaMemcpyDeviceToHost, h->stream));
+    if (aux) CK(h, cudaMemcpyAsync(aux, h->d_aux, b_aux, cudaMemcpyDeviceToHost, h->stream));
+    if (xpred) CK(h, cudaMemcpyAsync(xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
+    if (upred) CK(h, cudaMemcpyAsync(upred, h->d_u, b_u, cudaMemcpyDeviceToHost, h->stream));
+    if (sigma && M > 0) CK(h, cudaMemcpyAsync(sigma, h->d_sig, b_sig, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+static int check_ilqr(b200mpc_handle *h, const b200mpc_ilqr_params *p, int B, const void *in, const void *rec) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!p || !in || !rec || B < 1) return fail(h, B200MPC_ERR_ARG, "b200mpc_ilqr_solve: null argument or B < 1");
+    if (p->N < 1 || p->N > B200MPC_NMAX || p->max_iter < 1 || !(p->L > 0.0) || !(p->W > 0.0))
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_ilqr_solve: bad parameter value");
+    return B200MPC_OK;
+}
+
+int b200mpc_ilqr_solve_device(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B, const double *d_in,
+                              b200mpc_record *d_rec, double *d_xpred, double *d_upred) {
+    int rc = check_ilqr(h, prm, B, d_in, d_rec);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    IlqrKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.p = *prm;
+    kp.B = B;
+    kp.in_stride = ilqr_record_doubles(prm->N);
+    IlqrPlan pl(prm->N, kp.in_stride);
+    size_t smem = pl.bytes();
+    CK(h, cudaFuncSetAttribute(ilqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ilqr_kernel<<<B, 32, smem, h->stream>>>(kp, d_in, d_rec, d_xpred, d_upred);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+int b200mpc_ilqr_solve(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B, const double *in, b200mpc_record *rec,
+                       double *xpred, double *upred) {
+    int rc = check_ilqr(h, prm, B, in, rec);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    const int N = prm->N;
+    const size_t b_in = (size_t)ilqr_record_doubles(N) * 8 * B, b_rec = sizeof(b200mpc_record) * (size_t)B;
+    const size_t b_x = 48 * (size_t)(N + 1) * B, b_u = 16 * (size_t)N * B;
+    if ((rc = grow(h, &h->d_in, &h->c_in, b_in))) return rc;
+    if ((rc = grow(h, &h->d_rec, &h->c_rec, b_rec))) return rc;
+    if (xpred && (rc = grow(h, &h->d_x, &h->c_x, b_x))) return rc;
+    if (upred && (rc = grow(h, &h->d_u, &h->c_u, b_u))) return rc;
+    CK(h, cudaMemcpyAsync(h->d_in, in, b_in, cudaMemcpyHostToDevice, h->stream));
+    rc = b200mpc_ilqr_solve_device(h, prm, B, (const double *)h->d_in, (b200mpc_record *)h->d_rec,
+                                   xpred ? (double *)h->d_x : nullptr, upred ? (double *)h->d_u : nullptr);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(rec, h->d_rec, b_rec, cudaMemcpyDeviceToHost, h->stream));
+    if (xpred) CK(h, cudaMemcpyAsync(xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
+    if (upred) CK(h, cudaMemcpyAsync(upred, h->d_u, b_u, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+int b200mpc_argmin_cost_device(b200mpc_handle *h, const b200mpc_record *d_rec, int B, int max_status, int32_t *d_out) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!d_rec || !d_out || B < 1) return fail(h, B200MPC_ERR_ARG, "b200mpc_argmin_cost_device: bad arguments");
+    CK(h, cudaSetDevice(h->device));
+    argmin_cost_kernel<<<1, 256, 0, h->stream>>>(d_rec, B, max_status, d_out);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+}  // extern "C"

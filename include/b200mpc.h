@@ -1,0 +1,150 @@
+/* b200mpc -- C-ABI of the B200-native batched MPC solver (libb200mpc.so).
+ *
+ * The reference (HybridRobotics/car-racing) is pure Python and has no FFI of its own; the
+ * boundary it exposes for this path is the set of module-level solve functions that
+ * car_racing/utils/base.py calls by name (base.py:199,256,307,476,558).  Each entry point
+ * below is what a ctypes binding for one of those functions binds; car_racing_b200/control.py
+ * holds that binding and the drop-in Python functions with the reference signatures.
+ *
+ *   b200mpc_cbf_solve     <- control.mpc_lti          (car_racing/control/control.py:198-248)  M = 0
+ *                         <- control.mpccbf           (control.py:476-607)       M = rivals kept
+ *                         <- control.mpc_multi_agents (control.py:251-473)       per-stage targets
+ *   b200mpc_ilqr_solve    <- control.ilqr             (control.py:64-195, ilqr_helper.py:4-55)
+ *   b200mpc_argmin_cost   <- the argmin of OvertakeTrajPlanner.solve_optimization_problem
+ *                            (car_racing/planning/overtake_traj_planner.py:244)
+ *
+ * Conventions: plain pointers + sizes, IEEE double, C-contiguous, caller-owned buffers.
+ * `*_solve` take HOST pointers (pageable or pinned) and perform H2D + kernel + D2H on the
+ * handle's stream, synchronously.  `*_solve_device` take DEVICE pointers of the same layout
+ * and only enqueue the kernel on the handle's stream (no sync) -- used when inputs are
+ * already resident in HBM.  Every function returns 0 on success or a negative
+ * b200mpc_status; b200mpc_last_error() gives the text.  Non-convergence of an instance is NOT
+ * an error: it is reported per instance in rec[].status, as the reference's
+ * `except RuntimeError` paths do (control.py:600-603).
+ */
+#ifndef B200MPC_H
+#define B200MPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MPC_VERSION 100
+#define B200MPC_NMAX 64   /* max horizon */
+#define B200MPC_MMAX 4    /* max rivals per instance */
+
+typedef struct b200mpc_handle b200mpc_handle;
+
+enum b200mpc_status {
+    B200MPC_OK = 0,
+    B200MPC_ERR_ARG = -1,
+    B200MPC_ERR_CUDA = -2,
+    B200MPC_ERR_NOMEM = -3,
+    B200MPC_ERR_NODEVICE = -4
+};
+
+/* per-instance solver status (rec.status) */
+enum b200mpc_solve_status {
+    B200MPC_SOLVED = 0,        /* E_0 <= tol (or acceptable_tol for acceptable_iter iterations) */
+    B200MPC_MAX_ITER = 1,      /* iterate returned (reference: opti.debug.value, control.py:602) */
+    B200MPC_LINESEARCH = 2,    /* filter line search failed after the slack resets */
+    B200MPC_INERTIA = 3        /* inertia correction exhausted */
+};
+
+/* Problem data shared by every instance of a batch: the *Param objects of the reference
+ * (MPCCBFRacingParam base.py:272-291, SystemParam :708-713, CarParam :699-705) plus the
+ * constants hard-coded inside control.mpccbf / mpc_multi_agents. */
+typedef struct {
+    int32_t N;              /* num_horizon */
+    int32_t M;              /* rivals per instance in this batch, 0..B200MPC_MMAX (0 = mpc_lti) */
+    int32_t xt_per_stage;   /* 0: xtarget is (6,) per instance; 1: (N+1,6) per instance (control.py:373-382) */
+    int32_t reserved;
+    double A[36], B[12];    /* matrix_A, matrix_B, row-major (control.py:566-570) */
+    double Q[36], R[4];     /* matrix_Q, matrix_R (control.py:578-591) */
+    double umax[2];         /* delta_max, a_max (control.py:572-576) */
+    double vmin, vmax;      /* control.py:582-583 */
+    double width;           /* track.width (control.py:585-586) */
+    double alpha;           /* mpc_cbf_param.alpha (control.py:558) / 0.6 (control.py:285) */
+    double margin;          /* safety_margin 0.2 (control.py:527) / 0.15 (control.py:311) */
+    double L, W;            /* l_agent+l_obs, w_agent+w_obs (control.py:532-535) */
+    double slack_w;         /* 10000 (control.py:560) */
+} b200mpc_cbf_params;
+
+/* Interior-point options (IPOPT option names where they exist). */
+typedef struct {
+    double tol;             /* 1e-8 */
+    int32_t max_iter;       /* 200 */
+    int32_t acceptable_iter;/* 15 */
+    double acceptable_tol;  /* 1e-6 */
+    double mu_init;         /* 0.1 */
+    double rho;             /* l1 weight of the elastic CBF rows (scaled objective units), 1e3 */
+    double bound_push;      /* 1e-2 */
+    double bound_frac;      /* 1e-2 */
+    double max_grad;        /* nlp_scaling_max_gradient, 100 */
+} b200mpc_ipm_options;
+
+/* 32-byte per-instance record: what the planner's argmin / the multi-GPU all-gather moves. */
+typedef struct {
+    double cost;            /* optimal objective (the reference's `cost` expression) */
+    double u0[2];           /* u_pred[0,:] -- the value control.mpccbf returns (control.py:607) */
+    int32_t status;         /* b200mpc_solve_status */
+    int32_t iters;
+} b200mpc_record;
+
+int b200mpc_version(void);
+void b200mpc_default_ipm_options(b200mpc_ipm_options *opt);
+
+/* device < 0: current CUDA device.  max_batch bounds the staging buffers of the host-pointer API. */
+int b200mpc_create(int device, int max_batch, b200mpc_handle **out);
+void b200mpc_destroy(b200mpc_handle *h);
+const char *b200mpc_last_error(const b200mpc_handle *h); /* h may be NULL: last create() error */
+/* the handle's CUDA stream (cudaStream_t) as an integer, for event timing by the caller */
+uint64_t b200mpc_stream(const b200mpc_handle *h);
+/* number of kernel launches issued through this handle so far */
+uint64_t b200mpc_launch_count(const b200mpc_handle *h);
+
+/* doubles per instance of the packed input record for (N, M, xt_per_stage):
+ *   [x0 6][lap_off M][pad to even][xtarget 6 or 6(N+1)][obs j=0..M-1: s_0..s_N, ey_0..ey_N][pad to even]
+ * lap_off[j] = (num_cycle_ego - num_cycle_obs)*lap_length (control.py:538-540); obs rows are rows 4,5
+ * of get_trajectory_nsteps' (6,N+1) prediction (control.py:509-511). */
+int b200mpc_cbf_record_doubles(int N, int M, int xt_per_stage);
+
+/* Batched MPC-LTI / MPC-CBF / mpc_multi_agents solve.
+ *   in    : B packed records (see above)
+ *   rec   : B records (cost, u0, status, iters)
+ *   aux   : optional B x 4 doubles {kkt_err, elastic_max, n_refactor, n_backtrack}
+ *   xpred : optional B x (N+1) x 6   (x_pred of control.py:598)
+ *   upred : optional B x N x 2       (u_pred of control.py:599)
+ *   sigma : optional B x M x (N+1)   (cbf_slack of control.py:525)
+ */
+int b200mpc_cbf_solve(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b200mpc_ipm_options *opt, int B,
+                      const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *sigma);
+int b200mpc_cbf_solve_device(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b200mpc_ipm_options *opt, int B,
+                             const double *d_in, b200mpc_record *d_rec, double *d_aux, double *d_xpred, double *d_upred,
+                             double *d_sigma);
+
+/* iLQR (control.py:64-195).  Shared data: */
+typedef struct {
+    int32_t N;              /* num_horizon (50) */
+    int32_t max_iter;       /* 150 (base.py:176) */
+    double A[36], B[12], Q[36], R[4];
+    double L, W;            /* l_agent+l_obs, w_agent+w_obs (control.py:107-110) */
+} b200mpc_ilqr_params;
+
+/* doubles per instance: [x0 6][xtarget 6][lap_off 1][pad 1][s_0..s_N][ey_0..ey_N][pad to even] */
+int b200mpc_ilqr_record_doubles(int N);
+int b200mpc_ilqr_solve(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B, const double *in,
+                       b200mpc_record *rec, double *xpred, double *upred);
+int b200mpc_ilqr_solve_device(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B, const double *d_in,
+                              b200mpc_record *d_rec, double *d_xpred, double *d_upred);
+
+/* argmin over records (device pointers): index of the smallest cost among status<=max_status,
+ * lowest index wins ties (list.index(min(...)), overtake_traj_planner.py:244); *d_out = -1 if none. */
+int b200mpc_argmin_cost_device(b200mpc_handle *h, const b200mpc_record *d_rec, int B, int max_status, int32_t *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

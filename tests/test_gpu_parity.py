@@ -1,0 +1,203 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs.  Tolerances are BASELINE.json's: |du| < 1e-4, |dcost| < 1e-5 (FP64 both sides)."""
+import os
+
+import numpy as np
+import pytest
+
+from car_racing_b200 import scenarios
+
+pytestmark = pytest.mark.gpu
+TOL_U, TOL_C = 1e-4, 1e-5
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _compare(g, r, min_match=0.97):
+    both = (g["status"] == 0) & (r["status"] == 0)
+    du = np.abs(g["u0"] - r["u0"]).max(axis=1)
+    dc = np.abs(g["cost"] - r["cost"])
+    match = both & (du < TOL_U) & (dc < TOL_C)
+    info = dict(B=len(du), both_converged=int(both.sum()), match=int(match.sum()),
+                gpu_fail=int((g["status"] != 0).sum()), cpu_fail=int((r["status"] != 0).sum()),
+                worst_du=float(du[both].max()) if both.any() else 0.0, worst_dc=float(dc[both].max()) if both.any() else 0.0,
+                iters_equal=float((g["iters"] == r["iters"]).mean()))
+    print(info)
+    assert match.mean() >= min_match, info
+    return match, info
+
+
+def test_mpccbf_config2_parity(crb, oracle):
+    """North-star config: N=20, 3 static rivals, l_shape, seed 0."""
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(128, N=20, M=3, seed=0)
+    prm = scenarios.default_cbf_params(N=20)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
+    match, _ = _compare(g, r)
+    ok = match
+    assert np.abs(g["x"][ok] - r["x"][ok]).max() < 1e-4
+    assert np.abs(g["u"][ok] - r["u"][ok]).max() < 1e-4
+    assert np.abs(g["sigma"][ok] - r["sigma"][ok]).max() < 1e-6
+    assert g["kkt_err"][g["status"] == 0].max() <= 1e-6
+
+
+@pytest.mark.parametrize("N,M", [(10, 0), (20, 0), (10, 1), (12, 2), (20, 4), (5, 3), (1, 1), (32, 3)])
+def test_cbf_shapes_parity(crb, oracle, N, M):
+    """mpc_lti (M=0) and other horizon / rival-count combinations, incl. N=1 and M=MMAX."""
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(48, N=N, M=max(M, 1), seed=10 + N + M)
+    obs, lap_off = obs[:, :M], lap_off[:, :M]
+    prm = scenarios.default_cbf_params(N=N, width=0.8 if M == 0 else 1.0)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
+    _compare(g, r, min_match=0.95)
+
+
+def test_mpc_lti_anchor_on_gpu(crb):
+    prm = scenarios.default_cbf_params(N=10, width=0.8)
+    g = crb.solve_cbf_batch(np.zeros((1, 6)), np.array([0.8, 0, 0, 0, 0, 0.0]), np.zeros((1, 0, 2, 11)), None, prm)
+    assert g["status"][0] == 0
+    assert abs(g["u0"][0, 0] - 0.0033384) < 1e-6 and abs(g["u0"][0, 1] - 1.0) < 1e-6
+    assert abs(g["cost"][0] - 22.71576162) < 1e-6
+
+
+def test_moving_rivals_lap_offsets_per_stage_targets(crb, oracle):
+    """mpc_multi_agents-style data: per-stage targets, alpha 0.6, margin 0.15, moving rivals, ego on lap 1."""
+    N, M, B = 10, 2, 64
+    rng = np.random.default_rng(7)
+    lap = scenarios.LAP_LENGTH["goggle"]
+    x0, xt, obs, _ = scenarios.mpccbf_scenarios(B, N=N, M=M, seed=7, track="goggle")
+    x0[:, 4] += lap                                       # ego has completed one lap, rivals have not
+    lap_off = np.full((B, M), lap)
+    v = rng.uniform(0.0, 0.6, size=(B, M, 1))
+    obs[:, :, 0, :] += v * 0.1 * np.arange(N + 1)          # rivals move along s
+    obs[:, :, 0, 1:] += lap                                # quirk control.py:542: h_next carries no lap offset
+    xts = np.zeros((B, N + 1, 6))
+    xts[:, :, 0] = x0[:, 0:1]
+    xts[:, :, 5] = rng.uniform(-0.3, 0.3, size=(B, 1)) * np.linspace(0, 1, N + 1)
+    prm = scenarios.default_cbf_params(N=N, alpha=0.6, margin=0.15, Q=np.diag([10.0, 0, 0, 5.0, 0, 50.0]))
+    g = crb.solve_cbf_batch(x0, xts, obs, lap_off, prm)
+    r = oracle.solve_cbf_batch(x0, xts, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
+    _compare(g, r, min_match=0.95)
+
+
+def test_full_size_properties(crb):
+    """BASELINE.json size (B=1024): size-independent properties of the returned solutions."""
+    B, N, M = 1024, 20, 3
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=N, M=M, seed=1)
+    prm = scenarios.default_cbf_params(N=N)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    ok = g["status"] == 0
+    assert ok.mean() >= 0.99
+    assert g["kkt_err"][ok].max() <= 1e-6
+    x, u, sg = g["x"], g["u"], g["sigma"]
+    assert np.abs(x[:, 0] - x0).max() == 0.0                                        # control.py:497
+    dyn = x[:, 1:] - x[:, :-1] @ prm["A"].T - u @ prm["B"].T                          # control.py:566-570
+    assert np.abs(dyn[ok]).max() < 1e-8
+    assert (np.abs(u[ok, :, 0]) <= 0.5 + 1e-9).all() and (np.abs(u[ok, :, 1]) <= 1.0 + 1e-9).all()
+    assert (x[ok, 1:, 0] >= -1e-9).all() and (np.abs(x[ok, 1:, 5]) <= 1.0 + 1e-9).all() and (sg[ok] >= -1e-12).all()
+    ds = x[:, None, :, 4] - obs[:, :, 0, :]
+    de = x[:, None, :, 5] - obs[:, :, 1, :]
+    h = (ds / 0.4) ** 6 + (de / 0.2) ** 6 - 1.2 - sg
+    rows = h[:, :, 1:] - 0.2 * h[:, :, :-1]                                          # control.py:558
+    feas = ok & (g["elastic_max"] < 1e-7)
+    scale = np.maximum(1.0, np.abs(h[:, :, 1:]))
+    assert (rows[feas] / scale[feas]).min() > -1e-6
+    # objective value is consistent with the returned trajectory
+    dx = x - xt
+    cost = np.einsum("bki,ij,bkj->b", dx, prm["Q"], dx) + np.einsum("bki,ij,bkj->b", u, prm["R"], u) + 1e4 * sg.sum(axis=(1, 2))
+    assert np.abs(cost - g["cost"])[ok].max() < 1e-8
+    # determinism: a second run gives bit-identical results
+    g2 = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm, want=())
+    assert (g2["u0"] == g["u0"]).all() and (g2["iters"] == g["iters"]).all()
+
+
+def test_kkt_certificate_on_gpu_solutions(crb):
+    from kkt_check import certificate
+    N, M = 20, 3
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(8, N=N, M=M, seed=3)
+    prm = scenarios.default_cbf_params(N=N)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    n = 0
+    for b in range(8):
+        if g["status"][b] != 0 or g["elastic_max"][b] > 1e-7:
+            continue
+        c = certificate(x0[b], xt, obs[b], lap_off[b], prm, g["x"][b], g["u"][b], g["sigma"][b])
+        assert c["dyn"] < 1e-8 and c["row_viol"] < 1e-6 and c["stat"] < 1e-4 and c["comp"] < 1e-4, c
+        n += 1
+    assert n >= 6
+
+
+def test_ilqr_matches_reference_golden(crb):
+    """GPU iLQR against vectors produced by the unmodified reference control.ilqr."""
+    gold = np.load(os.path.join(GOLD, "ilqr_golden.npz"))
+    for N in sorted(set(gold["N"].tolist())):
+        idx = np.where(gold["N"] == N)[0]
+        x0, xt, obs, lap = gold["x0"][idx], gold["xt"][idx], gold["obs"][idx][:, :, :N + 1], gold["lap"][idx]
+        lap_off = (np.trunc(x0[:, 4] / lap) - np.trunc(obs[:, 0, 0] / lap)) * lap
+        prm = dict(A=gold["A"], B=gold["B"], Q=gold["Q"], R=gold["R"], N=int(N), max_iter=int(gold["max_iter"]), L=0.4, W=0.2)
+        g = crb.solve_ilqr_batch(x0, xt, obs, lap_off, prm)
+        assert np.abs(g["u0"] - gold["u0"][idx]).max() < 1e-9
+
+
+def test_ilqr_batch_vs_oracle(crb, oracle):
+    B, N = 512, 50
+    x0, xt, obs, lap_off = scenarios.ilqr_scenarios(B, N=N, seed=2)
+    p = scenarios.default_cbf_params()
+    prm = dict(A=p["A"], B=p["B"], Q=p["Q"], R=p["R"], N=N, max_iter=150, L=0.4, W=0.2)
+    g = crb.solve_ilqr_batch(x0, xt, obs, lap_off, prm)
+    r = oracle.solve_ilqr_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
+    same = g["iters"] == r["iters"]
+    du = np.abs(g["u0"] - r["u0"]).max(axis=1)
+    print("ilqr: same iteration count", same.mean(), "max du (same path)", du[same].max())
+    assert same.mean() >= 0.99 and du[same].max() < 1e-8
+    assert np.abs(g["u"][same] - r["u"][same]).max() < 1e-8 and np.abs(g["x"][same] - r["x"][same]).max() < 1e-8
+
+
+def test_drop_in_shims_on_gpu(crb, oracle):
+    """The reference-signature functions (control.py:476,198,64) with duck-typed vehicles."""
+    import types
+    from test_shims_host import Rival
+    lap = scenarios.LAP_LENGTH["l_shape"]
+    vehicles = {"ego": Rival(0, 0, 0), "car1": Rival(4.0, 0.2, 0.1), "car2": Rival(10.0, 0.2, -0.1)}
+    param = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 4.0, 0, 40.0]),
+                                  matrix_R=np.diag([0.1, 0.1]), num_horizon=10, alpha=0.8)
+    sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+    track = types.SimpleNamespace(width=1.0, lap_length=lap)
+    x = np.array([0.9, 0.0, 0.0, 0.02, 3.0, 0.05])
+    xt = np.array([0.8, 0, 0, 0, 0, 0.0]).reshape(6, 1)
+    u, det = crb.mpccbf(x, xt, param, vehicles, "ego", lap, 0.0, 0.1, False, track, sysp, return_details=True)
+    prm = scenarios.default_cbf_params(N=10)
+    obs = np.zeros((1, 1, 2, 11)); obs[0, 0, 0] = 4.0 + 0.02 * np.arange(11); obs[0, 0, 1] = 0.1
+    r = oracle.solve_cbf_batch(x[None], xt.ravel(), obs, None, prm)
+    assert u.shape == (2,) and np.abs(u - r["u0"][0]).max() < TOL_U and abs(det["cost"][0] - r["cost"][0]) < TOL_C
+    u2 = crb.mpc_lti(x, xt, types.SimpleNamespace(**{**param.__dict__}), sysp, track)
+    r2 = oracle.solve_cbf_batch(x[None], xt.ravel(), np.zeros((1, 0, 2, 11)), None, prm)
+    assert np.abs(u2 - r2["u0"][0]).max() < TOL_U
+    ip = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=param.matrix_Q, matrix_R=param.matrix_R,
+                               max_iter=150, num_horizon=50)
+    u3 = crb.ilqr(x, xt.ravel(), ip, {"ego": vehicles["ego"], "car1": vehicles["car1"]}, "ego", lap, 0.0, 0.1, track, sysp)
+    tr, _ = vehicles["car1"].get_trajectory_nsteps(0.0, 0.1, 51)
+    r3 = oracle.solve_ilqr_batch(x[None], xt.ravel(), tr[4:6][None], None,
+                                 dict(A=scenarios.LTI_A, B=scenarios.LTI_B, Q=param.matrix_Q, R=param.matrix_R, N=50, max_iter=150, L=0.4, W=0.2))
+    assert np.abs(u3 - r3["u0"][0]).max() < 1e-9
+
+
+def test_argmin_kernel_first_min(crb):
+    import ctypes as C
+    import torch
+    from car_racing_b200 import _capi
+    h = _capi.Handle()
+    rec = np.zeros(1000, dtype=_capi.RECORD_DTYPE)
+    rng = np.random.default_rng(0)
+    rec["cost"] = rng.integers(5, 50, size=1000).astype(float)
+    rec["status"] = rng.integers(0, 3, size=1000)
+    rec["cost"][[17, 400, 923]] = 1.0
+    rec["status"][[17, 400, 923]] = [2, 0, 0]
+    d = torch.from_numpy(rec.view(np.uint8)).cuda()
+    out = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    h.check(_capi.lib().b200mpc_argmin_cost_device(h.ptr, d.data_ptr(), 1000, 0, out.data_ptr()), "argmin")
+    torch.cuda.current_stream().synchronize(); torch.cuda.synchronize()
+    assert int(out.item()) == 400
+    h.check(_capi.lib().b200mpc_argmin_cost_device(h.ptr, d.data_ptr(), 1000, 2, out.data_ptr()), "argmin")
+    torch.cuda.synchronize()
+    assert int(out.item()) == 17

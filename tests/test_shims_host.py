@@ -1,0 +1,86 @@
+"""CPU tests of the drop-in shims' host logic (proximity filter, lap offsets, per-stage targets):
+the C-ABI call is intercepted, no GPU needed.  Scenario mirrors car_racing/tests/mpccbf_test.py:27-31."""
+import types
+
+import numpy as np
+import pytest
+
+from car_racing_b200 import control, scenarios
+
+
+class Rival:
+    def __init__(self, s0, v, ey, length=0.4, width=0.2):
+        self.param = types.SimpleNamespace(length=length, width=width)
+        self.s0, self.v, self.ey = s0, v, ey
+        self.xcurv = np.array([v, 0, 0, 0, s0, ey])
+
+    def get_trajectory_nsteps(self, t0, dt, n):
+        tr = np.zeros((6, n))
+        tr[4] = self.s0 + self.v * dt * np.arange(n)
+        tr[5] = self.ey
+        return tr, None
+
+
+def _capture(monkeypatch):
+    seen = {}
+
+    def fake(x0, xt, obs, lap_off, prm, want=("aux", "x", "u", "sigma"), handle=None, **opt):
+        seen.update(x0=np.array(x0), xt=np.array(xt), obs=np.array(obs), lap_off=lap_off, prm=prm)
+        N = prm["N"]
+        return dict(u=np.zeros((1, N, 2)) + 0.25, x=np.zeros((1, N + 1, 6)), status=np.array([0]), u0=np.zeros((1, 2)))
+    monkeypatch.setattr(control.batch, "solve_cbf_batch", fake)
+    return seen
+
+
+def test_mpccbf_filter_and_lap_offset(monkeypatch):
+    seen = _capture(monkeypatch)
+    lap = 19.2296
+    vehicles = {"ego": Rival(0, 0, 0), "car1": Rival(lap + 4.0, 0.2, 0.1), "car2": Rival(10.0, 0.2, -0.1),
+                "car3": Rival(2.0 * lap + 2.5, 0.0, 0.3)}
+    param = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.eye(6), matrix_R=np.eye(2),
+                                  num_horizon=10, alpha=0.8)
+    sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+    track = types.SimpleNamespace(width=1.0, lap_length=lap)
+    x = np.array([1.2, 0, 0, 0, 3.0, 0.0])
+    u = control.mpccbf(x, np.array([0.8, 0, 0, 0, 0, 0]).reshape(6, 1), param, vehicles, "ego", lap, 0.0, 0.1, False, track, sysp)
+    assert u.shape == (2,) and (u == 0.25).all()
+    # window is +-2*vx = 2.4 m: car1 (lap 1, s mod lap = 4.0) and car3 (lap 2, 2.5) are kept, car2 (10.0) is not
+    assert seen["obs"].shape == (1, 2, 2, 11)
+    assert np.allclose(seen["obs"][0, 0, 0], lap + 4.0 + 0.02 * np.arange(11)) and np.allclose(seen["obs"][0, 1, 1], 0.3)
+    assert np.allclose(seen["lap_off"], [[-lap, -2 * lap]])
+    assert seen["prm"]["alpha"] == 0.8 and seen["prm"]["margin"] == 0.2 and seen["prm"]["L"] == 0.4 and seen["prm"]["W"] == 0.2
+    assert seen["xt"].shape == (6,)
+
+
+def test_mpccbf_rejects_mixed_rival_sizes(monkeypatch):
+    _capture(monkeypatch)
+    vehicles = {"ego": Rival(0, 0, 0), "a": Rival(4.0, 0, 0.1), "b": Rival(4.5, 0, -0.3, length=0.6)}
+    param = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.eye(6), matrix_R=np.eye(2),
+                                  num_horizon=5, alpha=0.8)
+    sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+    with pytest.raises(NotImplementedError):
+        control.mpccbf(np.array([1.2, 0, 0, 0, 3.0, 0.0]), np.zeros(6), param, vehicles, "ego", 19.2296, 0.0, 0.1, False,
+                       types.SimpleNamespace(width=1.0), sysp)
+
+
+def test_mpc_multi_agents_targets(monkeypatch):
+    seen = _capture(monkeypatch)
+    lap = 19.1313
+    vehicles = {"ego": Rival(0, 0, 0), "car1": Rival(5.0, 1.0, -0.5), "car2": Rival(30.0, 1.0, 0.2)}
+    param = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.eye(6), matrix_R=np.eye(2),
+                                  num_horizon_ctrl=10)
+    sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+    track = types.SimpleNamespace(width=1.0, lap_length=lap)
+    traj = np.zeros((11, 6))
+    traj[:, 4] = 4.0 + 0.15 * np.arange(11)
+    traj[:, 5] = 0.05 * np.arange(11)
+    x = np.array([1.5, 0, 0, 0, 3.9, 0.1])
+    u, xp = control.mpc_multi_agents(x, param, track, None, None, None, sysp, target_traj_xcurv=traj, vehicles=vehicles,
+                                     agent_name="ego", direction_flag=0, sorted_vehicles=["car1", "car2"], time=None)
+    assert u.shape == (2,) and xp.shape == (11, 6)
+    xt = seen["xt"]
+    assert xt.shape == (1, 11, 6) and (xt[0, :, 0] == 1.5).all()
+    s = np.clip(1.5 * 0.1 * np.arange(11) + 3.9, 4.0, traj[-1, 4])
+    assert np.allclose(xt[0, :, 5], np.interp(s, traj[:, 4], traj[:, 5]))
+    assert seen["obs"].shape[1] == 1 and seen["prm"]["alpha"] == 0.6 and seen["prm"]["margin"] == 0.15
+    assert seen["prm"]["L"] == 0.4 and seen["prm"]["W"] == 0.2
