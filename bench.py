@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- MPC-CBF solves/sec (N=20, 6-state, 3 rivals), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A "step" is one pass of the hot path over one batch of B=1024 synthetic config-2 scenarios
+(car_racing_b200/scenarios.py, seed 1).  With N>1 (torchrun, one rank per
+GPU) every rank solves its own 1024-scenario shard (weak scaling) and the step ends with one NCCL
+all-gather of the 32-byte records + the argmin kernel.
+
+`value`    : whole-job solves/s with the packed inputs already resident in HBM (kernel only).
+`e2e`      : the same metric through the host-pointer C-ABI call (pinned host buffers; H2D of the
+             records, kernel, D2H of the 32-byte result records inside the timed region).
+`roofline` : algorithmic HBM bytes / kernel time against the measured copy bandwidth -- stated
+             honestly: this kernel is FP64-latency / shared-memory bound, not HBM bound.
+`--impl reference` times the CPU implementation of the path (the oracle port: CasADi/IPOPT is not
+installable here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MPC-CBF solves/sec (N=20, 6-state, 3 obs)"
+ALG_BYTES_PER_SOLVE = 1136 + 536      # 1136 B in (one packed record) + 536 B out
+N_H, M_OBS = 20, 3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def workload(B, seed):
+    from car_racing_b200 import batch, scenarios
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=N_H, M=M_OBS, seed=seed)
+    prm = scenarios.default_cbf_params(N=N_H)
+    rec, M, ps = batch.pack_cbf(x0, xt, obs, lap_off, N_H)
+    return (x0, xt, obs, lap_off), prm, rec
+
+
+def cpu_port_rate(B_sample, nthreads, seed=1):
+    """The CPU restatement (oracle/ocp_oracle.c) on `nthreads` host threads; returns (solves/s, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    from car_racing_b200 import scenarios
+    (x0, xt, obs, lap_off), prm, _ = workload(B_sample, seed)
+    orc.lib()
+    t = time.perf_counter()
+    orc.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=nthreads)
+    dt = time.perf_counter() - t
+    return B_sample / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path for this metric.  CasADi/IPOPT cannot be installed
+    here, so the arm times the oracle port on all host threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    B = args.batch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    from car_racing_b200 import scenarios
+    (x0, xt, obs, lap_off), prm, _ = workload(B, 1)
+    orc.lib()
+    for _ in range(args.warmup):
+        orc.solve_cbf_batch(x0[:64], xt, obs[:64], lap_off[:64], prm, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=cores)
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 (config 2)" % B,
+                       "note": "CasADi/IPOPT not installable offline; CPU port of the same NLP + interior point (oracle/ocp_oracle.c)"},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": "%d instances per step, %d pthreads" % (B, cores)},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="instances per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import car_racing_b200 as crb
+    from car_racing_b200 import _capi, sharding
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    _, prm, rec_host = workload(B, seed=1 + rank)            # each rank: its own shard of scenarios
+    h = _capi.Handle(device=local_rank, max_batch=B)
+    L = _capi.lib()
+    p = _capi.make_cbf_params(prm, M_OBS, False)
+    o = _capi.default_options()
+    ext = torch.cuda.ExternalStream(h.stream, device=dev)
+    d_in = torch.from_numpy(rec_host).to(dev)
+    d_rec = torch.zeros((B, 4), dtype=torch.float64, device=dev)
+    d_all = torch.zeros((world * B, 4), dtype=torch.float64, device=dev)
+    d_arg = torch.zeros(1, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_device():
+        rc = L.b200mpc_cbf_solve_device(h.ptr, C.byref(p), C.byref(o), B, d_in.data_ptr(), d_rec.data_ptr(), None, None, None, None)
+        h.check(rc, "b200mpc_cbf_solve_device")
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_rec)
+            h.check(L.b200mpc_argmin_cost_device(h.ptr, d_all.data_ptr(), world * B, 0, d_arg.data_ptr()), "argmin")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    launches0 = h.launch_count
+    with torch.cuda.stream(ext):
+        for _ in range(args.warmup):
+            flush.zero_()
+            step_device()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        # ---- kernel-resident timing: exactly K steps, CUDA events on the launching stream, L2 flushed between steps
+        evs = []
+        barrier()
+        wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            step_device()
+            e1.record(ext)
+            evs.append((e0, e1))
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = [a.elapsed_time(b) for a, b in evs]
+    launches_dev = h.launch_count - launches0
+    t_dev = float(np.sum(ms)) * 1e-3
+    status = sharding.tensor_to_records(d_rec)["status"]
+    conv = float((status == 0).mean())
+
+    # ---- end to end through the host-pointer C-ABI: pinned host records in, 32-byte records out
+    pin_in = torch.from_numpy(rec_host).pin_memory()
+    pin_out = torch.zeros((B, 4), dtype=torch.float64).pin_memory()
+    e2e_ms = []
+    with torch.cuda.stream(ext):
+        for k in range(args.warmup + args.steps):
+            flush.zero_()
+            ext.synchronize()
+            t0 = time.perf_counter()
+            rc = L.b200mpc_cbf_solve(h.ptr, C.byref(p), C.byref(o), B, pin_in.data_ptr(), pin_out.data_ptr(), None, None, None, None)
+            h.check(rc, "b200mpc_cbf_solve")
+            _ = float(pin_out[0, 0])                          # the step's result is read on the host
+            if k >= args.warmup:
+                e2e_ms.append(1e3 * (time.perf_counter() - t0))
+        barrier()
+        # p50 latency of a single solve (B=1) through the same call
+        lat = []
+        for k in range(60):
+            t0 = time.perf_counter()
+            L.b200mpc_cbf_solve(h.ptr, C.byref(p), C.byref(o), 1, pin_in.data_ptr(), pin_out.data_ptr(), None, None, None, None)
+            if k >= 10:
+                lat.append(1e3 * (time.perf_counter() - t0))
+    clocks = sampler.stop()
+    t_e2e = float(np.sum(e2e_ms)) * 1e-3
+    launches_total = h.launch_count - launches0
+
+    # ---- max over ranks
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e, wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, wall = [float(v) for v in tt.tolist()]
+        cv = torch.tensor([conv], dtype=torch.float64, device=dev)
+        dist.all_reduce(cv, op=dist.ReduceOp.MIN)
+        conv = float(cv.item())
+    total = B * world * args.steps
+    value = total / t_dev
+    hbm_peak, peak_src = peaks()
+    kernel_ms = float(np.mean(ms))
+    achieved = ALG_BYTES_PER_SOLVE * B / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    line = {
+        "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 per GPU (BASELINE config 2)" % B,
+                   "global_batch": B * world, "parallelism": "dp%d (independent scenario shards + 1 all-gather of 32-B records)" % world,
+                   "l2": "256 MiB buffer written between timed steps (inputs are 1.1 MB << L2)",
+                   "solver": "FP64 barrier-SQP (IPOPT conventions), Riccati KKT, tol 1e-8", "converged_frac": conv},
+        "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(rec_host.nbytes),
+                "d2h_bytes_per_step": int(B * 32), "ms_per_step": 1e3 * t_e2e / args.steps,
+                "p50_latency_ms_batch1": float(np.median(lat))},
+        "gpu_launches": int(launches_dev),
+        "gpu_launches_incl_e2e": int(launches_total),
+        "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "note": "algorithmic bytes = 1672 B/solve x %d; the kernel is FP64-latency/shared-memory bound, see profiles/ and DESIGN.md" % B},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, dt = cpu_port_rate(min(B, 1024), cores)
+        line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
+                                "sample": "the same %d scenarios, once, %d pthreads (%.1f s)" % (min(B, 1024), cores, dt)}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

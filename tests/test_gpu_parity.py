@@ -16,7 +16,8 @@ def _compare(g, r, min_match=0.97):
     both = (g["status"] == 0) & (r["status"] == 0)
     du = np.abs(g["u0"] - r["u0"]).max(axis=1)
     dc = np.abs(g["cost"] - r["cost"])
-    match = both & (du < TOL_U) & (dc < TOL_C)
+    same_fail = (g["status"] != 0) & (g["status"] == r["status"])   # both stop the same way on the same instance
+    match = (both & (du < TOL_U) & (dc < TOL_C)) | same_fail
     info = dict(B=len(du), both_converged=int(both.sum()), match=int(match.sum()),
                 gpu_fail=int((g["status"] != 0).sum()), cpu_fail=int((r["status"] != 0).sum()),
                 worst_du=float(du[both].max()) if both.any() else 0.0, worst_dc=float(dc[both].max()) if both.any() else 0.0,
