@@ -15,11 +15,15 @@
 // X_k = (x_k, sigma_k), U_k = (u_k, sigma_{k+1}); a non-positive pivot in any stage's
 // Cholesky is the inertia test.
 //
-// Execution style: the warp works in two modes.  Entry-parallel phases (assembly of the stage
-// Hessian, residuals, line-search evaluation) give every lane a few matrix entries with
-// compile-time trip counts and branch-free, uniform code.  The sequential recursions
-// (Cholesky of the 5x5 pivot block, forward sweep, costate sweep) are computed redundantly in
-// every lane's registers from broadcast shared-memory loads, so they need no warp barrier.
+// Execution style (measured: a lone warp pays ~4 issue cycles per shared-memory load and 2 per
+// DFMA, so the design minimises LDS count and keeps the model out of shared memory):
+//  * O(N) phases (residuals, derivatives, optimality error, assembly, line-search evaluation,
+//    updates) run with LANE = STAGE: each lane does all the work of one stage as straight-line
+//    code; the model matrices A, B, Q, R are compile-time-indexed kernel parameters, i.e.
+//    constant-bank operands of the DFMAs, not loads.
+//  * the backward Riccati sweep runs with LANE = COLUMN of the stage Hessian: P lives in
+//    registers (lane a holds row a), phases exchange transposes through small shared buffers.
+//  * the forward and costate sweeps carry the state redundantly in every lane's registers.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,9 +51,10 @@ __host__ __device__ inline int cbf_record_doubles(int N, int M, int xt_per_stage
 template <int M>
 struct SmemPlan {
     static constexpr int NXA = 6 + M, NUA = 2 + M, NZ = NXA + NUA;
+    static constexpr int NXAP = (NXA + 1) & ~1, NUAP = (NUA + 1) & ~1, NC = 8 + M;
     int N, R, NB, NW, OU, OS;
-    int oTM, oQQ, oRR, oQ, oR, oIN, oW, oD, oHD, oZL, oZU, oS, oT, oY, oZ, oV, oDG, oG, oSIGE, oYHAT, oJD, oJA, oLAM,
-        oCRES, oKFB, oKFF, oP, oPV, oPT, oGM, oGV, oCT, oYF, oQV, oDS, oGS, total;
+    int oIN, oW, oD, oHD, oZL, oZU, oS, oT, oY, oZ, oV, oDG, oG, oSIGE, oYHAT, oJD, oJA, oLAM, oCRES, oKFB, oKFF, oPT, oQV,
+        oGUU, oGVU, oYF, oYG, oS0, total;
     __host__ __device__ SmemPlan(int N_, int in_stride) {
         N = N_;
         R = M * N;
@@ -60,17 +65,16 @@ struct SmemPlan {
         int o = 2;  // doubles 0..1: mbarrier (8 B) + pad, keeps everything after 16-byte aligned
         auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
         oIN = take(in_stride);
-        oTM = take(NXA * NZ); oQQ = take(36); oRR = take(4); oQ = take(36); oR = take(4);
-        oW = take(NW); oD = take(NW); oHD = take(NW);
+        oW = take(NW + 2); oD = take(NW + 2); oHD = take(NW + 2);
         oZL = take(NB); oZU = take(4 * N);
         oS = take(R); oT = take(R); oY = take(R); oZ = take(R); oV = take(R);
         oDG = take(R); oG = take(R); oSIGE = take(R); oYHAT = take(R); oJD = take(R);
         oJA = take(4 * R);
-        oLAM = take(6 * N); oCRES = take(6 * N);
-        oKFB = take(N * NUA * NXA); oKFF = take(N * NUA);
-        oP = take(NXA * NXA); oPV = take(NXA); oPT = take(NXA * NZ);
-        oGM = take(NZ * NZ); oGV = take(NZ); oCT = take((M > 0 ? M : 1) * NZ);
-        oYF = take(NUA * (NXA + 1)); oQV = take(NXA); oDS = take(NZ); oGS = take(NZ);
+        oLAM = take(6 * N + 6); oCRES = take(6 * N + 6);
+        oKFB = take(N * NUA * NXAP); oKFF = take(N * NUAP);
+        oPT = take((NC + 1) * NXAP); oQV = take(NXAP);
+        oGUU = take(NUA * NUAP); oGVU = take(NUAP); oYF = take(NXA * NUAP); oYG = take(NUAP);
+        oS0 = take((M > 0 ? M : 1) * (M + 2));
         total = o;
     }
     __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(double); }
@@ -109,6 +113,36 @@ struct LogAcc {
     __device__ __forceinline__ double value() const { return log(m) + (double)e * 0.693147180559945309417232; }
 };
 
+// 16-byte shared-memory accesses (all array bases and the offsets used are even)
+__device__ __forceinline__ void ld6(const double *p, double (&v)[6]) {
+    double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2),
+            c = *reinterpret_cast<const double2 *>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+__device__ __forceinline__ void st6(double *p, const double (&v)[6]) {
+    *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]);
+    *reinterpret_cast<double2 *>(p + 4) = make_double2(v[4], v[5]);
+}
+template <int K>
+__device__ __forceinline__ void ldv(const double *p, double (&v)[K]) {  // K values, storage padded to even
+#pragma unroll
+    for (int i = 0; i + 1 < K; i += 2) {
+        double2 a = *reinterpret_cast<const double2 *>(p + i);
+        v[i] = a.x;
+        v[i + 1] = a.y;
+    }
+    if (K & 1) v[K - 1] = p[K - 1];
+}
+template <int K>
+__device__ __forceinline__ void stv(double *p, const double (&v)[K]) {
+#pragma unroll
+    for (int i = 0; i + 1 < K; i += 2) *reinterpret_cast<double2 *>(p + i) = make_double2(v[i], v[i + 1]);
+    if (K & 1) p[K - 1] = v[K - 1];
+}
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+
 // ---------------------------------------------------------------- TMA (bulk async copy) + mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -138,30 +172,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
         : "memory");
 }
 
-// number of 32-wide rounds needed to cover n entries (compile-time when n is)
-__host__ __device__ constexpr int rounds(int n) { return (n + 31) / 32; }
-
 // ---------------------------------------------------------------- the solver
-// NT > 0: horizon known at compile time (entry loops fully unrolled); NT == 0: runtime horizon.
-template <int NT, int M>
+template <int M>
 struct Ipm {
     static constexpr int NXA = 6 + M, NUA = 2 + M, NZ = NXA + NUA;
+    static constexpr int NXAP = (NXA + 1) & ~1, NUAP = (NUA + 1) & ~1, NC = 8 + M, MM = (M > 0 ? M : 1);
     const KParams &kp;
     const int lane, N, R, NB, NW, OU, OS;
-    double *TM, *QQ, *RR, *cQ, *cR, *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM,
-        *CRES, *KFB, *KFF, *P, *PV, *PT, *GM, *GV, *CT, *YF, *QV, *DS, *GS;
+    double *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM, *CRES, *KFB, *KFF, *PT,
+        *QVs, *GUU, *GVU, *YF, *YG, *S0;
     const double *xt, *obs, *lapoff;
     double df, mu, rho, a1;  // a1 = 1 - alpha
+    // lane = column role of the Riccati sweep (set once)
+    bool isx, iss, isu, isp;
+    int jrole, cmap;
+    double tcol[6], qqcol[6], rrcol[2];
+    double arow[6], brow[2];   // row `lane` of A and B (lanes < 6), for the forward sweep
 
     __device__ Ipm(const KParams &kp_, const SmemPlan<M> &pl, double *sm, int lane_)
         : kp(kp_), lane(lane_), N(pl.N), R(pl.R), NB(pl.NB), NW(pl.NW), OU(pl.OU), OS(pl.OS) {
-        TM = sm + pl.oTM; QQ = sm + pl.oQQ; RR = sm + pl.oRR; cQ = sm + pl.oQ; cR = sm + pl.oR; IN = sm + pl.oIN;
-        W = sm + pl.oW; D = sm + pl.oD; HD = sm + pl.oHD; ZL = sm + pl.oZL; ZU = sm + pl.oZU;
+        IN = sm + pl.oIN; W = sm + pl.oW; D = sm + pl.oD; HD = sm + pl.oHD; ZL = sm + pl.oZL; ZU = sm + pl.oZU;
         S = sm + pl.oS; T = sm + pl.oT; Y = sm + pl.oY; Z = sm + pl.oZ; V = sm + pl.oV;
         DG = sm + pl.oDG; GR = sm + pl.oG; SIGE = sm + pl.oSIGE; YHAT = sm + pl.oYHAT; JD = sm + pl.oJD;
         JA = sm + pl.oJA; LAM = sm + pl.oLAM; CRES = sm + pl.oCRES; KFB = sm + pl.oKFB; KFF = sm + pl.oKFF;
-        P = sm + pl.oP; PV = sm + pl.oPV; PT = sm + pl.oPT; GM = sm + pl.oGM; GV = sm + pl.oGV; CT = sm + pl.oCT;
-        YF = sm + pl.oYF; QV = sm + pl.oQV; DS = sm + pl.oDS; GS = sm + pl.oGS;
+        PT = sm + pl.oPT; QVs = sm + pl.oQV; GUU = sm + pl.oGUU; GVU = sm + pl.oGVU; YF = sm + pl.oYF; YG = sm + pl.oYG;
+        S0 = sm + pl.oS0;
         lapoff = IN + 6;
         xt = IN + kp.hdr;
         obs = IN + kp.obs_off;
@@ -169,67 +204,83 @@ struct Ipm {
         rho = kp.o.rho;
         df = 1.0;
         mu = kp.o.mu_init;
+        const int l = lane;
+        isx = l < 6;
+        iss = l >= 6 && l < NXA;
+        isu = l >= NXA && l < NXA + 2;
+        isp = l >= NXA + 2 && l < NZ;
+        jrole = iss ? l - 6 : (isp ? l - NXA - 2 : (isu ? l - NXA : 0));
+        cmap = isx ? l : (isu ? 6 + (l - NXA) : (isp ? 8 + (l - NXA - 2) : NC));  // NC = the all-zero row of PT
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            double va = 0.0, vb = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) va = (l == c) ? kp.p.A[6 * q + c] : va;
+#pragma unroll
+            for (int c = 0; c < 2; c++) vb = (l == NXA + c) ? kp.p.B[2 * q + c] : vb;
+            tcol[q] = isx ? va : vb;
+            qqcol[q] = 0.0;
+        }
+        rrcol[0] = rrcol[1] = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) {
+            double v = 0.0;
+#pragma unroll
+            for (int a = 0; a < 6; a++) v = (l == a) ? kp.p.A[6 * a + b] : v;
+            arow[b] = v;
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            double v = 0.0;
+#pragma unroll
+            for (int a = 0; a < 6; a++) v = (l == a) ? kp.p.B[2 * a + c] : v;
+            brow[c] = v;
+        }
+    }
+    // after the objective scaling df is known
+    __device__ void set_scaled_columns() {
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) v = (lane == c) ? Q2(q, c) : v;
+            qqcol[q] = df * v;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < 2; c++) v = (lane == NXA + c) ? R2(q, c) : v;
+            rrcol[q] = df * v;
+        }
     }
 
-    // A[a][b] and B[a][c] live inside the dense stage map TM (rows 0..5)
-    __device__ __forceinline__ double Am(int a, int b) const { return TM[a * NZ + b]; }
-    __device__ __forceinline__ double Bm(int a, int c) const { return TM[a * NZ + NXA + c]; }
+    // model constants with compile-time indices -> constant-bank operands
+    __device__ __forceinline__ double Am(int a, int b) const { return kp.p.A[6 * a + b]; }
+    __device__ __forceinline__ double Bm(int a, int c) const { return kp.p.B[2 * a + c]; }
+    __device__ __forceinline__ double Q2(int a, int b) const { return kp.p.Q[6 * a + b] + kp.p.Q[6 * b + a]; }
+    __device__ __forceinline__ double R2(int a, int b) const { return kp.p.R[2 * a + b] + kp.p.R[2 * b + a]; }
 
     // ---- indexing
-    __device__ __forceinline__ double xtv(int i, int a) const { return kp.p.xt_per_stage ? xt[6 * i + a] : xt[a]; }
+    __device__ __forceinline__ const double *xtp(int i) const { return kp.p.xt_per_stage ? xt + 6 * i : xt; }
     __device__ __forceinline__ double obs_s(int j, int i) const { return obs[(2 * j) * (N + 1) + i]; }
     __device__ __forceinline__ double obs_e(int j, int i) const { return obs[(2 * j + 1) * (N + 1) + i]; }
     __device__ __forceinline__ int isg(int j, int i) const { return OS + j * (N + 1) + i; }
-    // bounded variable b -> index in W and its bounds (ZU has slots only for b < 4N)
-    __device__ __forceinline__ void bvar(int b, int &wi, double &lb, double &ub, bool &hasU) const {
-        if (b < 2 * N) {
-            int i = 1 + (b >> 1);
-            bool ey = b & 1;
-            wi = 6 * i + (ey ? 5 : 0);
-            lb = ey ? -kp.p.width : kp.p.vmin;
-            ub = ey ? kp.p.width : kp.p.vmax;
-            hasU = true;
-        } else if (b < 4 * N) {
-            int e = b - 2 * N;
-            wi = OU + e;
-            ub = kp.p.umax[e & 1];
-            lb = -ub;
-            hasU = true;
-        } else {
-            wi = OS + (b - 4 * N);
-            lb = 0.0;
-            ub = 0.0;
-            hasU = false;
-        }
-    }
-    // index of the bound-multiplier slot of primal entry wi, or -1
-    __device__ __forceinline__ int bslot(int wi) const {
-        if (wi < OU) {
-            int i = wi / 6, a = wi - 6 * i;
-            if (i == 0 || (a != 0 && a != 5)) return -1;
-            return 2 * (i - 1) + (a == 5);
-        }
-        if (wi < OS) return 2 * N + (wi - OU);
-        return 4 * N + (wi - OS);
-    }
+    // bound-multiplier slots: x_i (i>=1): 2(i-1) (vx), 2(i-1)+1 (ey); u_k: 2N+2k, 2N+2k+1; sigma_{j,i}: 4N + j(N+1)+i
+    __device__ __forceinline__ int bsx(int i) const { return 2 * (i - 1); }
+    __device__ __forceinline__ int bsu(int k) const { return 2 * N + 2 * k; }
+    __device__ __forceinline__ int bss(int j, int i) const { return 4 * N + j * (N + 1) + i; }
 
-    // ---- row r=(j,i) evaluated at W + al*D : unscaled pieces
+    // ---- stage evaluation helpers (lane = stage)
     struct RowV { double ds, de, dsn, den, sg, sgn; };
-    template <bool useD>
-    __device__ __forceinline__ RowV row_vals(int j, int i, double al) const {
+    __device__ __forceinline__ RowV row_vals(int j, int i, const double (&x)[6], const double (&xn)[6], double sg, double sgn) const {
         RowV v;
-        double xs = W[6 * i + 4], xe = W[6 * i + 5], xsn = W[6 * i + 10], xen = W[6 * i + 11];
-        v.sg = W[isg(j, i)];
-        v.sgn = W[isg(j, i + 1)];
-        if (useD) {
-            xs += al * D[6 * i + 4]; xe += al * D[6 * i + 5]; xsn += al * D[6 * i + 10]; xen += al * D[6 * i + 11];
-            v.sg += al * D[isg(j, i)];
-            v.sgn += al * D[isg(j, i + 1)];
-        }
-        v.ds = xs - obs_s(j, i) - lapoff[j];   // control.py:539-540 (with lap offset)
-        v.de = xe - obs_e(j, i);
-        v.dsn = xsn - obs_s(j, i + 1);         // control.py:542 (quirk: no lap offset)
-        v.den = xen - obs_e(j, i + 1);
+        v.sg = sg;
+        v.sgn = sgn;
+        v.ds = x[4] - obs_s(j, i) - lapoff[j];   // control.py:539-540 (with lap offset)
+        v.de = x[5] - obs_e(j, i);
+        v.dsn = xn[4] - obs_s(j, i + 1);         // control.py:542 (quirk: no lap offset)
+        v.den = xn[5] - obs_e(j, i + 1);
         return v;
     }
     __device__ __forceinline__ double row_g(const RowV &v) const {  // unscaled h_next - (1-alpha) h  (control.py:558)
@@ -237,115 +288,69 @@ struct Ipm {
         double hn = p6(v.dsn) * kp.iL6 + p6(v.den) * kp.iW6 - 1.0 - kp.p.margin - v.sgn;
         return hn - a1 * h;
     }
-
-    // ---- dynamics residual c_k = x_{k+1} - A x_k - B u_k at W + al*D, entry e=(k,a)
+    // x_k, u_k at W + al*D
     template <bool useD>
-    __device__ __forceinline__ double dyn_res(int e, double al) const {
-        int k = e / 6, a = e - 6 * k;
-        double s = W[6 * (k + 1) + a];
-        if (useD) s += al * D[6 * (k + 1) + a];
+    __device__ __forceinline__ void load_x(int k, double al, double (&x)[6]) const {
+        ld6(W + 6 * k, x);
+        if (useD) {
+            double d[6];
+            ld6(D + 6 * k, d);
 #pragma unroll
-        for (int b = 0; b < 6; b++) {
-            double xv = W[6 * k + b];
-            if (useD) xv += al * D[6 * k + b];
-            s -= Am(a, b) * xv;
+            for (int a = 0; a < 6; a++) x[a] += al * d[a];
         }
-        double u0 = W[OU + 2 * k], u1 = W[OU + 2 * k + 1];
-        if (useD) { u0 += al * D[OU + 2 * k]; u1 += al * D[OU + 2 * k + 1]; }
-        s -= Bm(a, 0) * u0 + Bm(a, 1) * u1;
-        return s;
     }
-
-    // ---- constraint violation theta (1-norm) and barrier function phi at W + al*D, slacks moved by al
     template <bool useD>
-    __device__ void theta_phi(double al, double &theta, double &phi) const {
-        double th = 0.0, f = 0.0, tsum = 0.0;
-        LogAcc la;
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(6 * NT) : 1); t++)
-            for (int e = lane + 32 * t; e < 6 * N; e += (NT ? 1 << 30 : 32)) th += fabs(dyn_res<useD>(e, al));
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(M * NT) : 1); t++)
-            for (int r = lane + 32 * t; r < R; r += (NT ? 1 << 30 : 32)) {
-                int j = r / N, i = r - j * N;
-                RowV v = row_vals<useD>(j, i, al);
-                double g = DG[r] * row_g(v);
-                double s = S[r], tt = T[r];
-                if (useD) {
-                    double ds, dt, dy, dz, dv;
-                    row_step(r, ds, dt, dy, dz, dv);
-                    s += al * ds;
-                    tt += al * dt;
-                }
-                th += fabs(g + tt - s);
-                la.mul(s);
-                la.mul(tt);
-                tsum += tt;
-            }
-        // objective: stage terms (control.py:588-591), input terms (:578-579), slack penalty (:560,562)
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(6 * (NT + 1)) : 1); t++)
-            for (int e = lane + 32 * t; e < 6 * (N + 1); e += (NT ? 1 << 30 : 32)) {
-                int i = e / 6, a = e - 6 * i;
-                double acc = 0.0, da = 0.0;
-#pragma unroll
-                for (int b = 0; b < 6; b++) {
-                    double d = W[6 * i + b] - xtv(i, b);
-                    if (useD) d += al * D[6 * i + b];
-                    acc += cQ[6 * a + b] * d;
-                    da = (b == a) ? d : da;
-                }
-                f += da * acc;
-            }
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(2 * NT) : 1); t++)
-            for (int e = lane + 32 * t; e < 2 * N; e += (NT ? 1 << 30 : 32)) {
-                int i = e >> 1, a = e & 1;
-                double u0 = W[OU + 2 * i], u1 = W[OU + 2 * i + 1];
-                if (useD) { u0 += al * D[OU + 2 * i]; u1 += al * D[OU + 2 * i + 1]; }
-                f += (a ? u1 : u0) * (cR[2 * a] * u0 + cR[2 * a + 1] * u1);
-            }
-        double ss = 0.0;
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(M * (NT + 1)) : 1); t++)
-            for (int e = lane + 32 * t; e < M * (N + 1); e += (NT ? 1 << 30 : 32)) {
-                double sv = W[OS + e];
-                if (useD) sv += al * D[OS + e];
-                ss += sv;
-            }
-        f += kp.p.slack_w * ss;
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(4 * NT + M * (NT + 1)) : 1); t++)
-            for (int b = lane + 32 * t; b < NB; b += (NT ? 1 << 30 : 32)) {
-                int wi; double lb, ub; bool hu;
-                bvar(b, wi, lb, ub, hu);
-                double w = W[wi];
-                if (useD) w += al * D[wi];
-                la.mul(w - lb);
-                if (hu) la.mul(ub - w);
-            }
-        theta = warp_sum(th);
-        phi = df * warp_sum(f) + rho * warp_sum(tsum) - mu * warp_sum(la.value());
+    __device__ __forceinline__ void load_u(int k, double al, double (&u)[2]) const {
+        double2 a = ld2(W + OU + 2 * k);
+        u[0] = a.x; u[1] = a.y;
+        if (useD) {
+            double2 d = ld2(D + OU + 2 * k);
+            u[0] += al * d.x; u[1] += al * d.y;
+        }
     }
-
-    // unscaled objective at W
-    __device__ double objective() const {
+    // c_k = x_{k+1} - A x_k - B u_k
+    __device__ __forceinline__ void dyn_res(const double (&x)[6], const double (&xn)[6], const double (&u)[2], double (&c)[6]) const {
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            double s = xn[a];
+#pragma unroll
+            for (int b = 0; b < 6; b++) s -= Am(a, b) * x[b];
+            s -= Bm(a, 0) * u[0] + Bm(a, 1) * u[1];
+            c[a] = s;
+        }
+    }
+    // (x-xt)'Q(x-xt)
+    __device__ __forceinline__ double stage_cost(int i, const double (&x)[6]) const {
+        const double *t = xtp(i);
+        double d[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) d[a] = x[a] - t[a];
         double f = 0.0;
-        for (int e = lane; e < 6 * (N + 1); e += 32) {
-            int i = e / 6, a = e - 6 * i;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
             double acc = 0.0;
 #pragma unroll
-            for (int b = 0; b < 6; b++) acc += cQ[6 * a + b] * (W[6 * i + b] - xtv(i, b));
-            f += (W[6 * i + a] - xtv(i, a)) * acc;
+            for (int b = 0; b < 6; b++) acc += kp.p.Q[6 * a + b] * d[b];
+            f += d[a] * acc;
         }
-        for (int e = lane; e < 2 * N; e += 32) {
-            int i = e >> 1, a = e & 1;
-            double u0 = W[OU + 2 * i], u1 = W[OU + 2 * i + 1];
-            f += (a ? u1 : u0) * (cR[2 * a] * u0 + cR[2 * a + 1] * u1);
+        return f;
+    }
+    __device__ __forceinline__ double input_cost(const double (&u)[2]) const {
+        return u[0] * (kp.p.R[0] * u[0] + kp.p.R[1] * u[1]) + u[1] * (kp.p.R[2] * u[0] + kp.p.R[3] * u[1]);
+    }
+    // scaled gradient of the objective wrt x_i
+    __device__ __forceinline__ void grad_x(int i, const double (&x)[6], double (&g)[6]) const {
+        const double *t = xtp(i);
+        double d[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) d[a] = x[a] - t[a];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; b++) acc += Q2(a, b) * d[b];
+            g[a] = df * acc;
         }
-        double ss = 0.0;
-        for (int e = lane; e < M * (N + 1); e += 32) ss += W[OS + e];
-        return warp_sum(f + kp.p.slack_w * ss);
     }
 
     // ---- Newton steps of the row slacks / multipliers from JD (all at the current iterate)
@@ -362,108 +367,188 @@ struct Ipm {
         dz = mu * is - z - sig_s * ds;
     }
 
-    // ---- evaluate rows (GR, JA) and dynamics residual at the current iterate
+    // ---- constraint violation theta (1-norm) and barrier function phi at W + al*D, slacks moved by al
+    template <bool useD>
+    __device__ void theta_phi(double al, double &theta, double &phi) const {
+        double th = 0.0, f = 0.0, tsum = 0.0, ss = 0.0;
+        LogAcc la;
+        for (int k = lane; k <= N; k += 32) {
+            double x[6];
+            load_x<useD>(k, al, x);
+            f += stage_cost(k, x);                                   // control.py:588-591
+            if (k >= 1) {                                            // bounds on vx_k, ey_k (:582-586)
+                la.mul(x[0] - kp.p.vmin); la.mul(kp.p.vmax - x[0]);
+                la.mul(x[5] + kp.p.width); la.mul(kp.p.width - x[5]);
+            }
+            double sgk[MM];
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                double sv = W[isg(j, k)];
+                if (useD) sv += al * D[isg(j, k)];
+                sgk[j] = sv;
+                ss += sv;
+                la.mul(sv);                                          // sigma >= 0 (:559,561)
+            }
+            if (k < N) {
+                double xn[6], u[2], c[6];
+                load_x<useD>(k + 1, al, xn);
+                load_u<useD>(k, al, u);
+                f += input_cost(u);                                  // :578-579
+                la.mul(u[0] + kp.p.umax[0]); la.mul(kp.p.umax[0] - u[0]);
+                la.mul(u[1] + kp.p.umax[1]); la.mul(kp.p.umax[1] - u[1]);
+                dyn_res(x, xn, u, c);
+#pragma unroll
+                for (int a = 0; a < 6; a++) th += fabs(c[a]);
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    int r = j * N + k;
+                    double sgn = W[isg(j, k + 1)];
+                    if (useD) sgn += al * D[isg(j, k + 1)];
+                    double g = DG[r] * row_g(row_vals(j, k, x, xn, sgk[j], sgn));
+                    double s = S[r], tt = T[r];
+                    if (useD) {
+                        double ds, dt, dy, dz, dv;
+                        row_step(r, ds, dt, dy, dz, dv);
+                        s += al * ds;
+                        tt += al * dt;
+                    }
+                    th += fabs(g + tt - s);
+                    la.mul(s);
+                    la.mul(tt);
+                    tsum += tt;
+                }
+            }
+        }
+        f += kp.p.slack_w * ss;
+        theta = warp_sum(th);
+        phi = df * warp_sum(f) + rho * warp_sum(tsum) - mu * warp_sum(la.value());
+    }
+
+    // unscaled objective at W
+    __device__ double objective() const {
+        double f = 0.0, ss = 0.0;
+        for (int k = lane; k <= N; k += 32) {
+            double x[6];
+            load_x<false>(k, 0.0, x);
+            f += stage_cost(k, x);
+            if (k < N) {
+                double u[2];
+                load_u<false>(k, 0.0, u);
+                f += input_cost(u);
+            }
+#pragma unroll
+            for (int j = 0; j < M; j++) ss += W[isg(j, k)];
+        }
+        return warp_sum(f + kp.p.slack_w * ss);
+    }
+
+    // ---- evaluate rows (GR, JA) and dynamics residual at the current iterate (lane = stage)
     __device__ void eval_point() {
+        for (int k = lane; k < N; k += 32) {
+            double x[6], xn[6], u[2], c[6];
+            load_x<false>(k, 0.0, x);
+            load_x<false>(k + 1, 0.0, xn);
+            load_u<false>(k, 0.0, u);
+            dyn_res(x, xn, u, c);
+            st6(CRES + 6 * k, c);
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(6 * NT) : 1); t++)
-            for (int e = lane + 32 * t; e < 6 * N; e += (NT ? 1 << 30 : 32)) CRES[e] = dyn_res<false>(e, 0.0);
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(M * NT) : 1); t++)
-            for (int r = lane + 32 * t; r < R; r += (NT ? 1 << 30 : 32)) {
-                int j = r / N, i = r - j * N;
-                RowV v = row_vals<false>(j, i, 0.0);
+            for (int j = 0; j < M; j++) {
+                int r = j * N + k;
+                RowV v = row_vals(j, k, x, xn, W[isg(j, k)], W[isg(j, k + 1)]);
                 double sc = DG[r];
                 GR[r] = sc * row_g(v);
-                JA[4 * r + 0] = sc * (-a1 * 6.0 * p5(v.ds) * kp.iL6);
-                JA[4 * r + 1] = sc * (-a1 * 6.0 * p5(v.de) * kp.iW6);
-                JA[4 * r + 2] = sc * (6.0 * p5(v.dsn) * kp.iL6);
-                JA[4 * r + 3] = sc * (6.0 * p5(v.den) * kp.iW6);
+                double ja[4];
+                ja[0] = sc * (-a1 * 6.0 * p5(v.ds) * kp.iL6);
+                ja[1] = sc * (-a1 * 6.0 * p5(v.de) * kp.iW6);
+                ja[2] = sc * (6.0 * p5(v.dsn) * kp.iL6);
+                ja[3] = sc * (6.0 * p5(v.den) * kp.iW6);
+                stv<4>(JA + 4 * r, ja);
             }
+        }
         __syncwarp();
     }
 
-    // gradient of the scaled objective wrt primal entry wi (wi >= 6)
-    __device__ __forceinline__ double grad_f(int wi) const {
-        if (wi < OU) {
-            int i = wi / 6, a = wi - 6 * i;
-            double acc = 0.0;
-#pragma unroll
-            for (int b = 0; b < 6; b++) acc += QQ[6 * a + b] * (W[6 * i + b] - xtv(i, b));
-            return acc;
-        }
-        if (wi < OS) {
-            int e = wi - OU, i = e >> 1, a = e & 1;
-            return RR[2 * a] * W[OU + 2 * i] + RR[2 * a + 1] * W[OU + 2 * i + 1];
-        }
-        return df * kp.p.slack_w;
-    }
-
-    // J^T yv for primal entry wi (gather over the rows that touch it)
-    __device__ __forceinline__ double jt_times(int wi, const double *yv) const {
-        double acc = 0.0;
-        if (M == 0) return 0.0;
-        if (wi < OU) {
-            int i = wi / 6, a = wi - 6 * i;
-            if (a < 4) return 0.0;
-#pragma unroll
-            for (int j = 0; j < M; j++) {
-                if (i < N) acc += JA[4 * (j * N + i) + (a - 4)] * yv[j * N + i];
-                if (i >= 1) acc += JA[4 * (j * N + i - 1) + 2 + (a - 4)] * yv[j * N + i - 1];
-            }
-            return acc;
-        }
-        if (wi < OS) return 0.0;
-        int e = wi - OS, j = e / (N + 1), i = e - j * (N + 1);
-        if (i < N) acc += DG[j * N + i] * a1 * yv[j * N + i];
-        if (i >= 1) acc -= DG[j * N + i - 1] * yv[j * N + i - 1];
-        return acc;
-    }
-
-    // ---- optimality error pieces that do not depend on mu
+    // ---- optimality error pieces that do not depend on mu (lane = stage; stage k owns x_k, sigma_k, u_k, rows (.,k))
     struct Err { double dual, prim, ysum, zsum; };
     __device__ Err error_base() const {
         double dual = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0;
+        for (int k = lane; k <= N; k += 32) {
+            double lamn[6];  // lam_{k+1} (multiplier of c_k), zero for k = N
+            if (k < N) ld6(LAM + 6 * k, lamn);
+            else {
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(8 * NT + M * (NT + 1)) : 1); t++)
-            for (int wi = 6 + lane + 32 * t; wi < NW; wi += (NT ? 1 << 30 : 32)) {
-                double rw = grad_f(wi) - jt_times(wi, Y);
-                int bs = bslot(wi);
-                if (bs >= 0) rw += -ZL[bs] + ((wi < OS) ? ZU[bs] : 0.0);
-                if (wi < OU) {  // + lam_i - A' lam_{i+1}
-                    int i = wi / 6, a = wi - 6 * i;
-                    double s = LAM[6 * (i - 1) + a];
-                    if (i < N) {
+                for (int a = 0; a < 6; a++) lamn[a] = 0.0;
+            }
+            if (k >= 1) {
+                double x[6], g[6], lam[6];
+                load_x<false>(k, 0.0, x);
+                grad_x(k, x, g);
+                ld6(LAM + 6 * (k - 1), lam);
 #pragma unroll
-                        for (int b = 0; b < 6; b++) s -= Am(b, a) * LAM[6 * i + b];
-                    }
-                    rw += s;
-                } else if (wi < OS) {  // - B' lam_{i+1}
-                    int e = wi - OU, i = e >> 1, a = e & 1;
-                    double s = 0.0;
+                for (int a = 0; a < 6; a++) {
+                    double s = g[a] + lam[a];
 #pragma unroll
-                    for (int b = 0; b < 6; b++) s += Bm(b, a) * LAM[6 * i + b];
-                    rw -= s;
+                    for (int b = 0; b < 6; b++) s -= Am(b, a) * lamn[b];
+                    g[a] = s;
                 }
+#pragma unroll
+                for (int j = 0; j < M; j++) {  // - J'y
+                    if (k < N) {
+                        int r = j * N + k;
+                        g[4] -= JA[4 * r + 0] * Y[r];
+                        g[5] -= JA[4 * r + 1] * Y[r];
+                    }
+                    int r = j * N + k - 1;
+                    g[4] -= JA[4 * r + 2] * Y[r];
+                    g[5] -= JA[4 * r + 3] * Y[r];
+                }
+                double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
+                g[0] += -zl.x + zu.x;
+                g[5] += -zl.y + zu.y;
+                zsum += zl.x + zl.y + zu.x + zu.y;
+#pragma unroll
+                for (int a = 0; a < 6; a++) dual = fmax(dual, fabs(g[a]));
+            }
+#pragma unroll
+            for (int j = 0; j < M; j++) {  // sigma_{j,k}
+                double zl = ZL[bss(j, k)];
+                double rw = df * kp.p.slack_w - zl;
+                if (k < N) rw -= DG[j * N + k] * a1 * Y[j * N + k];
+                if (k >= 1) rw += DG[j * N + k - 1] * Y[j * N + k - 1];
                 dual = fmax(dual, fabs(rw));
+                zsum += zl;
             }
+            if (k < N) {
+                double u[2];
+                load_u<false>(k, 0.0, u);
+                double2 zl = ld2(ZL + bsu(k)), zu = ld2(ZU + bsu(k));
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(M * NT) : 1); t++)
-            for (int r = lane + 32 * t; r < R; r += (NT ? 1 << 30 : 32)) {
-                dual = fmax(dual, fabs(Y[r] - Z[r]));
-                dual = fmax(dual, fabs(rho - Y[r] - V[r]));
-                prim = fmax(prim, fabs(GR[r] + T[r] - S[r]));
-                zsum += Z[r] + V[r];
-                ysum += fabs(Y[r]);
+                for (int c = 0; c < 2; c++) {
+                    double s = df * (R2(c, 0) * u[0] + R2(c, 1) * u[1]);
+#pragma unroll
+                    for (int b = 0; b < 6; b++) s -= Bm(b, c) * lamn[b];
+                    s += c ? (-zl.y + zu.y) : (-zl.x + zu.x);
+                    dual = fmax(dual, fabs(s));
+                }
+                zsum += zl.x + zl.y + zu.x + zu.y;
+                double c6[6];
+                ld6(CRES + 6 * k, c6);
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+                    prim = fmax(prim, fabs(c6[a]));
+                    ysum += fabs(lamn[a]);
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    int r = j * N + k;
+                    dual = fmax(dual, fabs(Y[r] - Z[r]));
+                    dual = fmax(dual, fabs(rho - Y[r] - V[r]));
+                    prim = fmax(prim, fabs(GR[r] + T[r] - S[r]));
+                    zsum += Z[r] + V[r];
+                    ysum += fabs(Y[r]);
+                }
             }
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(6 * NT) : 1); t++)
-            for (int e = lane + 32 * t; e < 6 * N; e += (NT ? 1 << 30 : 32)) {
-                prim = fmax(prim, fabs(CRES[e]));
-                ysum += fabs(LAM[e]);
-            }
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(4 * NT + M * (NT + 1)) : 1); t++)
-            for (int b = lane + 32 * t; b < NB; b += (NT ? 1 << 30 : 32)) zsum += ZL[b] + ((b < 4 * N) ? ZU[b] : 0.0);
+        }
         Err e;
         e.dual = warp_max(dual);
         e.prim = warp_max(prim);
@@ -473,20 +558,33 @@ struct Ipm {
     }
     __device__ double comp_err(double m) const {
         double c = 0.0;
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(4 * NT + M * (NT + 1)) : 1); t++)
-            for (int b = lane + 32 * t; b < NB; b += (NT ? 1 << 30 : 32)) {
-                int wi; double lb, ub; bool hu;
-                bvar(b, wi, lb, ub, hu);
-                c = fmax(c, fabs((W[wi] - lb) * ZL[b] - m));
-                if (hu) c = fmax(c, fabs((ub - W[wi]) * ZU[b] - m));
+        for (int k = lane; k <= N; k += 32) {
+            if (k >= 1) {
+                double vx = W[6 * k], ey = W[6 * k + 5];
+                double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
+                c = fmax(c, fabs((vx - kp.p.vmin) * zl.x - m));
+                c = fmax(c, fabs((kp.p.vmax - vx) * zu.x - m));
+                c = fmax(c, fabs((ey + kp.p.width) * zl.y - m));
+                c = fmax(c, fabs((kp.p.width - ey) * zu.y - m));
             }
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(M * NT) : 1); t++)
-            for (int r = lane + 32 * t; r < R; r += (NT ? 1 << 30 : 32)) {
-                c = fmax(c, fabs(S[r] * Z[r] - m));
-                c = fmax(c, fabs(T[r] * V[r] - m));
+            for (int j = 0; j < M; j++) c = fmax(c, fabs(W[isg(j, k)] * ZL[bss(j, k)] - m));
+            if (k < N) {
+                double u[2];
+                load_u<false>(k, 0.0, u);
+                double2 zl = ld2(ZL + bsu(k)), zu = ld2(ZU + bsu(k));
+                c = fmax(c, fabs((u[0] + kp.p.umax[0]) * zl.x - m));
+                c = fmax(c, fabs((kp.p.umax[0] - u[0]) * zu.x - m));
+                c = fmax(c, fabs((u[1] + kp.p.umax[1]) * zl.y - m));
+                c = fmax(c, fabs((kp.p.umax[1] - u[1]) * zu.y - m));
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    int r = j * N + k;
+                    c = fmax(c, fabs(S[r] * Z[r] - m));
+                    c = fmax(c, fabs(T[r] * V[r] - m));
+                }
             }
+        }
         return warp_max(c);
     }
     __device__ double total_err(const Err &e, double m) const {
@@ -498,186 +596,220 @@ struct Ipm {
         return fmax(e.dual / sd, fmax(e.prim, comp_err(m) / sc));
     }
 
-    // ---- per-iteration assembly: HD (diag Hessian additions), base gradient (into D), SIGE, YHAT
+    // ---- per-iteration assembly (lane = stage): HD (diag Hessian additions), base gradient (into D), SIGE, YHAT
     __device__ void assemble() {
+        for (int k = lane; k <= N; k += 32) {
+            if (k >= 1) {
+                double x[6], g[6], hd[6];
+                load_x<false>(k, 0.0, x);
+                grad_x(k, x, g);
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(M * NT) : 1); t++)
-            for (int r = lane + 32 * t; r < R; r += (NT ? 1 << 30 : 32)) {
-                double s = S[r], tt = T[r];
-                double is = 1.0 / s, it = 1.0 / tt;
-                double sig_s = Z[r] * is, sig_t = V[r] * it;
-                double beta = sig_t / (sig_s + sig_t);
-                double rg = GR[r] + tt - s;
-                SIGE[r] = beta * sig_s;
-                YHAT[r] = (1.0 - beta) * (rho - mu * it) + beta * (mu * is - sig_s * rg);
+                for (int a = 0; a < 6; a++) hd[a] = 0.0;
+                double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
+                {
+                    double il = 1.0 / (x[0] - kp.p.vmin), iu = 1.0 / (kp.p.vmax - x[0]);
+                    hd[0] = zl.x * il + zu.x * iu;
+                    g[0] += -mu * il + mu * iu;
+                    il = 1.0 / (x[5] + kp.p.width);
+                    iu = 1.0 / (kp.p.width - x[5]);
+                    hd[5] = zl.y * il + zu.y * iu;
+                    g[5] += -mu * il + mu * iu;
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) {  // Hessian of -y_r g_r: diagonal on (s, ey) (control.py:544-557, degree 6)
+                    if (k < N) {
+                        int r = j * N + k;
+                        double yd = Y[r] * DG[r] * a1 * 30.0;
+                        hd[4] += yd * p4(x[4] - obs_s(j, k) - lapoff[j]) * kp.iL6;
+                        hd[5] += yd * p4(x[5] - obs_e(j, k)) * kp.iW6;
+                    }
+                    int r = j * N + k - 1;
+                    double yd = Y[r] * DG[r] * 30.0;
+                    hd[4] -= yd * p4(x[4] - obs_s(j, k)) * kp.iL6;
+                    hd[5] -= yd * p4(x[5] - obs_e(j, k)) * kp.iW6;
+                }
+                st6(HD + 6 * k, hd);
+                st6(D + 6 * k, g);  // base gradient of the barrier problem; D is overwritten by the forward pass
             }
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(8 * NT + M * (NT + 1)) : 1); t++)
-            for (int wi = 6 + lane + 32 * t; wi < NW; wi += (NT ? 1 << 30 : 32)) {
-                double hd = 0.0, g = grad_f(wi);
-                int bs = bslot(wi);
-                if (bs >= 0) {
-                    int wj; double lb, ub; bool hu;
-                    bvar(bs, wj, lb, ub, hu);
-                    double idl = 1.0 / (W[wi] - lb);
-                    hd += ZL[bs] * idl;
-                    g -= mu * idl;
-                    if (hu) {
-                        double idu = 1.0 / (ub - W[wi]);
-                        hd += ZU[bs] * idu;
-                        g += mu * idu;
-                    }
-                }
-                if (M > 0 && wi < OU) {  // Hessian of -y_r g_r: diagonal on (s, ey) (control.py:544-557, degree 6)
-                    int i = wi / 6, a = wi - 6 * i;
-                    if (a >= 4) {
-                        double iX6 = (a == 4) ? kp.iL6 : kp.iW6;
-#pragma unroll
-                        for (int j = 0; j < M; j++) {
-                            if (i < N) {
-                                int r = j * N + i;
-                                double d = W[wi] - ((a == 4) ? (obs_s(j, i) + lapoff[j]) : obs_e(j, i));
-                                hd += Y[r] * DG[r] * a1 * 30.0 * p4(d) * iX6;
-                            }
-                            {
-                                int r = j * N + i - 1;
-                                double d = W[wi] - ((a == 4) ? obs_s(j, i) : obs_e(j, i));
-                                hd -= Y[r] * DG[r] * 30.0 * p4(d) * iX6;
-                            }
-                        }
-                    }
-                }
-                HD[wi] = hd;
-                D[wi] = g;  // base gradient of the barrier problem; D is overwritten by the forward pass later
+            for (int j = 0; j < M; j++) {
+                double is = 1.0 / W[isg(j, k)];
+                HD[isg(j, k)] = ZL[bss(j, k)] * is;
+                D[isg(j, k)] = df * kp.p.slack_w - mu * is;
             }
+            if (k < N) {
+                double u[2];
+                load_u<false>(k, 0.0, u);
+                double2 zl = ld2(ZL + bsu(k)), zu = ld2(ZU + bsu(k));
+                double il0 = 1.0 / (u[0] + kp.p.umax[0]), iu0 = 1.0 / (kp.p.umax[0] - u[0]);
+                double il1 = 1.0 / (u[1] + kp.p.umax[1]), iu1 = 1.0 / (kp.p.umax[1] - u[1]);
+                st2(HD + OU + 2 * k, zl.x * il0 + zu.x * iu0, zl.y * il1 + zu.y * iu1);
+                st2(D + OU + 2 * k, df * (R2(0, 0) * u[0] + R2(0, 1) * u[1]) - mu * il0 + mu * iu0,
+                    df * (R2(1, 0) * u[0] + R2(1, 1) * u[1]) - mu * il1 + mu * iu1);
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    int r = j * N + k;
+                    double s = S[r], tt = T[r];
+                    double is = 1.0 / s, it = 1.0 / tt;
+                    double sig_s = Z[r] * is, sig_t = V[r] * it;
+                    double beta = sig_t / (sig_s + sig_t);
+                    double rg = GR[r] + tt - s;
+                    SIGE[r] = beta * sig_s;
+                    YHAT[r] = (1.0 - beta) * (rho - mu * it) + beta * (mu * is - sig_s * rg);
+                }
+            }
+        }
         __syncwarp();
     }
 
     // ---- Riccati backward sweep with primal regularisation dw.  Returns false if a pivot <= 0.
-    // Stage variables zeta = (dx 6, dsigma M | du 2, dsigma+ M); dX+ = TM * zeta + (rd, 0).
+    // Stage variables zeta = (dx 6, dsigma M | du 2, dsigma+ M); lane l < NZ owns column l of the stage Hessian G,
+    // lane a < NXA additionally owns row a of the value function P (registers).
     __device__ bool riccati_backward(double dw) {
-        // terminal value function: stage-N state block
+        double Pr[NXA], pv;
+        {   // terminal value function: stage-N state block
+            int idx = isx ? 6 * N + lane : (iss ? isg(jrole, N) : 0);
+            double dN = (isx || iss) ? HD[idx] + dw : 0.0;
+            pv = (isx || iss) ? D[idx] : 0.0;
 #pragma unroll
-        for (int t = 0; t < rounds(NXA * NXA); t++) {
-            int e = lane + 32 * t;
-            if (e < NXA * NXA) {
-                int a = e / NXA, b = e - a * NXA;
-                bool xx = (a < 6) && (b < 6);
-                double v = xx ? QQ[xx ? 6 * a + b : 0] : 0.0;
-                if (a == b) v += HD[(a < 6) ? 6 * N + a : isg(a - 6, N)] + dw;
-                P[e] = v;
-            }
+            for (int b = 0; b < NXA; b++) Pr[b] = ((b < 6) ? qqcol[b < 6 ? b : 0] : 0.0) + ((b == lane) ? dN : 0.0);
         }
-        if (lane < NXA) PV[lane] = (lane < 6) ? D[6 * N + lane] : D[isg(lane - 6, N)];
-        __syncwarp();
         bool ok = true;
         for (int k = N - 1; k >= 0; k--) {
-            // (1) PT = P * TM (dense, uniform); QV = PV - P[:,0:6]*c_k; row vectors CT; stage diagonal / gradient
+            // (1) row a of P*[A B] (constants as immediates), q = p - P[:,0:6] c_k; transpose through PT
+            double c6[6];
+            ld6(CRES + 6 * k, c6);
+            {
+                double ptx[8];
 #pragma unroll
-            for (int t = 0; t < rounds(NXA * NZ); t++) {
-                int e = lane + 32 * t;
-                if (e < NXA * NZ) {
-                    int a = e / NZ, c = e - a * NZ;
-                    double v = 0.0;
+                for (int c = 0; c < 6; c++) {
+                    double s = 0.0;
 #pragma unroll
-                    for (int b = 0; b < NXA; b++) v += P[a * NXA + b] * TM[b * NZ + c];
-                    PT[e] = v;
+                    for (int b = 0; b < 6; b++) s += Pr[b] * Am(b, c);
+                    ptx[c] = s;
                 }
-            }
-            if (lane < NXA) {
-                double v = PV[lane];
 #pragma unroll
-                for (int b = 0; b < 6; b++) v -= P[lane * NXA + b] * CRES[6 * k + b];
-                QV[lane] = v;
-            }
-            if (M > 0) {
+                for (int c = 0; c < 2; c++) {
+                    double s = 0.0;
 #pragma unroll
-                for (int t = 0; t < rounds(M * NZ); t++) {
-                    int e = lane + 32 * t;
-                    if (e < M * NZ) {
-                        int j = e / NZ, a = e - j * NZ, r = j * N + k;
-                        double q3 = JA[4 * r + 2], q4 = JA[4 * r + 3];
-                        double v = TM[4 * NZ + a] * q3 + TM[5 * NZ + a] * q4;   // (A'a_n | B'a_n)
-                        v += (a == 4) ? JA[4 * r + 0] : 0.0;
-                        v += (a == 5) ? JA[4 * r + 1] : 0.0;
-                        v += (a == 6 + j) ? DG[r] * a1 : 0.0;
-                        v -= (a == NXA + 2 + j) ? DG[r] : 0.0;
-                        CT[e] = v;
-                    }
+                    for (int b = 0; b < 6; b++) s += Pr[b] * Bm(b, c);
+                    ptx[6 + c] = s;
                 }
-            }
-            if (lane < NZ) {
-                int a = lane;
-                bool isx = a < 6, iss = (a >= 6) && (a < NXA), isu = (a >= NXA) && (a < NXA + 2);
-                int idx = isx ? 6 * k + a : (iss ? isg(a - 6, k) : (isu ? OU + 2 * k + (a - NXA) : 0));
-                bool live = (isx && k > 0) || iss || isu;
-                DS[a] = live ? HD[idx] + dw : 0.0;
-                GS[a] = live ? D[idx] : 0.0;
+                double qv = pv;
+#pragma unroll
+                for (int b = 0; b < 6; b++) qv -= Pr[b] * c6[b];
+                if (lane < NXA) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) PT[c * NXAP + lane] = ptx[c];
+#pragma unroll
+                    for (int j = 0; j < M; j++) PT[(8 + j) * NXAP + lane] = Pr[6 + j];
+                    QVs[lane] = qv;
+                }
             }
             __syncwarp();
-            // (2) G = base + TM' P TM + sum_j SIGE_j ct_j ct_j' ; gv likewise
+            // (2) column l of G = base + T'PT + sum_j SIGE_j ct_j ct_j', own gradient component
+            double g[NZ], gv;
+            {
+                double colv[NXAP], qvs[NXAP];
+                ldv<NXAP>(PT + cmap * NXAP, colv);
+                ldv<NXAP>(QVs, qvs);
 #pragma unroll
-            for (int t = 0; t < rounds(NZ * NZ); t++) {
-                int e = lane + 32 * t;
-                if (e < NZ * NZ) {
-                    int a = e / NZ, b = e - a * NZ;
-                    double v = 0.0;
+                for (int a = 0; a < 6; a++) {
+                    double s = qqcol[a];
 #pragma unroll
-                    for (int q = 0; q < NXA; q++) v += TM[q * NZ + a] * PT[q * NZ + b];
-                    bool xx = (a < 6) && (b < 6);
-                    v += xx ? QQ[xx ? 6 * a + b : 0] : 0.0;
-                    bool uu = (a >= NXA) && (a < NXA + 2) && (b >= NXA) && (b < NXA + 2);
-                    v += uu ? RR[uu ? 2 * (a - NXA) + (b - NXA) : 0] : 0.0;
-                    v += (a == b) ? DS[a] : 0.0;
-#pragma unroll
-                    for (int j = 0; j < M; j++) v += SIGE[j * N + k] * CT[j * NZ + a] * CT[j * NZ + b];
-                    GM[e] = v;
+                    for (int q = 0; q < 6; q++) s += Am(q, a) * colv[q];
+                    g[a] = s;
                 }
-            }
-            if (lane < NZ) {
-                int a = lane;
-                double v = GS[a];
 #pragma unroll
-                for (int q = 0; q < NXA; q++) v += TM[q * NZ + a] * QV[q];
+                for (int j = 0; j < M; j++) g[6 + j] = 0.0;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    double s = rrcol[c];
+#pragma unroll
+                    for (int q = 0; q < 6; q++) s += Bm(q, c) * colv[q];
+                    g[NXA + c] = s;
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) g[NXA + 2 + j] = colv[6 + j];
+                int idx = isx ? 6 * k + lane : (iss ? isg(jrole, k) : (isu ? OU + 2 * k + jrole : 0));
+                bool live = (isx && k > 0) || iss || isu;
+                double dsg = live ? HD[idx] + dw : 0.0;
+                gv = live ? D[idx] : 0.0;
+#pragma unroll
+                for (int a = 0; a < NZ; a++) g[a] += (a == lane) ? dsg : 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) gv += tcol[q] * qvs[q];
+#pragma unroll
+                for (int j = 0; j < M; j++) gv += (isp && jrole == j) ? qvs[6 + j] : 0.0;
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
-                    double er = -(JA[4 * r + 2] * CRES[6 * k + 4] + JA[4 * r + 3] * CRES[6 * k + 5]);
-                    v += (SIGE[r] * er - YHAT[r]) * CT[j * NZ + a];
+                    double ja[4];
+                    ldv<4>(JA + 4 * r, ja);
+                    double dgr = DG[r], sg = SIGE[r], yh = YHAT[r];
+                    double own = tcol[4] * ja[2] + tcol[5] * ja[3];
+                    own += (lane == 4) ? ja[0] : 0.0;
+                    own += (lane == 5) ? ja[1] : 0.0;
+                    own += (iss && jrole == j) ? dgr * a1 : 0.0;
+                    own -= (isp && jrole == j) ? dgr : 0.0;
+                    double w = sg * own;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) {
+                        double ct = Am(4, a) * ja[2] + Am(5, a) * ja[3];
+                        if (a == 4) ct += ja[0];
+                        if (a == 5) ct += ja[1];
+                        g[a] += ct * w;
+                    }
+                    g[6 + j] += (dgr * a1) * w;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) g[NXA + c] += (Bm(4, c) * ja[2] + Bm(5, c) * ja[3]) * w;
+                    g[NXA + 2 + j] -= dgr * w;
+                    double er = -(ja[2] * c6[4] + ja[3] * c6[5]);
+                    gv += (sg * er - yh) * own;
                 }
-                GV[a] = v;
+                if (lane >= NXA && lane < NZ) {
+                    double gu[NUAP];
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) gu[m] = g[NXA + m];
+                    if (NUAP > NUA) gu[NUAP - 1] = 0.0;
+                    stv<NUAP>(GUU + (lane - NXA) * NUAP, gu);
+                    GVU[lane - NXA] = gv;
+                }
             }
             __syncwarp();
-            // (3) Cholesky of G_uu, redundantly in every lane's registers (rsqrt: no division)
-            double Lm[NUA][NUA], rinv[NUA];
-#pragma unroll
-            for (int a = 0; a < NUA; a++)
-#pragma unroll
-                for (int b = 0; b <= a; b++) Lm[a][b] = GM[(NXA + a) * NZ + NXA + b];
-#pragma unroll
-            for (int j = 0; j < NUA; j++) {
-                double d = Lm[j][j];
-#pragma unroll
-                for (int q = 0; q < j; q++) d -= Lm[j][q] * Lm[j][q];
-                if (!(d > 0.0)) ok = false;
-                double ri = rsqrt(d);
-                rinv[j] = ri;
-#pragma unroll
-                for (int i = j + 1; i < NUA; i++) {
-                    double s = Lm[i][j];
-#pragma unroll
-                    for (int q = 0; q < j; q++) s -= Lm[i][q] * Lm[j][q];
-                    Lm[i][j] = s * ri;
-                }
-            }
-            if (!ok) return false;
-            // (4) lane c solves column c of  L Y = [G_ux | g_u],  K = -L^-T Y
-            if (lane <= NXA) {
-                int c = lane;
-                double yv[NUA], kv[NUA];
+            // (3) Cholesky of G_uu redundantly in every lane (rsqrt: no division); column solves
+            double Lm[NUA][NUA], rinv[NUA], yv[NUA];
+            {
 #pragma unroll
                 for (int a = 0; a < NUA; a++) {
-                    double s = (c < NXA) ? GM[(NXA + a) * NZ + c] : GV[NXA + a];
+                    double row[NUAP];
+                    ldv<NUAP>(GUU + a * NUAP, row);
+#pragma unroll
+                    for (int b = 0; b <= a; b++) Lm[a][b] = row[b];
+                }
+#pragma unroll
+                for (int j = 0; j < NUA; j++) {
+                    double d = Lm[j][j];
+#pragma unroll
+                    for (int q = 0; q < j; q++) d -= Lm[j][q] * Lm[j][q];
+                    if (!(d > 0.0)) ok = false;
+                    double ri = rsqrt(d);
+                    rinv[j] = ri;
+#pragma unroll
+                    for (int i = j + 1; i < NUA; i++) {
+                        double s = Lm[i][j];
+#pragma unroll
+                        for (int q = 0; q < j; q++) s -= Lm[i][q] * Lm[j][q];
+                        Lm[i][j] = s * ri;
+                    }
+                }
+                if (!ok) return false;
+                double gvu[NUAP], kv[NUA];
+                ldv<NUAP>(GVU, gvu);
+                const bool gcol = (lane == NZ);  // this lane solves the gradient column
+#pragma unroll
+                for (int a = 0; a < NUA; a++) {
+                    double s = gcol ? gvu[a] : g[NXA + a];
 #pragma unroll
                     for (int q = 0; q < a; q++) s -= Lm[a][q] * yv[q];
                     yv[a] = s * rinv[a];
@@ -689,42 +821,56 @@ struct Ipm {
                     for (int q = a + 1; q < NUA; q++) s -= Lm[q][a] * kv[q];
                     kv[a] = s * rinv[a];
                 }
+                if (lane < NXA) {
 #pragma unroll
-                for (int a = 0; a < NUA; a++) {
-                    YF[a * (NXA + 1) + c] = yv[a];
-                    if (c < NXA) KFB[(k * NUA + a) * NXA + c] = -kv[a];
-                    else KFF[k * NUA + a] = -kv[a];
+                    for (int m = 0; m < NUA; m++) KFB[(k * NUA + m) * NXAP + lane] = -kv[m];
+                    double yp[NUAP];
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) yp[m] = yv[m];
+                    if (NUAP > NUA) yp[NUAP - 1] = 0.0;
+                    stv<NUAP>(YF + lane * NUAP, yp);
+                } else if (gcol) {
+                    double yp[NUAP], kq[NUAP];
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) { yp[m] = yv[m]; kq[m] = -kv[m]; }
+                    if (NUAP > NUA) { yp[NUAP - 1] = 0.0; kq[NUAP - 1] = 0.0; }
+                    stv<NUAP>(YG, yp);
+                    stv<NUAP>(KFF + k * NUAP, kq);
                 }
             }
             __syncwarp();
-            // (5) P = G_xx - Y'Y,  PV = g_x - Y' y_g
+            // (4) row b of P = G_xx - Y'Y, p = g_x - Y' y_g (state lanes keep them in registers)
+            {
+                double yg[NUAP];
+                ldv<NUAP>(YG, yg);
+                double pn = gv;
 #pragma unroll
-            for (int t = 0; t < rounds(NXA * NXA); t++) {
-                int e = lane + 32 * t;
-                if (e < NXA * NXA) {
-                    int a = e / NXA, b = e - a * NXA;
-                    double v = GM[a * NZ + b];
+                for (int m = 0; m < NUA; m++) pn -= yv[m] * yg[m];
+                pv = pn;
 #pragma unroll
-                    for (int q = 0; q < NUA; q++) v -= YF[q * (NXA + 1) + a] * YF[q * (NXA + 1) + b];
-                    P[e] = v;
+                for (int a = 0; a < NXA; a++) {
+                    double ya[NUAP];
+                    ldv<NUAP>(YF + a * NUAP, ya);
+                    double s = g[a];
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) s -= ya[m] * yv[m];
+                    Pr[a] = s;
                 }
             }
-            if (lane < NXA) {
-                double v = GV[lane];
-#pragma unroll
-                for (int q = 0; q < NUA; q++) v -= YF[q * (NXA + 1) + lane] * YF[q * (NXA + 1) + NXA];
-                PV[lane] = v;
-            }
-            __syncwarp();
         }
-        // stage 0: x_0 is fixed (control.py:497), sigma_{.,0} is free: d sigma_0 = -P_ss^-1 p_s
+        // stage 0: x_0 is fixed (control.py:497), sigma_{.,0} is free: d sigma_0 = -P_ss^-1 p_s  -> QVs[6+j]
         if (M > 0) {
-            constexpr int MM = M > 0 ? M : 1;
+            if (iss) {
+#pragma unroll
+                for (int j = 0; j < M; j++) S0[jrole * (M + 2) + j] = Pr[6 + j];
+                S0[jrole * (M + 2) + M] = pv;
+            }
+            __syncwarp();
             double Ls[MM][MM], ri[MM], yv[MM], xv[MM];
 #pragma unroll
             for (int a = 0; a < M; a++)
 #pragma unroll
-                for (int b = 0; b <= a; b++) Ls[a][b] = P[(6 + a) * NXA + 6 + b];
+                for (int b = 0; b <= a; b++) Ls[a][b] = S0[a * (M + 2) + b];
 #pragma unroll
             for (int j = 0; j < M; j++) {
                 double d = Ls[j][j];
@@ -743,7 +889,7 @@ struct Ipm {
             if (!ok) return false;
 #pragma unroll
             for (int a = 0; a < M; a++) {
-                double s = -PV[6 + a];
+                double s = -S0[a * (M + 2) + M];
 #pragma unroll
                 for (int q = 0; q < a; q++) s -= Ls[a][q] * yv[q];
                 yv[a] = s * ri[a];
@@ -756,55 +902,46 @@ struct Ipm {
                 xv[a] = s * ri[a];
             }
             __syncwarp();
-            // QV[6+j] carries d sigma_0 to the forward pass (D still holds the base gradient until then)
             if (lane == 0) {
 #pragma unroll
-                for (int a = 0; a < M; a++) QV[6 + a] = xv[a];
+                for (int a = 0; a < M; a++) QVs[6 + a] = xv[a];
             }
             __syncwarp();
         }
         return true;
     }
 
-    // ---- forward sweep: D <- Newton direction.  Every lane carries dX_k in registers and computes the whole
-    //      stage redundantly from broadcast loads (no warp barrier inside the loop); lane a writes component a.
+    // ---- forward sweep: D <- Newton direction.  Every lane carries dX_k in registers.  Lane m < NUA evaluates
+    //      row m of the feedback law (K row from shared memory), lane a < 6 evaluates component a of the state
+    //      update with its private rows of A and B; results travel by shuffles -- no barrier, no model loads.
     __device__ void riccati_forward() {
-        double dx[NXA];
+        double dx[NXAP];
 #pragma unroll
-        for (int a = 0; a < 6; a++) dx[a] = 0.0;
+        for (int a = 0; a < NXAP; a++) dx[a] = 0.0;
 #pragma unroll
-        for (int j = 0; j < M; j++) dx[6 + j] = QV[6 + j];
+        for (int j = 0; j < M; j++) dx[6 + j] = QVs[6 + j];
         __syncwarp();
         if (lane < 6) D[lane] = 0.0;
-        if (M > 0 && lane < M) D[isg(lane, 0)] = QV[6 + lane];
+        if (M > 0 && lane < M) D[isg(lane, 0)] = QVs[6 + lane];
+        const int mrow = (lane < NUA) ? lane : 0;
+        const int arow_i = (lane < 6) ? lane : 0;
         for (int k = 0; k < N; k++) {
+            double kr[NXAP];
+            ldv<NXAP>(KFB + (k * NUA + mrow) * NXAP, kr);
+            double s = KFF[k * NUAP + mrow];
+            double t = -CRES[6 * k + arow_i];
+#pragma unroll
+            for (int c = 0; c < NXA; c++) s += kr[c] * dx[c];
+#pragma unroll
+            for (int b = 0; b < 6; b++) t += arow[b] * dx[b];
             double du[NUA];
 #pragma unroll
-            for (int m = 0; m < NUA; m++) {
-                double s = KFF[k * NUA + m];
-                const double *Kr = KFB + (k * NUA + m) * NXA;
+            for (int m = 0; m < NUA; m++) du[m] = __shfl_sync(0xffffffffu, s, m);
+            t += brow[0] * du[0] + brow[1] * du[1];
+            if (lane < NUA) D[(lane < 2) ? OU + 2 * k + lane : isg(lane - 2, k + 1)] = s;
+            if (lane < 6) D[6 * (k + 1) + lane] = t;
 #pragma unroll
-                for (int c = 0; c < NXA; c++) s += Kr[c] * dx[c];
-                du[m] = s;
-            }
-            double dn[6];
-#pragma unroll
-            for (int a = 0; a < 6; a++) {
-                double s = -CRES[6 * k + a];
-#pragma unroll
-                for (int b = 0; b < 6; b++) s += Am(a, b) * dx[b];
-                s += Bm(a, 0) * du[0] + Bm(a, 1) * du[1];
-                dn[a] = s;
-            }
-            // publish: lane m < NUA writes dU component m, lane 8+a writes dx_{k+1}[a]
-#pragma unroll
-            for (int m = 0; m < NUA; m++)
-                if (lane == m) D[(m < 2) ? OU + 2 * k + m : isg(m - 2, k + 1)] = du[m];
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-                if (lane == 8 + a) D[6 * (k + 1) + a] = dn[a];
-#pragma unroll
-            for (int a = 0; a < 6; a++) dx[a] = dn[a];
+            for (int a = 0; a < 6; a++) dx[a] = __shfl_sync(0xffffffffu, t, a);
 #pragma unroll
             for (int j = 0; j < M; j++) dx[6 + j] = du[2 + j];
         }
@@ -813,7 +950,7 @@ struct Ipm {
 };
 
 // ---------------------------------------------------------------- kernel
-template <int NT, int M>
+template <int M>
 __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KParams kp, const double *__restrict__ in,
                                                      b200mpc_record *__restrict__ rec, double *__restrict__ aux,
                                                      double *__restrict__ xpred, double *__restrict__ upred,
@@ -821,15 +958,15 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x;
     const int inst = blockIdx.x;
-    const SmemPlan<M> pl(NT ? NT : kp.p.N, kp.in_stride);
-    Ipm<NT, M> S_(kp, pl, sm, lane);
-    Ipm<NT, M> &q = S_;
-    using IP = Ipm<NT, M>;
-    constexpr int NXA = IP::NXA, NZ = IP::NZ;
-    const int N = q.N, R = q.R, NB = q.NB, NW = q.NW, OU = q.OU, OS = q.OS;
+    const SmemPlan<M> pl(kp.p.N, kp.in_stride);
+    Ipm<M> S_(kp, pl, sm, lane);
+    Ipm<M> &q = S_;
+    using IP = Ipm<M>;
+    constexpr int NXAP = IP::NXAP, NC = IP::NC;
+    const int N = q.N, R = q.R, NW = q.NW, OU = q.OU, OS = q.OS;
     const b200mpc_ipm_options &o = kp.o;
 
-    // ---- stage the instance record with one TMA bulk copy; build the shared model meanwhile
+    // ---- stage the instance record with one TMA bulk copy
     uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
     const uint32_t in_bytes = (uint32_t)kp.in_stride * 8u;
     if (lane == 0) mbar_init(bar, 1);
@@ -838,87 +975,115 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         mbar_expect_tx(bar, in_bytes);
         bulk_g2s(q.IN, in + (size_t)inst * kp.in_stride, in_bytes, bar);
     }
-    // TM: dX+ = TM * zeta :  rows 0..5 = [A | 0 | B | 0], rows 6+j = unit vector on dsigma+_j
-    for (int e = lane; e < NXA * NZ; e += 32) {
-        int a = e / NZ, c = e - a * NZ;
-        double v = 0.0;
-        if (a < 6) {
-            if (c < 6) v = kp.p.A[6 * a + c];
-            else if (c >= NXA && c < NXA + 2) v = kp.p.B[2 * a + (c - NXA)];
-        } else if (c == NXA + 2 + (a - 6))
-            v = 1.0;
-        q.TM[e] = v;
-    }
-    for (int e = lane; e < 36; e += 32) q.cQ[e] = kp.p.Q[e];
-    if (lane < 4) q.cR[lane] = kp.p.R[lane];
+    for (int e = lane; e < NW + 2; e += 32) { q.W[e] = 0.0; q.D[e] = 0.0; q.HD[e] = 0.0; }
+    for (int e = lane; e < (NC + 1) * NXAP; e += 32) q.PT[e] = 0.0;   // includes the all-zero row NC
+    for (int e = lane; e < 6 * N + 6; e += 32) { q.LAM[e] = 0.0; q.CRES[e] = 0.0; }
     mbar_wait(bar, 0);
     __syncwarp();
 
-    // ---- start point: u = 0 roll-out from x_0, sigma = 0, pushed into the bounds
-    for (int e = lane; e < NW; e += 32) q.W[e] = 0.0;
-    __syncwarp();
-    if (lane < 6) q.W[lane] = q.IN[lane];
-    __syncwarp();
-    for (int i = 1; i <= N; i++) {
-        if (lane < 6) {
-            double s = 0.0;
+    // ---- start point: u = 0 roll-out from x_0 (every lane redundantly, constants as immediates), sigma = 0,
+    //      pushed into the bounds
+    {
+        double x[6];
+        ld6(q.IN, x);
+        if (lane == 0) st6(q.W, x);
+        for (int i = 1; i <= N; i++) {
+            double xn[6];
 #pragma unroll
-            for (int b = 0; b < 6; b++) s += q.Am(lane, b) * q.W[6 * (i - 1) + b];
-            q.W[6 * i + lane] = s;
+            for (int a = 0; a < 6; a++) {
+                double s = 0.0;
+#pragma unroll
+                for (int b = 0; b < 6; b++) s += q.Am(a, b) * x[b];
+                xn[a] = s;
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) x[a] = xn[a];
+            if (lane == (i & 31)) st6(q.W + 6 * i, x);
         }
-        __syncwarp();
     }
-    for (int b = lane; b < NB; b += 32) {
-        int wi; double lb, ub; bool hu;
-        q.bvar(b, wi, lb, ub, hu);
-        double w = q.W[wi];
-        double pl_ = o.bound_push * fmax(1.0, fabs(lb));
-        if (hu) pl_ = fmin(pl_, o.bound_frac * (ub - lb));
-        if (w < lb + pl_) w = lb + pl_;
-        if (hu) {
-            double pu = fmin(o.bound_push * fmax(1.0, fabs(ub)), o.bound_frac * (ub - lb));
-            if (w > ub - pu) w = ub - pu;
+    __syncwarp();
+    for (int k = lane; k <= N; k += 32) {
+        if (k >= 1) {   // bound_push / bound_frac on vx_k, ey_k
+            double lb[2] = {kp.p.vmin, -kp.p.width}, ub[2] = {kp.p.vmax, kp.p.width};
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                int wi = 6 * k + (c ? 5 : 0);
+                double w = q.W[wi];
+                double pl_ = fmin(o.bound_push * fmax(1.0, fabs(lb[c])), o.bound_frac * (ub[c] - lb[c]));
+                double pu = fmin(o.bound_push * fmax(1.0, fabs(ub[c])), o.bound_frac * (ub[c] - lb[c]));
+                if (w < lb[c] + pl_) w = lb[c] + pl_;
+                if (w > ub[c] - pu) w = ub[c] - pu;
+                q.W[wi] = w;
+                q.ZL[q.bsx(k) + c] = 1.0;
+                q.ZU[q.bsx(k) + c] = 1.0;
+            }
         }
-        q.W[wi] = w;
-        q.ZL[b] = 1.0;
-        if (hu) q.ZU[b] = 1.0;
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            q.W[q.isg(j, k)] = o.bound_push;   // sigma = 0 pushed off its lower bound 0: push*max(1,|0|)
+            q.ZL[q.bss(j, k)] = 1.0;
+        }
+        if (k < N) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                double ub = kp.p.umax[c], lb = -ub;
+                double w = 0.0;
+                double pl_ = fmin(o.bound_push * fmax(1.0, fabs(lb)), o.bound_frac * (ub - lb));
+                if (w < lb + pl_) w = lb + pl_;
+                if (w > ub - pl_) w = ub - pl_;
+                q.W[OU + 2 * k + c] = w;
+                q.ZL[q.bsu(k) + c] = 1.0;
+                q.ZU[q.bsu(k) + c] = 1.0;
+            }
+        }
     }
-    for (int e = lane; e < 6 * N; e += 32) q.LAM[e] = 0.0;
-    // unscaled (Q+Q'), (R+R') first: the scaling factor is derived from them
-    for (int e = lane; e < 36; e += 32) { int a = e / 6, b = e - 6 * a; q.QQ[e] = kp.p.Q[6 * a + b] + kp.p.Q[6 * b + a]; }
-    if (lane < 4) { int a = lane >> 1, b = lane & 1; q.RR[lane] = kp.p.R[2 * a + b] + kp.p.R[2 * b + a]; }
     __syncwarp();
     // ---- gradient-based scaling at the start (nlp_scaling_max_gradient)
     {
-        double gm = 0.0;
-        for (int wi = 6 + lane; wi < NW; wi += 32) gm = fmax(gm, fabs(q.grad_f(wi)));  // df == 1 here
+        double gm = (M > 0) ? kp.p.slack_w : 0.0;
+        for (int k = lane; k <= N; k += 32) {
+            if (k >= 1) {
+                double x[6], g[6];
+                q.template load_x<false>(k, 0.0, x);
+                q.grad_x(k, x, g);   // df == 1 here
+#pragma unroll
+                for (int a = 0; a < 6; a++) gm = fmax(gm, fabs(g[a]));
+            }
+            if (k < N) {
+                double u[2];
+                q.template load_u<false>(k, 0.0, u);
+                gm = fmax(gm, fabs(q.R2(0, 0) * u[0] + q.R2(0, 1) * u[1]));
+                gm = fmax(gm, fabs(q.R2(1, 0) * u[0] + q.R2(1, 1) * u[1]));
+            }
+        }
         gm = warp_max(gm);
         q.df = gm > o.max_grad ? o.max_grad / gm : 1.0;
-        __syncwarp();
-        for (int e = lane; e < 36; e += 32) q.QQ[e] *= q.df;
-        if (lane < 4) q.RR[lane] *= q.df;
-        for (int r = lane; r < R; r += 32) {
-            int j = r / N, i = r - j * N;
-            typename IP::RowV v = q.template row_vals<false>(j, i, 0.0);
-            double rm = fmax(q.a1, 1.0);  // |d/dsigma_i| = (1-alpha), |d/dsigma_{i+1}| = 1
-            rm = fmax(rm, fmax(fabs(6.0 * p5(v.dsn) * kp.iL6), fabs(6.0 * p5(v.den) * kp.iW6)));
-            if (i > 0) rm = fmax(rm, q.a1 * fmax(fabs(6.0 * p5(v.ds) * kp.iL6), fabs(6.0 * p5(v.de) * kp.iW6)));
-            q.DG[r] = rm > o.max_grad ? o.max_grad / rm : 1.0;
-        }
-        __syncwarp();
-        for (int r = lane; r < R; r += 32) {
-            int j = r / N, i = r - j * N;
-            double g = q.DG[r] * q.row_g(q.template row_vals<false>(j, i, 0.0));
-            double t = fmax(0.0, -g) + o.bound_push;
-            q.T[r] = t;
-            q.S[r] = g + t;
-            q.Z[r] = 1.0;
-            q.V[r] = 1.0;
-            q.Y[r] = 0.0;
-            q.JD[r] = 0.0;
-            q.SIGE[r] = 0.0;
-            q.YHAT[r] = 0.0;
-            q.GR[r] = g;
+        q.set_scaled_columns();
+        for (int k = lane; k < N; k += 32) {
+            double x[6], xn[6];
+            q.template load_x<false>(k, 0.0, x);
+            q.template load_x<false>(k + 1, 0.0, xn);
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                int r = j * N + k;
+                typename IP::RowV v = q.row_vals(j, k, x, xn, q.W[q.isg(j, k)], q.W[q.isg(j, k + 1)]);
+                double rm = fmax(q.a1, 1.0);  // |d/dsigma_i| = (1-alpha), |d/dsigma_{i+1}| = 1
+                rm = fmax(rm, fmax(fabs(6.0 * p5(v.dsn) * kp.iL6), fabs(6.0 * p5(v.den) * kp.iW6)));
+                if (k > 0) rm = fmax(rm, q.a1 * fmax(fabs(6.0 * p5(v.ds) * kp.iL6), fabs(6.0 * p5(v.de) * kp.iW6)));
+                double dgr = rm > o.max_grad ? o.max_grad / rm : 1.0;
+                q.DG[r] = dgr;
+                double g = dgr * q.row_g(v);
+                double t = fmax(0.0, -g) + o.bound_push;
+                q.T[r] = t;
+                q.S[r] = g + t;
+                q.Z[r] = 1.0;
+                q.V[r] = 1.0;
+                q.Y[r] = 0.0;
+                q.JD[r] = 0.0;
+                q.SIGE[r] = 0.0;
+                q.YHAT[r] = 0.0;
+                q.GR[r] = g;
+            }
         }
         __syncwarp();
     }
@@ -931,10 +1096,12 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     int nfilt = 0, fpos = 0;
     int iter = 0, status = B200MPC_MAX_ITER, n_acc = 0, n_refac = 0, n_back = 0, n_reset = 0;
     double dw_last = 0.0, E0 = 0.0;
+    bool last_needed = false;
 
     const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99;
     const double gamma_theta = 1e-5, gamma_phi = 1e-8, delta_sw = 1.0, s_theta = 1.1, s_phi = 2.3, eta_phi = 1e-8;
     const double gamma_alpha = 0.05, kappa_sigma = 1e10;
+    const bool one_round = (N < 32);   // every stage has its own lane
 
 #ifdef B200MPC_PHASE_CLOCKS
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -970,7 +1137,19 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         // ---- Newton step by Riccati, with inertia correction
         q.assemble();
         PCLK(1)
-        double dw_try = 0.0;
+        // grad(phi)'d needs the base gradient of this lane's stage, which the forward sweep overwrites in D
+        double gbx[6] = {0, 0, 0, 0, 0, 0}, gbu[2] = {0, 0}, gbs[IP::MM];
+#pragma unroll
+        for (int j = 0; j < IP::MM; j++) gbs[j] = 0.0;
+        if (one_round && lane <= N) {
+            ld6(q.D + 6 * lane, gbx);
+            if (lane < N) { double2 t2 = ld2(q.D + OU + 2 * lane); gbu[0] = t2.x; gbu[1] = t2.y; }
+#pragma unroll
+            for (int j = 0; j < M; j++) gbs[j] = q.D[q.isg(j, lane)];
+        }
+        // IPOPT always retries dw = 0 first; when the previous iteration needed a correction we start from
+        // dw_last/3 instead (saves one full sweep per iteration on the non-convex stragglers)
+        double dw_try = last_needed ? fmax(1e-20, dw_last / 3.0) : 0.0;
         bool fail = false;
         for (;;) {
             if (q.riccati_backward(dw_try)) break;
@@ -981,79 +1160,100 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         }
         if (fail) { status = B200MPC_INERTIA; break; }
         if (dw_try > 0.0) dw_last = dw_try;
+        last_needed = dw_try > 0.0;
         PCLK(2)
-        // ---- grad(phi)'d needs the base gradient that still sits in D: keep this lane's entries in registers
-        //      across the forward sweep that overwrites D (entries wi = 6+lane+32t).
-        constexpr int GT = NT ? rounds(8 * NT + M * (NT + 1)) : 8;
-        double gbase[GT];
-#pragma unroll
-        for (int t = 0; t < GT; t++) {
-            int wi = 6 + lane + 32 * t;
-            gbase[t] = (wi < NW) ? q.D[wi] : 0.0;
-        }
-        __syncwarp();
         q.riccati_forward();
         PCLK(3)
-        // ---- rows: J d, step bounds, directional derivative
+        // ---- rows: J d, step bounds, directional derivative (lane = stage)
+        for (int k = lane; k < N; k += 32) {
+            double dxk[6], dxn[6];
+            ld6(q.D + 6 * k, dxk);
+            ld6(q.D + 6 * (k + 1), dxn);
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(M * NT) : 1); t++)
-            for (int r = lane + 32 * t; r < R; r += (NT ? 1 << 30 : 32)) {
-                int j = r / N, i = r - j * N;
-                double jd = q.JA[4 * r + 0] * q.D[6 * i + 4] + q.JA[4 * r + 1] * q.D[6 * i + 5] + q.DG[r] * q.a1 * q.D[q.isg(j, i)] +
-                            q.JA[4 * r + 2] * q.D[6 * i + 10] + q.JA[4 * r + 3] * q.D[6 * i + 11] - q.DG[r] * q.D[q.isg(j, i + 1)];
-                q.JD[r] = jd;
+            for (int j = 0; j < M; j++) {
+                int r = j * N + k;
+                double ja[4];
+                ldv<4>(q.JA + 4 * r, ja);
+                q.JD[r] = ja[0] * dxk[4] + ja[1] * dxk[5] + q.DG[r] * q.a1 * q.D[q.isg(j, k)] + ja[2] * dxn[4] + ja[3] * dxn[5] -
+                          q.DG[r] * q.D[q.isg(j, k + 1)];
             }
+        }
         __syncwarp();
         double a_max = 1.0, a_z = 1.0, gphi = 0.0, th = 0.0;
+        for (int k = lane; k <= N; k += 32) {
+            if (k >= 1) {
+                double x[6], d[6];
+                q.template load_x<false>(k, 0.0, x);
+                ld6(q.D + 6 * k, d);
+                double2 zl = ld2(q.ZL + q.bsx(k)), zu = ld2(q.ZU + q.bsx(k));
+                double lbv[2] = {kp.p.vmin, -kp.p.width}, ubv[2] = {kp.p.vmax, kp.p.width};
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(4 * NT + M * (NT + 1)) : 1); t++)
-            for (int b = lane + 32 * t; b < NB; b += (NT ? 1 << 30 : 32)) {
-                int wi; double lb, ub; bool hu;
-                q.bvar(b, wi, lb, ub, hu);
-                double w = q.W[wi], d = q.D[wi];
-                double dl = w - lb, zl = q.ZL[b];
-                double dzl = mu / dl - zl - zl / dl * d;
-                if (d < 0.0) a_max = fmin(a_max, -tau * dl / d);
-                if (dzl < 0.0) a_z = fmin(a_z, -tau * zl / dzl);
-                if (hu) {
-                    double du = ub - w, zu = q.ZU[b];
-                    double dzu = mu / du - zu + zu / du * d;
-                    if (d > 0.0) a_max = fmin(a_max, tau * du / d);
-                    if (dzu < 0.0) a_z = fmin(a_z, -tau * zu / dzu);
+                for (int c = 0; c < 2; c++) {
+                    double w = c ? x[5] : x[0], dd = c ? d[5] : d[0];
+                    double zlc = c ? zl.y : zl.x, zuc = c ? zu.y : zu.x;
+                    double dl = w - lbv[c], du = ubv[c] - w;
+                    double dzl = mu / dl - zlc - zlc / dl * dd, dzu = mu / du - zuc + zuc / du * dd;
+                    if (dd < 0.0) a_max = fmin(a_max, -tau * dl / dd);
+                    if (dd > 0.0) a_max = fmin(a_max, tau * du / dd);
+                    if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc / dzl);
+                    if (dzu < 0.0) a_z = fmin(a_z, -tau * zuc / dzu);
+                }
+                if (one_round) {
+#pragma unroll
+                    for (int a = 0; a < 6; a++) gphi += gbx[a] * d[a];
+                } else {   // long horizons: recompute the base gradient from the iterate
+                    double g[6];
+                    q.grad_x(k, x, g);
+                    g[0] += -mu / (x[0] - kp.p.vmin) + mu / (kp.p.vmax - x[0]);
+                    g[5] += -mu / (x[5] + kp.p.width) + mu / (kp.p.width - x[5]);
+#pragma unroll
+                    for (int a = 0; a < 6; a++) gphi += g[a] * d[a];
                 }
             }
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(M * NT) : 1); t++)
-            for (int r = lane + 32 * t; r < R; r += (NT ? 1 << 30 : 32)) {
-                double ds, dt, dy, dz, dv;
-                q.row_step(r, ds, dt, dy, dz, dv);
-                double s = q.S[r], tt = q.T[r];
-                if (ds < 0.0) a_max = fmin(a_max, -tau * s / ds);
-                if (dt < 0.0) a_max = fmin(a_max, -tau * tt / dt);
-                if (dz < 0.0) a_z = fmin(a_z, -tau * q.Z[r] / dz);
-                if (dv < 0.0) a_z = fmin(a_z, -tau * q.V[r] / dv);
-                gphi += rho * dt - mu * (ds / s + dt / tt);
-                th += fabs(q.GR[r] + tt - s);
+            for (int j = 0; j < M; j++) {
+                double w = q.W[q.isg(j, k)], dd = q.D[q.isg(j, k)], zlc = q.ZL[q.bss(j, k)];
+                double dzl = mu / w - zlc - zlc / w * dd;
+                if (dd < 0.0) a_max = fmin(a_max, -tau * w / dd);
+                if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc / dzl);
+                gphi += (one_round ? gbs[j] : (q.df * kp.p.slack_w - mu / w)) * dd;
             }
+            if (k < N) {
+                double u[2];
+                q.template load_u<false>(k, 0.0, u);
+                double2 dd2 = ld2(q.D + OU + 2 * k);
+                double2 zl = ld2(q.ZL + q.bsu(k)), zu = ld2(q.ZU + q.bsu(k));
 #pragma unroll
-        for (int t = 0; t < GT; t++) {
-            int wi = 6 + lane + 32 * t;
-            if (wi < NW) gphi += gbase[t] * q.D[wi];
-        }
-        if (NT == 0) {
-            for (int wi = 6 + 32 * GT + lane; wi < NW; wi += 32) {  // horizons beyond the register window: recompute
-                double g = q.grad_f(wi);
-                int bs = q.bslot(wi);
-                if (bs >= 0) {
-                    int wj; double lb, ub; bool hu;
-                    q.bvar(bs, wj, lb, ub, hu);
-                    g -= mu / (q.W[wi] - lb);
-                    if (hu) g += mu / (ub - q.W[wi]);
+                for (int c = 0; c < 2; c++) {
+                    double w = u[c], dd = c ? dd2.y : dd2.x, zlc = c ? zl.y : zl.x, zuc = c ? zu.y : zu.x;
+                    double dl = w + kp.p.umax[c], du = kp.p.umax[c] - w;
+                    double dzl = mu / dl - zlc - zlc / dl * dd, dzu = mu / du - zuc + zuc / du * dd;
+                    if (dd < 0.0) a_max = fmin(a_max, -tau * dl / dd);
+                    if (dd > 0.0) a_max = fmin(a_max, tau * du / dd);
+                    if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc / dzl);
+                    if (dzu < 0.0) a_z = fmin(a_z, -tau * zuc / dzu);
+                    double gb = one_round ? gbu[c] : (q.df * (q.R2(c, 0) * u[0] + q.R2(c, 1) * u[1]) - mu / dl + mu / du);
+                    gphi += gb * dd;
                 }
-                gphi += g * q.D[wi];
+                double c6[6];
+                ld6(q.CRES + 6 * k, c6);
+#pragma unroll
+                for (int a = 0; a < 6; a++) th += fabs(c6[a]);
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    int r = j * N + k;
+                    double ds, dt, dy, dz, dv;
+                    q.row_step(r, ds, dt, dy, dz, dv);
+                    double s = q.S[r], tt = q.T[r];
+                    if (ds < 0.0) a_max = fmin(a_max, -tau * s / ds);
+                    if (dt < 0.0) a_max = fmin(a_max, -tau * tt / dt);
+                    if (dz < 0.0) a_z = fmin(a_z, -tau * q.Z[r] / dz);
+                    if (dv < 0.0) a_z = fmin(a_z, -tau * q.V[r] / dv);
+                    gphi += rho * dt - mu * (ds / s + dt / tt);
+                    th += fabs(q.GR[r] + tt - s);
+                }
             }
         }
-        for (int e = lane; e < 6 * N; e += 32) th += fabs(q.CRES[e]);
         a_max = warp_min(a_max);
         a_z = warp_min(a_z);
         gphi = warp_sum(gphi);
@@ -1122,95 +1322,125 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         // ---- accept: multipliers of the dynamics by the costate recursion, from
         //      K d + Jc' lam+ = rhs  =>  lam+_i = (rhs - K d)_{x_i} + A' lam+_{i+1}
         // (a) residuals res_i = (rhs - K d)_{x_i} for all stages in parallel -> CRES (dead until the next eval)
+        for (int i = lane + 1; i <= N; i += 32) {
+            double x[6], d[6], g[6], hd[6], res[6];
+            q.template load_x<false>(i, 0.0, x);
+            ld6(q.D + 6 * i, d);
+            ld6(q.HD + 6 * i, hd);
+            q.grad_x(i, x, g);
+            g[0] += -mu / (x[0] - kp.p.vmin) + mu / (kp.p.vmax - x[0]);
+            g[5] += -mu / (x[5] + kp.p.width) + mu / (kp.p.width - x[5]);
 #pragma unroll
-        for (int t = 0; t < (NT ? rounds(6 * NT) : 1); t++)
-            for (int e = lane + 32 * t; e < 6 * N; e += (NT ? 1 << 30 : 32)) {
-                int i = 1 + e / 6, a = e - 6 * (i - 1);
-                int wi = 6 * i + a;
-                double g = q.grad_f(wi);
-                int bs = q.bslot(wi);
-                if (bs >= 0) {
-                    int wj; double lb, ub; bool hu;
-                    q.bvar(bs, wj, lb, ub, hu);
-                    g += -mu / (q.W[wi] - lb) + mu / (ub - q.W[wi]);
-                }
-                double kd = (q.HD[wi] + dw_try) * q.D[wi];
+            for (int a2 = 0; a2 < 6; a2++) {
+                double kd = (hd[a2] + dw_try) * d[a2];
 #pragma unroll
-                for (int b = 0; b < 6; b++) kd += q.QQ[6 * a + b] * q.D[6 * i + b];
-                double res = -g - kd;
-                if (M > 0 && a >= 4) {
-#pragma unroll
-                    for (int j = 0; j < M; j++) {
-                        if (i < N) {
-                            int r = j * N + i;
-                            res += q.JA[4 * r + (a - 4)] * (q.YHAT[r] - q.SIGE[r] * q.JD[r]);
-                        }
-                        int r = j * N + i - 1;
-                        res += q.JA[4 * r + 2 + (a - 4)] * (q.YHAT[r] - q.SIGE[r] * q.JD[r]);
-                    }
-                }
-                q.CRES[e] = res;
+                for (int b = 0; b < 6; b++) kd += q.df * q.Q2(a2, b) * d[b];
+                res[a2] = -g[a2] - kd;
             }
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                if (i < N) {
+                    int r = j * N + i;
+                    double yp = q.YHAT[r] - q.SIGE[r] * q.JD[r];
+                    res[4] += q.JA[4 * r + 0] * yp;
+                    res[5] += q.JA[4 * r + 1] * yp;
+                }
+                int r = j * N + i - 1;
+                double yp = q.YHAT[r] - q.SIGE[r] * q.JD[r];
+                res[4] += q.JA[4 * r + 2] * yp;
+                res[5] += q.JA[4 * r + 3] * yp;
+            }
+            st6(q.CRES + 6 * (i - 1), res);
+        }
         __syncwarp();
-        // (b) the recursion itself, redundantly in every lane (no barrier); lane a<6 blends component a into LAM
+        // (b) the recursion itself: lane a < 6 owns component a (its column of A is q.tcol), lam+_{i+1} travels by
+        //     shuffles; no barrier inside the loop
         {
             double ln[6];
 #pragma unroll
             for (int a2 = 0; a2 < 6; a2++) ln[a2] = 0.0;
+            const int comp = (lane < 6) ? lane : 0;
             for (int i = N; i >= 1; i--) {
-                double lc[6];
+                double sres = q.CRES[6 * (i - 1) + comp];
 #pragma unroll
-                for (int a2 = 0; a2 < 6; a2++) {
-                    double s = q.CRES[6 * (i - 1) + a2];
-#pragma unroll
-                    for (int b = 0; b < 6; b++) s += q.Am(b, a2) * ln[b];
-                    lc[a2] = s;
+                for (int b = 0; b < 6; b++) sres += q.tcol[b] * ln[b];
+                if (lane < 6) {
+                    double lo = q.LAM[6 * (i - 1) + lane];
+                    q.LAM[6 * (i - 1) + lane] = lo + a * (sres - lo);
                 }
 #pragma unroll
-                for (int a2 = 0; a2 < 6; a2++) {
-                    if (lane == a2) {
-                        double lo = q.LAM[6 * (i - 1) + a2];
-                        q.LAM[6 * (i - 1) + a2] = lo + a * (lc[a2] - lo);
-                    }
-                    ln[a2] = lc[a2];
+                for (int a2 = 0; a2 < 6; a2++) ln[a2] = __shfl_sync(0xffffffffu, sres, a2);
+            }
+        }
+        // bound multipliers (old point), primal step, kappa_sigma safeguard (new point): lane = stage
+        for (int k = lane; k <= N; k += 32) {
+            if (k >= 1) {
+                double x[6], d[6];
+                q.template load_x<false>(k, 0.0, x);
+                ld6(q.D + 6 * k, d);
+                double2 zl = ld2(q.ZL + q.bsx(k)), zu = ld2(q.ZU + q.bsx(k));
+                double lbv[2] = {kp.p.vmin, -kp.p.width}, ubv[2] = {kp.p.vmax, kp.p.width};
+                double zln[2], zun[2];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    double w = c ? x[5] : x[0], dd = c ? d[5] : d[0];
+                    double zlc = c ? zl.y : zl.x, zuc = c ? zu.y : zu.x;
+                    double dl = w - lbv[c], du = ubv[c] - w;
+                    zlc += a_z * (mu / dl - zlc - zlc / dl * dd);
+                    zuc += a_z * (mu / du - zuc + zuc / du * dd);
+                    double wn = w + a * dd, dln = wn - lbv[c], dun = ubv[c] - wn;
+                    zln[c] = fmax(fmin(zlc, kappa_sigma * mu / dln), mu / (kappa_sigma * dln));
+                    zun[c] = fmax(fmin(zuc, kappa_sigma * mu / dun), mu / (kappa_sigma * dun));
+                }
+                st2(q.ZL + q.bsx(k), zln[0], zln[1]);
+                st2(q.ZU + q.bsx(k), zun[0], zun[1]);
+#pragma unroll
+                for (int a2 = 0; a2 < 6; a2++) x[a2] += a * d[a2];
+                st6(q.W + 6 * k, x);
+            }
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                double w = q.W[q.isg(j, k)], dd = q.D[q.isg(j, k)], zlc = q.ZL[q.bss(j, k)];
+                zlc += a_z * (mu / w - zlc - zlc / w * dd);
+                double wn = w + a * dd;
+                q.ZL[q.bss(j, k)] = fmax(fmin(zlc, kappa_sigma * mu / wn), mu / (kappa_sigma * wn));
+                q.W[q.isg(j, k)] = wn;
+            }
+            if (k < N) {
+                double u[2];
+                q.template load_u<false>(k, 0.0, u);
+                double2 dd2 = ld2(q.D + OU + 2 * k);
+                double2 zl = ld2(q.ZL + q.bsu(k)), zu = ld2(q.ZU + q.bsu(k));
+                double zln[2], zun[2], un[2];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    double w = u[c], dd = c ? dd2.y : dd2.x, zlc = c ? zl.y : zl.x, zuc = c ? zu.y : zu.x;
+                    double dl = w + kp.p.umax[c], du = kp.p.umax[c] - w;
+                    zlc += a_z * (mu / dl - zlc - zlc / dl * dd);
+                    zuc += a_z * (mu / du - zuc + zuc / du * dd);
+                    double wn = w + a * dd, dln = wn + kp.p.umax[c], dun = kp.p.umax[c] - wn;
+                    zln[c] = fmax(fmin(zlc, kappa_sigma * mu / dln), mu / (kappa_sigma * dln));
+                    zun[c] = fmax(fmin(zuc, kappa_sigma * mu / dun), mu / (kappa_sigma * dun));
+                    un[c] = wn;
+                }
+                st2(q.ZL + q.bsu(k), zln[0], zln[1]);
+                st2(q.ZU + q.bsu(k), zun[0], zun[1]);
+                st2(q.W + OU + 2 * k, un[0], un[1]);
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    int r = j * N + k;
+                    double ds, dt, dy, dz, dv;
+                    q.row_step(r, ds, dt, dy, dz, dv);
+                    double s = q.S[r] + a * ds, tt = q.T[r] + a * dt;
+                    q.Y[r] += a * dy;
+                    double z = q.Z[r] + a_z * dz, v = q.V[r] + a_z * dv;
+                    q.Z[r] = fmax(fmin(z, kappa_sigma * mu / s), mu / (kappa_sigma * s));
+                    q.V[r] = fmax(fmin(v, kappa_sigma * mu / tt), mu / (kappa_sigma * tt));
+                    q.S[r] = s;
+                    q.T[r] = tt;
                 }
             }
         }
-        // bound multipliers (old point), then primal step, then kappa_sigma safeguard (new point)
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(4 * NT + M * (NT + 1)) : 1); t++)
-            for (int b = lane + 32 * t; b < NB; b += (NT ? 1 << 30 : 32)) {
-                int wi; double lb, ub; bool hu;
-                q.bvar(b, wi, lb, ub, hu);
-                double w = q.W[wi], d = q.D[wi];
-                double dl = w - lb, zl = q.ZL[b];
-                zl += a_z * (mu / dl - zl - zl / dl * d);
-                double wn = w + a * d, dln = wn - lb;
-                q.ZL[b] = fmax(fmin(zl, kappa_sigma * mu / dln), mu / (kappa_sigma * dln));
-                if (hu) {
-                    double du = ub - w, zu = q.ZU[b];
-                    zu += a_z * (mu / du - zu + zu / du * d);
-                    double dun = ub - wn;
-                    q.ZU[b] = fmax(fmin(zu, kappa_sigma * mu / dun), mu / (kappa_sigma * dun));
-                }
-            }
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(M * NT) : 1); t++)
-            for (int r = lane + 32 * t; r < R; r += (NT ? 1 << 30 : 32)) {
-                double ds, dt, dy, dz, dv;
-                q.row_step(r, ds, dt, dy, dz, dv);
-                double s = q.S[r] + a * ds, tt = q.T[r] + a * dt;
-                q.Y[r] += a * dy;
-                double z = q.Z[r] + a_z * dz, v = q.V[r] + a_z * dv;
-                q.Z[r] = fmax(fmin(z, kappa_sigma * mu / s), mu / (kappa_sigma * s));
-                q.V[r] = fmax(fmin(v, kappa_sigma * mu / tt), mu / (kappa_sigma * tt));
-                q.S[r] = s;
-                q.T[r] = tt;
-            }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < (NT ? rounds(8 * NT + M * (NT + 1)) : 1); t++)
-            for (int wi = 6 + lane + 32 * t; wi < NW; wi += (NT ? 1 << 30 : 32)) q.W[wi] += a * q.D[wi];
         __syncwarp();
         iter++;
         PCLK(6)

@@ -218,6 +218,7 @@ def ipm_solve(P, verbose=False, **kw):
     z, y, lam = np.ones(m), np.zeros(m), np.zeros(me)
     mu = o["mu_init"]
     dw_last = 0.0
+    last_needed = False
     dl = lambda w: np.where(hasL, w - lbw, 1.0)
     du = lambda w: np.where(hasU, ubw - w, 1.0)
     nb = int(hasL.sum() + hasU.sum()) + m + (m if el else 0)
@@ -292,7 +293,7 @@ def ipm_solve(P, verbose=False, **kw):
         H = P.hessL(w, df, y * dg)
         rhs_w = -(df * P.grad(w)) + np.where(hasL, mu / dl(w), 0) - np.where(hasU, mu / du(w), 0) + J.T @ yhat
         cval = P.c(w)
-        dw_try = 0.0
+        dw_try = max(1e-20, dw_last / 3.0) if last_needed else 0.0
         K0 = H + np.diag(SigW) + J.T @ (Sig_e[:, None] * J)
         while True:
             K = K0 + dw_try * np.eye(n)
@@ -308,6 +309,7 @@ def ipm_solve(P, verbose=False, **kw):
                 raise RuntimeError("inertia correction failed")
         if dw_try > 0:
             dw_last = dw_try
+        last_needed = dw_try > 0
         sol = np.linalg.solve(KKT, np.concatenate([rhs_w, -cval]))
         dwv = sol[:n]
         dlam = sol[n:] - lam

@@ -379,6 +379,7 @@ int orc_solve(const orc_problem *p, const orc_options *o, orc_result *res) {
     double th0 = theta_of(c, w, s, t, cres, g);
     double theta_max = 1e4 * dmax(1.0, th0), theta_min = 1e-4 * dmax(1.0, th0);
     double filt_th[FILT_MAX], filt_ph[FILT_MAX];
+    int last_needed = 0;
     int nfilt = 0, iter = 0, status = 1, n_acc = 0, n_refac = 0, n_back = 0, n_reset = 0;
     double E0 = 0.0;
     for (;;) {
@@ -437,7 +438,9 @@ int orc_solve(const orc_problem *p, const orc_options *o, orc_result *res) {
                     for (int b = 0; b < 6; b++) sacc += p->A[6 * a + b] * dp[IX(i) + b];
                 dp[IX(i + 1) + a] = sacc;
             }
-        double dw_try = 0.0;
+        /* IPOPT always retries dw = 0 first; when the previous iteration needed a correction we start
+         * from dw_last/3 instead (deviation 3) */
+        double dw_try = last_needed ? dmax(1e-20, dw_last / 3.0) : 0.0;
         for (;;) {
             memset(K, 0, sizeof(double) * (size_t)n * n);
             for (int i = 1; i <= N; i++)
@@ -495,6 +498,7 @@ int orc_solve(const orc_problem *p, const orc_options *o, orc_result *res) {
             if (dw_try > 1e40) { status = 3; goto done; }
         }
         if (dw_try > 0.0) dw_last = dw_try;
+        last_needed = dw_try > 0.0;
         /* reduced rhs = Z'(rhs - K dp) */
         for (int a = 0; a < n; a++) {
             double sacc = rhs[a];
