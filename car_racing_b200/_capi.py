@@ -16,7 +16,7 @@ NMAX, MMAX = 64, 4
 
 class CbfParams(C.Structure):
     _fields_ = [
-        ("N", C.c_int32), ("M", C.c_int32), ("xt_per_stage", C.c_int32), ("reserved", C.c_int32),
+        ("N", C.c_int32), ("M", C.c_int32), ("xt_per_stage", C.c_int32), ("flags", C.c_int32),
         ("A", C.c_double * 36), ("B", C.c_double * 12), ("Q", C.c_double * 36), ("R", C.c_double * 4),
         ("umax", C.c_double * 2), ("vmin", C.c_double), ("vmax", C.c_double), ("width", C.c_double),
         ("alpha", C.c_double), ("margin", C.c_double), ("L", C.c_double), ("W", C.c_double),
@@ -45,7 +45,7 @@ assert RECORD_DTYPE.itemsize == 32
 
 EXPORTS = [
     "b200mpc_version", "b200mpc_default_ipm_options", "b200mpc_create", "b200mpc_destroy", "b200mpc_last_error",
-    "b200mpc_stream", "b200mpc_launch_count", "b200mpc_cbf_record_doubles", "b200mpc_cbf_solve",
+    "b200mpc_stream", "b200mpc_launch_count", "b200mpc_cbf_record_doubles", "b200mpc_cbf_record_doubles_ex", "b200mpc_cbf_solve",
     "b200mpc_cbf_solve_device", "b200mpc_ilqr_record_doubles", "b200mpc_ilqr_solve", "b200mpc_ilqr_solve_device",
     "b200mpc_argmin_cost_device",
 ]
@@ -77,6 +77,7 @@ def lib():
     L.b200mpc_launch_count.argtypes = [vp]
     L.b200mpc_launch_count.restype = C.c_uint64
     L.b200mpc_cbf_record_doubles.argtypes = [ip, ip, ip]
+    L.b200mpc_cbf_record_doubles_ex.argtypes = [ip, ip, ip, ip]
     L.b200mpc_ilqr_record_doubles.argtypes = [ip]
     cbf_args = [vp, C.POINTER(CbfParams), C.POINTER(IpmOptions), ip, dp, dp, dp, dp, dp, dp]
     L.b200mpc_cbf_solve.argtypes = cbf_args
@@ -163,9 +164,12 @@ def _fill(dst, src, n):
     C.memmove(dst, a.ctypes.data, a.nbytes)
 
 
-def make_cbf_params(prm, M, xt_per_stage):
+FLAG_STAGE_BOUNDS, FLAG_EY_RATE = 1, 2
+
+
+def make_cbf_params(prm, M, xt_per_stage, flags=0):
     p = CbfParams()
-    p.N, p.M, p.xt_per_stage = int(prm["N"]), int(M), int(bool(xt_per_stage))
+    p.N, p.M, p.xt_per_stage, p.flags = int(prm["N"]), int(M), int(bool(xt_per_stage)), int(flags)
     _fill(p.A, prm["A"], 36); _fill(p.B, prm["B"], 12); _fill(p.Q, prm["Q"], 36); _fill(p.R, prm["R"], 4)
     _fill(p.umax, prm["umax"], 2)
     for k in ("vmin", "vmax", "width", "alpha", "margin", "L", "W", "slack_w"):

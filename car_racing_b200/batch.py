@@ -19,19 +19,29 @@ def default_handle():
     return _default_handle
 
 
-def cbf_record_doubles(N, M, xt_per_stage):
+def cbf_record_doubles(N, M, xt_per_stage, flags=0):
     hdr = (6 + M + 1) & ~1
     n = hdr + (6 * (N + 1) if xt_per_stage else 6) + 2 * M * (N + 1)
-    return (n + 1) & ~1
+    n = (n + 1) & ~1
+    if flags & _capi.FLAG_STAGE_BOUNDS:
+        n += 4 * (N + 1)
+    if flags & _capi.FLAG_EY_RATE:
+        n += (N + 1) & ~1
+    return n
 
 
 def ilqr_record_doubles(N):
     return (14 + 2 * (N + 1) + 1) & ~1
 
 
-def pack_cbf(x0, xt, obs, lap_off, N, out=None):
+NO_BOUND = 1e300
+
+
+def pack_cbf(x0, xt, obs, lap_off, N, out=None, xlb=None, xub=None, wd=None):
     """x0 (B,6); xt (6,), (B,6) or (B,N+1,6); obs (B,M,2,N+1) = rows 4,5 of each rival's predicted
-    trajectory (control.py:509-511); lap_off (B,M) or None.  Returns (records (B,stride), M, xt_per_stage)."""
+    trajectory (control.py:509-511); lap_off (B,M) or None.  Optional planner blocks: xlb/xub (B,N+1,2)
+    per-stage bounds on (vx, ey) (+-inf = none), wd (B,N) ey-rate weights.
+    Returns (records (B,stride), M, xt_per_stage) -- flags follow from which optional blocks are given."""
     x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)))
     B = x0.shape[0]
     obs = np.asarray(obs, dtype=np.float64)
@@ -41,7 +51,8 @@ def pack_cbf(x0, xt, obs, lap_off, N, out=None):
         raise ValueError(f"at most {_capi.MMAX} rivals per instance are supported, got {M}")
     xt = np.asarray(xt, dtype=np.float64)
     per_stage = xt.ndim == 3
-    stride = cbf_record_doubles(N, M, per_stage)
+    flags = (_capi.FLAG_STAGE_BOUNDS if xlb is not None else 0) | (_capi.FLAG_EY_RATE if wd is not None else 0)
+    stride = cbf_record_doubles(N, M, per_stage, flags)
     rec = np.zeros((B, stride)) if out is None else out
     hdr = (6 + M + 1) & ~1
     rec[:, 0:6] = x0
@@ -55,6 +66,14 @@ def pack_cbf(x0, xt, obs, lap_off, N, out=None):
         o = hdr + 6
     if M:
         rec[:, o:o + 2 * M * (N + 1)] = obs.reshape(B, 2 * M * (N + 1))
+    o = cbf_record_doubles(N, M, per_stage, 0)
+    if xlb is not None:
+        lo = np.clip(np.asarray(xlb, dtype=np.float64).reshape(B, N + 1, 2), -NO_BOUND, NO_BOUND)
+        hi = np.clip(np.asarray(xub, dtype=np.float64).reshape(B, N + 1, 2), -NO_BOUND, NO_BOUND)
+        rec[:, o:o + 4 * (N + 1)] = np.concatenate([lo, hi], axis=2).reshape(B, 4 * (N + 1))
+        o += 4 * (N + 1)
+    if wd is not None:
+        rec[:, o:o + N] = np.asarray(wd, dtype=np.float64).reshape(B, N)
     return rec, M, per_stage
 
 
@@ -76,14 +95,14 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def solve_cbf_packed(records, prm, M, xt_per_stage, want=("aux", "x", "u", "sigma"), handle=None, **opt):
+def solve_cbf_packed(records, prm, M, xt_per_stage, want=("aux", "x", "u", "sigma"), handle=None, flags=0, **opt):
     """Host-pointer call: H2D + kernel + D2H inside b200mpc_cbf_solve."""
     h = handle or default_handle()
     records = np.ascontiguousarray(records, dtype=np.float64)
     B, N = records.shape[0], int(prm["N"])
-    if records.shape[1] != cbf_record_doubles(N, M, xt_per_stage):
-        raise ValueError("record stride does not match (N, M, xt_per_stage)")
-    p = _capi.make_cbf_params(prm, M, xt_per_stage)
+    if records.shape[1] != cbf_record_doubles(N, M, xt_per_stage, flags):
+        raise ValueError("record stride does not match (N, M, xt_per_stage, flags)")
+    p = _capi.make_cbf_params(prm, M, xt_per_stage, flags)
     o = _capi.default_options(**opt)
     rec = np.zeros(B, dtype=_capi.RECORD_DTYPE)
     aux = np.zeros((B, 4)) if "aux" in want else None
@@ -107,10 +126,13 @@ def solve_cbf_packed(records, prm, M, xt_per_stage, want=("aux", "x", "u", "sigm
     return out
 
 
-def solve_cbf_batch(x0, xt, obs, lap_off, prm, want=("aux", "x", "u", "sigma"), handle=None, **opt):
-    """Batched control.mpccbf / mpc_lti / mpc_multi_agents solve (control.py:476-607,198-248,251-473)."""
-    records, M, per_stage = pack_cbf(x0, xt, obs, lap_off, int(prm["N"]))
-    return solve_cbf_packed(records, prm, M, per_stage, want=want, handle=handle, **opt)
+def solve_cbf_batch(x0, xt, obs, lap_off, prm, want=("aux", "x", "u", "sigma"), handle=None, xlb=None, xub=None, wd=None,
+                    **opt):
+    """Batched control.mpccbf / mpc_lti / mpc_multi_agents solve (control.py:476-607,198-248,251-473); with
+    xlb/xub/wd also the planner's candidate QP (planning/overtake_traj_planner.py:248-379)."""
+    records, M, per_stage = pack_cbf(x0, xt, obs, lap_off, int(prm["N"]), xlb=xlb, xub=xub, wd=wd)
+    flags = (_capi.FLAG_STAGE_BOUNDS if xlb is not None else 0) | (_capi.FLAG_EY_RATE if wd is not None else 0)
+    return solve_cbf_packed(records, prm, M, per_stage, want=want, handle=handle, flags=flags, **opt)
 
 
 def solve_ilqr_batch(x0, xt, obs, lap_off, prm, want=("x", "u"), handle=None):

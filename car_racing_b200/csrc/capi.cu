@@ -113,6 +113,10 @@ int b200mpc_cbf_record_doubles(int N, int M, int xt_per_stage) {
     if (N < 1 || N > B200MPC_NMAX || M < 0 || M > B200MPC_MMAX) return B200MPC_ERR_ARG;
     return cbf_record_doubles(N, M, xt_per_stage);
 }
+int b200mpc_cbf_record_doubles_ex(int N, int M, int xt_per_stage, int flags) {
+    if (N < 1 || N > B200MPC_NMAX || M < 0 || M > B200MPC_MMAX) return B200MPC_ERR_ARG;
+    return cbf_record_doubles(N, M, xt_per_stage, flags);
+}
 int b200mpc_ilqr_record_doubles(int N) {
     if (N < 1 || N > B200MPC_NMAX) return B200MPC_ERR_ARG;
     return ilqr_record_doubles(N);
@@ -151,9 +155,11 @@ static KParams make_kp(const b200mpc_cbf_params *p, const b200mpc_ipm_options *o
     kp.p = *p;
     kp.o = *o;
     kp.B = B;
-    kp.in_stride = cbf_record_doubles(p->N, p->M, p->xt_per_stage);
+    kp.in_stride = cbf_record_doubles(p->N, p->M, p->xt_per_stage, p->flags);
     kp.hdr = cbf_hdr_doubles(p->M);
     kp.obs_off = kp.hdr + (p->xt_per_stage ? 6 * (p->N + 1) : 6);
+    kp.bnd_off = cbf_base_doubles(p->N, p->M, p->xt_per_stage);
+    kp.wd_off = kp.bnd_off + ((p->flags & B200MPC_FLAG_STAGE_BOUNDS) ? 4 * (p->N + 1) : 0);
     double L2 = p->L * p->L, W2 = p->W * p->W;
     kp.iL6 = 1.0 / (L2 * L2 * L2);
     kp.iW6 = 1.0 / (W2 * W2 * W2);
@@ -185,7 +191,7 @@ int b200mpc_cbf_solve(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b2
     if (rc) return rc;
     CK(h, cudaSetDevice(h->device));
     const int N = prm->N, M = prm->M;
-    const size_t stride = (size_t)cbf_record_doubles(N, M, prm->xt_per_stage);
+    const size_t stride = (size_t)cbf_record_doubles(N, M, prm->xt_per_stage, prm->flags);
     const size_t b_in = stride * 8 * B, b_rec = sizeof(b200mpc_record) * (size_t)B, b_aux = 32 * (size_t)B;
     const size_t b_x = 48 * (size_t)(N + 1) * B, b_u = 16 * (size_t)N * B, b_sig = 8 * (size_t)M * (N + 1) * B;
     if ((rc = grow(h, &h->d_in, &h->c_in, b_in))) return rc;

@@ -38,13 +38,21 @@ struct KParams {
     int32_t in_stride;  // doubles per instance record
     int32_t hdr;        // offset of xtarget inside the record
     int32_t obs_off;    // offset of the rival block inside the record
+    int32_t bnd_off;    // offset of the per-stage bound block (flag STAGE_BOUNDS)
+    int32_t wd_off;     // offset of the ey-rate weights (flag EY_RATE)
     double iL6, iW6;    // 1/L^6, 1/W^6
 };
 
 __host__ __device__ inline int cbf_hdr_doubles(int M) { return (6 + M + 1) & ~1; }
-__host__ __device__ inline int cbf_record_doubles(int N, int M, int xt_per_stage) {
+__host__ __device__ inline int cbf_record_doubles(int N, int M, int xt_per_stage, int flags = 0) {
     int n = cbf_hdr_doubles(M) + (xt_per_stage ? 6 * (N + 1) : 6) + 2 * M * (N + 1);
-    return (n + 1) & ~1;
+    n = (n + 1) & ~1;
+    if (flags & B200MPC_FLAG_STAGE_BOUNDS) n += 4 * (N + 1);
+    if (flags & B200MPC_FLAG_EY_RATE) n += (N + 1) & ~1;
+    return n;
+}
+__host__ __device__ inline int cbf_base_doubles(int N, int M, int xt_per_stage) {
+    return (cbf_hdr_doubles(M) + (xt_per_stage ? 6 * (N + 1) : 6) + 2 * M * (N + 1) + 1) & ~1;
 }
 
 // ---------------------------------------------------------------- shared memory plan
@@ -54,7 +62,7 @@ struct SmemPlan {
     static constexpr int NXAP = (NXA + 1) & ~1, NUAP = (NUA + 1) & ~1, NC = 8 + M;
     int N, R, NB, NW, OU, OS;
     int oIN, oW, oD, oHD, oZL, oZU, oS, oT, oY, oZ, oV, oDG, oG, oSIGE, oYHAT, oJD, oJA, oLAM, oCRES, oKFB, oKFF, oPT, oQV,
-        oGUU, oGVU, oYF, oYG, oS0, total;
+        oGUU, oGVU, oYF, oYG, oS0, oJDC, total;
     __host__ __device__ SmemPlan(int N_, int in_stride) {
         N = N_;
         R = M * N;
@@ -75,6 +83,7 @@ struct SmemPlan {
         oPT = take((NC + 1) * NXAP); oQV = take(NXAP);
         oGUU = take(NUA * NUAP); oGVU = take(NUAP); oYF = take(NXA * NUAP); oYG = take(NUAP);
         oS0 = take((M > 0 ? M : 1) * (M + 2));
+        oJDC = take(N + 2);
         total = o;
     }
     __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(double); }
@@ -180,8 +189,10 @@ struct Ipm {
     const KParams &kp;
     const int lane, N, R, NB, NW, OU, OS;
     double *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM, *CRES, *KFB, *KFF, *PT,
-        *QVs, *GUU, *GVU, *YF, *YG, *S0;
-    const double *xt, *obs, *lapoff;
+        *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC;
+    const double *xt, *obs, *lapoff, *bnd, *wdp;
+    bool psb, hwd;       // per-stage bounds / ey-rate cost present (planner QP)
+    int nb_count;        // number of bound + row multipliers (for the error scaling)
     double df, mu, rho, a1;  // a1 = 1 - alpha
     // lane = column role of the Riccati sweep (set once)
     bool isx, iss, isu, isp;
@@ -197,6 +208,12 @@ struct Ipm {
         JA = sm + pl.oJA; LAM = sm + pl.oLAM; CRES = sm + pl.oCRES; KFB = sm + pl.oKFB; KFF = sm + pl.oKFF;
         PT = sm + pl.oPT; QVs = sm + pl.oQV; GUU = sm + pl.oGUU; GVU = sm + pl.oGVU; YF = sm + pl.oYF; YG = sm + pl.oYG;
         S0 = sm + pl.oS0;
+        JDC = sm + pl.oJDC;
+        psb = (kp.p.flags & B200MPC_FLAG_STAGE_BOUNDS) != 0;
+        hwd = (kp.p.flags & B200MPC_FLAG_EY_RATE) != 0;
+        bnd = IN + kp.bnd_off;
+        wdp = IN + kp.wd_off;
+        nb_count = 0;
         lapoff = IN + 6;
         xt = IN + kp.hdr;
         obs = IN + kp.obs_off;
@@ -260,6 +277,22 @@ struct Ipm {
     __device__ __forceinline__ double Bm(int a, int c) const { return kp.p.B[2 * a + c]; }
     __device__ __forceinline__ double Q2(int a, int b) const { return kp.p.Q[6 * a + b] + kp.p.Q[6 * b + a]; }
     __device__ __forceinline__ double R2(int a, int b) const { return kp.p.R[2 * a + b] + kp.p.R[2 * b + a]; }
+
+    // ---- bounds on (vx_i, ey_i): c = 0 -> vx, c = 1 -> ey.  |bound| >= 1e299 (or inf) means "none".
+    __device__ __forceinline__ double xlb(int i, int c) const { return psb ? bnd[4 * i + c] : (c ? -kp.p.width : kp.p.vmin); }
+    __device__ __forceinline__ double xub(int i, int c) const { return psb ? bnd[4 * i + 2 + c] : (c ? kp.p.width : kp.p.vmax); }
+    static __device__ __forceinline__ bool has(double b) { return fabs(b) < 1e299; }
+    __device__ __forceinline__ double wdk(int k) const { return hwd ? wdp[k] : 0.0; }
+    // barrier gradient terms -mu/(x-l) + mu/(u-x) of the bounded components of x_i, added to g[0], g[5]
+    __device__ __forceinline__ void barrier_grad_x(int i, const double (&x)[6], double (&g)[6]) const {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            double lb = xlb(i, c), ub = xub(i, c), w = c ? x[5] : x[0], t = 0.0;
+            if (has(lb)) t -= mu / (w - lb);
+            if (has(ub)) t += mu / (ub - w);
+            g[c ? 5 : 0] += t;
+        }
+    }
 
     // ---- indexing
     __device__ __forceinline__ const double *xtp(int i) const { return kp.p.xt_per_stage ? xt + 6 * i : xt; }
@@ -351,6 +384,11 @@ struct Ipm {
             for (int b = 0; b < 6; b++) acc += Q2(a, b) * d[b];
             g[a] = df * acc;
         }
+        if (hwd) {   // d/d ey_i of  wd_{i-1}(ey_i-ey_{i-1})^2 + wd_i(ey_{i+1}-ey_i)^2
+            double t = wdp[i - 1] * (x[5] - W[6 * (i - 1) + 5]);
+            if (i < N) t -= wdp[i] * (W[6 * (i + 1) + 5] - x[5]);
+            g[5] += 2.0 * df * t;
+        }
     }
 
     // ---- Newton steps of the row slacks / multipliers from JD (all at the current iterate)
@@ -377,8 +415,12 @@ struct Ipm {
             load_x<useD>(k, al, x);
             f += stage_cost(k, x);                                   // control.py:588-591
             if (k >= 1) {                                            // bounds on vx_k, ey_k (:582-586)
-                la.mul(x[0] - kp.p.vmin); la.mul(kp.p.vmax - x[0]);
-                la.mul(x[5] + kp.p.width); la.mul(kp.p.width - x[5]);
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    double lb = xlb(k, c), ub = xub(k, c), w = c ? x[5] : x[0];
+                    if (has(lb)) la.mul(w - lb);
+                    if (has(ub)) la.mul(ub - w);
+                }
             }
             double sgk[MM];
 #pragma unroll
@@ -397,6 +439,7 @@ struct Ipm {
                 la.mul(u[0] + kp.p.umax[0]); la.mul(kp.p.umax[0] - u[0]);
                 la.mul(u[1] + kp.p.umax[1]); la.mul(kp.p.umax[1] - u[1]);
                 dyn_res(x, xn, u, c);
+                if (hwd) f += wdp[k] * (xn[5] - x[5]) * (xn[5] - x[5]);   // overtake_traj_planner.py:325-327
 #pragma unroll
                 for (int a = 0; a < 6; a++) th += fabs(c[a]);
 #pragma unroll
@@ -435,6 +478,7 @@ struct Ipm {
                 double u[2];
                 load_u<false>(k, 0.0, u);
                 f += input_cost(u);
+                if (hwd) { double de = W[6 * (k + 1) + 5] - x[5]; f += wdp[k] * de * de; }
             }
 #pragma unroll
             for (int j = 0; j < M; j++) ss += W[isg(j, k)];
@@ -562,10 +606,10 @@ struct Ipm {
             if (k >= 1) {
                 double vx = W[6 * k], ey = W[6 * k + 5];
                 double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
-                c = fmax(c, fabs((vx - kp.p.vmin) * zl.x - m));
-                c = fmax(c, fabs((kp.p.vmax - vx) * zu.x - m));
-                c = fmax(c, fabs((ey + kp.p.width) * zl.y - m));
-                c = fmax(c, fabs((kp.p.width - ey) * zu.y - m));
+                if (has(xlb(k, 0))) c = fmax(c, fabs((vx - xlb(k, 0)) * zl.x - m));
+                if (has(xub(k, 0))) c = fmax(c, fabs((xub(k, 0) - vx) * zu.x - m));
+                if (has(xlb(k, 1))) c = fmax(c, fabs((ey - xlb(k, 1)) * zl.y - m));
+                if (has(xub(k, 1))) c = fmax(c, fabs((xub(k, 1) - ey) * zu.y - m));
             }
 #pragma unroll
             for (int j = 0; j < M; j++) c = fmax(c, fabs(W[isg(j, k)] * ZL[bss(j, k)] - m));
@@ -589,7 +633,7 @@ struct Ipm {
     }
     __device__ double total_err(const Err &e, double m) const {
         const double s_max = 100.0;
-        int nb = NB + 4 * N + 2 * R;  // lower + upper bound multipliers + row (z, v)
+        int nb = nb_count;  // lower + upper bound multipliers + row (z, v)
         int nmul = 6 * N + R + nb;
         double sd = fmax(s_max, (e.ysum + e.zsum) / (double)(nmul > 0 ? nmul : 1)) / s_max;
         double sc = fmax(s_max, e.zsum / (double)(nb > 0 ? nb : 1)) / s_max;
@@ -607,11 +651,14 @@ struct Ipm {
                 for (int a = 0; a < 6; a++) hd[a] = 0.0;
                 double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
                 {
-                    double il = 1.0 / (x[0] - kp.p.vmin), iu = 1.0 / (kp.p.vmax - x[0]);
+                    double lb = xlb(k, 0), ub = xub(k, 0);
+                    double il = has(lb) ? 1.0 / (x[0] - lb) : 0.0, iu = has(ub) ? 1.0 / (ub - x[0]) : 0.0;
                     hd[0] = zl.x * il + zu.x * iu;
                     g[0] += -mu * il + mu * iu;
-                    il = 1.0 / (x[5] + kp.p.width);
-                    iu = 1.0 / (kp.p.width - x[5]);
+                    lb = xlb(k, 1);
+                    ub = xub(k, 1);
+                    il = has(lb) ? 1.0 / (x[5] - lb) : 0.0;
+                    iu = has(ub) ? 1.0 / (ub - x[5]) : 0.0;
                     hd[5] = zl.y * il + zu.y * iu;
                     g[5] += -mu * il + mu * iu;
                 }
@@ -766,6 +813,16 @@ struct Ipm {
                     g[NXA + 2 + j] -= dgr * w;
                     double er = -(ja[2] * c6[4] + ja[3] * c6[5]);
                     gv += (sg * er - yh) * own;
+                }
+                if (hwd) {   // curvature of wd_k (ey_{k+1}-ey_k)^2: a pure "cost row" J = e5'(dx_{k+1}-dx_k), weight 2 df wd_k
+                    double sg = 2.0 * df * wdp[k];
+                    double own = tcol[5] - ((lane == 5) ? 1.0 : 0.0);
+                    double w = sg * own;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) g[a] += (Am(5, a) - ((a == 5) ? 1.0 : 0.0)) * w;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) g[NXA + c] += Bm(5, c) * w;
+                    gv += (sg * (-c6[5])) * own;
                 }
                 if (lane >= NXA && lane < NZ) {
                     double gu[NUAP];
@@ -1002,26 +1059,36 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         }
     }
     __syncwarp();
+    int nbc = 0;
     for (int k = lane; k <= N; k += 32) {
         if (k >= 1) {   // bound_push / bound_frac on vx_k, ey_k
-            double lb[2] = {kp.p.vmin, -kp.p.width}, ub[2] = {kp.p.vmax, kp.p.width};
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 int wi = 6 * k + (c ? 5 : 0);
                 double w = q.W[wi];
-                double pl_ = fmin(o.bound_push * fmax(1.0, fabs(lb[c])), o.bound_frac * (ub[c] - lb[c]));
-                double pu = fmin(o.bound_push * fmax(1.0, fabs(ub[c])), o.bound_frac * (ub[c] - lb[c]));
-                if (w < lb[c] + pl_) w = lb[c] + pl_;
-                if (w > ub[c] - pu) w = ub[c] - pu;
+                double lb = q.xlb(k, c), ub = q.xub(k, c);
+                bool hl = IP::has(lb), hu = IP::has(ub);
+                if (hl) {
+                    double pl_ = o.bound_push * fmax(1.0, fabs(lb));
+                    if (hu) pl_ = fmin(pl_, o.bound_frac * (ub - lb));
+                    if (w < lb + pl_) w = lb + pl_;
+                }
+                if (hu) {
+                    double pu = o.bound_push * fmax(1.0, fabs(ub));
+                    if (hl) pu = fmin(pu, o.bound_frac * (ub - lb));
+                    if (w > ub - pu) w = ub - pu;
+                }
                 q.W[wi] = w;
-                q.ZL[q.bsx(k) + c] = 1.0;
-                q.ZU[q.bsx(k) + c] = 1.0;
+                q.ZL[q.bsx(k) + c] = hl ? 1.0 : 0.0;
+                q.ZU[q.bsx(k) + c] = hu ? 1.0 : 0.0;
+                nbc += (hl ? 1 : 0) + (hu ? 1 : 0);
             }
         }
 #pragma unroll
         for (int j = 0; j < M; j++) {
             q.W[q.isg(j, k)] = o.bound_push;   // sigma = 0 pushed off its lower bound 0: push*max(1,|0|)
             q.ZL[q.bss(j, k)] = 1.0;
+            nbc += 1;
         }
         if (k < N) {
 #pragma unroll
@@ -1035,8 +1102,12 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 q.ZL[q.bsu(k) + c] = 1.0;
                 q.ZU[q.bsu(k) + c] = 1.0;
             }
+            nbc += 4 + 2 * M;   // u bounds + (z, v) of the rows of this stage
         }
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) nbc += __shfl_xor_sync(0xffffffffu, nbc, off);
+    q.nb_count = nbc;
     __syncwarp();
     // ---- gradient-based scaling at the start (nlp_scaling_max_gradient)
     {
@@ -1177,6 +1248,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 q.JD[r] = ja[0] * dxk[4] + ja[1] * dxk[5] + q.DG[r] * q.a1 * q.D[q.isg(j, k)] + ja[2] * dxn[4] + ja[3] * dxn[5] -
                           q.DG[r] * q.D[q.isg(j, k + 1)];
             }
+            q.JDC[k] = dxn[5] - dxk[5];
         }
         __syncwarp();
         double a_max = 1.0, a_z = 1.0, gphi = 0.0, th = 0.0;
@@ -1186,17 +1258,23 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 q.template load_x<false>(k, 0.0, x);
                 ld6(q.D + 6 * k, d);
                 double2 zl = ld2(q.ZL + q.bsx(k)), zu = ld2(q.ZU + q.bsx(k));
-                double lbv[2] = {kp.p.vmin, -kp.p.width}, ubv[2] = {kp.p.vmax, kp.p.width};
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     double w = c ? x[5] : x[0], dd = c ? d[5] : d[0];
                     double zlc = c ? zl.y : zl.x, zuc = c ? zu.y : zu.x;
-                    double dl = w - lbv[c], du = ubv[c] - w;
-                    double dzl = mu / dl - zlc - zlc / dl * dd, dzu = mu / du - zuc + zuc / du * dd;
-                    if (dd < 0.0) a_max = fmin(a_max, -tau * dl / dd);
-                    if (dd > 0.0) a_max = fmin(a_max, tau * du / dd);
-                    if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc / dzl);
-                    if (dzu < 0.0) a_z = fmin(a_z, -tau * zuc / dzu);
+                    double lb = q.xlb(k, c), ub = q.xub(k, c);
+                    if (IP::has(lb)) {
+                        double dl = w - lb;
+                        double dzl = mu / dl - zlc - zlc / dl * dd;
+                        if (dd < 0.0) a_max = fmin(a_max, -tau * dl / dd);
+                        if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc / dzl);
+                    }
+                    if (IP::has(ub)) {
+                        double du = ub - w;
+                        double dzu = mu / du - zuc + zuc / du * dd;
+                        if (dd > 0.0) a_max = fmin(a_max, tau * du / dd);
+                        if (dzu < 0.0) a_z = fmin(a_z, -tau * zuc / dzu);
+                    }
                 }
                 if (one_round) {
 #pragma unroll
@@ -1204,8 +1282,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 } else {   // long horizons: recompute the base gradient from the iterate
                     double g[6];
                     q.grad_x(k, x, g);
-                    g[0] += -mu / (x[0] - kp.p.vmin) + mu / (kp.p.vmax - x[0]);
-                    g[5] += -mu / (x[5] + kp.p.width) + mu / (kp.p.width - x[5]);
+                    q.barrier_grad_x(k, x, g);
 #pragma unroll
                     for (int a = 0; a < 6; a++) gphi += g[a] * d[a];
                 }
@@ -1328,8 +1405,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             ld6(q.D + 6 * i, d);
             ld6(q.HD + 6 * i, hd);
             q.grad_x(i, x, g);
-            g[0] += -mu / (x[0] - kp.p.vmin) + mu / (kp.p.vmax - x[0]);
-            g[5] += -mu / (x[5] + kp.p.width) + mu / (kp.p.width - x[5]);
+            q.barrier_grad_x(i, x, g);
 #pragma unroll
             for (int a2 = 0; a2 < 6; a2++) {
                 double kd = (hd[a2] + dw_try) * d[a2];
@@ -1349,6 +1425,10 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 double yp = q.YHAT[r] - q.SIGE[r] * q.JD[r];
                 res[4] += q.JA[4 * r + 2] * yp;
                 res[5] += q.JA[4 * r + 3] * yp;
+            }
+            if (q.hwd) {   // -(K d) of the ey-rate curvature rows (i-1 as "next", i as "current")
+                res[5] -= 2.0 * q.df * q.wdp[i - 1] * q.JDC[i - 1];
+                if (i < N) res[5] += 2.0 * q.df * q.wdp[i] * q.JDC[i];
             }
             st6(q.CRES + 6 * (i - 1), res);
         }
@@ -1379,18 +1459,25 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 q.template load_x<false>(k, 0.0, x);
                 ld6(q.D + 6 * k, d);
                 double2 zl = ld2(q.ZL + q.bsx(k)), zu = ld2(q.ZU + q.bsx(k));
-                double lbv[2] = {kp.p.vmin, -kp.p.width}, ubv[2] = {kp.p.vmax, kp.p.width};
                 double zln[2], zun[2];
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     double w = c ? x[5] : x[0], dd = c ? d[5] : d[0];
                     double zlc = c ? zl.y : zl.x, zuc = c ? zu.y : zu.x;
-                    double dl = w - lbv[c], du = ubv[c] - w;
-                    zlc += a_z * (mu / dl - zlc - zlc / dl * dd);
-                    zuc += a_z * (mu / du - zuc + zuc / du * dd);
-                    double wn = w + a * dd, dln = wn - lbv[c], dun = ubv[c] - wn;
-                    zln[c] = fmax(fmin(zlc, kappa_sigma * mu / dln), mu / (kappa_sigma * dln));
-                    zun[c] = fmax(fmin(zuc, kappa_sigma * mu / dun), mu / (kappa_sigma * dun));
+                    double lb = q.xlb(k, c), ub = q.xub(k, c);
+                    double wn = w + a * dd;
+                    zln[c] = 0.0;
+                    zun[c] = 0.0;
+                    if (IP::has(lb)) {
+                        double dl = w - lb, dln = wn - lb;
+                        zlc += a_z * (mu / dl - zlc - zlc / dl * dd);
+                        zln[c] = fmax(fmin(zlc, kappa_sigma * mu / dln), mu / (kappa_sigma * dln));
+                    }
+                    if (IP::has(ub)) {
+                        double du = ub - w, dun = ub - wn;
+                        zuc += a_z * (mu / du - zuc + zuc / du * dd);
+                        zun[c] = fmax(fmin(zuc, kappa_sigma * mu / dun), mu / (kappa_sigma * dun));
+                    }
                 }
                 st2(q.ZL + q.bsx(k), zln[0], zln[1]);
                 st2(q.ZU + q.bsx(k), zun[0], zun[1]);

@@ -60,7 +60,7 @@ typedef struct {
     int32_t N;              /* num_horizon */
     int32_t M;              /* rivals per instance in this batch, 0..B200MPC_MMAX (0 = mpc_lti) */
     int32_t xt_per_stage;   /* 0: xtarget is (6,) per instance; 1: (N+1,6) per instance (control.py:373-382) */
-    int32_t reserved;
+    int32_t flags;          /* B200MPC_FLAG_* : optional per-instance blocks appended to the record */
     double A[36], B[12];    /* matrix_A, matrix_B, row-major (control.py:566-570) */
     double Q[36], R[4];     /* matrix_Q, matrix_R (control.py:578-591) */
     double umax[2];         /* delta_max, a_max (control.py:572-576) */
@@ -71,6 +71,11 @@ typedef struct {
     double L, W;            /* l_agent+l_obs, w_agent+w_obs (control.py:532-535) */
     double slack_w;         /* 10000 (control.py:560) */
 } b200mpc_cbf_params;
+
+/* flags: planner-candidate QP (planning/overtake_traj_planner.py:248-379) */
+#define B200MPC_FLAG_STAGE_BOUNDS 1 /* record carries per-stage bounds on (vx_i, ey_i): (N+1) x {lb_vx, lb_ey, ub_vx, ub_ey};
+                                       +-1e300 or +-inf = no bound (:276-324); vmin/vmax/width are then ignored */
+#define B200MPC_FLAG_EY_RATE 2      /* record carries wd[0..N-1]: cost += wd[i]*(ey_{i+1}-ey_i)^2 (:325-327) */
 
 /* Interior-point options (IPOPT option names where they exist). */
 typedef struct {
@@ -105,11 +110,14 @@ uint64_t b200mpc_stream(const b200mpc_handle *h);
 /* number of kernel launches issued through this handle so far */
 uint64_t b200mpc_launch_count(const b200mpc_handle *h);
 
-/* doubles per instance of the packed input record for (N, M, xt_per_stage):
+/* doubles per instance of the packed input record for (N, M, xt_per_stage) and flags == 0:
  *   [x0 6][lap_off M][pad to even][xtarget 6 or 6(N+1)][obs j=0..M-1: s_0..s_N, ey_0..ey_N][pad to even]
+ * with flags the record continues with [bounds 4(N+1)] and/or [wd N][pad to even]
+ * (b200mpc_cbf_record_doubles_ex gives the total).
  * lap_off[j] = (num_cycle_ego - num_cycle_obs)*lap_length (control.py:538-540); obs rows are rows 4,5
  * of get_trajectory_nsteps' (6,N+1) prediction (control.py:509-511). */
 int b200mpc_cbf_record_doubles(int N, int M, int xt_per_stage);
+int b200mpc_cbf_record_doubles_ex(int N, int M, int xt_per_stage, int flags);
 
 /* Batched MPC-LTI / MPC-CBF / mpc_multi_agents solve.
  *   in    : B packed records (see above)

@@ -60,6 +60,10 @@ static double eval_f(const ctx_t *c, const double *w) {
     }
     double ss = 0.0;
     for (int k = 0; k < c->ns; k++) ss += w[c->nx + c->nu + k];
+    for (int i = 0; i < c->N; i++) {   /* planner: 30*(ey_{i+1}-ey_i)^2 (overtake_traj_planner.py:325-327) */
+        double d = w[IX(i + 1) + 5] - XK(c, w, i, 5);
+        f += p->wd[i] * d * d;
+    }
     return f + p->slack_w * ss;
 }
 
@@ -80,6 +84,11 @@ static void eval_grad(const ctx_t *c, const double *w, double *g) {
         g[IU(c, i) + 1] = (p->R[1] + p->R[2]) * u[0] + 2 * p->R[3] * u[1];
     }
     for (int k = 0; k < c->ns; k++) g[c->nx + c->nu + k] = p->slack_w;
+    for (int i = 0; i < c->N; i++) {
+        double d = w[IX(i + 1) + 5] - XK(c, w, i, 5);
+        g[IX(i + 1) + 5] += 2.0 * p->wd[i] * d;
+        if (i > 0) g[IX(i) + 5] -= 2.0 * p->wd[i] * d;
+    }
 }
 
 /* dynamics residual c_i = x_{i+1} - A x_i - B u_i, i=0..N-1 */
@@ -317,8 +326,13 @@ int orc_solve(const orc_problem *p, const orc_options *o, orc_result *res) {
     /* ---- bounds */
     for (int k = 0; k < n; k++) { lb[k] = -HUGE_VAL; ub[k] = HUGE_VAL; }
     for (int i = 1; i <= N; i++) {
-        lb[IX(i) + 0] = p->vmin; ub[IX(i) + 0] = p->vmax;
-        lb[IX(i) + 5] = -p->width; ub[IX(i) + 5] = p->width;
+        if (p->per_stage_bounds) {
+            lb[IX(i) + 0] = p->xlb[2 * i]; ub[IX(i) + 0] = p->xub[2 * i];
+            lb[IX(i) + 5] = p->xlb[2 * i + 1]; ub[IX(i) + 5] = p->xub[2 * i + 1];
+        } else {
+            lb[IX(i) + 0] = p->vmin; ub[IX(i) + 0] = p->vmax;
+            lb[IX(i) + 5] = -p->width; ub[IX(i) + 5] = p->width;
+        }
     }
     for (int i = 0; i < N; i++)
         for (int a = 0; a < 2; a++) { lb[IU(c, i) + a] = -p->umax[a]; ub[IU(c, i) + a] = p->umax[a]; }
@@ -451,6 +465,17 @@ int orc_solve(const orc_problem *p, const orc_options *o, orc_result *res) {
                 K[(size_t)k0 * n + k0] = c->df * 2 * p->R[0];
                 K[(size_t)k0 * n + k0 + 1] = K[(size_t)(k0 + 1) * n + k0] = c->df * (p->R[1] + p->R[2]);
                 K[(size_t)(k0 + 1) * n + k0 + 1] = c->df * 2 * p->R[3];
+            }
+            for (int i = 0; i < N; i++) {
+                double h2 = 2.0 * c->df * p->wd[i];
+                int kn = IX(i + 1) + 5;
+                K[(size_t)kn * n + kn] += h2;
+                if (i > 0) {
+                    int kc = IX(i) + 5;
+                    K[(size_t)kc * n + kc] += h2;
+                    K[(size_t)kc * n + kn] -= h2;
+                    K[(size_t)kn * n + kc] -= h2;
+                }
             }
             for (int k = 0; k < n; k++) K[(size_t)k * n + k] += hd[k] + sigw[k] + dw_try;
             for (int r = 0; r < m; r++) {

@@ -41,6 +41,11 @@ typedef struct {
     double obs_s[ORC_MMAX][ORC_NMAX + 1];  /* rival s prediction, row 4 of obs_traj */
     double obs_ey[ORC_MMAX][ORC_NMAX + 1]; /* rival ey prediction, row 5 */
     double lap_off[ORC_MMAX]; /* (num_cycle_ego-num_cycle_obs)*lap_length, applied to h only (:539-542) */
+    /* planner-candidate extensions (planning/overtake_traj_planner.py:248-379); all off when zero */
+    int per_stage_bounds;               /* 1: use xlb/xub instead of vmin/vmax/width */
+    double xlb[(ORC_NMAX + 1) * 2];     /* per stage i: lower bound on (vx_i, ey_i), -HUGE_VAL = none (:276-324) */
+    double xub[(ORC_NMAX + 1) * 2];     /* per stage i: upper bound on (vx_i, ey_i), +HUGE_VAL = none */
+    double wd[ORC_NMAX];                /* cost += wd[i]*(ey_{i+1}-ey_i)^2, i=0..N-1 (:325-327: 30 for i=1..N-2) */
 } orc_problem;
 
 typedef struct {

@@ -27,6 +27,9 @@ class Problem(C.Structure):
         ("obs_s", (C.c_double * (NMAX + 1)) * MMAX),
         ("obs_ey", (C.c_double * (NMAX + 1)) * MMAX),
         ("lap_off", C.c_double * MMAX),
+        ("per_stage_bounds", C.c_int),
+        ("xlb", C.c_double * ((NMAX + 1) * 2)), ("xub", C.c_double * ((NMAX + 1) * 2)),
+        ("wd", C.c_double * NMAX),
     ]
 
 
@@ -98,7 +101,7 @@ def _fill(dst, src):
     C.memmove(dst, a.ctypes.data, a.nbytes)
 
 
-def solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=1, **opt):
+def solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=1, xlb=None, xub=None, wd=None, **opt):
     """x0 (B,6); xt (B,N+1,6) or (6,); obs (B,M,2,N+1) [s, ey]; lap_off (B,M); prm: dict of
     model/limits (A,B,Q,R,N,umax,vmin,vmax,width,alpha,margin,L,W,slack_w).  Returns dict of arrays."""
     x0 = np.atleast_2d(np.asarray(x0, float))
@@ -122,6 +125,12 @@ def solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=1, **opt):
         for j in range(M):
             _fill(p.obs_s[j], obs[b, j, 0]); _fill(p.obs_ey[j], obs[b, j, 1])
             p.lap_off[j] = lap_off[b, j]
+        if xlb is not None:
+            p.per_stage_bounds = 1
+            _fill(p.xlb, np.asarray(xlb, float).reshape(Bn, N + 1, 2)[b])
+            _fill(p.xub, np.asarray(xub, float).reshape(Bn, N + 1, 2)[b])
+        if wd is not None:
+            _fill(p.wd, np.asarray(wd, float).reshape(Bn, N)[b])
     o = default_options(**opt)
     R = (Result * Bn)()
     lib().orc_solve_batch(P, Bn, C.byref(o), R, nthreads)

@@ -202,3 +202,51 @@ def test_argmin_kernel_first_min(crb):
     h.check(_capi.lib().b200mpc_argmin_cost_device(h.ptr, d.data_ptr(), 1000, 2, out.data_ptr()), "argmin")
     torch.cuda.synchronize()
     assert int(out.item()) == 17
+
+
+def _planner_batch(seeds):
+    from car_racing_b200 import planning
+    from planner_cases import make_planner
+    kws, offs, prm = [], [], None
+    for seed in seeds:
+        p = make_planner(seed, num_veh=2 + seed % 2)
+        N = p.racing_game_param.num_horizon_planner
+        ego = p.vehicles["ego"]
+        prm = planning.planner_params(p.racing_game_param.matrix_A, p.racing_game_param.matrix_B, N)
+        for c in range(len(p.sorted_vehicles) + 1):
+            xlb, xub = planning.candidate_bounds(c, p.xcurv_ego, p.sorted_vehicles, p.obs_infos, 0.4, 0.2, 1.0, p.track.lap_length, N)
+            if not planning.x0_feasible(ego.xcurv, xlb, xub) or (xlb[1:N, 1] > xub[1:N, 1] - 0.05).any():
+                continue
+            s_ref, ey_ref = planning.candidate_targets(c, ego.xcurv, p.bezier_xcurvs, p.bezier_funcs, N)
+            kw, off = planning.pack_candidates(ego.xcurv, s_ref[None], ey_ref[None], xlb[None], xub[None], N)
+            kws.append(kw)
+            offs.append(off)
+    cat = {k: (np.concatenate([kw[k] for kw in kws]) if kws[0][k] is not None else None) for k in kws[0]}
+    return cat, np.concatenate(offs), prm
+
+
+def test_planner_candidate_qp_parity(crb, oracle):
+    """Planner candidate QPs (overtake_traj_planner.py:248-379): per-stage bounds + ey-rate cost, R = 0."""
+    kw, off, prm = _planner_batch(range(24))
+    assert kw["x0"].shape[0] >= 40
+    g = crb.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, prm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"])
+    r = oracle.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, prm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"],
+                               nthreads=os.cpu_count() or 1)
+    match, info = _compare(g, r, min_match=0.97)
+    ok = (g["status"] == 0) & (r["status"] == 0)
+    assert ok.mean() >= 0.9
+    assert np.abs(g["x"][ok] - r["x"][ok]).max() < 1e-5
+
+
+def test_planner_drop_in_on_gpu(crb, oracle):
+    from car_racing_b200 import planning
+    from planner_cases import make_planner
+    for seed in (3, 7, 11):
+        p1, p2 = make_planner(seed), make_planner(seed)
+        t1, f1, st1, s1 = planning.solve_optimization_problem(p1)     # default solver: the GPU batch call
+        t2, f2, st2, s2 = planning.solve_optimization_problem(
+            p2, solver=lambda x0, xt, obs, lo, prm, **k: oracle.solve_cbf_batch(x0, xt, obs, lo, prm, **k))
+        assert f1 == f2 and np.abs(s1 - s2).max() < 1e-5 and t1.shape == (11, 6)
+        fin = np.isfinite(p2.candidate_costs)
+        assert (np.isfinite(p1.candidate_costs) == fin).all()
+        assert np.abs(p1.candidate_costs[fin] - p2.candidate_costs[fin]).max() < 1e-5
