@@ -182,7 +182,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
 }
 
 // ---------------------------------------------------------------- the solver
-template <int M>
+template <int M, int FL>
 struct Ipm {
     static constexpr int NXA = 6 + M, NUA = 2 + M, NZ = NXA + NUA;
     static constexpr int NXAP = (NXA + 1) & ~1, NUAP = (NUA + 1) & ~1, NC = 8 + M, MM = (M > 0 ? M : 1);
@@ -191,7 +191,8 @@ struct Ipm {
     double *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM, *CRES, *KFB, *KFF, *PT,
         *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC;
     const double *xt, *obs, *lapoff, *bnd, *wdp;
-    bool psb, hwd;       // per-stage bounds / ey-rate cost present (planner QP)
+    // per-stage bounds / ey-rate cost present (planner QP): compile-time so that the MPC-CBF path pays nothing
+    static constexpr bool psb = (FL & B200MPC_FLAG_STAGE_BOUNDS) != 0, hwd = (FL & B200MPC_FLAG_EY_RATE) != 0;
     int nb_count;        // number of bound + row multipliers (for the error scaling)
     double df, mu, rho, a1;  // a1 = 1 - alpha
     // lane = column role of the Riccati sweep (set once)
@@ -209,8 +210,6 @@ struct Ipm {
         PT = sm + pl.oPT; QVs = sm + pl.oQV; GUU = sm + pl.oGUU; GVU = sm + pl.oGVU; YF = sm + pl.oYF; YG = sm + pl.oYG;
         S0 = sm + pl.oS0;
         JDC = sm + pl.oJDC;
-        psb = (kp.p.flags & B200MPC_FLAG_STAGE_BOUNDS) != 0;
-        hwd = (kp.p.flags & B200MPC_FLAG_EY_RATE) != 0;
         bnd = IN + kp.bnd_off;
         wdp = IN + kp.wd_off;
         nb_count = 0;
@@ -281,7 +280,7 @@ struct Ipm {
     // ---- bounds on (vx_i, ey_i): c = 0 -> vx, c = 1 -> ey.  |bound| >= 1e299 (or inf) means "none".
     __device__ __forceinline__ double xlb(int i, int c) const { return psb ? bnd[4 * i + c] : (c ? -kp.p.width : kp.p.vmin); }
     __device__ __forceinline__ double xub(int i, int c) const { return psb ? bnd[4 * i + 2 + c] : (c ? kp.p.width : kp.p.vmax); }
-    static __device__ __forceinline__ bool has(double b) { return fabs(b) < 1e299; }
+    static __device__ __forceinline__ bool has(double b) { return !psb || fabs(b) < 1e299; }
     __device__ __forceinline__ double wdk(int k) const { return hwd ? wdp[k] : 0.0; }
     // barrier gradient terms -mu/(x-l) + mu/(u-x) of the bounded components of x_i, added to g[0], g[5]
     __device__ __forceinline__ void barrier_grad_x(int i, const double (&x)[6], double (&g)[6]) const {
@@ -1007,7 +1006,7 @@ struct Ipm {
 };
 
 // ---------------------------------------------------------------- kernel
-template <int M>
+template <int M, int FL>
 __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KParams kp, const double *__restrict__ in,
                                                      b200mpc_record *__restrict__ rec, double *__restrict__ aux,
                                                      double *__restrict__ xpred, double *__restrict__ upred,
@@ -1016,9 +1015,9 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     const int lane = threadIdx.x;
     const int inst = blockIdx.x;
     const SmemPlan<M> pl(kp.p.N, kp.in_stride);
-    Ipm<M> S_(kp, pl, sm, lane);
-    Ipm<M> &q = S_;
-    using IP = Ipm<M>;
+    Ipm<M, FL> S_(kp, pl, sm, lane);
+    Ipm<M, FL> &q = S_;
+    using IP = Ipm<M, FL>;
     constexpr int NXAP = IP::NXAP, NC = IP::NC;
     const int N = q.N, R = q.R, NW = q.NW, OU = q.OU, OS = q.OS;
     const b200mpc_ipm_options &o = kp.o;
