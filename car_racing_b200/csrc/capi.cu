@@ -124,15 +124,15 @@ int b200mpc_ilqr_record_doubles(int N) {
 
 }  // extern "C"
 
-template <int M, int FL>
+template <int M, int FL, int NT>
 static int launch_cbf(b200mpc_handle *h, const KParams &kp, const double *d_in, b200mpc_record *d_rec, double *d_aux,
                       double *d_x, double *d_u, double *d_sig) {
     SmemPlan<M> pl(kp.p.N, kp.in_stride);
     size_t smem = pl.bytes();
     if ((int)smem > h->max_smem_optin)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: horizon too long for one CTA's shared memory");
-    CK(h, cudaFuncSetAttribute(ocp_ipm_kernel<M, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ocp_ipm_kernel<M, FL><<<kp.B, 32, smem, h->stream>>>(kp, d_in, d_rec, d_aux, d_x, d_u, d_sig);
+    CK(h, cudaFuncSetAttribute(ocp_ipm_kernel<M, FL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ocp_ipm_kernel<M, FL, NT><<<kp.B, 32, smem, h->stream>>>(kp, d_in, d_rec, d_aux, d_x, d_u, d_sig);
     CK(h, cudaGetLastError());
     h->launches++;
     return B200MPC_OK;
@@ -177,15 +177,19 @@ int b200mpc_cbf_solve_device(b200mpc_handle *h, const b200mpc_cbf_params *prm, c
     KParams kp = make_kp(prm, opt, B);
     // the planner-candidate blocks are compiled in only where the reference uses them (no rival rows there)
     if (prm->flags == (B200MPC_FLAG_STAGE_BOUNDS | B200MPC_FLAG_EY_RATE) && prm->M == 0)
-        return launch_cbf<0, 3>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        return launch_cbf<0, 3, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
     if (prm->flags != 0)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: flags are supported as STAGE_BOUNDS|EY_RATE with M = 0 only");
+    // horizon-specialised instantiation of the BASELINE.json north-star configuration (per-stage xtarget excluded:
+    // the record stride differs)
+    if (prm->N == 20 && prm->M == 3 && !prm->xt_per_stage)
+        return launch_cbf<3, 0, 20>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
     switch (prm->M) {
-        case 0: return launch_cbf<0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-        case 1: return launch_cbf<1, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-        case 2: return launch_cbf<2, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-        case 3: return launch_cbf<3, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-        case 4: return launch_cbf<4, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        case 0: return launch_cbf<0, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        case 1: return launch_cbf<1, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        case 2: return launch_cbf<2, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        case 3: return launch_cbf<3, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
+        case 4: return launch_cbf<4, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
     }
     return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: M out of range");
 }

@@ -62,7 +62,7 @@ struct SmemPlan {
     static constexpr int NXAP = (NXA + 1) & ~1, NUAP = (NUA + 1) & ~1, NC = 8 + M;
     int N, R, NB, NW, OU, OS;
     int oIN, oW, oD, oHD, oZL, oZU, oS, oT, oY, oZ, oV, oDG, oG, oSIGE, oYHAT, oJD, oJA, oLAM, oCRES, oKFB, oKFF, oPT, oQV,
-        oGUU, oGVU, oYF, oYG, oS0, oJDC, total;
+        oGUU, oGVU, oYF, oYG, oS0, oJDC, oGX, total;
     __host__ __device__ SmemPlan(int N_, int in_stride) {
         N = N_;
         R = M * N;
@@ -84,6 +84,7 @@ struct SmemPlan {
         oGUU = take(NUA * NUAP); oGVU = take(NUAP); oYF = take(NXA * NUAP); oYG = take(NUAP);
         oS0 = take((M > 0 ? M : 1) * (M + 2));
         oJDC = take(N + 2);
+        oGX = take(6 * (N + 1));
         total = o;
     }
     __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(double); }
@@ -182,14 +183,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
 }
 
 // ---------------------------------------------------------------- the solver
-template <int M, int FL>
+// NT > 0: horizon known at compile time (all shared-memory offsets become immediates); NT == 0: runtime horizon
+template <int M, int FL, int NT>
 struct Ipm {
     static constexpr int NXA = 6 + M, NUA = 2 + M, NZ = NXA + NUA;
     static constexpr int NXAP = (NXA + 1) & ~1, NUAP = (NUA + 1) & ~1, NC = 8 + M, MM = (M > 0 ? M : 1);
     const KParams &kp;
-    const int lane, N, R, NB, NW, OU, OS;
+    const int lane;
+    static constexpr bool kStaticN = NT > 0;
+    const int N, R, NB, NW, OU, OS;
     double *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM, *CRES, *KFB, *KFF, *PT,
-        *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC;
+        *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC, *GX;
     const double *xt, *obs, *lapoff, *bnd, *wdp;
     // per-stage bounds / ey-rate cost present (planner QP): compile-time so that the MPC-CBF path pays nothing
     static constexpr bool psb = (FL & B200MPC_FLAG_STAGE_BOUNDS) != 0, hwd = (FL & B200MPC_FLAG_EY_RATE) != 0;
@@ -202,7 +206,8 @@ struct Ipm {
     double arow[6], brow[2];   // row `lane` of A and B (lanes < 6), for the forward sweep
 
     __device__ Ipm(const KParams &kp_, const SmemPlan<M> &pl, double *sm, int lane_)
-        : kp(kp_), lane(lane_), N(pl.N), R(pl.R), NB(pl.NB), NW(pl.NW), OU(pl.OU), OS(pl.OS) {
+        : kp(kp_), lane(lane_), N(NT ? NT : pl.N), R(M * (NT ? NT : pl.N)), NB(NT ? 4 * NT + M * (NT + 1) : pl.NB),
+          NW(NT ? 8 * NT + 6 + M * (NT + 1) : pl.NW), OU(NT ? 6 * (NT + 1) : pl.OU), OS(NT ? 8 * NT + 6 : pl.OS) {
         IN = sm + pl.oIN; W = sm + pl.oW; D = sm + pl.oD; HD = sm + pl.oHD; ZL = sm + pl.oZL; ZU = sm + pl.oZU;
         S = sm + pl.oS; T = sm + pl.oT; Y = sm + pl.oY; Z = sm + pl.oZ; V = sm + pl.oV;
         DG = sm + pl.oDG; GR = sm + pl.oG; SIGE = sm + pl.oSIGE; YHAT = sm + pl.oYHAT; JD = sm + pl.oJD;
@@ -210,6 +215,7 @@ struct Ipm {
         PT = sm + pl.oPT; QVs = sm + pl.oQV; GUU = sm + pl.oGUU; GVU = sm + pl.oGVU; YF = sm + pl.oYF; YG = sm + pl.oYG;
         S0 = sm + pl.oS0;
         JDC = sm + pl.oJDC;
+        GX = sm + pl.oGX;
         bnd = IN + kp.bnd_off;
         wdp = IN + kp.wd_off;
         nb_count = 0;
@@ -340,16 +346,26 @@ struct Ipm {
             u[0] += al * d.x; u[1] += al * d.y;
         }
     }
-    // c_k = x_{k+1} - A x_k - B u_k
-    __device__ __forceinline__ void dyn_res(const double (&x)[6], const double (&xn)[6], const double (&u)[2], double (&c)[6]) const {
-#pragma unroll
+    // The once-per-iteration phases keep their matrix loops ROLLED (#pragma unroll 1 over the output row):
+    // fully unrolled they were ~20k instructions of straight-line code and the instruction cache, not the
+    // arithmetic, set their speed (ncu: stall_no_inst 43 % of samples).  The row index is uniform across the
+    // warp, so A, B, Q are read with register-indexed constant-bank loads.
+    // c_k = x_{k+1} - A x_k - B u_k ; x_{k+1} is read from shared memory (+al*D); returns sum_a |c_a|, optionally stores c
+    template <bool useD, bool store>
+    __device__ __forceinline__ double dyn_res(int k, double al, const double (&x)[6], const double (&u)[2]) const {
+        double acc = 0.0;
+#pragma unroll 1
         for (int a = 0; a < 6; a++) {
-            double s = xn[a];
+            double s = W[6 * (k + 1) + a];
+            if (useD) s += al * D[6 * (k + 1) + a];
+            const double *Ar = kp.p.A + 6 * a;
 #pragma unroll
-            for (int b = 0; b < 6; b++) s -= Am(a, b) * x[b];
-            s -= Bm(a, 0) * u[0] + Bm(a, 1) * u[1];
-            c[a] = s;
+            for (int b = 0; b < 6; b++) s -= Ar[b] * x[b];
+            s -= kp.p.B[2 * a] * u[0] + kp.p.B[2 * a + 1] * u[1];
+            if (store) CRES[6 * k + a] = s;
+            acc += fabs(s);
         }
+        return acc;
     }
     // (x-xt)'Q(x-xt)
     __device__ __forceinline__ double stage_cost(int i, const double (&x)[6]) const {
@@ -358,36 +374,44 @@ struct Ipm {
 #pragma unroll
         for (int a = 0; a < 6; a++) d[a] = x[a] - t[a];
         double f = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int a = 0; a < 6; a++) {
-            double acc = 0.0;
+            const double *Qr = kp.p.Q + 6 * a;
+            double acc = 0.0, da = 0.0;
 #pragma unroll
-            for (int b = 0; b < 6; b++) acc += kp.p.Q[6 * a + b] * d[b];
-            f += d[a] * acc;
+            for (int b = 0; b < 6; b++) {
+                acc += Qr[b] * d[b];
+                da = (b == a) ? d[b] : da;
+            }
+            f += da * acc;
         }
         return f;
     }
     __device__ __forceinline__ double input_cost(const double (&u)[2]) const {
         return u[0] * (kp.p.R[0] * u[0] + kp.p.R[1] * u[1]) + u[1] * (kp.p.R[2] * u[0] + kp.p.R[3] * u[1]);
     }
-    // scaled gradient of the objective wrt x_i
-    __device__ __forceinline__ void grad_x(int i, const double (&x)[6], double (&g)[6]) const {
+    // scaled gradient of the objective wrt x_i -> dst[0..5] (shared memory); returns max |.|
+    __device__ __forceinline__ double grad_x_store(int i, const double (&x)[6], double *dst) const {
         const double *t = xtp(i);
         double d[6];
 #pragma unroll
         for (int a = 0; a < 6; a++) d[a] = x[a] - t[a];
-#pragma unroll
+        double gm = 0.0;
+#pragma unroll 1
         for (int a = 0; a < 6; a++) {
             double acc = 0.0;
 #pragma unroll
-            for (int b = 0; b < 6; b++) acc += Q2(a, b) * d[b];
-            g[a] = df * acc;
+            for (int b = 0; b < 6; b++) acc += (kp.p.Q[6 * a + b] + kp.p.Q[6 * b + a]) * d[b];
+            acc *= df;
+            if (hwd && a == 5) {   // d/d ey_i of  wd_{i-1}(ey_i-ey_{i-1})^2 + wd_i(ey_{i+1}-ey_i)^2
+                double tt = wdp[i - 1] * (x[5] - W[6 * (i - 1) + 5]);
+                if (i < N) tt -= wdp[i] * (W[6 * (i + 1) + 5] - x[5]);
+                acc += 2.0 * df * tt;
+            }
+            dst[a] = acc;
+            gm = fmax(gm, fabs(acc));
         }
-        if (hwd) {   // d/d ey_i of  wd_{i-1}(ey_i-ey_{i-1})^2 + wd_i(ey_{i+1}-ey_i)^2
-            double t = wdp[i - 1] * (x[5] - W[6 * (i - 1) + 5]);
-            if (i < N) t -= wdp[i] * (W[6 * (i + 1) + 5] - x[5]);
-            g[5] += 2.0 * df * t;
-        }
+        return gm;
     }
 
     // ---- Newton steps of the row slacks / multipliers from JD (all at the current iterate)
@@ -431,16 +455,14 @@ struct Ipm {
                 la.mul(sv);                                          // sigma >= 0 (:559,561)
             }
             if (k < N) {
-                double xn[6], u[2], c[6];
+                double xn[6], u[2];
                 load_x<useD>(k + 1, al, xn);
                 load_u<useD>(k, al, u);
                 f += input_cost(u);                                  // :578-579
                 la.mul(u[0] + kp.p.umax[0]); la.mul(kp.p.umax[0] - u[0]);
                 la.mul(u[1] + kp.p.umax[1]); la.mul(kp.p.umax[1] - u[1]);
-                dyn_res(x, xn, u, c);
+                th += dyn_res<useD, false>(k, al, x, u);
                 if (hwd) f += wdp[k] * (xn[5] - x[5]) * (xn[5] - x[5]);   // overtake_traj_planner.py:325-327
-#pragma unroll
-                for (int a = 0; a < 6; a++) th += fabs(c[a]);
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
@@ -488,12 +510,12 @@ struct Ipm {
     // ---- evaluate rows (GR, JA) and dynamics residual at the current iterate (lane = stage)
     __device__ void eval_point() {
         for (int k = lane; k < N; k += 32) {
-            double x[6], xn[6], u[2], c[6];
+            double x[6], xn[6], u[2];
             load_x<false>(k, 0.0, x);
             load_x<false>(k + 1, 0.0, xn);
             load_u<false>(k, 0.0, u);
-            dyn_res(x, xn, u, c);
-            st6(CRES + 6 * k, c);
+            dyn_res<false, true>(k, 0.0, x, u);
+            grad_x_store(k + 1, xn, GX + 6 * (k + 1));   // objective gradient of x_{k+1}, shared by the later phases
 #pragma unroll
             for (int j = 0; j < M; j++) {
                 int r = j * N + k;
@@ -523,34 +545,30 @@ struct Ipm {
                 for (int a = 0; a < 6; a++) lamn[a] = 0.0;
             }
             if (k >= 1) {
-                double x[6], g[6], lam[6];
-                load_x<false>(k, 0.0, x);
-                grad_x(k, x, g);
-                ld6(LAM + 6 * (k - 1), lam);
+                double jy4 = 0.0, jy5 = 0.0;
 #pragma unroll
-                for (int a = 0; a < 6; a++) {
-                    double s = g[a] + lam[a];
-#pragma unroll
-                    for (int b = 0; b < 6; b++) s -= Am(b, a) * lamn[b];
-                    g[a] = s;
-                }
-#pragma unroll
-                for (int j = 0; j < M; j++) {  // - J'y
+                for (int j = 0; j < M; j++) {  // J'y on (s, ey)
                     if (k < N) {
                         int r = j * N + k;
-                        g[4] -= JA[4 * r + 0] * Y[r];
-                        g[5] -= JA[4 * r + 1] * Y[r];
+                        jy4 += JA[4 * r + 0] * Y[r];
+                        jy5 += JA[4 * r + 1] * Y[r];
                     }
                     int r = j * N + k - 1;
-                    g[4] -= JA[4 * r + 2] * Y[r];
-                    g[5] -= JA[4 * r + 3] * Y[r];
+                    jy4 += JA[4 * r + 2] * Y[r];
+                    jy5 += JA[4 * r + 3] * Y[r];
                 }
                 double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
-                g[0] += -zl.x + zu.x;
-                g[5] += -zl.y + zu.y;
                 zsum += zl.x + zl.y + zu.x + zu.y;
+#pragma unroll 1
+                for (int a = 0; a < 6; a++) {
+                    double s = GX[6 * k + a] + LAM[6 * (k - 1) + a];
 #pragma unroll
-                for (int a = 0; a < 6; a++) dual = fmax(dual, fabs(g[a]));
+                    for (int b = 0; b < 6; b++) s -= kp.p.A[6 * b + a] * lamn[b];
+                    if (a == 0) s += -zl.x + zu.x;
+                    if (a == 4) s -= jy4;
+                    if (a == 5) s += -jy5 - zl.y + zu.y;
+                    dual = fmax(dual, fabs(s));
+                }
             }
 #pragma unroll
             for (int j = 0; j < M; j++) {  // sigma_{j,k}
@@ -645,7 +663,7 @@ struct Ipm {
             if (k >= 1) {
                 double x[6], g[6], hd[6];
                 load_x<false>(k, 0.0, x);
-                grad_x(k, x, g);
+                ld6(GX + 6 * k, g);
 #pragma unroll
                 for (int a = 0; a < 6; a++) hd[a] = 0.0;
                 double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
@@ -1006,7 +1024,7 @@ struct Ipm {
 };
 
 // ---------------------------------------------------------------- kernel
-template <int M, int FL>
+template <int M, int FL, int NT>
 __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KParams kp, const double *__restrict__ in,
                                                      b200mpc_record *__restrict__ rec, double *__restrict__ aux,
                                                      double *__restrict__ xpred, double *__restrict__ upred,
@@ -1014,10 +1032,10 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x;
     const int inst = blockIdx.x;
-    const SmemPlan<M> pl(kp.p.N, kp.in_stride);
-    Ipm<M, FL> S_(kp, pl, sm, lane);
-    Ipm<M, FL> &q = S_;
-    using IP = Ipm<M, FL>;
+    const SmemPlan<M> pl(NT ? NT : kp.p.N, NT ? cbf_record_doubles(NT, M, 0, FL) : kp.in_stride);
+    Ipm<M, FL, NT> S_(kp, pl, sm, lane);
+    Ipm<M, FL, NT> &q = S_;
+    using IP = Ipm<M, FL, NT>;
     constexpr int NXAP = IP::NXAP, NC = IP::NC;
     const int N = q.N, R = q.R, NW = q.NW, OU = q.OU, OS = q.OS;
     const b200mpc_ipm_options &o = kp.o;
@@ -1113,11 +1131,9 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         double gm = (M > 0) ? kp.p.slack_w : 0.0;
         for (int k = lane; k <= N; k += 32) {
             if (k >= 1) {
-                double x[6], g[6];
+                double x[6];
                 q.template load_x<false>(k, 0.0, x);
-                q.grad_x(k, x, g);   // df == 1 here
-#pragma unroll
-                for (int a = 0; a < 6; a++) gm = fmax(gm, fabs(g[a]));
+                gm = fmax(gm, q.grad_x_store(k, x, q.GX + 6 * k));   // df == 1 here
             }
             if (k < N) {
                 double u[2];
@@ -1280,7 +1296,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                     for (int a = 0; a < 6; a++) gphi += gbx[a] * d[a];
                 } else {   // long horizons: recompute the base gradient from the iterate
                     double g[6];
-                    q.grad_x(k, x, g);
+                    ld6(q.GX + 6 * k, g);
                     q.barrier_grad_x(k, x, g);
 #pragma unroll
                     for (int a = 0; a < 6; a++) gphi += g[a] * d[a];
@@ -1399,37 +1415,41 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         //      K d + Jc' lam+ = rhs  =>  lam+_i = (rhs - K d)_{x_i} + A' lam+_{i+1}
         // (a) residuals res_i = (rhs - K d)_{x_i} for all stages in parallel -> CRES (dead until the next eval)
         for (int i = lane + 1; i <= N; i += 32) {
-            double x[6], d[6], g[6], hd[6], res[6];
+            double x[6], d[6], g[6];
             q.template load_x<false>(i, 0.0, x);
             ld6(q.D + 6 * i, d);
-            ld6(q.HD + 6 * i, hd);
-            q.grad_x(i, x, g);
+            ld6(q.GX + 6 * i, g);
             q.barrier_grad_x(i, x, g);
-#pragma unroll
-            for (int a2 = 0; a2 < 6; a2++) {
-                double kd = (hd[a2] + dw_try) * d[a2];
-#pragma unroll
-                for (int b = 0; b < 6; b++) kd += q.df * q.Q2(a2, b) * d[b];
-                res[a2] = -g[a2] - kd;
-            }
+            double r4 = 0.0, r5 = 0.0;
 #pragma unroll
             for (int j = 0; j < M; j++) {
                 if (i < N) {
                     int r = j * N + i;
                     double yp = q.YHAT[r] - q.SIGE[r] * q.JD[r];
-                    res[4] += q.JA[4 * r + 0] * yp;
-                    res[5] += q.JA[4 * r + 1] * yp;
+                    r4 += q.JA[4 * r + 0] * yp;
+                    r5 += q.JA[4 * r + 1] * yp;
                 }
                 int r = j * N + i - 1;
                 double yp = q.YHAT[r] - q.SIGE[r] * q.JD[r];
-                res[4] += q.JA[4 * r + 2] * yp;
-                res[5] += q.JA[4 * r + 3] * yp;
+                r4 += q.JA[4 * r + 2] * yp;
+                r5 += q.JA[4 * r + 3] * yp;
             }
             if (q.hwd) {   // -(K d) of the ey-rate curvature rows (i-1 as "next", i as "current")
-                res[5] -= 2.0 * q.df * q.wdp[i - 1] * q.JDC[i - 1];
-                if (i < N) res[5] += 2.0 * q.df * q.wdp[i] * q.JDC[i];
+                r5 -= 2.0 * q.df * q.wdp[i - 1] * q.JDC[i - 1];
+                if (i < N) r5 += 2.0 * q.df * q.wdp[i] * q.JDC[i];
             }
-            st6(q.CRES + 6 * (i - 1), res);
+            const double g0 = g[0], g5 = g[5];
+#pragma unroll 1
+            for (int a2 = 0; a2 < 6; a2++) {
+                double kd = (q.HD[6 * i + a2] + dw_try) * q.D[6 * i + a2];
+#pragma unroll
+                for (int b = 0; b < 6; b++) kd += q.df * (kp.p.Q[6 * a2 + b] + kp.p.Q[6 * b + a2]) * d[b];
+                double gg = (a2 == 0) ? g0 : ((a2 == 5) ? g5 : q.GX[6 * i + a2]);
+                double res = -gg - kd;
+                if (a2 == 4) res += r4;
+                if (a2 == 5) res += r5;
+                q.CRES[6 * (i - 1) + a2] = res;
+            }
         }
         __syncwarp();
         // (b) the recursion itself: lane a < 6 owns component a (its column of A is q.tcol), lam+_{i+1} travels by
