@@ -106,6 +106,25 @@ __device__ __forceinline__ double warp_min(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// branch-free FP64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) + two Newton
+// steps.  The compiler's IEEE division carries a slow-path call per site (~20 instructions, 2 branches); the
+// solver's operands are positive, finite and far from the denormal range, and 1-ulp differences are irrelevant here.
+__device__ __forceinline__ double rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double rsq(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double h = 0.5 * x;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y * fma(-h * y, y, 1.5);
+}
 __device__ __forceinline__ double p4(double a) { double b = a * a; return b * b; }
 __device__ __forceinline__ double p5(double a) { double b = a * a; return b * b * a; }
 __device__ __forceinline__ double p6(double a) { double b = a * a; return b * b * b; }
@@ -293,8 +312,8 @@ struct Ipm {
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             double lb = xlb(i, c), ub = xub(i, c), w = c ? x[5] : x[0], t = 0.0;
-            if (has(lb)) t -= mu / (w - lb);
-            if (has(ub)) t += mu / (ub - w);
+            if (has(lb)) t -= mu * rcp(w - lb);
+            if (has(ub)) t += mu * rcp(ub - w);
             g[c ? 5 : 0] += t;
         }
     }
@@ -417,12 +436,12 @@ struct Ipm {
     // ---- Newton steps of the row slacks / multipliers from JD (all at the current iterate)
     __device__ __forceinline__ void row_step(int r, double &ds, double &dt, double &dy, double &dz, double &dv) const {
         double s = S[r], t = T[r], z = Z[r], v = V[r];
-        double is = 1.0 / s, it = 1.0 / t;
+        double is = rcp(s), it = rcp(t);
         double sig_s = z * is, sig_t = v * it;
         double rg = GR[r] + t - s;
         double jd = JD[r];
         dy = YHAT[r] - SIGE[r] * jd - Y[r];
-        dt = (mu * is + mu * it - rho - sig_s * rg - sig_s * jd) / (sig_s + sig_t);
+        dt = (mu * is + mu * it - rho - sig_s * rg - sig_s * jd) * rcp(sig_s + sig_t);
         dv = mu * it - v - sig_t * dt;
         ds = jd + dt + rg;
         dz = mu * is - z - sig_s * ds;
@@ -669,13 +688,13 @@ struct Ipm {
                 double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
                 {
                     double lb = xlb(k, 0), ub = xub(k, 0);
-                    double il = has(lb) ? 1.0 / (x[0] - lb) : 0.0, iu = has(ub) ? 1.0 / (ub - x[0]) : 0.0;
+                    double il = has(lb) ? rcp(x[0] - lb) : 0.0, iu = has(ub) ? rcp(ub - x[0]) : 0.0;
                     hd[0] = zl.x * il + zu.x * iu;
                     g[0] += -mu * il + mu * iu;
                     lb = xlb(k, 1);
                     ub = xub(k, 1);
-                    il = has(lb) ? 1.0 / (x[5] - lb) : 0.0;
-                    iu = has(ub) ? 1.0 / (ub - x[5]) : 0.0;
+                    il = has(lb) ? rcp(x[5] - lb) : 0.0;
+                    iu = has(ub) ? rcp(ub - x[5]) : 0.0;
                     hd[5] = zl.y * il + zu.y * iu;
                     g[5] += -mu * il + mu * iu;
                 }
@@ -697,7 +716,7 @@ struct Ipm {
             }
 #pragma unroll
             for (int j = 0; j < M; j++) {
-                double is = 1.0 / W[isg(j, k)];
+                double is = rcp(W[isg(j, k)]);
                 HD[isg(j, k)] = ZL[bss(j, k)] * is;
                 D[isg(j, k)] = df * kp.p.slack_w - mu * is;
             }
@@ -705,8 +724,8 @@ struct Ipm {
                 double u[2];
                 load_u<false>(k, 0.0, u);
                 double2 zl = ld2(ZL + bsu(k)), zu = ld2(ZU + bsu(k));
-                double il0 = 1.0 / (u[0] + kp.p.umax[0]), iu0 = 1.0 / (kp.p.umax[0] - u[0]);
-                double il1 = 1.0 / (u[1] + kp.p.umax[1]), iu1 = 1.0 / (kp.p.umax[1] - u[1]);
+                double il0 = rcp(u[0] + kp.p.umax[0]), iu0 = rcp(kp.p.umax[0] - u[0]);
+                double il1 = rcp(u[1] + kp.p.umax[1]), iu1 = rcp(kp.p.umax[1] - u[1]);
                 st2(HD + OU + 2 * k, zl.x * il0 + zu.x * iu0, zl.y * il1 + zu.y * iu1);
                 st2(D + OU + 2 * k, df * (R2(0, 0) * u[0] + R2(0, 1) * u[1]) - mu * il0 + mu * iu0,
                     df * (R2(1, 0) * u[0] + R2(1, 1) * u[1]) - mu * il1 + mu * iu1);
@@ -714,9 +733,9 @@ struct Ipm {
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     double s = S[r], tt = T[r];
-                    double is = 1.0 / s, it = 1.0 / tt;
+                    double is = rcp(s), it = rcp(tt);
                     double sig_s = Z[r] * is, sig_t = V[r] * it;
-                    double beta = sig_t / (sig_s + sig_t);
+                    double beta = sig_t * rcp(sig_s + sig_t);
                     double rg = GR[r] + tt - s;
                     SIGE[r] = beta * sig_s;
                     YHAT[r] = (1.0 - beta) * (rho - mu * it) + beta * (mu * is - sig_s * rg);
@@ -867,7 +886,7 @@ struct Ipm {
 #pragma unroll
                     for (int q = 0; q < j; q++) d -= Lm[j][q] * Lm[j][q];
                     if (!(d > 0.0)) ok = false;
-                    double ri = rsqrt(d);
+                    double ri = rsq(d);
                     rinv[j] = ri;
 #pragma unroll
                     for (int i = j + 1; i < NUA; i++) {
@@ -951,7 +970,7 @@ struct Ipm {
 #pragma unroll
                 for (int q = 0; q < j; q++) d -= Ls[j][q] * Ls[j][q];
                 if (!(d > 0.0)) ok = false;
-                ri[j] = rsqrt(d);
+                ri[j] = rsq(d);
 #pragma unroll
                 for (int i = j + 1; i < M; i++) {
                     double s = Ls[i][j];
@@ -1278,17 +1297,18 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                     double w = c ? x[5] : x[0], dd = c ? d[5] : d[0];
                     double zlc = c ? zl.y : zl.x, zuc = c ? zu.y : zu.x;
                     double lb = q.xlb(k, c), ub = q.xub(k, c);
+                    double idd = rcp(dd);   // +-inf for dd == 0 is never selected below
                     if (IP::has(lb)) {
                         double dl = w - lb;
-                        double dzl = mu / dl - zlc - zlc / dl * dd;
-                        if (dd < 0.0) a_max = fmin(a_max, -tau * dl / dd);
-                        if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc / dzl);
+                        double dzl = (mu - zlc * dd) * rcp(dl) - zlc;
+                        if (dd < 0.0) a_max = fmin(a_max, -tau * dl * idd);
+                        if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc * rcp(dzl));
                     }
                     if (IP::has(ub)) {
                         double du = ub - w;
-                        double dzu = mu / du - zuc + zuc / du * dd;
-                        if (dd > 0.0) a_max = fmin(a_max, tau * du / dd);
-                        if (dzu < 0.0) a_z = fmin(a_z, -tau * zuc / dzu);
+                        double dzu = (mu + zuc * dd) * rcp(du) - zuc;
+                        if (dd > 0.0) a_max = fmin(a_max, tau * du * idd);
+                        if (dzu < 0.0) a_z = fmin(a_z, -tau * zuc * rcp(dzu));
                     }
                 }
                 if (one_round) {
@@ -1305,10 +1325,10 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
 #pragma unroll
             for (int j = 0; j < M; j++) {
                 double w = q.W[q.isg(j, k)], dd = q.D[q.isg(j, k)], zlc = q.ZL[q.bss(j, k)];
-                double dzl = mu / w - zlc - zlc / w * dd;
-                if (dd < 0.0) a_max = fmin(a_max, -tau * w / dd);
-                if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc / dzl);
-                gphi += (one_round ? gbs[j] : (q.df * kp.p.slack_w - mu / w)) * dd;
+                double dzl = (mu - zlc * dd) * rcp(w) - zlc;
+                if (dd < 0.0) a_max = fmin(a_max, -tau * w * rcp(dd));
+                if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc * rcp(dzl));
+                gphi += (one_round ? gbs[j] : (q.df * kp.p.slack_w - mu * rcp(w))) * dd;
             }
             if (k < N) {
                 double u[2];
@@ -1319,12 +1339,13 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 for (int c = 0; c < 2; c++) {
                     double w = u[c], dd = c ? dd2.y : dd2.x, zlc = c ? zl.y : zl.x, zuc = c ? zu.y : zu.x;
                     double dl = w + kp.p.umax[c], du = kp.p.umax[c] - w;
-                    double dzl = mu / dl - zlc - zlc / dl * dd, dzu = mu / du - zuc + zuc / du * dd;
-                    if (dd < 0.0) a_max = fmin(a_max, -tau * dl / dd);
-                    if (dd > 0.0) a_max = fmin(a_max, tau * du / dd);
-                    if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc / dzl);
-                    if (dzu < 0.0) a_z = fmin(a_z, -tau * zuc / dzu);
-                    double gb = one_round ? gbu[c] : (q.df * (q.R2(c, 0) * u[0] + q.R2(c, 1) * u[1]) - mu / dl + mu / du);
+                    double idl = rcp(dl), idu = rcp(du), idd = rcp(dd);
+                    double dzl = (mu - zlc * dd) * idl - zlc, dzu = (mu + zuc * dd) * idu - zuc;
+                    if (dd < 0.0) a_max = fmin(a_max, -tau * dl * idd);
+                    if (dd > 0.0) a_max = fmin(a_max, tau * du * idd);
+                    if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc * rcp(dzl));
+                    if (dzu < 0.0) a_z = fmin(a_z, -tau * zuc * rcp(dzu));
+                    double gb = one_round ? gbu[c] : (q.df * (q.R2(c, 0) * u[0] + q.R2(c, 1) * u[1]) - mu * idl + mu * idu);
                     gphi += gb * dd;
                 }
                 double c6[6];
@@ -1337,11 +1358,11 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                     double ds, dt, dy, dz, dv;
                     q.row_step(r, ds, dt, dy, dz, dv);
                     double s = q.S[r], tt = q.T[r];
-                    if (ds < 0.0) a_max = fmin(a_max, -tau * s / ds);
-                    if (dt < 0.0) a_max = fmin(a_max, -tau * tt / dt);
-                    if (dz < 0.0) a_z = fmin(a_z, -tau * q.Z[r] / dz);
-                    if (dv < 0.0) a_z = fmin(a_z, -tau * q.V[r] / dv);
-                    gphi += rho * dt - mu * (ds / s + dt / tt);
+                    if (ds < 0.0) a_max = fmin(a_max, -tau * s * rcp(ds));
+                    if (dt < 0.0) a_max = fmin(a_max, -tau * tt * rcp(dt));
+                    if (dz < 0.0) a_z = fmin(a_z, -tau * q.Z[r] * rcp(dz));
+                    if (dv < 0.0) a_z = fmin(a_z, -tau * q.V[r] * rcp(dv));
+                    gphi += rho * dt - mu * (ds * rcp(s) + dt * rcp(tt));
                     th += fabs(q.GR[r] + tt - s);
                 }
             }
@@ -1488,14 +1509,14 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                     zln[c] = 0.0;
                     zun[c] = 0.0;
                     if (IP::has(lb)) {
-                        double dl = w - lb, dln = wn - lb;
-                        zlc += a_z * (mu / dl - zlc - zlc / dl * dd);
-                        zln[c] = fmax(fmin(zlc, kappa_sigma * mu / dln), mu / (kappa_sigma * dln));
+                        double dl = w - lb, muidln = mu * rcp(wn - lb);
+                        zlc += a_z * ((mu - zlc * dd) * rcp(dl) - zlc);
+                        zln[c] = fmax(fmin(zlc, kappa_sigma * muidln), muidln * (1.0 / kappa_sigma));
                     }
                     if (IP::has(ub)) {
-                        double du = ub - w, dun = ub - wn;
-                        zuc += a_z * (mu / du - zuc + zuc / du * dd);
-                        zun[c] = fmax(fmin(zuc, kappa_sigma * mu / dun), mu / (kappa_sigma * dun));
+                        double du = ub - w, muidun = mu * rcp(ub - wn);
+                        zuc += a_z * ((mu + zuc * dd) * rcp(du) - zuc);
+                        zun[c] = fmax(fmin(zuc, kappa_sigma * muidun), muidun * (1.0 / kappa_sigma));
                     }
                 }
                 st2(q.ZL + q.bsx(k), zln[0], zln[1]);
@@ -1507,9 +1528,9 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
 #pragma unroll
             for (int j = 0; j < M; j++) {
                 double w = q.W[q.isg(j, k)], dd = q.D[q.isg(j, k)], zlc = q.ZL[q.bss(j, k)];
-                zlc += a_z * (mu / w - zlc - zlc / w * dd);
-                double wn = w + a * dd;
-                q.ZL[q.bss(j, k)] = fmax(fmin(zlc, kappa_sigma * mu / wn), mu / (kappa_sigma * wn));
+                zlc += a_z * ((mu - zlc * dd) * rcp(w) - zlc);
+                double wn = w + a * dd, muiwn = mu * rcp(wn);
+                q.ZL[q.bss(j, k)] = fmax(fmin(zlc, kappa_sigma * muiwn), muiwn * (1.0 / kappa_sigma));
                 q.W[q.isg(j, k)] = wn;
             }
             if (k < N) {
@@ -1522,11 +1543,11 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 for (int c = 0; c < 2; c++) {
                     double w = u[c], dd = c ? dd2.y : dd2.x, zlc = c ? zl.y : zl.x, zuc = c ? zu.y : zu.x;
                     double dl = w + kp.p.umax[c], du = kp.p.umax[c] - w;
-                    zlc += a_z * (mu / dl - zlc - zlc / dl * dd);
-                    zuc += a_z * (mu / du - zuc + zuc / du * dd);
-                    double wn = w + a * dd, dln = wn + kp.p.umax[c], dun = kp.p.umax[c] - wn;
-                    zln[c] = fmax(fmin(zlc, kappa_sigma * mu / dln), mu / (kappa_sigma * dln));
-                    zun[c] = fmax(fmin(zuc, kappa_sigma * mu / dun), mu / (kappa_sigma * dun));
+                    zlc += a_z * ((mu - zlc * dd) * rcp(dl) - zlc);
+                    zuc += a_z * ((mu + zuc * dd) * rcp(du) - zuc);
+                    double wn = w + a * dd, muidln = mu * rcp(wn + kp.p.umax[c]), muidun = mu * rcp(kp.p.umax[c] - wn);
+                    zln[c] = fmax(fmin(zlc, kappa_sigma * muidln), muidln * (1.0 / kappa_sigma));
+                    zun[c] = fmax(fmin(zuc, kappa_sigma * muidun), muidun * (1.0 / kappa_sigma));
                     un[c] = wn;
                 }
                 st2(q.ZL + q.bsu(k), zln[0], zln[1]);
@@ -1540,8 +1561,9 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                     double s = q.S[r] + a * ds, tt = q.T[r] + a * dt;
                     q.Y[r] += a * dy;
                     double z = q.Z[r] + a_z * dz, v = q.V[r] + a_z * dv;
-                    q.Z[r] = fmax(fmin(z, kappa_sigma * mu / s), mu / (kappa_sigma * s));
-                    q.V[r] = fmax(fmin(v, kappa_sigma * mu / tt), mu / (kappa_sigma * tt));
+                    double muis = mu * rcp(s), muit = mu * rcp(tt);
+                    q.Z[r] = fmax(fmin(z, kappa_sigma * muis), muis * (1.0 / kappa_sigma));
+                    q.V[r] = fmax(fmin(v, kappa_sigma * muit), muit * (1.0 / kappa_sigma));
                     q.S[r] = s;
                     q.T[r] = tt;
                 }
