@@ -252,3 +252,80 @@ def test_planner_drop_in_on_gpu(crb, oracle):
         fin = np.isfinite(p2.candidate_costs)
         assert (np.isfinite(p1.candidate_costs) == fin).all()
         assert np.abs(p1.candidate_costs[fin] - p2.candidate_costs[fin]).max() < 1e-5
+
+
+def test_max_sizes_and_odd_batches(crb, oracle):
+    """Maximum horizon / rival count of the C-ABI (N=64, M=4) and batch sizes that are not a multiple of anything."""
+    N, M = 64, 4
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(9, N=N, M=M, seed=21)
+    obs[:, :, 0, :] += 3.0                                  # keep the long horizon feasible: rivals further ahead
+    prm = scenarios.default_cbf_params(N=N)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
+    _compare(g, r, min_match=0.85)
+    for B in (1, 3, 33):
+        x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=20, M=3, seed=30 + B)
+        prm = scenarios.default_cbf_params(N=20)
+        g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+        r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+        _compare(g, r, min_match=0.95)
+        assert g["x"].shape == (B, 21, 6) and g["sigma"].shape == (B, 3, 21)
+
+
+def test_blocked_lane_elastic_rows(crb, oracle):
+    """A rival parked right in front of the ego across the whole lane: the CBF rows cannot all hold; both solvers
+    must report the same (elastic) outcome instead of diverging -- the reference's IPOPT would fail here (control.py:600-603)."""
+    N, M, B = 20, 3, 16
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=N, M=M, seed=5)
+    x0[:, 0] = 1.4
+    obs[:, :, 0, :] = x0[:, None, 4:5] + 0.55
+    obs[:, 0, 1, :], obs[:, 1, 1, :], obs[:, 2, 1, :] = -0.55, 0.0, 0.55
+    x0[:, 5] = 0.27
+    prm = scenarios.default_cbf_params(N=N)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
+    same_status = g["status"] == r["status"]
+    both = (g["status"] == 0) & (r["status"] == 0)
+    print("status gpu", g["status"], "cpu", r["status"], "elastic gpu", g["elastic_max"].round(4))
+    assert same_status.mean() >= 0.8
+    if both.any():
+        assert np.abs(g["elastic_max"][both] - r["elastic_max"][both]).max() < 1e-4
+        assert np.abs(g["cost"][both] - r["cost"][both]).max() < 1e-3 * np.abs(r["cost"][both]).max()
+
+
+def test_capi_argument_validation(crb):
+    """Bad arguments are reported through the return code + b200mpc_last_error, never by a crash."""
+    import ctypes as C
+    from car_racing_b200 import _capi, batch
+    h = _capi.Handle()
+    L = _capi.lib()
+    prm = scenarios.default_cbf_params(N=20)
+    rec_in = np.zeros((2, batch.cbf_record_doubles(20, 3, False)))
+    rec_out = np.zeros(2, dtype=_capi.RECORD_DTYPE)
+    o = _capi.default_options()
+
+    def call(p, B=2, inp=rec_in, out=rec_out, opt=o):
+        return L.b200mpc_cbf_solve(h.ptr, C.byref(p), C.byref(opt), B, None if inp is None else inp.ctypes.data_as(C.c_void_p),
+                                   None if out is None else out.ctypes.data_as(C.c_void_p), None, None, None, None)
+    p = _capi.make_cbf_params(prm, 3, False)
+    p.N = 65
+    assert call(p) == -1 and b"out of range" in L.b200mpc_last_error(h.ptr)
+    p = _capi.make_cbf_params(prm, 3, False)
+    p.M = 5
+    assert call(p) == -1
+    p = _capi.make_cbf_params(prm, 3, False)
+    assert call(p, B=0) == -1 and call(p, inp=None) == -1 and call(p, out=None) == -1
+    p.alpha = 1.5
+    assert call(p) == -1
+    p = _capi.make_cbf_params(prm, 3, False, flags=1)
+    assert call(p) == -1 and b"flags" in L.b200mpc_last_error(h.ptr)
+    bad = _capi.default_options()
+    bad.max_iter = 0
+    assert call(_capi.make_cbf_params(prm, 3, False), opt=bad) == -1
+    ip = _capi.make_ilqr_params(dict(A=prm["A"], B=prm["B"], Q=prm["Q"], R=prm["R"], N=70, max_iter=10, L=0.4, W=0.2))
+    assert L.b200mpc_ilqr_solve(h.ptr, C.byref(ip), 1, rec_in.ctypes.data_as(C.c_void_p), rec_out.ctypes.data_as(C.c_void_p), None, None) == -1
+    with pytest.raises(ValueError):
+        batch.solve_cbf_packed(np.zeros((2, 7)), prm, 3, False)
+    # a valid call still works afterwards
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(2, N=20, M=3, seed=1)
+    assert (crb.solve_cbf_batch(x0, xt, obs, lap_off, prm, handle=h)["status"] == 0).all()
