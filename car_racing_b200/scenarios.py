@@ -99,3 +99,74 @@ def ilqr_scenarios(B, N=50, seed=1, track="l_shape"):
         obs[b, 1, :] = rng.uniform(-0.7, 0.7)
     xt = np.array([0.8, 0.0, 0.0, 0.0, 0.0, 0.0])
     return x0, xt, obs, np.zeros(B)
+
+
+def default_lmpc_params(N=12, **over):
+    """LMPCRacingParam / SystemParam defaults (base.py:351-376, 708-713) and x_track of control.py:649."""
+    p = dict(Q=np.zeros((6, 6)), R=np.diag([1.0, 0.25]), dR=5 * np.diag([0.8, 0.0]), N=N, umax=[0.5, 1.0], vmax=10.0,
+             width=1.0, xtrk=np.array([5.0, 0, 0, 0, 0, 0]))
+    p.update(over)
+    return p
+
+
+def _pid_lap(vt, T, rng, s0=0.0):
+    """A stored lap: the identified LTI model driven by the reference's PID law (control.py:15-25)."""
+    x = np.array([vt, 0.0, 0.0, rng.uniform(-.02, .02), s0, rng.uniform(-.05, .05)])
+    xs, us = [x.copy()], []
+    for _ in range(T):
+        u = np.array([-0.6 * x[5] - 0.9 * x[3], 1.5 * (vt - x[0])])
+        u = np.clip(u, [-0.5, -1.0], [0.5, 1.0])
+        x = LTI_A @ x + LTI_B @ u
+        xs.append(x.copy())
+        us.append(u)
+    return np.array(xs), np.array(us)
+
+
+def select_points(ss_xcurv, Qfun, it, x0, num_ss_points, shift=0):
+    """lmpc_helper.select_points (control/lmpc_helper.py:267-282): l1-nearest stored state of lap `it`, then the next
+    `num_ss_points` rows."""
+    xcurv = ss_xcurv[:, :, it]
+    norm = np.abs(xcurv - np.asarray(x0)[None, :]).sum(axis=1)
+    m = int(np.argmin(norm))
+    lo = int(shift + m) if m + shift >= 0 else int(m)
+    n = int(num_ss_points)
+    return xcurv[lo:lo + n, :].T, Qfun[lo:lo + n, it]
+
+
+def lmpc_scenarios(B, N=12, num_ss_points=44, num_ss_iter=2, seed=1, ltv_noise=5e-4):
+    """Config 4: B sampled (x0, u_old); safe set = 22 consecutive points from each of two stored
+    laps (control.py:625-638) that pass close to x0; LTV model = the identified LTI model plus a small per-stage
+    perturbation (not on the s column: it would be multiplied by the absolute arc length) and an affine term.
+    Returns x0 (B,6), u_old (B,2), A (B,N,6,6), Bm (B,N,6,2), C (B,N,6), SS (B,6,K), Qfun (B,K)."""
+    rng = np.random.default_rng(seed)
+    K = num_ss_points
+    per = K // num_ss_iter
+    x0 = np.zeros((B, 6)); u_old = np.zeros((B, 2))
+    A = np.zeros((B, N, 6, 6)); Bm = np.zeros((B, N, 6, 2)); C = np.zeros((B, N, 6))
+    SS = np.zeros((B, 6, K)); Qf = np.zeros((B, K))
+    for b in range(B):
+        warm, _ = _pid_lap(rng.uniform(1.1, 1.4), 40, rng, s0=rng.uniform(0.0, 15.0))
+        xb = warm[-1]
+        starts, cols, qs = [], [], []
+        for jj in range(num_ss_iter):
+            vt = 1.3 - 0.12 * jj                                  # the older lap is slower
+            xs = xb + rng.normal(scale=[0.03, 0.004, 0.01, 0.004, 0.02, 0.015])
+            x, seg = xs.copy(), []
+            for _ in range(per):
+                seg.append(x.copy())
+                u = np.clip([-0.6 * x[5] - 0.9 * x[3], 1.5 * (vt - x[0])], [-0.5, -1.0], [0.5, 1.0])
+                x = LTI_A @ x + LTI_B @ u
+            starts.append(xs)
+            cols.append(np.array(seg).T)
+            qs.append((200.0 + 15.0 * jj) - np.arange(per))      # time-to-go: decreasing along the lap, older lap costlier
+        w = rng.uniform(0.35, 0.65)
+        x0[b] = w * starts[0] + (1 - w) * starts[1] + rng.normal(scale=1e-3, size=6)
+        u_old[b] = np.clip([-0.6 * x0[b, 5] - 0.9 * x0[b, 3], 1.5 * (1.25 - x0[b, 0])], [-0.5, -1.0], [0.5, 1.0])
+        nz = ltv_noise * rng.normal(size=(N, 6, 6))
+        nz[:, :, 4] = 0.0
+        A[b] = LTI_A + nz
+        Bm[b] = LTI_B + ltv_noise * rng.normal(size=(N, 6, 2))
+        C[b] = ltv_noise * rng.normal(size=(N, 6))
+        SS[b] = np.concatenate(cols, axis=1)
+        Qf[b] = np.concatenate(qs)
+    return x0, u_old, A, Bm, C, SS, Qf

@@ -105,6 +105,28 @@ typedef struct {
 int orc_ilqr_solve(const orc_ilqr_problem *p, orc_ilqr_result *r);
 int orc_ilqr_solve_batch(const orc_ilqr_problem *p, int B, orc_ilqr_result *r, int nthreads);
 
+/* ---- LMPC restatement (control.py:610-730; lmpc_oracle.c) ---- */
+#define ORC_KMAX 64 /* max safe-set points (num_ss_points = 44, base.py:358) */
+typedef struct {
+    int N, K;                          /* num_horizon (12), number of selected safe-set points (44) */
+    double Q[36], R[4], dR[4];         /* matrix_Q, matrix_R, matrix_dR (base.py:354-357) */
+    double xtrk[6];                    /* x_track = [5,0,0,0,0,0] (control.py:649) */
+    double umax[2], vmax, width;       /* delta_max, a_max, v_max, lap_width (control.py:658-666) */
+    double x0[6], u_old[2];            /* xcurv (:650), u_old (:675) */
+    double A[ORC_NMAX * 36], B[ORC_NMAX * 12], C[ORC_NMAX * 6];   /* matrix_Atv/Btv/Ctv[i] (:653-656) */
+    double SS[6 * ORC_KMAX];           /* ss_point_selected_tot, row-major 6 x K (:690-691) */
+    double Qfun[ORC_KMAX];             /* Qfun_selected_tot (:695) */
+} orc_lmpc_problem;
+
+typedef struct {
+    double x[(ORC_NMAX + 1) * 6], u[ORC_NMAX * 2], lambda[ORC_KMAX];
+    double cost, kkt_err;
+    int status, iters;
+} orc_lmpc_result;
+
+int orc_lmpc_solve(const orc_lmpc_problem *p, const orc_options *o, orc_lmpc_result *r);
+int orc_lmpc_solve_batch(const orc_lmpc_problem *p, int B, const orc_options *o, orc_lmpc_result *r, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,27 @@ class IlqrResult(C.Structure):
     ]
 
 
+KMAX = 64
+
+
+class LmpcProblem(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("K", C.c_int),
+        ("Q", C.c_double * 36), ("R", C.c_double * 4), ("dR", C.c_double * 4),
+        ("xtrk", C.c_double * 6), ("umax", C.c_double * 2), ("vmax", C.c_double), ("width", C.c_double),
+        ("x0", C.c_double * 6), ("u_old", C.c_double * 2),
+        ("A", C.c_double * (NMAX * 36)), ("B", C.c_double * (NMAX * 12)), ("C", C.c_double * (NMAX * 6)),
+        ("SS", C.c_double * (6 * KMAX)), ("Qfun", C.c_double * KMAX),
+    ]
+
+
+class LmpcResult(C.Structure):
+    _fields_ = [
+        ("x", C.c_double * ((NMAX + 1) * 6)), ("u", C.c_double * (NMAX * 2)), ("lam", C.c_double * KMAX),
+        ("cost", C.c_double), ("kkt_err", C.c_double), ("status", C.c_int), ("iters", C.c_int),
+    ]
+
+
 _lib = None
 
 
@@ -85,6 +106,7 @@ def lib():
         _lib.orc_default_options.argtypes = [C.POINTER(Options)]
         _lib.orc_solve_batch.argtypes = [C.POINTER(Problem), C.c_int, C.POINTER(Options), C.POINTER(Result), C.c_int]
         _lib.orc_ilqr_solve_batch.argtypes = [C.POINTER(IlqrProblem), C.c_int, C.POINTER(IlqrResult), C.c_int]
+        _lib.orc_lmpc_solve_batch.argtypes = [C.POINTER(LmpcProblem), C.c_int, C.POINTER(Options), C.POINTER(LmpcResult), C.c_int]
     return _lib
 
 
@@ -173,3 +195,32 @@ def solve_ilqr_batch(x0, xt, obs, lap_off, prm, nthreads=1):
         u=np.array([np.frombuffer(r.u, dtype=np.float64)[: 2 * N].reshape(N, 2) for r in R]),
         x=np.array([np.frombuffer(r.x, dtype=np.float64)[: 6 * (N + 1)].reshape(N + 1, 6) for r in R]),
     )
+
+
+def solve_lmpc_batch(x0, u_old, A, B, Cm, SS, Qfun, prm, nthreads=1, **opt):
+    """control.lmpc's QP.  x0 (Bn,6); u_old (Bn,2); A (Bn,N,6,6); B (Bn,N,6,2); Cm (Bn,N,6); SS (Bn,6,K); Qfun (Bn,K);
+    prm: Q, R, dR, N, umax, vmax, width, xtrk."""
+    x0 = np.atleast_2d(np.asarray(x0, float))
+    Bn = x0.shape[0]
+    N = int(prm["N"])
+    SS = np.asarray(SS, float).reshape(Bn, 6, -1)
+    K = SS.shape[2]
+    A = np.asarray(A, float).reshape(Bn, N, 36); B = np.asarray(B, float).reshape(Bn, N, 12); Cm = np.asarray(Cm, float).reshape(Bn, N, 6)
+    u_old = np.asarray(u_old, float).reshape(Bn, 2); Qfun = np.asarray(Qfun, float).reshape(Bn, K)
+    P = (LmpcProblem * Bn)()
+    for b in range(Bn):
+        p = P[b]
+        p.N, p.K = N, K
+        _fill(p.Q, prm["Q"]); _fill(p.R, prm["R"]); _fill(p.dR, prm["dR"]); _fill(p.xtrk, prm["xtrk"]); _fill(p.umax, prm["umax"])
+        p.vmax, p.width = prm["vmax"], prm["width"]
+        _fill(p.x0, x0[b]); _fill(p.u_old, u_old[b])
+        _fill(p.A, A[b]); _fill(p.B, B[b]); _fill(p.C, Cm[b]); _fill(p.SS, SS[b]); _fill(p.Qfun, Qfun[b])
+    o = default_options(**opt)
+    R = (LmpcResult * Bn)()
+    lib().orc_lmpc_solve_batch(P, Bn, C.byref(o), R, nthreads)
+    return dict(
+        x=np.array([np.frombuffer(r.x, dtype=np.float64)[: 6 * (N + 1)].reshape(N + 1, 6) for r in R]),
+        u=np.array([np.frombuffer(r.u, dtype=np.float64)[: 2 * N].reshape(N, 2) for r in R]),
+        lam=np.array([np.frombuffer(r.lam, dtype=np.float64)[:K] for r in R]),
+        cost=np.array([r.cost for r in R]), kkt_err=np.array([r.kkt_err for r in R]),
+        status=np.array([r.status for r in R]), iters=np.array([r.iters for r in R]))
