@@ -40,6 +40,16 @@ class IlqrParams(C.Structure):
     ]
 
 
+class LmpcParams(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("K", C.c_int32),
+        ("Q", C.c_double * 36), ("R", C.c_double * 4), ("dR", C.c_double * 4), ("xtrk", C.c_double * 6),
+        ("umax", C.c_double * 2), ("vmax", C.c_double), ("width", C.c_double),
+    ]
+
+
+LMPC_NMAX, LMPC_KMAX = 16, 64
+
 RECORD_DTYPE = np.dtype([("cost", "<f8"), ("u0", "<f8", (2,)), ("status", "<i4"), ("iters", "<i4")])
 assert RECORD_DTYPE.itemsize == 32
 
@@ -47,7 +57,7 @@ EXPORTS = [
     "b200mpc_version", "b200mpc_default_ipm_options", "b200mpc_create", "b200mpc_destroy", "b200mpc_last_error",
     "b200mpc_stream", "b200mpc_launch_count", "b200mpc_cbf_record_doubles", "b200mpc_cbf_record_doubles_ex", "b200mpc_cbf_solve",
     "b200mpc_cbf_solve_device", "b200mpc_ilqr_record_doubles", "b200mpc_ilqr_solve", "b200mpc_ilqr_solve_device",
-    "b200mpc_argmin_cost_device",
+    "b200mpc_argmin_cost_device", "b200mpc_lmpc_record_doubles", "b200mpc_lmpc_solve", "b200mpc_lmpc_solve_device",
 ]
 
 _lib = None
@@ -86,6 +96,10 @@ def lib():
     L.b200mpc_ilqr_solve.argtypes = ilqr_args
     L.b200mpc_ilqr_solve_device.argtypes = ilqr_args
     L.b200mpc_argmin_cost_device.argtypes = [vp, dp, ip, ip, dp]
+    L.b200mpc_lmpc_record_doubles.argtypes = [ip, ip]
+    lmpc_args = [vp, C.POINTER(LmpcParams), C.POINTER(IpmOptions), ip, dp, dp, dp, dp, dp, dp]
+    L.b200mpc_lmpc_solve.argtypes = lmpc_args
+    L.b200mpc_lmpc_solve_device.argtypes = lmpc_args
     _lib = L
     return L
 
@@ -182,4 +196,13 @@ def make_ilqr_params(prm):
     p.N, p.max_iter = int(prm["N"]), int(prm["max_iter"])
     _fill(p.A, prm["A"], 36); _fill(p.B, prm["B"], 12); _fill(p.Q, prm["Q"], 36); _fill(p.R, prm["R"], 4)
     p.L, p.W = float(prm["L"]), float(prm["W"])
+    return p
+
+
+def make_lmpc_params(prm, K):
+    p = LmpcParams()
+    p.N, p.K = int(prm["N"]), int(K)
+    _fill(p.Q, prm["Q"], 36); _fill(p.R, prm["R"], 4); _fill(p.dR, prm["dR"], 4); _fill(p.xtrk, prm["xtrk"], 6)
+    _fill(p.umax, prm["umax"], 2)
+    p.vmax, p.width = float(prm["vmax"]), float(prm["width"])
     return p

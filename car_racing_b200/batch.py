@@ -34,6 +34,10 @@ def ilqr_record_doubles(N):
     return (14 + 2 * (N + 1) + 1) & ~1
 
 
+def lmpc_record_doubles(N, K):
+    return (8 + 54 * N + 7 * K + 1) & ~1
+
+
 NO_BOUND = 1e300
 
 
@@ -153,4 +157,52 @@ def solve_ilqr_batch(x0, xt, obs, lap_off, prm, want=("x", "u"), handle=None):
         out["x"] = x
     if u is not None:
         out["u"] = u
+    return out
+
+
+def pack_lmpc(x0, u_old, A, B, Cm, SS, Qfun, N):
+    """x0 (Bn,6); u_old (Bn,2); A (Bn,N,6,6); B (Bn,N,6,2); Cm (Bn,N,6); SS (Bn,6,K); Qfun (Bn,K)."""
+    x0 = np.atleast_2d(np.asarray(x0, dtype=np.float64))
+    Bn = x0.shape[0]
+    SS = np.asarray(SS, dtype=np.float64).reshape(Bn, 6, -1)
+    K = SS.shape[2]
+    if not (2 <= N <= _capi.LMPC_NMAX and 1 <= K <= _capi.LMPC_KMAX):
+        raise ValueError(f"LMPC sizes out of range: N={N} (2..{_capi.LMPC_NMAX}), K={K} (1..{_capi.LMPC_KMAX})")
+    rec = np.zeros((Bn, lmpc_record_doubles(N, K)))
+    rec[:, 0:6] = x0
+    rec[:, 6:8] = np.asarray(u_old, dtype=np.float64).reshape(Bn, 2)
+    o = 8
+    rec[:, o:o + 36 * N] = np.asarray(A, dtype=np.float64).reshape(Bn, 36 * N); o += 36 * N
+    rec[:, o:o + 12 * N] = np.asarray(B, dtype=np.float64).reshape(Bn, 12 * N); o += 12 * N
+    rec[:, o:o + 6 * N] = np.asarray(Cm, dtype=np.float64).reshape(Bn, 6 * N); o += 6 * N
+    rec[:, o:o + 6 * K] = SS.reshape(Bn, 6 * K); o += 6 * K
+    rec[:, o:o + K] = np.asarray(Qfun, dtype=np.float64).reshape(Bn, K)
+    return rec, K
+
+
+def solve_lmpc_batch(x0, u_old, A, B, Cm, SS, Qfun, prm, want=("aux", "x", "u", "lambda"), handle=None, **opt):
+    """Batched control.lmpc QP (control.py:610-730): LTV model, safe-set convex hull terminal constraint."""
+    h = handle or default_handle()
+    N = int(prm["N"])
+    records, K = pack_lmpc(x0, u_old, A, B, Cm, SS, Qfun, N)
+    Bn = records.shape[0]
+    p = _capi.make_lmpc_params(prm, K)
+    o = _capi.default_options(**opt)
+    rec = np.zeros(Bn, dtype=_capi.RECORD_DTYPE)
+    aux = np.zeros((Bn, 4)) if "aux" in want else None
+    x = np.zeros((Bn, N + 1, 6)) if "x" in want else None
+    u = np.zeros((Bn, N, 2)) if "u" in want else None
+    lam = np.zeros((Bn, K)) if "lambda" in want else None
+    rc = _capi.lib().b200mpc_lmpc_solve(h.ptr, C.byref(p), C.byref(o), Bn, _ptr(records), _ptr(rec), _ptr(aux), _ptr(x), _ptr(u),
+                                        _ptr(lam))
+    h.check(rc, "b200mpc_lmpc_solve")
+    out = dict(u0=rec["u0"].copy(), cost=rec["cost"].copy(), status=rec["status"].copy(), iters=rec["iters"].copy(), record=rec)
+    if aux is not None:
+        out.update(kkt_err=aux[:, 0], n_backtrack=aux[:, 3].astype(int))
+    if x is not None:
+        out["x"] = x
+    if u is not None:
+        out["u"] = u
+    if lam is not None:
+        out["lambda"] = lam
     return out

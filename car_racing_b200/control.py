@@ -164,11 +164,41 @@ def ilqr(xcurv, xtarget, ilqr_param, vehicles, agent_name, lap_length, time, tim
     return r["u"][0, 0, :]
 
 
+def lmpc(xcurv, lmpc_param, matrix_Atv, matrix_Btv, matrix_Ctv, ss_curv, Qfun, iter, lap_length, lap_width, u_old,
+         system_param):
+    """control.lmpc (control.py:610-730): select the safe-set points (:625-638, lmpc_helper.select_points), solve the
+    QP on the GPU, return the reference's 6-tuple (:723-730)."""
+    from .scenarios import select_points
+    cols, qs = [], []
+    for jj in range(0, lmpc_param.num_ss_iter):
+        pts, q = select_points(ss_curv, Qfun, iter - jj - 1, xcurv, lmpc_param.num_ss_points / lmpc_param.num_ss_iter,
+                               lmpc_param.shift)
+        cols.append(pts)
+        qs.append(q)
+    ss_point_selected_tot = np.concatenate(cols, axis=1)
+    Qfun_selected_tot = np.concatenate(qs, axis=0)
+    N = int(lmpc_param.num_horizon)
+    prm = dict(Q=np.asarray(lmpc_param.matrix_Q, float), R=np.asarray(lmpc_param.matrix_R, float),
+               dR=np.asarray(lmpc_param.matrix_dR, float), N=N, umax=[system_param.delta_max, system_param.a_max],
+               vmax=system_param.v_max, width=lap_width, xtrk=np.array([5.0, 0, 0, 0, 0, 0]))
+    A = np.asarray([np.asarray(matrix_Atv[i], float) for i in range(N)])
+    B = np.asarray([np.asarray(matrix_Btv[i], float) for i in range(N)])
+    Cm = np.asarray([np.asarray(matrix_Ctv[i], float).reshape(6) for i in range(N)])
+    res = batch.solve_lmpc_batch(np.asarray(xcurv, float)[None], np.asarray(u_old, float).reshape(1, 2), A[None], B[None], Cm[None],
+                                 ss_point_selected_tot[None], Qfun_selected_tot[None], prm, want=("x", "u"))
+    if res["status"][0] != 0:
+        print("solver fail to find the solution, the non-converged solution is used")   # control.py:718
+    x_pred, u_pred = res["x"][0], res["u"][0]
+    lin_points = np.concatenate((x_pred[1:, :], np.array([x_pred[-1, :]])), axis=0)
+    lin_input = np.vstack((u_pred[1:, :], u_pred[-1, :]))
+    return u_pred, x_pred, ss_point_selected_tot, Qfun_selected_tot, lin_points, lin_input
+
+
 def install(control_module=None):
     """Swap the reference's solve functions for the GPU ones (module-level monkey patch).
     `control_module` defaults to the reference's `control.control` if it is importable."""
     if control_module is None:
         from control import control as control_module  # the reference's own package layout (setup.cfg:16-17)
-    for name in ("mpc_lti", "mpccbf", "mpc_multi_agents", "ilqr"):
+    for name in ("mpc_lti", "mpccbf", "mpc_multi_agents", "ilqr", "lmpc"):
         setattr(control_module, name, globals()[name])
     return control_module

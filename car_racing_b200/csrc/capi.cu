@@ -8,6 +8,7 @@
 
 #include "../../include/b200mpc.h"
 #include "ilqr.cuh"
+#include "lmpc.cuh"
 #include "ocp_ipm.cuh"
 
 using namespace b200mpc;
@@ -120,6 +121,10 @@ int b200mpc_cbf_record_doubles_ex(int N, int M, int xt_per_stage, int flags) {
 int b200mpc_ilqr_record_doubles(int N) {
     if (N < 1 || N > B200MPC_NMAX) return B200MPC_ERR_ARG;
     return ilqr_record_doubles(N);
+}
+int b200mpc_lmpc_record_doubles(int N, int K) {
+    if (N < 2 || N > B200MPC_LMPC_NMAX || K < 1 || K > B200MPC_LMPC_KMAX) return B200MPC_ERR_ARG;
+    return lmpc_record_doubles(N, K);
 }
 
 }  // extern "C"
@@ -269,6 +274,68 @@ int b200mpc_ilqr_solve(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B,
     CK(h, cudaMemcpyAsync(rec, h->d_rec, b_rec, cudaMemcpyDeviceToHost, h->stream));
     if (xpred) CK(h, cudaMemcpyAsync(xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
     if (upred) CK(h, cudaMemcpyAsync(upred, h->d_u, b_u, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+static int check_lmpc(b200mpc_handle *h, const b200mpc_lmpc_params *p, const b200mpc_ipm_options *o, int B, const void *in,
+                      const void *rec) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!p || !o || !in || !rec || B < 1) return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_solve: null argument or B < 1");
+    if (p->N < 2 || p->N > B200MPC_LMPC_NMAX || p->K < 1 || p->K > B200MPC_LMPC_KMAX)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_solve: N or K out of range");
+    if (!(p->umax[0] > 0.0) || !(p->umax[1] > 0.0) || !(p->width > 0.0) || !(o->tol > 0.0) || o->max_iter < 1)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_solve: bad parameter value");
+    return B200MPC_OK;
+}
+
+int b200mpc_lmpc_solve_device(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const b200mpc_ipm_options *opt, int B,
+                              const double *d_in, b200mpc_record *d_rec, double *d_aux, double *d_xpred, double *d_upred,
+                              double *d_lambda) {
+    int rc = check_lmpc(h, prm, opt, B, d_in, d_rec);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    LmpcKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.p = *prm;
+    kp.o = *opt;
+    kp.B = B;
+    kp.in_stride = lmpc_record_doubles(prm->N, prm->K);
+    LmpcPlan pl(prm->N, prm->K, kp.in_stride);
+    size_t smem = pl.bytes();
+    if ((int)smem > h->max_smem_optin)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_solve: N, K too large for one CTA's shared memory");
+    CK(h, cudaFuncSetAttribute(lmpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lmpc_kernel<<<B, 32, smem, h->stream>>>(kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_lambda);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+int b200mpc_lmpc_solve(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const b200mpc_ipm_options *opt, int B,
+                       const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *lambda) {
+    int rc = check_lmpc(h, prm, opt, B, in, rec);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    const int N = prm->N, K = prm->K;
+    const size_t b_in = (size_t)lmpc_record_doubles(N, K) * 8 * B, b_rec = sizeof(b200mpc_record) * (size_t)B, b_aux = 32 * (size_t)B;
+    const size_t b_x = 48 * (size_t)(N + 1) * B, b_u = 16 * (size_t)N * B, b_l = 8 * (size_t)K * B;
+    if ((rc = grow(h, &h->d_in, &h->c_in, b_in))) return rc;
+    if ((rc = grow(h, &h->d_rec, &h->c_rec, b_rec))) return rc;
+    if (aux && (rc = grow(h, &h->d_aux, &h->c_aux, b_aux))) return rc;
+    if (xpred && (rc = grow(h, &h->d_x, &h->c_x, b_x))) return rc;
+    if (upred && (rc = grow(h, &h->d_u, &h->c_u, b_u))) return rc;
+    if (lambda && (rc = grow(h, &h->d_sig, &h->c_sig, b_l))) return rc;
+    CK(h, cudaMemcpyAsync(h->d_in, in, b_in, cudaMemcpyHostToDevice, h->stream));
+    rc = b200mpc_lmpc_solve_device(h, prm, opt, B, (const double *)h->d_in, (b200mpc_record *)h->d_rec,
+                                   aux ? (double *)h->d_aux : nullptr, xpred ? (double *)h->d_x : nullptr,
+                                   upred ? (double *)h->d_u : nullptr, lambda ? (double *)h->d_sig : nullptr);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(rec, h->d_rec, b_rec, cudaMemcpyDeviceToHost, h->stream));
+    if (aux) CK(h, cudaMemcpyAsync(aux, h->d_aux, b_aux, cudaMemcpyDeviceToHost, h->stream));
+    if (xpred) CK(h, cudaMemcpyAsync(xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
+    if (upred) CK(h, cudaMemcpyAsync(upred, h->d_u, b_u, cudaMemcpyDeviceToHost, h->stream));
+    if (lambda) CK(h, cudaMemcpyAsync(lambda, h->d_sig, b_l, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }

@@ -1,0 +1,549 @@
+// b200mpc: batched LMPC solve -- the QP of control.lmpc (car_racing/control/control.py:610-730):
+//   vars  x_0..x_N, u_0..u_{N-1}, lambda (K safe-set weights); slack is forced to 0 by :693-694 and dropped
+//   min   sum_{i<N}[(x_i-x_trk)'Q(.) + u_i'R u_i + (u_i-u_{i-1})'dR(.)] + (x_N-x_trk)'Q(.) + Qfun'lambda   (:667-695)
+//   s.t.  x_0 = xcurv; x_{i+1} = A_i x_i + B_i u_i + C_i (LTV, :653-656); vx_i<=v_max, |ey_i|<=lap_width, i<N (:658-660)
+//         |u| <= (delta_max, a_max) (:662-666); lambda >= 0, x_N = SS lambda, 1'lambda = 1 (:689-692)
+// One warp per instance, same interior-point definition as the MPC-CBF kernel (the QP is convex).
+//
+// Linear algebra: NOT a Riccati sweep.  Near the optimum only ~3 of the 44 lambdas leave their bound, so any stage-wise
+// elimination of the terminal hull constraint meets a 7x7 Schur complement with condition number > 1e15 (measured in the
+// oracle's first draft).  Instead the states are condensed through the LTV model once per solve (dx = G du + dx_p, G in
+// shared memory) and the reduced KKT system in (du, dlambda, nu) -- 75x75 at N=12, K=44 -- is solved by a warp-level LU
+// with partial pivoting.  Dynamics multipliers follow from the costate recursion.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/b200mpc.h"
+#include "ocp_ipm.cuh"
+
+namespace b200mpc {
+
+struct LmpcKParams {
+    b200mpc_lmpc_params p;
+    b200mpc_ipm_options o;
+    int32_t B, in_stride;
+};
+
+__host__ __device__ inline int lmpc_record_doubles(int N, int K) { return (8 + 54 * N + 7 * K + 1) & ~1; }
+
+struct LmpcPlan {
+    int N, K, NX, NU, NW, NR, ND, ME;
+    int oIN, oW, oD, oZL, oZU, oGF, oRHS, oSIG, oDP, oKD, oLAM, oLAMN, oCEQ, oG, oRQ, oKK, oPIV, total;
+    __host__ __device__ LmpcPlan(int N_, int K_, int in_stride) {
+        N = N_; K = K_;
+        NX = 6 * (N + 1); NU = 2 * N; NW = NX + NU + K; NR = NU + K; ND = NR + 7; ME = 6 * N + 7;
+        int o = 2;
+        auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+        oIN = take(in_stride);
+        oW = take(NW); oD = take(NW); oZL = take(NW); oZU = take(NW); oGF = take(NW); oRHS = take(NW); oSIG = take(NW);
+        oDP = take(NX); oKD = take(NX);
+        oLAM = take(ME); oLAMN = take(ME); oCEQ = take(ME);
+        oG = take(6 * N * NU); oRQ = take(NU * NU);
+        oKK = take(ND * (ND + 1)); oPIV = take(ND);
+        total = o;
+    }
+    __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(double); }
+};
+
+__global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKParams kp, const double *__restrict__ in,
+                                                  b200mpc_record *__restrict__ rec, double *__restrict__ aux,
+                                                  double *__restrict__ xpred, double *__restrict__ upred,
+                                                  double *__restrict__ lambda_out) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x, inst = blockIdx.x;
+    const int N = kp.p.N, K = kp.p.K;
+    const LmpcPlan pl(N, K, kp.in_stride);
+    const int NX = pl.NX, NU = pl.NU, NW = pl.NW, NR = pl.NR, ND = pl.ND, ME = pl.ME, OU = NX, OL = NX + NU, LD = ND + 1;
+    double *IN = sm + pl.oIN, *W = sm + pl.oW, *D = sm + pl.oD, *ZL = sm + pl.oZL, *ZU = sm + pl.oZU, *GF = sm + pl.oGF;
+    double *RHS = sm + pl.oRHS, *SIG = sm + pl.oSIG, *DP = sm + pl.oDP, *KD = sm + pl.oKD, *LAM = sm + pl.oLAM, *LAMN = sm + pl.oLAMN;
+    double *CEQ = sm + pl.oCEQ, *G = sm + pl.oG, *RQ = sm + pl.oRQ, *KK = sm + pl.oKK;
+    const b200mpc_ipm_options &o = kp.o;
+
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
+    const uint32_t in_bytes = (uint32_t)kp.in_stride * 8u;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    if (lane == 0) {
+        mbar_expect_tx(bar, in_bytes);
+        bulk_g2s(IN, in + (size_t)inst * kp.in_stride, in_bytes, bar);
+    }
+    for (int e = lane; e < NW; e += 32) { W[e] = 0.0; D[e] = 0.0; ZL[e] = 0.0; ZU[e] = 0.0; }
+    for (int e = lane; e < ME; e += 32) { LAM[e] = 0.0; LAMN[e] = 0.0; }
+    for (int e = lane; e < NX; e += 32) { DP[e] = 0.0; KD[e] = 0.0; }
+    mbar_wait(bar, 0);
+    __syncwarp();
+    const double *x0 = IN, *u_old = IN + 6, *Am = IN + 8, *Bm = Am + 36 * N, *Cm = Bm + 12 * N, *SS = Cm + 6 * N, *Qf = SS + 6 * K;
+    const double *Q = kp.p.Q, *R = kp.p.R, *dR = kp.p.dR, *xtrk = kp.p.xtrk;
+
+    // ---- bounds as functions of the index in W
+    auto has_l = [&](int e) -> bool {
+        if (e < NX) { int i = e / 6, a = e - 6 * i; return i >= 1 && i < N && a == 5; }
+        return true;   // u box, lambda >= 0
+    };
+    auto has_u = [&](int e) -> bool {
+        if (e < NX) { int i = e / 6, a = e - 6 * i; return i >= 1 && i < N && (a == 0 || a == 5); }
+        return e < OL;
+    };
+    auto lbv = [&](int e) -> double {
+        if (e < NX) return -kp.p.width;
+        if (e < OL) return -kp.p.umax[(e - OU) & 1];
+        return 0.0;
+    };
+    auto ubv = [&](int e) -> double {
+        if (e < NX) { int a = e % 6; return a == 0 ? kp.p.vmax : kp.p.width; }
+        return kp.p.umax[(e - OU) & 1];
+    };
+
+    // ---- start: u = 0 roll-out through the LTV model, lambda = 1/K, pushed into the bounds
+    if (lane < 6) W[lane] = x0[lane];
+    __syncwarp();
+    for (int i = 0; i < N; i++) {
+        if (lane < 6) {
+            double s = Cm[6 * i + lane];
+            for (int b = 0; b < 6; b++) s += Am[36 * i + 6 * lane + b] * W[6 * i + b];
+            W[6 * (i + 1) + lane] = s;
+        }
+        __syncwarp();
+    }
+    for (int k = lane; k < K; k += 32) W[OL + k] = 1.0 / (double)K;
+    __syncwarp();
+    int nbc = 0;
+    for (int e = 6 + lane; e < NW; e += 32) {
+        bool hl = has_l(e), hu = has_u(e);
+        double w = W[e], lb = lbv(e), ub = ubv(e);
+        if (hl) {
+            double p_ = o.bound_push * fmax(1.0, fabs(lb));
+            if (hu) p_ = fmin(p_, o.bound_frac * (ub - lb));
+            if (w < lb + p_) w = lb + p_;
+        }
+        if (hu) {
+            double p_ = o.bound_push * fmax(1.0, fabs(ub));
+            if (hl) p_ = fmin(p_, o.bound_frac * (ub - lb));
+            if (w > ub - p_) w = ub - p_;
+        }
+        W[e] = w;
+        ZL[e] = hl ? 1.0 : 0.0;
+        ZU[e] = hu ? 1.0 : 0.0;
+        nbc += (hl ? 1 : 0) + (hu ? 1 : 0);
+    }
+    for (int off = 16; off > 0; off >>= 1) nbc += __shfl_xor_sync(0xffffffffu, nbc, off);
+    __syncwarp();
+    // ---- G: x_i = sum_l G[6(i-1)+a][2l+b] u_l + ...   (rows for x_1..x_N)
+    for (int e = lane; e < 6 * N * NU; e += 32) G[e] = 0.0;
+    __syncwarp();
+    for (int i = 0; i < N; i++) {   // row block of x_{i+1}
+        for (int e = lane; e < 6 * NU; e += 32) {
+            int a = e / NU, c = e - a * NU, l = c >> 1;
+            double v = 0.0;
+            if (l == i) v = Bm[12 * i + 2 * a + (c & 1)];
+            else if (l < i) {
+                for (int b = 0; b < 6; b++) v += Am[36 * i + 6 * a + b] * G[(6 * (i - 1) + b) * NU + c];
+            }
+            G[(6 * i + a) * NU + c] = v;
+        }
+        __syncwarp();
+    }
+
+    double df = 1.0, mu = o.mu_init;
+    // ---- objective, gradient (into GF, unscaled), equality residual
+    auto objective = [&](const double *Wp, double al, bool useD) -> double {
+        double f = 0.0;
+        for (int e = lane; e < 6 * (N + 1); e += 32) {
+            int i = e / 6, a = e - 6 * i;
+            double acc = 0.0, da = 0.0;
+            for (int b = 0; b < 6; b++) {
+                double d = Wp[6 * i + b] + (useD ? al * D[6 * i + b] : 0.0) - xtrk[b];
+                acc += Q[6 * a + b] * d;
+                if (b == a) da = d;
+            }
+            f += da * acc;
+        }
+        for (int i = lane; i < N; i += 32) {
+            double u0 = Wp[OU + 2 * i] + (useD ? al * D[OU + 2 * i] : 0.0), u1 = Wp[OU + 2 * i + 1] + (useD ? al * D[OU + 2 * i + 1] : 0.0);
+            double p0 = i ? Wp[OU + 2 * i - 2] + (useD ? al * D[OU + 2 * i - 2] : 0.0) : u_old[0];
+            double p1 = i ? Wp[OU + 2 * i - 1] + (useD ? al * D[OU + 2 * i - 1] : 0.0) : u_old[1];
+            double d0 = u0 - p0, d1 = u1 - p1;
+            f += u0 * (R[0] * u0 + R[1] * u1) + u1 * (R[2] * u0 + R[3] * u1) + d0 * (dR[0] * d0 + dR[1] * d1) + d1 * (dR[2] * d0 + dR[3] * d1);
+        }
+        for (int k = lane; k < K; k += 32) f += Qf[k] * (Wp[OL + k] + (useD ? al * D[OL + k] : 0.0));
+        return warp_sum(f);
+    };
+    auto gradient = [&]() {   // GF <- unscaled gradient of f at W
+        for (int e = 6 + lane; e < NW; e += 32) {
+            double g;
+            if (e < NX) {
+                int i = e / 6, a = e - 6 * i;
+                g = 0.0;
+                for (int b = 0; b < 6; b++) g += (Q[6 * a + b] + Q[6 * b + a]) * (W[6 * i + b] - xtrk[b]);
+            } else if (e < OL) {
+                int i = (e - OU) >> 1, a = (e - OU) & 1;
+                double u0 = W[OU + 2 * i], u1 = W[OU + 2 * i + 1];
+                double p0 = i ? W[OU + 2 * i - 2] : u_old[0], p1 = i ? W[OU + 2 * i - 1] : u_old[1];
+                double d0 = u0 - p0, d1 = u1 - p1;
+                g = (R[2 * a] + R[a]) * u0 + (R[2 * a + 1] + R[2 + a]) * u1 + (dR[2 * a] + dR[a]) * d0 + (dR[2 * a + 1] + dR[2 + a]) * d1;
+                if (i < N - 1) {
+                    double n0 = W[OU + 2 * i + 2] - u0, n1 = W[OU + 2 * i + 3] - u1;
+                    g -= (dR[2 * a] + dR[a]) * n0 + (dR[2 * a + 1] + dR[2 + a]) * n1;
+                }
+            } else
+                g = Qf[e - OL];
+            GF[e] = g;
+        }
+    };
+    auto residual = [&](double al, bool useD, double *out) -> double {   // equality residuals at W+al*D; returns the 1-norm
+        double th = 0.0;
+        for (int e = lane; e < ME; e += 32) {
+            double s;
+            if (e < 6 * N) {
+                int i = e / 6, a = e - 6 * i;
+                s = W[6 * (i + 1) + a] + (useD ? al * D[6 * (i + 1) + a] : 0.0) - Cm[6 * i + a];
+                for (int b = 0; b < 6; b++) s -= Am[36 * i + 6 * a + b] * (W[6 * i + b] + (useD ? al * D[6 * i + b] : 0.0));
+                s -= Bm[12 * i + 2 * a] * (W[OU + 2 * i] + (useD ? al * D[OU + 2 * i] : 0.0)) +
+                     Bm[12 * i + 2 * a + 1] * (W[OU + 2 * i + 1] + (useD ? al * D[OU + 2 * i + 1] : 0.0));
+            } else if (e < 6 * N + 6) {
+                int a = e - 6 * N;
+                s = W[6 * N + a] + (useD ? al * D[6 * N + a] : 0.0);
+                for (int k = 0; k < K; k++) s -= SS[a * K + k] * (W[OL + k] + (useD ? al * D[OL + k] : 0.0));
+            } else {
+                s = -1.0;
+                for (int k = 0; k < K; k++) s += W[OL + k] + (useD ? al * D[OL + k] : 0.0);
+            }
+            if (out) out[e] = s;
+            th += fabs(s);
+        }
+        return warp_sum(th);
+    };
+    auto barrier = [&](double al, bool useD) -> double {
+        LogAcc la;
+        for (int e = 6 + lane; e < NW; e += 32) {
+            double w = W[e] + (useD ? al * D[e] : 0.0);
+            if (has_l(e)) la.mul(w - lbv(e));
+            if (has_u(e)) la.mul(ubv(e) - w);
+        }
+        return warp_sum(la.value());
+    };
+    // optimality error (same scaling as the oracle); needs GF, CEQ current
+    auto kkt_error = [&](double m) -> double {
+        double dual = 0.0, prim = 0.0, comp = 0.0, zsum = 0.0, ysum = 0.0;
+        for (int e = 6 + lane; e < NW; e += 32) {
+            double rw = df * GF[e] - ZL[e] + ZU[e];
+            if (e < NX) {
+                int i = e / 6, a = e - 6 * i;
+                rw += LAM[6 * (i - 1) + a];
+                if (i < N) { for (int b = 0; b < 6; b++) rw -= Am[36 * i + 6 * b + a] * LAM[6 * i + b]; }
+                else rw += LAM[6 * N + a];
+            } else if (e < OL) {
+                int i = (e - OU) >> 1, a = (e - OU) & 1;
+                for (int b = 0; b < 6; b++) rw -= Bm[12 * i + 2 * b + a] * LAM[6 * i + b];
+            } else {
+                int k = e - OL;
+                rw += LAM[6 * N + 6];
+                for (int a = 0; a < 6; a++) rw -= SS[a * K + k] * LAM[6 * N + a];
+            }
+            dual = fmax(dual, fabs(rw));
+            if (has_l(e)) { comp = fmax(comp, fabs((W[e] - lbv(e)) * ZL[e] - m)); zsum += ZL[e]; }
+            if (has_u(e)) { comp = fmax(comp, fabs((ubv(e) - W[e]) * ZU[e] - m)); zsum += ZU[e]; }
+        }
+        for (int e = lane; e < ME; e += 32) { prim = fmax(prim, fabs(CEQ[e])); ysum += fabs(LAM[e]); }
+        dual = warp_max(dual); prim = warp_max(prim); comp = warp_max(comp); zsum = warp_sum(zsum); ysum = warp_sum(ysum);
+        const double s_max = 100.0;
+        int nmul = ME + nbc;
+        double sd = fmax(s_max, (ysum + zsum) / (double)(nmul > 0 ? nmul : 1)) / s_max;
+        double sc = fmax(s_max, zsum / (double)(nbc > 0 ? nbc : 1)) / s_max;
+        return fmax(dual / sd, fmax(prim, comp / sc));
+    };
+
+    // ---- scaling
+    gradient();
+    __syncwarp();
+    {
+        double gm = 0.0;
+        for (int e = 6 + lane; e < NW; e += 32) gm = fmax(gm, fabs(GF[e]));
+        gm = warp_max(gm);
+        df = gm > o.max_grad ? o.max_grad / gm : 1.0;
+    }
+    // RQ = sum_i G_i' (df*(Q+Q')) G_i  (iteration independent)
+    for (int e = lane; e < NU * NU; e += 32) {
+        int a = e / NU, b = e - a * NU;
+        double s = 0.0;
+        for (int i = 0; i < N; i++)
+            for (int p_ = 0; p_ < 6; p_++) {
+                double t = 0.0;
+                for (int q_ = 0; q_ < 6; q_++) t += (Q[6 * p_ + q_] + Q[6 * q_ + p_]) * G[(6 * i + q_) * NU + b];
+                s += G[(6 * i + p_) * NU + a] * t;
+            }
+        RQ[e] = df * s;
+    }
+    __syncwarp();
+    double th0 = residual(0.0, false, CEQ);
+    __syncwarp();
+    const double theta_max = 1e4 * fmax(1.0, th0), theta_min = 1e-4 * fmax(1.0, th0);
+    double f_th0 = 0.0, f_ph0 = 0.0, f_th1 = 0.0, f_ph1 = 0.0;
+    int nfilt = 0, fpos = 0, iter = 0, status = B200MPC_MAX_ITER, n_acc = 0, n_back = 0;
+    double E0 = 0.0;
+    const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99;
+    const double gamma_theta = 1e-5, gamma_phi = 1e-8, delta_sw = 1.0, s_theta = 1.1, s_phi = 2.3, eta_phi = 1e-8;
+    const double gamma_alpha = 0.05, kappa_sigma = 1e10;
+
+    for (;;) {
+        gradient();
+        residual(0.0, false, CEQ);
+        __syncwarp();
+        E0 = kkt_error(0.0);
+        if (E0 <= o.tol) { status = B200MPC_SOLVED; break; }
+        if (E0 <= o.acceptable_tol) {
+            if (++n_acc >= o.acceptable_iter) { status = B200MPC_SOLVED; break; }
+        } else
+            n_acc = 0;
+        if (iter >= o.max_iter) { status = B200MPC_MAX_ITER; break; }
+        for (;;) {
+            double em = kkt_error(mu);
+            if (em <= kappa_eps * mu && mu > o.tol / 11.0) {
+                mu = fmax(o.tol / 11.0, fmin(kappa_mu * mu, mu * sqrt(mu)));
+                nfilt = 0;
+                fpos = 0;
+            } else
+                break;
+        }
+        const double tau = fmax(tau_min, 1.0 - mu);
+        // ---- barrier diagonal and right-hand side
+        for (int e = 6 + lane; e < NW; e += 32) {
+            double sw = 0.0, b = -df * GF[e];
+            if (has_l(e)) { double id = rcp(W[e] - lbv(e)); sw += ZL[e] * id; b += mu * id; }
+            if (has_u(e)) { double id = rcp(ubv(e) - W[e]); sw += ZU[e] * id; b -= mu * id; }
+            SIG[e] = sw;
+            RHS[e] = b;
+        }
+        // particular solution of the dynamics rows (du = 0)
+        if (lane < 6) DP[lane] = 0.0;
+        __syncwarp();
+        for (int i = 0; i < N; i++) {
+            if (lane < 6) {
+                double s = -CEQ[6 * i + lane];
+                for (int b = 0; b < 6; b++) s += Am[36 * i + 6 * lane + b] * DP[6 * i + b];
+                DP[6 * (i + 1) + lane] = s;
+            }
+            __syncwarp();
+        }
+        // KD = K_xx dp  (x part of K applied to the particular solution)
+        for (int e = 6 + lane; e < NX; e += 32) {
+            int i = e / 6, a = e - 6 * i;
+            double s = SIG[e] * DP[e];
+            for (int b = 0; b < 6; b++) s += df * (Q[6 * a + b] + Q[6 * b + a]) * DP[6 * i + b];
+            KD[e] = s;
+        }
+        __syncwarp();
+        // ---- reduced KKT matrix  [Rh E'; E 0 | rhs]
+        for (int e = lane; e < ND * LD; e += 32) KK[e] = 0.0;
+        __syncwarp();
+        for (int e = lane; e < NU * NU; e += 32) {   // Rh_uu = RQ + G' diag(sig_x) G + K_uu
+            int a = e / NU, b = e - a * NU;
+            double s = RQ[e];
+            for (int r = 0; r < 6 * N; r++) {
+                double sg = SIG[6 + r];
+                if (sg != 0.0) s += G[r * NU + a] * sg * G[r * NU + b];
+            }
+            int ia = a >> 1, ib = b >> 1, ca = a & 1, cb = b & 1;
+            double r2 = R[2 * ca + cb] + R[2 * cb + ca], d2 = dR[2 * ca + cb] + dR[2 * cb + ca];
+            if (ia == ib) s += df * (r2 + d2 + ((ia < N - 1) ? d2 : 0.0)) + ((a == b) ? SIG[OU + a] : 0.0);
+            else if (ia == ib + 1 || ib == ia + 1) s -= df * d2;
+            KK[a * LD + b] = s;
+        }
+        for (int k = lane; k < K; k += 32) {
+            KK[(NU + k) * LD + NU + k] = SIG[OL + k];
+            for (int a = 0; a < 6; a++) {
+                KK[(NU + k) * LD + NR + a] = -SS[a * K + k];
+                KK[(NR + a) * LD + NU + k] = -SS[a * K + k];
+            }
+            KK[(NU + k) * LD + NR + 6] = 1.0;
+            KK[(NR + 6) * LD + NU + k] = 1.0;
+            KK[(NU + k) * LD + ND] = RHS[OL + k];
+        }
+        for (int e = lane; e < 6 * NU; e += 32) {
+            int a = e / NU, c = e - a * NU;
+            double v = G[(6 * (N - 1) + a) * NU + c];
+            KK[(NR + a) * LD + c] = v;
+            KK[c * LD + NR + a] = v;
+        }
+        for (int c = lane; c < NU; c += 32) {   // rr_u = rhs_u + G'(rhs_x - K_xx dp)
+            double s = RHS[OU + c];
+            for (int r = 0; r < 6 * N; r++) s += G[r * NU + c] * (RHS[6 + r] - KD[6 + r]);
+            KK[c * LD + ND] = s;
+        }
+        if (lane < 6) KK[(NR + lane) * LD + ND] = -(CEQ[6 * N + lane] + DP[6 * N + lane]);
+        if (lane == 6) KK[(NR + 6) * LD + ND] = -CEQ[6 * N + 6];
+        __syncwarp();
+        // ---- LU with partial pivoting on the augmented matrix (ND x ND+1), then back substitution
+        bool singular = false;
+        for (int k = 0; k < ND; k++) {
+            double best = -1.0;
+            int bi = k;
+            for (int r = k + lane; r < ND; r += 32) {
+                double v = fabs(KK[r * LD + k]);
+                if (v > best) { best = v; bi = r; }
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (!(best > 1e-300)) { singular = true; break; }
+            if (bi != k) {
+                for (int c = k + lane; c < LD; c += 32) {
+                    double t = KK[k * LD + c];
+                    KK[k * LD + c] = KK[bi * LD + c];
+                    KK[bi * LD + c] = t;
+                }
+            }
+            __syncwarp();
+            double inv = 1.0 / KK[k * LD + k];
+            // eliminate: lanes over (row, column) pairs of the trailing block
+            for (int r = k + 1 + (lane >> 3); r < ND; r += 4) {   // 4 rows at a time, 8 lanes per row
+                double f = KK[r * LD + k] * inv;
+                if (f != 0.0)
+                    for (int c = k + 1 + (lane & 7); c < LD; c += 8) KK[r * LD + c] -= f * KK[k * LD + c];
+            }
+            __syncwarp();
+        }
+        if (singular) { status = B200MPC_INERTIA; break; }
+        for (int k = ND - 1; k >= 0; k--) {   // back substitution, solution overwrites the rhs column
+            double s = 0.0;
+            for (int c = k + 1 + lane; c < ND; c += 32) s += KK[k * LD + c] * KK[c * LD + ND];
+            s = warp_sum(s);
+            if (lane == 0) KK[k * LD + ND] = (KK[k * LD + ND] - s) / KK[k * LD + k];
+            __syncwarp();
+        }
+        // ---- direction: du, dlambda from the solve; dx = G du + dp; nu+ ; costate recursion for the dynamics multipliers
+        for (int e = lane; e < NR; e += 32) D[OU + e] = KK[e * LD + ND];
+        for (int e = lane; e < 7; e += 32) LAMN[6 * N + e] = KK[(NR + e) * LD + ND];
+        __syncwarp();
+        for (int e = 6 + lane; e < NX; e += 32) {
+            double s = DP[e];
+            for (int c = 0; c < NU; c++) s += G[(e - 6) * NU + c] * D[OU + c];
+            D[e] = s;
+        }
+        if (lane < 6) D[lane] = 0.0;
+        __syncwarp();
+        // res_x = rhs_x - (K d)_x  -> KD
+        for (int e = 6 + lane; e < NX; e += 32) {
+            int i = e / 6, a = e - 6 * i;
+            double s = SIG[e] * D[e];
+            for (int b = 0; b < 6; b++) s += df * (Q[6 * a + b] + Q[6 * b + a]) * D[6 * i + b];
+            KD[e] = RHS[e] - s;
+        }
+        __syncwarp();
+        for (int i = N; i >= 1; i--) {
+            if (lane < 6) {
+                double s = KD[6 * i + lane];
+                if (i < N) { for (int b = 0; b < 6; b++) s += Am[36 * i + 6 * b + lane] * LAMN[6 * i + b]; }
+                else s -= LAMN[6 * N + lane];
+                LAMN[6 * (i - 1) + lane] = s;
+            }
+            __syncwarp();
+        }
+        // ---- step sizes, directional derivative
+        double a_max = 1.0, a_z = 1.0, gphi = 0.0;
+        for (int e = 6 + lane; e < NW; e += 32) {
+            double d = D[e], w = W[e];
+            gphi += df * GF[e] * d;
+            if (has_l(e)) {
+                double dl = w - lbv(e), zl = ZL[e];
+                double dzl = (mu - zl * d) * rcp(dl) - zl;
+                if (d < 0.0) a_max = fmin(a_max, -tau * dl / d);
+                if (dzl < 0.0) a_z = fmin(a_z, -tau * zl / dzl);
+                gphi -= mu * d * rcp(dl);
+            }
+            if (has_u(e)) {
+                double du = ubv(e) - w, zu = ZU[e];
+                double dzu = (mu + zu * d) * rcp(du) - zu;
+                if (d > 0.0) a_max = fmin(a_max, tau * du / d);
+                if (dzu < 0.0) a_z = fmin(a_z, -tau * zu / dzu);
+                gphi += mu * d * rcp(du);
+            }
+        }
+        a_max = warp_min(a_max); a_z = warp_min(a_z); gphi = warp_sum(gphi);
+        double th = 0.0;
+        for (int e = lane; e < ME; e += 32) th += fabs(CEQ[e]);
+        th = warp_sum(th);
+        double ph = df * objective(W, 0.0, false) - mu * barrier(0.0, false);
+        double amin;
+        if (gphi < 0.0 && th <= theta_min)
+            amin = gamma_alpha * fmin(gamma_theta, fmin(gamma_phi * th / (-gphi), delta_sw * pow(th, s_theta) / pow(-gphi, s_phi)));
+        else if (gphi < 0.0)
+            amin = gamma_alpha * fmin(gamma_theta, gamma_phi * th / (-gphi));
+        else
+            amin = gamma_alpha * gamma_theta;
+        double a = a_max;
+        bool accepted = false, ftype = false;
+        int nls = 0;
+        while (a >= amin || nls == 0) {
+            double tht = residual(a, true, nullptr);
+            double pht = df * objective(W, a, true) - mu * barrier(a, true);
+            bool dom = false;
+            if (lane < nfilt && tht >= f_th0 && pht >= f_ph0) dom = true;
+            if (lane + 32 < nfilt && tht >= f_th1 && pht >= f_ph1) dom = true;
+            bool okf = (tht < theta_max) && !__any_sync(0xffffffffu, dom);
+            if (okf) {
+                bool sw = gphi < 0.0 && a * pow(-gphi, s_phi) > delta_sw * pow(th, s_theta);
+                if (th <= theta_min && sw) {
+                    if (pht <= ph + eta_phi * a * gphi) { accepted = true; ftype = true; }
+                } else if (tht <= (1.0 - gamma_theta) * th || pht <= ph - gamma_phi * th)
+                    accepted = true;
+            }
+            if (accepted) break;
+            a *= 0.5;
+            nls++;
+            n_back++;
+        }
+        if (!accepted) { status = B200MPC_LINESEARCH; break; }
+        if (!ftype) {
+            double nth = (1.0 - gamma_theta) * th, nph = ph - gamma_phi * th;
+            int slot = fpos >> 5, ln = fpos & 31;
+            if (lane == ln) {
+                if (slot == 0) { f_th0 = nth; f_ph0 = nph; }
+                else { f_th1 = nth; f_ph1 = nph; }
+            }
+            fpos = (fpos + 1) & 63;
+            if (nfilt < 64) nfilt++;
+        }
+        // ---- update
+        for (int e = 6 + lane; e < NW; e += 32) {
+            double d = D[e], w = W[e], wn = w + a * d;
+            if (has_l(e)) {
+                double dl = w - lbv(e), zl = ZL[e];
+                zl += a_z * ((mu - zl * d) * rcp(dl) - zl);
+                double m1 = mu * rcp(wn - lbv(e));
+                ZL[e] = fmax(fmin(zl, kappa_sigma * m1), m1 * (1.0 / kappa_sigma));
+            }
+            if (has_u(e)) {
+                double du = ubv(e) - w, zu = ZU[e];
+                zu += a_z * ((mu + zu * d) * rcp(du) - zu);
+                double m1 = mu * rcp(ubv(e) - wn);
+                ZU[e] = fmax(fmin(zu, kappa_sigma * m1), m1 * (1.0 / kappa_sigma));
+            }
+            W[e] = wn;
+        }
+        for (int e = lane; e < ME; e += 32) LAM[e] += a * (LAMN[e] - LAM[e]);
+        __syncwarp();
+        iter++;
+    }
+    double cost = objective(W, 0.0, false);
+    if (lane == 0) {
+        b200mpc_record rc;
+        rc.cost = cost;
+        rc.u0[0] = W[OU];
+        rc.u0[1] = W[OU + 1];
+        rc.status = status;
+        rc.iters = iter;
+        rec[inst] = rc;
+    }
+    if (aux != nullptr && lane < 4) aux[(size_t)inst * 4 + lane] = (lane == 0) ? E0 : (lane == 3 ? (double)n_back : 0.0);
+    if (xpred != nullptr)
+        for (int e = lane; e < NX; e += 32) xpred[(size_t)inst * NX + e] = W[e];
+    if (upred != nullptr)
+        for (int e = lane; e < NU; e += 32) upred[(size_t)inst * NU + e] = W[OU + e];
+    if (lambda_out != nullptr)
+        for (int e = lane; e < K; e += 32) lambda_out[(size_t)inst * K + e] = W[OL + e];
+}
+
+}  // namespace b200mpc

@@ -160,7 +160,7 @@ def lmpc_scenarios(B, N=12, num_ss_points=44, num_ss_iter=2, seed=1, ltv_noise=5
             cols.append(np.array(seg).T)
             qs.append((200.0 + 15.0 * jj) - np.arange(per))      # time-to-go: decreasing along the lap, older lap costlier
         w = rng.uniform(0.35, 0.65)
-        x0[b] = w * starts[0] + (1 - w) * starts[1] + rng.normal(scale=1e-3, size=6)
+        x0[b] = w * starts[0] + (1 - w) * starts[-1] + rng.normal(scale=1e-3, size=6)
         u_old[b] = np.clip([-0.6 * x0[b, 5] - 0.9 * x0[b, 3], 1.5 * (1.25 - x0[b, 0])], [-0.5, -1.0], [0.5, 1.0])
         nz = ltv_noise * rng.normal(size=(N, 6, 6))
         nz[:, :, 4] = 0.0

@@ -148,6 +148,27 @@ int b200mpc_ilqr_solve(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B,
 int b200mpc_ilqr_solve_device(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B, const double *d_in,
                               b200mpc_record *d_rec, double *d_xpred, double *d_upred);
 
+/* LMPC (control.py:610-730): the per-step QP over the LTV model and the convex hull of the selected safe set.
+ * Replaces the CasADi `opti.solve()` at control.py:703.  Shared data: */
+#define B200MPC_LMPC_NMAX 16 /* num_horizon (12, base.py:351) */
+#define B200MPC_LMPC_KMAX 64 /* selected safe-set points (num_ss_points = 44, base.py:358) */
+typedef struct {
+    int32_t N, K;
+    double Q[36], R[4], dR[4];   /* matrix_Q, matrix_R, matrix_dR (base.py:354-357) */
+    double xtrk[6];              /* x_track (control.py:649) */
+    double umax[2], vmax, width; /* delta_max, a_max, v_max, lap_width (control.py:658-666) */
+} b200mpc_lmpc_params;
+
+/* doubles per instance: [x0 6][u_old 2][A_0..A_{N-1} 36 each, row-major][B_i 12 each][C_i 6 each]
+ *                       [SS 6 x K row-major][Qfun K][pad to even]
+ * outputs as b200mpc_cbf_solve, plus lambda: optional B x K (lin_comb_lambda of control.py:618). */
+int b200mpc_lmpc_record_doubles(int N, int K);
+int b200mpc_lmpc_solve(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const b200mpc_ipm_options *opt, int B,
+                       const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *lambda);
+int b200mpc_lmpc_solve_device(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const b200mpc_ipm_options *opt, int B,
+                              const double *d_in, b200mpc_record *d_rec, double *d_aux, double *d_xpred, double *d_upred,
+                              double *d_lambda);
+
 /* argmin over records (device pointers): index of the smallest cost among status<=max_status,
  * lowest index wins ties (list.index(min(...)), overtake_traj_planner.py:244); *d_out = -1 if none. */
 int b200mpc_argmin_cost_device(b200mpc_handle *h, const b200mpc_record *d_rec, int B, int max_status, int32_t *d_out);

@@ -221,6 +221,7 @@ def solve_lmpc_batch(x0, u_old, A, B, Cm, SS, Qfun, prm, nthreads=1, **opt):
     return dict(
         x=np.array([np.frombuffer(r.x, dtype=np.float64)[: 6 * (N + 1)].reshape(N + 1, 6) for r in R]),
         u=np.array([np.frombuffer(r.u, dtype=np.float64)[: 2 * N].reshape(N, 2) for r in R]),
+        u0=np.array([np.frombuffer(r.u, dtype=np.float64)[:2].copy() for r in R]),
         lam=np.array([np.frombuffer(r.lam, dtype=np.float64)[:K] for r in R]),
         cost=np.array([r.cost for r in R]), kkt_err=np.array([r.kkt_err for r in R]),
         status=np.array([r.status for r in R]), iters=np.array([r.iters for r in R]))

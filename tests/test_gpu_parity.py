@@ -329,3 +329,70 @@ def test_capi_argument_validation(crb):
     # a valid call still works afterwards
     x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(2, N=20, M=3, seed=1)
     assert (crb.solve_cbf_batch(x0, xt, obs, lap_off, prm, handle=h)["status"] == 0).all()
+
+
+def test_lmpc_config4_parity(crb, oracle):
+    """control.lmpc's QP: N=12, 44 safe-set points, LTV model."""
+    B = 96
+    sc = scenarios.lmpc_scenarios(B, seed=5)
+    prm = scenarios.default_lmpc_params()
+    g = crb.solve_lmpc_batch(*sc, prm)
+    r = oracle.solve_lmpc_batch(*sc, prm, nthreads=os.cpu_count() or 1)
+    match, info = _compare(g, r)
+    assert info["both_converged"] >= 0.8 * B
+    ok = (g["status"] == 0) & (r["status"] == 0)
+    assert np.abs(g["x"][ok] - r["x"][ok]).max() < 1e-4
+    assert np.abs(g["u"][ok] - r["u"][ok]).max() < 1e-4
+    assert np.abs(g["lambda"][ok] - r["lam"][ok]).max() < 1e-4
+    # hull constraint and simplex hold on the GPU result itself
+    x0, u_old, A, Bm, Cm, SS, Qf = sc
+    assert np.abs(np.einsum("bak,bk->ba", SS, g["lambda"])[ok] - g["x"][ok, -1]).max() < 1e-6
+    assert np.abs(g["lambda"][ok].sum(axis=1) - 1).max() < 1e-7 and g["lambda"][ok].min() > -1e-9
+    xn = np.einsum("bnij,bnj->bni", A, g["x"][:, :-1]) + np.einsum("bnij,bnj->bni", Bm, g["u"]) + Cm
+    assert np.abs(xn - g["x"][:, 1:])[ok].max() < 1e-7
+    assert g["kkt_err"][ok].max() <= 1e-6
+
+
+@pytest.mark.parametrize("N,K", [(2, 1), (3, 16), (5, 24), (8, 33), (16, 64), (12, 21)])
+def test_lmpc_shapes_parity(crb, oracle, N, K):
+    ni = 1 if K % 2 else 2
+    sc = scenarios.lmpc_scenarios(24, N=N, num_ss_points=K, num_ss_iter=ni, seed=N + K)
+    prm = scenarios.default_lmpc_params(N=N, Q=np.diag([0.5, 0, 0, 0.1, 0, 2.0]))
+    g = crb.solve_lmpc_batch(*sc, prm)
+    r = oracle.solve_lmpc_batch(*sc, prm, nthreads=os.cpu_count() or 1)
+    _, info = _compare(g, r, min_match=0.9)
+    if K > 1:   # K = 1 pins x_N to one stored state: infeasible, both sides must stop the same way
+        assert info["both_converged"] >= 0.7 * 24
+
+
+def test_lmpc_drop_in_on_gpu(crb, oracle):
+    """control.lmpc shim: same 6-tuple as control.py:723-730."""
+    from types import SimpleNamespace
+    from car_racing_b200 import control
+    rng = np.random.default_rng(0)
+    sc = scenarios.lmpc_scenarios(1, seed=9)
+    x0, u_old, A, Bm, Cm, SS, Qf = [a[0] for a in sc]
+    # stored laps as the reference holds them: ss_xcurv (T, 6, laps), Qfun (T, laps); rows = the 22 points of each lap
+    T = 60
+    ss = np.zeros((T, 6, 2)); qf = np.zeros((T, 2))
+    for lap in range(2):
+        ss[:, :, lap] = 1e3                       # far from x0 except the stored block
+        ss[10:32, :, lap] = SS[:, 22 * (1 - lap):22 * (2 - lap)].T
+        qf[10:32, lap] = Qf[22 * (1 - lap):22 * (2 - lap)]
+        for k in range(32, T):                    # the lap continues past the stored block
+            ss[k, :, lap] = ss[31, :, lap]
+            ss[k, 4, lap] += 0.12 * (k - 31)
+            qf[k, lap] = qf[31, lap] - (k - 31)
+    lp = SimpleNamespace(num_ss_iter=2, num_ss_points=44, shift=0, num_horizon=12, matrix_Q=np.zeros((6, 6)),
+                         matrix_R=np.diag([1.0, 0.25]), matrix_dR=5 * np.diag([0.8, 0.0]))
+    sp = SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10.0)
+    u_pred, x_pred, ss_sel, q_sel, lin_points, lin_input = control.lmpc(x0, lp, list(A), list(Bm), list(Cm), ss, qf, 2, 20.0, 1.0,
+                                                                       u_old, sp)
+    assert u_pred.shape == (12, 2) and x_pred.shape == (13, 6) and ss_sel.shape[0] == 6 and lin_points.shape == (13, 6)
+    assert lin_input.shape == (12, 2)
+    K = ss_sel.shape[1]
+    r = oracle.solve_lmpc_batch(x0[None], u_old[None], A[None], Bm[None], Cm[None], ss_sel[None], q_sel[None],
+                                scenarios.default_lmpc_params())
+    if r["status"][0] == 0:
+        assert np.abs(u_pred - r["u"][0]).max() < 1e-4 and np.abs(x_pred - r["x"][0]).max() < 1e-4
+    assert np.allclose(lin_points[:-1], x_pred[1:]) and np.allclose(lin_input[:-1], u_pred[1:])
