@@ -99,7 +99,7 @@ def build():
 def lib():
     global _lib
     if _lib is None:
-        so = os.path.join(_HERE, "_build", "liboracle.so")
+        so = os.environ.get("B200MPC_ORACLE_SO") or os.path.join(_HERE, "_build", "liboracle.so")   # override: experiments only
         if not os.path.exists(so):
             build()
         _lib = C.CDLL(so)
