@@ -1,0 +1,120 @@
+"""Secondary measurements: batch sweep of the north-star configuration and throughput of
+configs 3 (planner candidates), 4 (LMPC) and 5 (iLQR) through the host-pointer C-ABI (H2D + kernel + D2H),
+with the CPU oracle port on the same inputs beside each.  Not the bench contract -- bench.py is; this
+writes one JSON document to stdout / --out for profiles/.
+
+    python tools/config_sweep.py --out profiles/r01k_config_sweep.json
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import car_racing_b200 as crb                      # noqa: E402
+from car_racing_b200 import scenarios              # noqa: E402
+
+
+def timed(fn, reps=7, warm=2):
+    for _ in range(warm):
+        out = fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        ts.append(time.perf_counter() - t0)
+    ts = np.array(ts)
+    return out, float(np.median(ts)), float(np.percentile(ts, 10)), float(np.percentile(ts, 90))
+
+
+def cpu_timed(fn):
+    t0 = time.perf_counter()
+    out = fn()
+    return out, time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    from oracle import oracle
+    ncpu = os.cpu_count() or 1
+    doc = {"host_threads": ncpu, "timing": "median wall time of the host-pointer call (H2D + kernel + D2H), 7 reps after 2 warm-ups"}
+
+    # ---- config 2 batch sweep
+    prm = scenarios.default_cbf_params(N=20)
+    sweep = []
+    for B in (1, 8, 64, 256, 1024, 2048, 4096, 8192, 16384, 65536):
+        x0, xt, obs, lo = scenarios.mpccbf_scenarios(min(B, 8192), N=20, M=3, seed=1)
+        if B > 8192:
+            rep = B // 8192
+            x0, obs, lo = np.tile(x0, (rep, 1)), np.tile(obs, (rep, 1, 1, 1)), np.tile(lo, (rep, 1))
+        rec, M, ps = crb.pack_cbf(x0, xt, obs, lo, 20)
+        g, t, p10, p90 = timed(lambda: crb.solve_cbf_packed(rec, prm, M, ps, want=()), reps=5 if B >= 16384 else 7)
+        sweep.append(dict(B=B, ms=t * 1e3, ms_p10=p10 * 1e3, ms_p90=p90 * 1e3, solves_per_s=B / t,
+                          converged=float((g["status"] == 0).mean()), iters_mean=float(g["iters"].mean()),
+                          iters_max=int(g["iters"].max())))
+        print("config2", sweep[-1], flush=True)
+    doc["config2_batch_sweep"] = sweep
+
+    # ---- config 3: planner candidate QPs (N=10), 64 candidates per planner call
+    from test_gpu_parity import _planner_batch
+    kw, off, pprm = _planner_batch(range(32))
+    C = kw["x0"].shape[0]
+    g, t, p10, p90 = timed(lambda: crb.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, pprm, xlb=kw["xlb"], xub=kw["xub"],
+                                                       wd=kw["wd"], want=("x",)))
+    ent = dict(candidates=C, ms=t * 1e3, candidates_per_s=C / t, converged=float((g["status"] == 0).mean()))
+    if not a.no_cpu:
+        r, tc = cpu_timed(lambda: oracle.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, pprm, xlb=kw["xlb"], xub=kw["xub"],
+                                                         wd=kw["wd"], nthreads=ncpu))
+        ent.update(cpu_port_ms=tc * 1e3, cpu_port_candidates_per_s=C / tc)
+    doc["config3_planner"] = ent
+    print("config3", ent, flush=True)
+
+    # ---- config 4: LMPC, 512 per GPU
+    lprm = scenarios.default_lmpc_params()
+    out4 = []
+    for B in (1, 512, 4096):
+        sc = scenarios.lmpc_scenarios(min(B, 512), seed=3)
+        if B > 512:
+            sc = tuple(np.tile(v, (B // 512,) + (1,) * (v.ndim - 1)) for v in sc)
+        g, t, p10, p90 = timed(lambda: crb.solve_lmpc_batch(*sc, lprm, want=()))
+        ent = dict(B=B, ms=t * 1e3, solves_per_s=B / t, converged=float((g["status"] == 0).mean()), iters_mean=float(g["iters"].mean()))
+        if not a.no_cpu and B == 512:
+            r, tc = cpu_timed(lambda: oracle.solve_lmpc_batch(*sc, lprm, nthreads=ncpu))
+            ent.update(cpu_port_ms=tc * 1e3, cpu_port_solves_per_s=B / tc)
+        out4.append(ent)
+        print("config4", ent, flush=True)
+    doc["config4_lmpc"] = out4
+
+    # ---- config 5: iLQR N=50, 1024 per GPU
+    p = scenarios.default_cbf_params()
+    iprm = dict(A=p["A"], B=p["B"], Q=p["Q"], R=p["R"], N=50, max_iter=150, L=0.4, W=0.2)
+    out5 = []
+    for B in (1, 1024, 8192):
+        x0, xt, obs, lo = scenarios.ilqr_scenarios(B, N=50, seed=1)
+        g, t, p10, p90 = timed(lambda: crb.solve_ilqr_batch(x0, xt, obs, lo, iprm, want=()))
+        ent = dict(B=B, ms=t * 1e3, solves_per_s=B / t, iters_mean=float(g["iters"].mean()))
+        if not a.no_cpu and B == 1024:
+            r, tc = cpu_timed(lambda: oracle.solve_ilqr_batch(x0, xt, obs, lo, iprm, nthreads=ncpu))
+            ent.update(cpu_port_ms=tc * 1e3, cpu_port_solves_per_s=B / tc)
+        out5.append(ent)
+        print("config5", ent, flush=True)
+    doc["config5_ilqr"] = out5
+    doc["reference_python_ilqr_note"] = "SURVEY.md 8(d): the reference's own numpy iLQR measured p50 20.1 ms per solve (1 core)"
+    s = json.dumps(doc, indent=1)
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write(s + "\n")
+    print(s)
+
+
+if __name__ == "__main__":
+    main()
