@@ -62,7 +62,7 @@ struct SmemPlan {
     static constexpr int NXAP = (NXA + 1) & ~1, NUAP = (NUA + 1) & ~1, NC = 8 + M;
     int N, R, NB, NW, OU, OS;
     int oIN, oW, oD, oHD, oZL, oZU, oS, oT, oY, oZ, oV, oDG, oG, oSIGE, oYHAT, oJD, oJA, oLAM, oCRES, oKFB, oKFF, oPT, oQV,
-        oGUU, oGVU, oYF, oYG, oS0, oJDC, oGX, total;
+        oGUU, oGVU, oYF, oYG, oS0, oJDC, oGX, oAB, total;
     __host__ __device__ SmemPlan(int N_, int in_stride) {
         N = N_;
         R = M * N;
@@ -85,6 +85,7 @@ struct SmemPlan {
         oS0 = take((M > 0 ? M : 1) * (M + 2));
         oJDC = take(N + 2);
         oGX = take(6 * (N + 1));
+        oAB = take(48);   // rows of [A | B] for the Riccati sweep (16-byte loads instead of constant-bank loads)
         total = o;
     }
     __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(double); }
@@ -107,7 +108,7 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 // branch-free FP64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) + two Newton
-// steps.  The compiler's IEEE division carries a slow-path call per site (~20 instructions, 2 branches); the
+// steps (quadratic: 20 -> 40 -> 80 bits).  The compiler's IEEE division carries a slow-path call per site (~20 instructions, 2 branches); the
 // solver's operands are positive, finite and far from the denormal range, and 1-ulp differences are irrelevant here.
 __device__ __forceinline__ double rcp(double x) {
     double r;
@@ -121,8 +122,7 @@ __device__ __forceinline__ double rsq(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double h = 0.5 * x;
-    y = y * fma(-h * y, y, 1.5);
-    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);   // seed 1e-6 -> 1.3e-12 -> 4e-16 (measured over 60 binades, profiles/r01k_rsq_accuracy.txt)
     return y * fma(-h * y, y, 1.5);
 }
 __device__ __forceinline__ double p4(double a) { double b = a * a; return b * b; }
@@ -212,7 +212,7 @@ struct Ipm {
     static constexpr bool kStaticN = NT > 0;
     const int N, R, NB, NW, OU, OS;
     double *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM, *CRES, *KFB, *KFF, *PT,
-        *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC, *GX;
+        *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC, *GX, *ABs;
     const double *xt, *obs, *lapoff, *bnd, *wdp;
     // per-stage bounds / ey-rate cost present (planner QP): compile-time so that the MPC-CBF path pays nothing
     static constexpr bool psb = (FL & B200MPC_FLAG_STAGE_BOUNDS) != 0, hwd = (FL & B200MPC_FLAG_EY_RATE) != 0;
@@ -235,6 +235,7 @@ struct Ipm {
         S0 = sm + pl.oS0;
         JDC = sm + pl.oJDC;
         GX = sm + pl.oGX;
+        ABs = sm + pl.oAB;
         bnd = IN + kp.bnd_off;
         wdp = IN + kp.wd_off;
         nb_count = 0;
@@ -748,7 +749,16 @@ struct Ipm {
     // ---- Riccati backward sweep with primal regularisation dw.  Returns false if a pivot <= 0.
     // Stage variables zeta = (dx 6, dsigma M | du 2, dsigma+ M); lane l < NZ owns column l of the stage Hessian G,
     // lane a < NXA additionally owns row a of the value function P (registers).
+#ifdef B200MPC_PHASE_CLOCKS
+    long long bc[5] = {0, 0, 0, 0, 0};
+#define BCLK(k) { long long t_ = clock64(); bc[k] += t_ - tb0; tb0 = t_; }
+#else
+#define BCLK(k)
+#endif
     __device__ bool riccati_backward(double dw) {
+#ifdef B200MPC_PHASE_CLOCKS
+        long long tb0 = clock64();
+#endif
         double Pr[NXA], pv;
         {   // terminal value function: stage-N state block
             int idx = isx ? 6 * N + lane : (iss ? isg(jrole, N) : 0);
@@ -765,22 +775,16 @@ struct Ipm {
             {
                 double ptx[8];
 #pragma unroll
-                for (int c = 0; c < 6; c++) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int b = 0; b < 6; b++) s += Pr[b] * Am(b, c);
-                    ptx[c] = s;
-                }
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int b = 0; b < 6; b++) s += Pr[b] * Bm(b, c);
-                    ptx[6 + c] = s;
-                }
+                for (int c = 0; c < 8; c++) ptx[c] = 0.0;
                 double qv = pv;
 #pragma unroll
-                for (int b = 0; b < 6; b++) qv -= Pr[b] * c6[b];
+                for (int b = 0; b < 6; b++) {
+                    double ab[8];
+                    ldv<8>(ABs + 8 * b, ab);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) ptx[c] += Pr[b] * ab[c];
+                    qv -= Pr[b] * c6[b];
+                }
                 if (lane < NXA) {
 #pragma unroll
                     for (int c = 0; c < 8; c++) PT[c * NXAP + lane] = ptx[c];
@@ -790,6 +794,7 @@ struct Ipm {
                 }
             }
             __syncwarp();
+            BCLK(0)
             // (2) column l of G = base + T'PT + sum_j SIGE_j ct_j ct_j', own gradient component
             double g[NZ], gv;
             {
@@ -797,20 +802,28 @@ struct Ipm {
                 ldv<NXAP>(PT + cmap * NXAP, colv);
                 ldv<NXAP>(QVs, qvs);
 #pragma unroll
-                for (int a = 0; a < 6; a++) {
-                    double s = qqcol[a];
-#pragma unroll
-                    for (int q = 0; q < 6; q++) s += Am(q, a) * colv[q];
-                    g[a] = s;
-                }
+                for (int a = 0; a < 6; a++) g[a] = qqcol[a];
 #pragma unroll
                 for (int j = 0; j < M; j++) g[6 + j] = 0.0;
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    double s = rrcol[c];
+                for (int c = 0; c < 2; c++) g[NXA + c] = rrcol[c];
+                double ab4[8], ab5[8];
 #pragma unroll
-                    for (int q = 0; q < 6; q++) s += Bm(q, c) * colv[q];
-                    g[NXA + c] = s;
+                for (int q = 0; q < 6; q++) {
+                    double ab[8];
+                    ldv<8>(ABs + 8 * q, ab);
+#pragma unroll
+                    for (int a = 0; a < 6; a++) g[a] += ab[a] * colv[q];
+#pragma unroll
+                    for (int c = 0; c < 2; c++) g[NXA + c] += ab[6 + c] * colv[q];
+                    if (q == 4) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) ab4[c] = ab[c];
+                    }
+                    if (q == 5) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) ab5[c] = ab[c];
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < M; j++) g[NXA + 2 + j] = colv[6 + j];
@@ -838,14 +851,14 @@ struct Ipm {
                     double w = sg * own;
 #pragma unroll
                     for (int a = 0; a < 6; a++) {
-                        double ct = Am(4, a) * ja[2] + Am(5, a) * ja[3];
+                        double ct = ab4[a] * ja[2] + ab5[a] * ja[3];
                         if (a == 4) ct += ja[0];
                         if (a == 5) ct += ja[1];
                         g[a] += ct * w;
                     }
                     g[6 + j] += (dgr * a1) * w;
 #pragma unroll
-                    for (int c = 0; c < 2; c++) g[NXA + c] += (Bm(4, c) * ja[2] + Bm(5, c) * ja[3]) * w;
+                    for (int c = 0; c < 2; c++) g[NXA + c] += (ab4[6 + c] * ja[2] + ab5[6 + c] * ja[3]) * w;
                     g[NXA + 2 + j] -= dgr * w;
                     double er = -(ja[2] * c6[4] + ja[3] * c6[5]);
                     gv += (sg * er - yh) * own;
@@ -855,9 +868,9 @@ struct Ipm {
                     double own = tcol[5] - ((lane == 5) ? 1.0 : 0.0);
                     double w = sg * own;
 #pragma unroll
-                    for (int a = 0; a < 6; a++) g[a] += (Am(5, a) - ((a == 5) ? 1.0 : 0.0)) * w;
+                    for (int a = 0; a < 6; a++) g[a] += (ab5[a] - ((a == 5) ? 1.0 : 0.0)) * w;
 #pragma unroll
-                    for (int c = 0; c < 2; c++) g[NXA + c] += Bm(5, c) * w;
+                    for (int c = 0; c < 2; c++) g[NXA + c] += ab5[6 + c] * w;
                     gv += (sg * (-c6[5])) * own;
                 }
                 if (lane >= NXA && lane < NZ) {
@@ -870,6 +883,7 @@ struct Ipm {
                 }
             }
             __syncwarp();
+            BCLK(1)
             // (3) Cholesky of G_uu redundantly in every lane (rsqrt: no division); column solves
             double Lm[NUA][NUA], rinv[NUA], yv[NUA];
             {
@@ -896,7 +910,6 @@ struct Ipm {
                         Lm[i][j] = s * ri;
                     }
                 }
-                if (!ok) return false;
                 double gvu[NUAP], kv[NUA];
                 ldv<NUAP>(GVU, gvu);
                 const bool gcol = (lane == NZ);  // this lane solves the gradient column
@@ -914,6 +927,7 @@ struct Ipm {
                     for (int q = a + 1; q < NUA; q++) s -= Lm[q][a] * kv[q];
                     kv[a] = s * rinv[a];
                 }
+                if (!ok) return false;   // checked after the solves so that they overlap the factorisation's latency
                 if (lane < NXA) {
 #pragma unroll
                     for (int m = 0; m < NUA; m++) KFB[(k * NUA + m) * NXAP + lane] = -kv[m];
@@ -932,6 +946,7 @@ struct Ipm {
                 }
             }
             __syncwarp();
+            BCLK(2)
             // (4) row b of P = G_xx - Y'Y, p = g_x - Y' y_g (state lanes keep them in registers)
             {
                 double yg[NUAP];
@@ -950,6 +965,7 @@ struct Ipm {
                     Pr[a] = s;
                 }
             }
+            BCLK(3)
         }
         // stage 0: x_0 is fixed (control.py:497), sigma_{.,0} is free: d sigma_0 = -P_ss^-1 p_s  -> QVs[6+j]
         if (M > 0) {
@@ -1071,6 +1087,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     for (int e = lane; e < NW + 2; e += 32) { q.W[e] = 0.0; q.D[e] = 0.0; q.HD[e] = 0.0; }
     for (int e = lane; e < (NC + 1) * NXAP; e += 32) q.PT[e] = 0.0;   // includes the all-zero row NC
     for (int e = lane; e < 6 * N + 6; e += 32) { q.LAM[e] = 0.0; q.CRES[e] = 0.0; }
+    for (int e = lane; e < 48; e += 32) { int r_ = e >> 3, c_ = e & 7; q.ABs[e] = (c_ < 6) ? kp.p.A[6 * r_ + c_] : kp.p.B[2 * r_ + (c_ - 6)]; }
     mbar_wait(bar, 0);
     __syncwarp();
 
@@ -1576,7 +1593,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
 #ifdef B200MPC_PHASE_CLOCKS
     // profiling build: phase cycle counters replace x_pred (first 8 doubles of the instance's slot)
     if (xpred != nullptr && lane == 0)
-        for (int k = 0; k < 8; k++) xpred[(size_t)inst * 6 * (N + 1) + k] = (double)pc[k];
+        for (int k = 0; k < 13; k++) xpred[(size_t)inst * 6 * (N + 1) + k] = (k < 8) ? (double)pc[k] : (double)q.bc[k - 8];
     xpred = nullptr;
 #endif
 
