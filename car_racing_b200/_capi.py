@@ -49,6 +49,16 @@ class LmpcParams(C.Structure):
 
 
 LMPC_NMAX, LMPC_KMAX = 16, 64
+SYSID_LMAX, SYSID_PMAX = 4, 64
+
+
+class SysidParams(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("num_laps", C.c_int32), ("max_num_point", C.c_int32), ("num_segments", C.c_int32),
+        ("lap_rows", C.c_int32 * SYSID_LMAX), ("lap_stride", C.c_int32), ("reserved", C.c_int32),
+        ("dt", C.c_double), ("h", C.c_double), ("lap_length", C.c_double),
+    ]
+
 
 RECORD_DTYPE = np.dtype([("cost", "<f8"), ("u0", "<f8", (2,)), ("status", "<i4"), ("iters", "<i4")])
 assert RECORD_DTYPE.itemsize == 32
@@ -58,6 +68,7 @@ EXPORTS = [
     "b200mpc_stream", "b200mpc_launch_count", "b200mpc_cbf_record_doubles", "b200mpc_cbf_record_doubles_ex", "b200mpc_cbf_solve",
     "b200mpc_cbf_solve_device", "b200mpc_ilqr_record_doubles", "b200mpc_ilqr_solve", "b200mpc_ilqr_solve_device",
     "b200mpc_argmin_cost_device", "b200mpc_lmpc_record_doubles", "b200mpc_lmpc_solve", "b200mpc_lmpc_solve_device",
+    "b200mpc_lmpc_sysid", "b200mpc_lmpc_sysid_device",
 ]
 
 _lib = None
@@ -100,6 +111,9 @@ def lib():
     lmpc_args = [vp, C.POINTER(LmpcParams), C.POINTER(IpmOptions), ip, dp, dp, dp, dp, dp, dp]
     L.b200mpc_lmpc_solve.argtypes = lmpc_args
     L.b200mpc_lmpc_solve_device.argtypes = lmpc_args
+    sysid_args = [vp, C.POINTER(SysidParams), ip, dp, dp, dp, dp, ip, ip, dp, dp]
+    L.b200mpc_lmpc_sysid.argtypes = sysid_args
+    L.b200mpc_lmpc_sysid_device.argtypes = sysid_args
     _lib = L
     return L
 

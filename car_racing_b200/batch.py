@@ -206,3 +206,58 @@ def solve_lmpc_batch(x0, u_old, A, B, Cm, SS, Qfun, prm, want=("aux", "x", "u", 
     if lam is not None:
         out["lambda"] = lam
     return out
+
+
+def pack_laps(ss_xcurv, u_ss, time_ss, used_laps):
+    """Stored laps of the reference (ss_xcurv (T,6,L), u_ss (T,2,L), time_ss (L); base.py:430-435) -> the kernel's
+    structure-of-arrays block [lap][vx, vy, wz, delta, a][lap_stride] and the per-lap row counts."""
+    used_laps = list(used_laps)
+    rows = [int(time_ss[l]) for l in used_laps]
+    stride = (max(rows) + 2 + 1) & ~1
+    if stride > np.asarray(ss_xcurv).shape[0]:
+        stride = np.asarray(ss_xcurv).shape[0]
+    laps = np.zeros((len(used_laps), 5, stride))
+    for k, l in enumerate(used_laps):
+        laps[k, 0:3, :] = np.asarray(ss_xcurv, dtype=np.float64)[:stride, 0:3, l].T
+        laps[k, 3:5, :] = np.asarray(u_ss, dtype=np.float64)[:stride, :, l].T
+    return laps, rows, stride
+
+
+def estimate_abc_batch(lin_points, lin_input, ss_xcurv, u_ss, time_ss, used_laps, point_and_tangent, dt, max_num_point=40,
+                       h=5.0, want=("idx", "status"), handle=None, out=None, out_stride=None, out_offset=0):
+    """Batched LMPCRacingGame.estimate_ABC (base.py:585-622).  lin_points (Bn,N+1,6)|(N+1,6), lin_input (Bn,N,2)|(N,2).
+    Returns A (Bn,N,6,6), B (Bn,N,6,2), C (Bn,N,6) [+ idx, status].  With `out` (Bn,out_stride) the model block is written
+    into caller records (e.g. LMPC records, out_offset 8) instead."""
+    hd = handle or default_handle()
+    lp = np.asarray(lin_points, dtype=np.float64)
+    li = np.asarray(lin_input, dtype=np.float64)
+    if lp.ndim == 2:
+        lp, li = lp[None], li[None]
+    Bn, N = li.shape[0], li.shape[1]
+    lin = np.ascontiguousarray(np.concatenate([lp[:, :N, :], li], axis=2))       # (Bn, N, 8)
+    laps, rows, stride = pack_laps(ss_xcurv, u_ss, time_ss, used_laps)
+    pat = np.asarray(point_and_tangent, dtype=np.float64)
+    seg = np.ascontiguousarray(pat[:, 3:6])
+    p = _capi.SysidParams()
+    p.N, p.num_laps, p.max_num_point, p.num_segments = N, len(rows), int(max_num_point), seg.shape[0]
+    for k, r in enumerate(rows):
+        p.lap_rows[k] = r
+    p.lap_stride = stride
+    p.dt, p.h, p.lap_length = float(dt), float(h), float(pat[-1, 3] + pat[-1, 4])
+    own = out is None
+    if own:
+        out_stride, out_offset = 54 * N, 0
+        out = np.zeros((Bn, out_stride))
+    idx = np.zeros((Bn, N, len(rows), int(max_num_point)), dtype=np.int32) if "idx" in want else None
+    st = np.zeros((Bn, N), dtype=np.int32) if "status" in want else None
+    rc = _capi.lib().b200mpc_lmpc_sysid(hd.ptr, C.byref(p), Bn, _ptr(lin), _ptr(laps), _ptr(seg), _ptr(out), int(out_stride),
+                                        int(out_offset), _ptr(idx), _ptr(st))
+    hd.check(rc, "b200mpc_lmpc_sysid")
+    blk = out[:, out_offset:out_offset + 54 * N]
+    res = dict(A=blk[:, :36 * N].reshape(Bn, N, 6, 6), B=blk[:, 36 * N:48 * N].reshape(Bn, N, 6, 2),
+               C=blk[:, 48 * N:54 * N].reshape(Bn, N, 6))
+    if idx is not None:
+        res["idx"] = idx
+    if st is not None:
+        res["status"] = st
+    return res

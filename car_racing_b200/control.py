@@ -194,6 +194,20 @@ def lmpc(xcurv, lmpc_param, matrix_Atv, matrix_Btv, matrix_Ctv, ss_curv, Qfun, i
     return u_pred, x_pred, ss_point_selected_tot, Qfun_selected_tot, lin_points, lin_input
 
 
+def estimate_ABC(self):
+    """Drop-in for LMPCRacingGame.estimate_ABC (utils/base.py:585-622; bind with types.MethodType or assign to the class):
+    the N sequential regression_and_linearization calls become one launch.  Returns the reference's 4-tuple."""
+    N = self.lmpc_param.num_horizon
+    used_iter = range(self.iter - 2, self.iter)                      # lap_used_for_linearization = 2 (base.py:600-601)
+    r = batch.estimate_abc_batch(self.lin_points, self.lin_input, self.ss_xcurv, self.u_ss, self.time_ss, used_iter,
+                                 self.point_and_tangent, self.timestep, max_num_point=40)
+    Atv = [r["A"][0, i].copy() for i in range(N)]
+    Btv = [r["B"][0, i].copy() for i in range(N)]
+    Ctv = [r["C"][0, i].reshape(X_DIM, 1).copy() for i in range(N)]
+    index_used_list = [[row[row >= 0].astype(np.int64) for row in r["idx"][0, i]] for i in range(N)]
+    return Atv, Btv, Ctv, index_used_list
+
+
 def install(control_module=None):
     """Swap the reference's solve functions for the GPU ones (module-level monkey patch).
     `control_module` defaults to the reference's `control.control` if it is importable."""

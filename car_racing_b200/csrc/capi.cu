@@ -10,6 +10,7 @@
 #include "ilqr.cuh"
 #include "lmpc.cuh"
 #include "ocp_ipm.cuh"
+#include "sysid.cuh"
 
 using namespace b200mpc;
 
@@ -21,7 +22,8 @@ struct b200mpc_handle {
     int max_smem_optin = 0;
     // staging buffers for the host-pointer API (grown on demand)
     void *d_in = nullptr, *d_rec = nullptr, *d_aux = nullptr, *d_x = nullptr, *d_u = nullptr, *d_sig = nullptr;
-    size_t c_in = 0, c_rec = 0, c_aux = 0, c_x = 0, c_u = 0, c_sig = 0;
+    void *d_laps = nullptr, *d_seg = nullptr, *d_idx = nullptr, *d_stat = nullptr;
+    size_t c_in = 0, c_rec = 0, c_aux = 0, c_x = 0, c_u = 0, c_sig = 0, c_laps = 0, c_seg = 0, c_idx = 0, c_stat = 0;
     uint64_t launches = 0;
     std::string err;
 };
@@ -99,7 +101,7 @@ void b200mpc_destroy(b200mpc_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void *bufs[] = {h->d_in, h->d_rec, h->d_aux, h->d_x, h->d_u, h->d_sig};
+    void *bufs[] = {h->d_in, h->d_rec, h->d_aux, h->d_x, h->d_u, h->d_sig, h->d_laps, h->d_seg, h->d_idx, h->d_stat};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -336,6 +338,78 @@ int b200mpc_lmpc_solve(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const 
     if (xpred) CK(h, cudaMemcpyAsync(xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
     if (upred) CK(h, cudaMemcpyAsync(upred, h->d_u, b_u, cudaMemcpyDeviceToHost, h->stream));
     if (lambda) CK(h, cudaMemcpyAsync(lambda, h->d_sig, b_l, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+static size_t sysid_smem(const b200mpc_sysid_params *p) {
+    size_t d = (size_t)((p->lap_stride + 1) & ~1) + (size_t)((p->num_laps * p->max_num_point + 1) & ~1) / 2 +
+               (size_t)p->num_laps * p->max_num_point + 40 + 96 + 56;
+    return d * sizeof(double);
+}
+
+static int check_sysid(b200mpc_handle *h, const b200mpc_sysid_params *p, int B, const void *lin, const void *laps,
+                       const void *seg, const void *out, int out_stride, int out_offset) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!p || !lin || !laps || !seg || !out || B < 1) return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_sysid: null argument or B < 1");
+    if (p->N < 1 || p->N > B200MPC_NMAX || p->num_laps < 1 || p->num_laps > B200MPC_SYSID_LMAX || p->max_num_point < 1 ||
+        p->max_num_point > B200MPC_SYSID_PMAX || p->num_segments < 1 || p->lap_stride < 2)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_sysid: size out of range");
+    for (int l = 0; l < p->num_laps; l++)
+        if (p->lap_rows[l] < 2 || p->lap_rows[l] >= p->lap_stride)
+            return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_sysid: lap_rows must satisfy 2 <= time_ss < lap_stride");
+    if (!(p->dt > 0.0) || !(p->h > 0.0) || !(p->lap_length > 0.0) || out_offset < 0 || out_stride < out_offset + 54 * p->N)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_sysid: bad parameter value");
+    if ((int)sysid_smem(p) > h->max_smem_optin) return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_sysid: laps too long for shared memory");
+    return B200MPC_OK;
+}
+
+int b200mpc_lmpc_sysid_device(b200mpc_handle *h, const b200mpc_sysid_params *prm, int B, const double *d_lin,
+                              const double *d_laps, const double *d_segments, double *d_out, int out_stride, int out_offset,
+                              int32_t *d_idx, int32_t *d_status) {
+    int rc = check_sysid(h, prm, B, d_lin, d_laps, d_segments, d_out, out_stride, out_offset);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    SysidKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.p = *prm;
+    kp.B = B;
+    kp.out_stride = out_stride;
+    kp.out_offset = out_offset;
+    size_t smem = sysid_smem(prm);
+    CK(h, cudaFuncSetAttribute(sysid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sysid_kernel<<<B * prm->N, 32, smem, h->stream>>>(kp, d_lin, d_laps, d_segments, d_out, d_idx, d_status);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+int b200mpc_lmpc_sysid(b200mpc_handle *h, const b200mpc_sysid_params *prm, int B, const double *lin, const double *laps,
+                       const double *segments, double *out, int out_stride, int out_offset, int32_t *idx, int32_t *status) {
+    int rc = check_sysid(h, prm, B, lin, laps, segments, out, out_stride, out_offset);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    const int N = prm->N;
+    const size_t b_lin = (size_t)B * N * 64, b_laps = (size_t)prm->num_laps * 5 * prm->lap_stride * 8, b_seg = (size_t)prm->num_segments * 24;
+    const size_t b_out = (size_t)B * out_stride * 8, b_idx = (size_t)B * N * prm->num_laps * prm->max_num_point * 4, b_st = (size_t)B * N * 4;
+    if ((rc = grow(h, &h->d_in, &h->c_in, b_lin))) return rc;
+    if ((rc = grow(h, &h->d_laps, &h->c_laps, b_laps))) return rc;
+    if ((rc = grow(h, &h->d_seg, &h->c_seg, b_seg))) return rc;
+    if ((rc = grow(h, &h->d_x, &h->c_x, b_out))) return rc;
+    if (idx && (rc = grow(h, &h->d_idx, &h->c_idx, b_idx))) return rc;
+    if (status && (rc = grow(h, &h->d_stat, &h->c_stat, b_st))) return rc;
+    CK(h, cudaMemcpyAsync(h->d_in, lin, b_lin, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_laps, laps, b_laps, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_seg, segments, b_seg, cudaMemcpyHostToDevice, h->stream));
+    rc = b200mpc_lmpc_sysid_device(h, prm, B, (const double *)h->d_in, (const double *)h->d_laps, (const double *)h->d_seg,
+                                   (double *)h->d_x, out_stride, out_offset, idx ? (int32_t *)h->d_idx : nullptr,
+                                   status ? (int32_t *)h->d_stat : nullptr);
+    if (rc) return rc;
+    // only the model block of each record comes back: the caller's other fields stay untouched
+    CK(h, cudaMemcpy2DAsync(out + out_offset, (size_t)out_stride * 8, (const double *)h->d_x + out_offset, (size_t)out_stride * 8,
+                            (size_t)54 * N * 8, B, cudaMemcpyDeviceToHost, h->stream));
+    if (idx) CK(h, cudaMemcpyAsync(idx, h->d_idx, b_idx, cudaMemcpyDeviceToHost, h->stream));
+    if (status) CK(h, cudaMemcpyAsync(status, h->d_stat, b_st, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }

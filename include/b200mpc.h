@@ -10,6 +10,8 @@
  *                         <- control.mpccbf           (control.py:476-607)       M = rivals kept
  *                         <- control.mpc_multi_agents (control.py:251-473)       per-stage targets
  *   b200mpc_ilqr_solve    <- control.ilqr             (control.py:64-195, ilqr_helper.py:4-55)
+ *   b200mpc_lmpc_solve    <- control.lmpc             (control.py:610-730)
+ *   b200mpc_lmpc_sysid    <- LMPCRacingGame.estimate_ABC (utils/base.py:585-622, control/lmpc_helper.py:26-264)
  *   b200mpc_argmin_cost   <- the argmin of OvertakeTrajPlanner.solve_optimization_problem
  *                            (car_racing/planning/overtake_traj_planner.py:244)
  *
@@ -168,6 +170,38 @@ int b200mpc_lmpc_solve(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const 
 int b200mpc_lmpc_solve_device(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const b200mpc_ipm_options *opt, int B,
                               const double *d_in, b200mpc_record *d_rec, double *d_aux, double *d_xpred, double *d_upred,
                               double *d_lambda);
+
+/* LMPC model identification: LMPCRacingGame.estimate_ABC (utils/base.py:585-622) = per horizon stage
+ * lmpc_helper.regression_and_linearization (control/lmpc_helper.py:26-201).  Replaces the N sequential calls (each
+ * 2 nearest-neighbour scans over whole stored laps + 3 cvxopt solves) by one launch, one warp per (instance, stage). */
+#define B200MPC_SYSID_LMAX 4  /* laps used for the regression (2: iter-2, iter-1; base.py:600-601) */
+#define B200MPC_SYSID_PMAX 64 /* max_num_point (40, base.py:602) */
+typedef struct {
+    int32_t N;                 /* horizon stages (lmpc_param.num_horizon) */
+    int32_t num_laps;          /* laps in `laps`, 1..B200MPC_SYSID_LMAX */
+    int32_t max_num_point;     /* 1..B200MPC_SYSID_PMAX */
+    int32_t num_segments;      /* rows of `segments` (track.point_and_tangent) */
+    int32_t lap_rows[B200MPC_SYSID_LMAX]; /* time_ss of each lap: rows 0..time_ss-2 are candidates, row t+1 is the target */
+    int32_t lap_stride;        /* allocated rows per (lap, field) */
+    int32_t reserved;
+    double dt;                 /* timestep */
+    double h;                  /* kernel bandwidth, 5 (lmpc_helper.py:45) */
+    double lap_length;         /* point_and_tangent[-1,3] + point_and_tangent[-1,4] (lmpc_helper.py:143) */
+} b200mpc_sysid_params;
+
+/* lin      : B x N x 8   (lin_points[i, 0:6], lin_input[i, 0:2]) per instance and stage
+ * laps     : num_laps x 5 x lap_stride, fields (vx, vy, wz, delta, a) of the stored laps (ss_xcurv[:, 0:3, lap], u_ss[:, :, lap])
+ * segments : num_segments x 3  (s_start, length, curvature) = point_and_tangent[:, 3:6]
+ * out      : per instance A_0..A_{N-1} (36 each, row-major), B_i (12 each), C_i (6 each) written at
+ *            out + b*out_stride + out_offset -- with out_offset = 8 and out_stride = b200mpc_lmpc_record_doubles(N, K)
+ *            this is the model block of the LMPC record, so the two kernels chain on the device
+ * idx      : optional B x N x num_laps x max_num_point selected rows (-1 padded) = index_used_list (base.py:621)
+ * status   : optional B x N, 0 ok, bit0 singular normal equations, bit1 s outside the track table, bit2 < 5 points */
+int b200mpc_lmpc_sysid(b200mpc_handle *h, const b200mpc_sysid_params *prm, int B, const double *lin, const double *laps,
+                       const double *segments, double *out, int out_stride, int out_offset, int32_t *idx, int32_t *status);
+int b200mpc_lmpc_sysid_device(b200mpc_handle *h, const b200mpc_sysid_params *prm, int B, const double *d_lin,
+                              const double *d_laps, const double *d_segments, double *d_out, int out_stride, int out_offset,
+                              int32_t *d_idx, int32_t *d_status);
 
 /* argmin over records (device pointers): index of the smallest cost among status<=max_status,
  * lowest index wins ties (list.index(min(...)), overtake_traj_planner.py:244); *d_out = -1 if none. */

@@ -396,3 +396,69 @@ def test_lmpc_drop_in_on_gpu(crb, oracle):
     if r["status"][0] == 0:
         assert np.abs(u_pred - r["u"][0]).max() < 1e-4 and np.abs(x_pred - r["x"][0]).max() < 1e-4
     assert np.allclose(lin_points[:-1], x_pred[1:]) and np.allclose(lin_input[:-1], u_pred[1:])
+
+
+def _sysid_gold():
+    g = np.load(os.path.join(GOLD, "sysid_golden.npz"))
+    return {k: g[k] for k in g.files}
+
+
+def test_sysid_matches_reference_golden(crb):
+    """LMPC model identification against outputs of the reference's own
+    regression_and_linearization (tests/golden/make_sysid_golden.py)."""
+    g = _sysid_gold()
+    r = crb.estimate_abc_batch(g["lin_points"], g["lin_input"], g["ss"], g["us"], g["time_ss"], [0, 1], g["point_and_tangent"],
+                               float(g["dt"]), int(g["max_num_point"]))
+    assert (r["status"] == 0).all()
+    assert (r["idx"] == g["idx"]).all()                     # same neighbours, same order
+    # regression rows: normal equations with cond ~1e6 solved in a different summation order -> 1e-8; analytic rows: exact
+    assert np.abs(r["A"] - g["A"]).max() < 1e-8 and np.abs(r["B"] - g["B"]).max() < 1e-8 and np.abs(r["C"] - g["C"]).max() < 1e-8
+    assert np.abs(r["A"][:, :, 3:] - g["A"][:, :, 3:]).max() < 1e-13 and np.abs(r["C"][:, :, 3:] - g["C"][:, :, 3:]).max() < 1e-11
+
+
+def test_sysid_batch_vs_restatement_and_few_points(crb):
+    import sysid_numpy
+    g = _sysid_gold()
+    rng = np.random.default_rng(3)
+    Bn, N = 40, 12
+    lap = rng.integers(0, 2, Bn)
+    t0 = np.array([rng.integers(1, g["time_ss"][l] - N - 3) for l in lap])
+    lp = np.stack([g["ss"][t:t + N + 1, :, l] for t, l in zip(t0, lap)]) + rng.normal(scale=0.01, size=(Bn, N + 1, 6))
+    lp[:, :, 4] = np.abs(lp[:, :, 4]) + 1e-3
+    li = np.stack([g["us"][t:t + N, :, l] for t, l in zip(t0, lap)]) + rng.normal(scale=0.01, size=(Bn, N, 2))
+    r = crb.estimate_abc_batch(lp, li, g["ss"], g["us"], g["time_ss"], [0, 1], g["point_and_tangent"], 0.1)
+    A, B, C, idx = sysid_numpy.estimate_abc(lp, li, g["ss"], g["us"], g["time_ss"], [0, 1], g["point_and_tangent"], 0.1)
+    assert (r["idx"] == idx).all() and (r["status"] == 0).all()
+    assert np.abs(r["A"] - A).max() < 1e-8 and np.abs(r["B"] - B).max() < 1e-8 and np.abs(r["C"] - C).max() < 1e-8
+    # fewer than max_num_point rows inside the bandwidth: "all rows, in row order" branch (lmpc_helper.py:234-235)
+    ss2, us2 = g["ss"].copy(), g["us"].copy()
+    ss2[30:, 0, :] += 80.0                                   # vx far away: scaled distance 8 > h for rows >= 30
+    ts2 = g["time_ss"].copy()
+    lp2, li2 = lp[:4].copy(), li[:4].copy()
+    lp2[:, :, 0] = ss2[5, 0, 0]
+    r2 = crb.estimate_abc_batch(lp2, li2, ss2, us2, ts2, [0, 1], g["point_and_tangent"], 0.1)
+    A2, B2, C2, idx2 = sysid_numpy.estimate_abc(lp2, li2, ss2, us2, ts2, [0, 1], g["point_and_tangent"], 0.1)
+    assert (r2["idx"] == idx2).all() and (idx2[:, :, :, 30:] == -1).all()
+    assert np.abs(r2["A"] - A2).max() < 1e-7 and np.abs(r2["C"] - C2).max() < 1e-7
+
+
+def test_sysid_chains_into_lmpc_records_and_drop_in(crb, oracle):
+    """estimate_ABC writes the model block of LMPC records in place; LMPCRacingGame.estimate_ABC drop-in returns lists."""
+    from types import SimpleNamespace
+    from car_racing_b200 import batch, control
+    g = _sysid_gold()
+    N, K = 12, 44
+    stride = batch.lmpc_record_doubles(N, K)
+    rec = np.full((3, stride), 7.0)
+    r = crb.estimate_abc_batch(g["lin_points"][:3], g["lin_input"][:3], g["ss"], g["us"], g["time_ss"], [0, 1],
+                               g["point_and_tangent"], 0.1, out=rec, out_stride=stride, out_offset=8)
+    assert (rec[:, :8] == 7.0).all() and (rec[:, 8 + 54 * N:] == 7.0).all()
+    assert np.abs(rec[:, 8:8 + 36 * N].reshape(3, N, 6, 6) - g["A"][:3]).max() < 1e-8
+    assert np.abs(rec[:, 8 + 48 * N:8 + 54 * N].reshape(3, N, 6) - g["C"][:3]).max() < 1e-8
+    game = SimpleNamespace(lmpc_param=SimpleNamespace(num_horizon=N), iter=2, lin_points=g["lin_points"][5],
+                           lin_input=g["lin_input"][5], ss_xcurv=g["ss"], u_ss=g["us"], time_ss=g["time_ss"],
+                           point_and_tangent=g["point_and_tangent"], timestep=0.1)
+    Atv, Btv, Ctv, used = control.estimate_ABC(game)
+    assert len(Atv) == N and Atv[0].shape == (6, 6) and Btv[0].shape == (6, 2) and Ctv[0].shape == (6, 1) and len(used[0]) == 2
+    assert np.abs(np.array(Atv) - g["A"][5]).max() < 1e-8 and np.abs(np.array(Ctv)[:, :, 0] - g["C"][5]).max() < 1e-8
+    assert (used[3][1] == g["idx"][5, 3, 1]).all()
