@@ -308,7 +308,7 @@ int b200mpc_lmpc_solve_device(b200mpc_handle *h, const b200mpc_lmpc_params *prm,
     if ((int)smem > h->max_smem_optin)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_solve: N, K too large for one CTA's shared memory");
     CK(h, cudaFuncSetAttribute(lmpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lmpc_kernel<<<B, 32, smem, h->stream>>>(kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_lambda);
+    lmpc_kernel<<<B, LMPC_NT, smem, h->stream>>>(kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_lambda);
     CK(h, cudaGetLastError());
     h->launches++;
     return B200MPC_OK;

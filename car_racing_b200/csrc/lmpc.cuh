@@ -3,13 +3,14 @@
 //   min   sum_{i<N}[(x_i-x_trk)'Q(.) + u_i'R u_i + (u_i-u_{i-1})'dR(.)] + (x_N-x_trk)'Q(.) + Qfun'lambda   (:667-695)
 //   s.t.  x_0 = xcurv; x_{i+1} = A_i x_i + B_i u_i + C_i (LTV, :653-656); vx_i<=v_max, |ey_i|<=lap_width, i<N (:658-660)
 //         |u| <= (delta_max, a_max) (:662-666); lambda >= 0, x_N = SS lambda, 1'lambda = 1 (:689-692)
-// One warp per instance, same interior-point definition as the MPC-CBF kernel (the QP is convex).
+// One CTA of 4 warps per instance (occupancy is set by shared memory: 79 KB at N=12, K=44 -> 2 CTAs/SM, so the extra
+// warps are free), same interior-point definition as the MPC-CBF kernel (the QP is convex).
 //
 // Linear algebra: NOT a Riccati sweep.  Near the optimum only ~3 of the 44 lambdas leave their bound, so any stage-wise
 // elimination of the terminal hull constraint meets a 7x7 Schur complement with condition number > 1e15 (measured in the
 // oracle's first draft).  Instead the states are condensed through the LTV model once per solve (dx = G du + dx_p, G in
-// shared memory) and the reduced KKT system in (du, dlambda, nu) -- 75x75 at N=12, K=44 -- is solved by a warp-level LU
-// with partial pivoting.  Dynamics multipliers follow from the costate recursion.
+// shared memory) and the reduced KKT system in (du, dlambda, nu) -- 75x75 at N=12, K=44 -- is solved by a CTA-level LU
+// with partial pivoting (16 rows x 8 column lanes per pass).  Dynamics multipliers follow from the costate recursion.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,7 +29,7 @@ __host__ __device__ inline int lmpc_record_doubles(int N, int K) { return (8 + 5
 
 struct LmpcPlan {
     int N, K, NX, NU, NW, NR, ND, ME;
-    int oIN, oW, oD, oZL, oZU, oGF, oRHS, oSIG, oDP, oKD, oLAM, oLAMN, oCEQ, oG, oRQ, oKK, oPIV, total;
+    int oIN, oW, oD, oZL, oZU, oGF, oRHS, oSIG, oDP, oKD, oLAM, oLAMN, oCEQ, oG, oRQ, oKK, oPIV, oRED, oXS, total;
     __host__ __device__ LmpcPlan(int N_, int K_, int in_stride) {
         N = N_; K = K_;
         NX = 6 * (N + 1); NU = 2 * N; NW = NX + NU + K; NR = NU + K; ND = NR + 7; ME = 6 * N + 7;
@@ -39,39 +40,57 @@ struct LmpcPlan {
         oDP = take(NX); oKD = take(NX);
         oLAM = take(ME); oLAMN = take(ME); oCEQ = take(ME);
         oG = take(6 * N * NU); oRQ = take(NU * NU);
-        oKK = take(ND * (ND + 1)); oPIV = take(ND);
+        oKK = take(ND * (ND + 1)); oPIV = take(ND + 2); oRED = take(16); oXS = take(ND);
         total = o;
     }
     __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(double); }
 };
 
-__global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKParams kp, const double *__restrict__ in,
+constexpr int LMPC_NT = 128;   // threads per instance
+
+__global__ void __launch_bounds__(LMPC_NT) lmpc_kernel(const __grid_constant__ LmpcKParams kp, const double *__restrict__ in,
                                                   b200mpc_record *__restrict__ rec, double *__restrict__ aux,
                                                   double *__restrict__ xpred, double *__restrict__ upred,
                                                   double *__restrict__ lambda_out) {
     extern __shared__ __align__(16) double sm[];
-    const int lane = threadIdx.x, inst = blockIdx.x;
+    constexpr int NT = LMPC_NT;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, inst = blockIdx.x;
     const int N = kp.p.N, K = kp.p.K;
     const LmpcPlan pl(N, K, kp.in_stride);
     const int NX = pl.NX, NU = pl.NU, NW = pl.NW, NR = pl.NR, ND = pl.ND, ME = pl.ME, OU = NX, OL = NX + NU, LD = ND + 1;
     double *IN = sm + pl.oIN, *W = sm + pl.oW, *D = sm + pl.oD, *ZL = sm + pl.oZL, *ZU = sm + pl.oZU, *GF = sm + pl.oGF;
     double *RHS = sm + pl.oRHS, *SIG = sm + pl.oSIG, *DP = sm + pl.oDP, *KD = sm + pl.oKD, *LAM = sm + pl.oLAM, *LAMN = sm + pl.oLAMN;
-    double *CEQ = sm + pl.oCEQ, *G = sm + pl.oG, *RQ = sm + pl.oRQ, *KK = sm + pl.oKK;
+    double *CEQ = sm + pl.oCEQ, *G = sm + pl.oG, *RQ = sm + pl.oRQ, *KK = sm + pl.oKK, *PIV = sm + pl.oPIV, *RED = sm + pl.oRED, *XS = sm + pl.oXS;
+    int red_phase = 0;
+    // block reductions: one barrier each (two alternating scratch rows)
+    auto bred = [&](double v, int op) -> double {
+        v = (op == 0) ? warp_sum(v) : ((op == 1) ? warp_max(v) : warp_min(v));
+        double *r = RED + 4 * (red_phase & 1) + ((red_phase & 2) ? 8 : 0);
+        red_phase++;
+        if (lane == 0) r[wid] = v;
+        __syncthreads();
+        if (op == 0) return (r[0] + r[1]) + (r[2] + r[3]);
+        if (op == 1) return fmax(fmax(r[0], r[1]), fmax(r[2], r[3]));
+        return fmin(fmin(r[0], r[1]), fmin(r[2], r[3]));
+    };
+    auto bsum = [&](double v) { return bred(v, 0); };
+    auto bmax = [&](double v) { return bred(v, 1); };
+    auto bmin = [&](double v) { return bred(v, 2); };
     const b200mpc_ipm_options &o = kp.o;
 
     uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
     const uint32_t in_bytes = (uint32_t)kp.in_stride * 8u;
-    if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
-    if (lane == 0) {
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
         mbar_expect_tx(bar, in_bytes);
         bulk_g2s(IN, in + (size_t)inst * kp.in_stride, in_bytes, bar);
     }
-    for (int e = lane; e < NW; e += 32) { W[e] = 0.0; D[e] = 0.0; ZL[e] = 0.0; ZU[e] = 0.0; }
-    for (int e = lane; e < ME; e += 32) { LAM[e] = 0.0; LAMN[e] = 0.0; }
-    for (int e = lane; e < NX; e += 32) { DP[e] = 0.0; KD[e] = 0.0; }
+    for (int e = tid; e < NW; e += NT) { W[e] = 0.0; D[e] = 0.0; ZL[e] = 0.0; ZU[e] = 0.0; }
+    for (int e = tid; e < ME; e += NT) { LAM[e] = 0.0; LAMN[e] = 0.0; }
+    for (int e = tid; e < NX; e += NT) { DP[e] = 0.0; KD[e] = 0.0; }
     mbar_wait(bar, 0);
-    __syncwarp();
+    __syncthreads();
     const double *x0 = IN, *u_old = IN + 6, *Am = IN + 8, *Bm = Am + 36 * N, *Cm = Bm + 12 * N, *SS = Cm + 6 * N, *Qf = SS + 6 * K;
     const double *Q = kp.p.Q, *R = kp.p.R, *dR = kp.p.dR, *xtrk = kp.p.xtrk;
 
@@ -95,20 +114,23 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
     };
 
     // ---- start: u = 0 roll-out through the LTV model, lambda = 1/K, pushed into the bounds
-    if (lane < 6) W[lane] = x0[lane];
-    __syncwarp();
-    for (int i = 0; i < N; i++) {
-        if (lane < 6) {
-            double s = Cm[6 * i + lane];
-            for (int b = 0; b < 6; b++) s += Am[36 * i + 6 * lane + b] * W[6 * i + b];
-            W[6 * (i + 1) + lane] = s;
-        }
+    if (wid == 0) {   // sequential recursions run on warp 0 with warp barriers
+        if (lane < 6) W[lane] = x0[lane];
         __syncwarp();
+        for (int i = 0; i < N; i++) {
+            if (lane < 6) {
+                double s = Cm[6 * i + lane];
+                for (int b = 0; b < 6; b++) s += Am[36 * i + 6 * lane + b] * W[6 * i + b];
+                W[6 * (i + 1) + lane] = s;
+            }
+            __syncwarp();
+        }
     }
-    for (int k = lane; k < K; k += 32) W[OL + k] = 1.0 / (double)K;
-    __syncwarp();
+    __syncthreads();
+    for (int k = tid; k < K; k += NT) W[OL + k] = 1.0 / (double)K;
+    __syncthreads();
     int nbc = 0;
-    for (int e = 6 + lane; e < NW; e += 32) {
+    for (int e = 6 + tid; e < NW; e += NT) {
         bool hl = has_l(e), hu = has_u(e);
         double w = W[e], lb = lbv(e), ub = ubv(e);
         if (hl) {
@@ -126,13 +148,13 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
         ZU[e] = hu ? 1.0 : 0.0;
         nbc += (hl ? 1 : 0) + (hu ? 1 : 0);
     }
-    for (int off = 16; off > 0; off >>= 1) nbc += __shfl_xor_sync(0xffffffffu, nbc, off);
-    __syncwarp();
+    nbc = (int)(bsum((double)nbc) + 0.5);
+    __syncthreads();
     // ---- G: x_i = sum_l G[6(i-1)+a][2l+b] u_l + ...   (rows for x_1..x_N)
-    for (int e = lane; e < 6 * N * NU; e += 32) G[e] = 0.0;
-    __syncwarp();
+    for (int e = tid; e < 6 * N * NU; e += NT) G[e] = 0.0;
+    __syncthreads();
     for (int i = 0; i < N; i++) {   // row block of x_{i+1}
-        for (int e = lane; e < 6 * NU; e += 32) {
+        for (int e = tid; e < 6 * NU; e += NT) {
             int a = e / NU, c = e - a * NU, l = c >> 1;
             double v = 0.0;
             if (l == i) v = Bm[12 * i + 2 * a + (c & 1)];
@@ -141,14 +163,14 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             }
             G[(6 * i + a) * NU + c] = v;
         }
-        __syncwarp();
+        __syncthreads();
     }
 
     double df = 1.0, mu = o.mu_init;
     // ---- objective, gradient (into GF, unscaled), equality residual
     auto objective = [&](const double *Wp, double al, bool useD) -> double {
         double f = 0.0;
-        for (int e = lane; e < 6 * (N + 1); e += 32) {
+        for (int e = tid; e < 6 * (N + 1); e += NT) {
             int i = e / 6, a = e - 6 * i;
             double acc = 0.0, da = 0.0;
             for (int b = 0; b < 6; b++) {
@@ -158,18 +180,18 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             }
             f += da * acc;
         }
-        for (int i = lane; i < N; i += 32) {
+        for (int i = tid; i < N; i += NT) {
             double u0 = Wp[OU + 2 * i] + (useD ? al * D[OU + 2 * i] : 0.0), u1 = Wp[OU + 2 * i + 1] + (useD ? al * D[OU + 2 * i + 1] : 0.0);
             double p0 = i ? Wp[OU + 2 * i - 2] + (useD ? al * D[OU + 2 * i - 2] : 0.0) : u_old[0];
             double p1 = i ? Wp[OU + 2 * i - 1] + (useD ? al * D[OU + 2 * i - 1] : 0.0) : u_old[1];
             double d0 = u0 - p0, d1 = u1 - p1;
             f += u0 * (R[0] * u0 + R[1] * u1) + u1 * (R[2] * u0 + R[3] * u1) + d0 * (dR[0] * d0 + dR[1] * d1) + d1 * (dR[2] * d0 + dR[3] * d1);
         }
-        for (int k = lane; k < K; k += 32) f += Qf[k] * (Wp[OL + k] + (useD ? al * D[OL + k] : 0.0));
-        return warp_sum(f);
+        for (int k = tid; k < K; k += NT) f += Qf[k] * (Wp[OL + k] + (useD ? al * D[OL + k] : 0.0));
+        return bsum(f);
     };
     auto gradient = [&]() {   // GF <- unscaled gradient of f at W
-        for (int e = 6 + lane; e < NW; e += 32) {
+        for (int e = 6 + tid; e < NW; e += NT) {
             double g;
             if (e < NX) {
                 int i = e / 6, a = e - 6 * i;
@@ -192,7 +214,7 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
     };
     auto residual = [&](double al, bool useD, double *out) -> double {   // equality residuals at W+al*D; returns the 1-norm
         double th = 0.0;
-        for (int e = lane; e < ME; e += 32) {
+        for (int e = tid; e < ME; e += NT) {
             double s;
             if (e < 6 * N) {
                 int i = e / 6, a = e - 6 * i;
@@ -211,21 +233,21 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             if (out) out[e] = s;
             th += fabs(s);
         }
-        return warp_sum(th);
+        return bsum(th);
     };
     auto barrier = [&](double al, bool useD) -> double {
         LogAcc la;
-        for (int e = 6 + lane; e < NW; e += 32) {
+        for (int e = 6 + tid; e < NW; e += NT) {
             double w = W[e] + (useD ? al * D[e] : 0.0);
             if (has_l(e)) la.mul(w - lbv(e));
             if (has_u(e)) la.mul(ubv(e) - w);
         }
-        return warp_sum(la.value());
+        return bsum(la.value());
     };
     // optimality error (same scaling as the oracle); needs GF, CEQ current
     auto kkt_error = [&](double m) -> double {
         double dual = 0.0, prim = 0.0, comp = 0.0, zsum = 0.0, ysum = 0.0;
-        for (int e = 6 + lane; e < NW; e += 32) {
+        for (int e = 6 + tid; e < NW; e += NT) {
             double rw = df * GF[e] - ZL[e] + ZU[e];
             if (e < NX) {
                 int i = e / 6, a = e - 6 * i;
@@ -244,8 +266,8 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             if (has_l(e)) { comp = fmax(comp, fabs((W[e] - lbv(e)) * ZL[e] - m)); zsum += ZL[e]; }
             if (has_u(e)) { comp = fmax(comp, fabs((ubv(e) - W[e]) * ZU[e] - m)); zsum += ZU[e]; }
         }
-        for (int e = lane; e < ME; e += 32) { prim = fmax(prim, fabs(CEQ[e])); ysum += fabs(LAM[e]); }
-        dual = warp_max(dual); prim = warp_max(prim); comp = warp_max(comp); zsum = warp_sum(zsum); ysum = warp_sum(ysum);
+        for (int e = tid; e < ME; e += NT) { prim = fmax(prim, fabs(CEQ[e])); ysum += fabs(LAM[e]); }
+        dual = bmax(dual); prim = bmax(prim); comp = bmax(comp); zsum = bsum(zsum); ysum = bsum(ysum);
         const double s_max = 100.0;
         int nmul = ME + nbc;
         double sd = fmax(s_max, (ysum + zsum) / (double)(nmul > 0 ? nmul : 1)) / s_max;
@@ -255,15 +277,15 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
 
     // ---- scaling
     gradient();
-    __syncwarp();
+    __syncthreads();
     {
         double gm = 0.0;
-        for (int e = 6 + lane; e < NW; e += 32) gm = fmax(gm, fabs(GF[e]));
-        gm = warp_max(gm);
+        for (int e = 6 + tid; e < NW; e += NT) gm = fmax(gm, fabs(GF[e]));
+        gm = bmax(gm);
         df = gm > o.max_grad ? o.max_grad / gm : 1.0;
     }
     // RQ = sum_i G_i' (df*(Q+Q')) G_i  (iteration independent)
-    for (int e = lane; e < NU * NU; e += 32) {
+    for (int e = tid; e < NU * NU; e += NT) {
         int a = e / NU, b = e - a * NU;
         double s = 0.0;
         for (int i = 0; i < N; i++)
@@ -274,9 +296,9 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             }
         RQ[e] = df * s;
     }
-    __syncwarp();
+    __syncthreads();
     double th0 = residual(0.0, false, CEQ);
-    __syncwarp();
+    __syncthreads();
     const double theta_max = 1e4 * fmax(1.0, th0), theta_min = 1e-4 * fmax(1.0, th0);
     double f_th0 = 0.0, f_ph0 = 0.0, f_th1 = 0.0, f_ph1 = 0.0;
     int nfilt = 0, fpos = 0, iter = 0, status = B200MPC_MAX_ITER, n_acc = 0, n_back = 0;
@@ -288,7 +310,7 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
     for (;;) {
         gradient();
         residual(0.0, false, CEQ);
-        __syncwarp();
+        __syncthreads();
         E0 = kkt_error(0.0);
         if (E0 <= o.tol) { status = B200MPC_SOLVED; break; }
         if (E0 <= o.acceptable_tol) {
@@ -307,7 +329,7 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
         }
         const double tau = fmax(tau_min, 1.0 - mu);
         // ---- barrier diagonal and right-hand side
-        for (int e = 6 + lane; e < NW; e += 32) {
+        for (int e = 6 + tid; e < NW; e += NT) {
             double sw = 0.0, b = -df * GF[e];
             if (has_l(e)) { double id = rcp(W[e] - lbv(e)); sw += ZL[e] * id; b += mu * id; }
             if (has_u(e)) { double id = rcp(ubv(e) - W[e]); sw += ZU[e] * id; b -= mu * id; }
@@ -315,28 +337,31 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             RHS[e] = b;
         }
         // particular solution of the dynamics rows (du = 0)
-        if (lane < 6) DP[lane] = 0.0;
-        __syncwarp();
-        for (int i = 0; i < N; i++) {
-            if (lane < 6) {
-                double s = -CEQ[6 * i + lane];
-                for (int b = 0; b < 6; b++) s += Am[36 * i + 6 * lane + b] * DP[6 * i + b];
-                DP[6 * (i + 1) + lane] = s;
-            }
+        if (wid == 0) {
+            if (lane < 6) DP[lane] = 0.0;
             __syncwarp();
+            for (int i = 0; i < N; i++) {
+                if (lane < 6) {
+                    double s = -CEQ[6 * i + lane];
+                    for (int b = 0; b < 6; b++) s += Am[36 * i + 6 * lane + b] * DP[6 * i + b];
+                    DP[6 * (i + 1) + lane] = s;
+                }
+                __syncwarp();
+            }
         }
+        __syncthreads();
         // KD = K_xx dp  (x part of K applied to the particular solution)
-        for (int e = 6 + lane; e < NX; e += 32) {
+        for (int e = 6 + tid; e < NX; e += NT) {
             int i = e / 6, a = e - 6 * i;
             double s = SIG[e] * DP[e];
             for (int b = 0; b < 6; b++) s += df * (Q[6 * a + b] + Q[6 * b + a]) * DP[6 * i + b];
             KD[e] = s;
         }
-        __syncwarp();
+        __syncthreads();
         // ---- reduced KKT matrix  [Rh E'; E 0 | rhs]
-        for (int e = lane; e < ND * LD; e += 32) KK[e] = 0.0;
-        __syncwarp();
-        for (int e = lane; e < NU * NU; e += 32) {   // Rh_uu = RQ + G' diag(sig_x) G + K_uu
+        for (int e = tid; e < ND * LD; e += NT) KK[e] = 0.0;
+        __syncthreads();
+        for (int e = tid; e < NU * NU; e += NT) {   // Rh_uu = RQ + G' diag(sig_x) G + K_uu
             int a = e / NU, b = e - a * NU;
             double s = RQ[e];
             for (int r = 0; r < 6 * N; r++) {
@@ -349,7 +374,7 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             else if (ia == ib + 1 || ib == ia + 1) s -= df * d2;
             KK[a * LD + b] = s;
         }
-        for (int k = lane; k < K; k += 32) {
+        for (int k = tid; k < K; k += NT) {
             KK[(NU + k) * LD + NU + k] = SIG[OL + k];
             for (int a = 0; a < 6; a++) {
                 KK[(NU + k) * LD + NR + a] = -SS[a * K + k];
@@ -359,91 +384,101 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             KK[(NR + 6) * LD + NU + k] = 1.0;
             KK[(NU + k) * LD + ND] = RHS[OL + k];
         }
-        for (int e = lane; e < 6 * NU; e += 32) {
+        for (int e = tid; e < 6 * NU; e += NT) {
             int a = e / NU, c = e - a * NU;
             double v = G[(6 * (N - 1) + a) * NU + c];
             KK[(NR + a) * LD + c] = v;
             KK[c * LD + NR + a] = v;
         }
-        for (int c = lane; c < NU; c += 32) {   // rr_u = rhs_u + G'(rhs_x - K_xx dp)
+        for (int c = tid; c < NU; c += NT) {   // rr_u = rhs_u + G'(rhs_x - K_xx dp)
             double s = RHS[OU + c];
             for (int r = 0; r < 6 * N; r++) s += G[r * NU + c] * (RHS[6 + r] - KD[6 + r]);
             KK[c * LD + ND] = s;
         }
-        if (lane < 6) KK[(NR + lane) * LD + ND] = -(CEQ[6 * N + lane] + DP[6 * N + lane]);
-        if (lane == 6) KK[(NR + 6) * LD + ND] = -CEQ[6 * N + 6];
-        __syncwarp();
-        // ---- LU with partial pivoting on the augmented matrix (ND x ND+1), then back substitution
+        if (tid < 6) KK[(NR + tid) * LD + ND] = -(CEQ[6 * N + tid] + DP[6 * N + tid]);
+        if (tid == 6) KK[(NR + 6) * LD + ND] = -CEQ[6 * N + 6];
+        __syncthreads();
+        // ---- LU with partial pivoting on the augmented matrix (ND x ND+1), then column-oriented back substitution
         bool singular = false;
         for (int k = 0; k < ND; k++) {
-            double best = -1.0;
-            int bi = k;
-            for (int r = k + lane; r < ND; r += 32) {
-                double v = fabs(KK[r * LD + k]);
-                if (v > best) { best = v; bi = r; }
+            if (wid == 0) {   // pivot search: warp 0 over the rows k..ND-1 of column k
+                double best = -1.0;
+                int bi = k;
+                for (int r = k + lane; r < ND; r += 32) {
+                    double v = fabs(KK[r * LD + k]);
+                    if (v > best) { best = v; bi = r; }
+                }
+                for (int off = 16; off > 0; off >>= 1) {
+                    double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == 0) { PIV[ND] = (double)bi; PIV[ND + 1] = best; }
             }
-            for (int off = 16; off > 0; off >>= 1) {
-                double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            if (!(best > 1e-300)) { singular = true; break; }
+            __syncthreads();
+            const int bi = (int)PIV[ND];
+            if (!(PIV[ND + 1] > 1e-300)) { singular = true; break; }
             if (bi != k) {
-                for (int c = k + lane; c < LD; c += 32) {
+                for (int c = k + tid; c < LD; c += NT) {
                     double t = KK[k * LD + c];
                     KK[k * LD + c] = KK[bi * LD + c];
                     KK[bi * LD + c] = t;
                 }
+                __syncthreads();
             }
-            __syncwarp();
-            double inv = 1.0 / KK[k * LD + k];
-            // eliminate: lanes over (row, column) pairs of the trailing block
-            for (int r = k + 1 + (lane >> 3); r < ND; r += 4) {   // 4 rows at a time, 8 lanes per row
+            const double inv = rcp(KK[k * LD + k]);
+            if (tid == 0) PIV[k] = inv;
+            // eliminate: 16 rows per pass, 8 column lanes per row
+            for (int r = k + 1 + (tid >> 3); r < ND; r += NT / 8) {
                 double f = KK[r * LD + k] * inv;
                 if (f != 0.0)
-                    for (int c = k + 1 + (lane & 7); c < LD; c += 8) KK[r * LD + c] -= f * KK[k * LD + c];
+                    for (int c = k + 1 + (tid & 7); c < LD; c += 8) KK[r * LD + c] -= f * KK[k * LD + c];
             }
-            __syncwarp();
+            __syncthreads();
         }
         if (singular) { status = B200MPC_INERTIA; break; }
-        for (int k = ND - 1; k >= 0; k--) {   // back substitution, solution overwrites the rhs column
-            double s = 0.0;
-            for (int c = k + 1 + lane; c < ND; c += 32) s += KK[k * LD + c] * KK[c * LD + ND];
-            s = warp_sum(s);
-            if (lane == 0) KK[k * LD + ND] = (KK[k * LD + ND] - s) / KK[k * LD + k];
-            __syncwarp();
+        for (int k = ND - 1; k >= 0; k--) {   // x_k = rhs_k / u_kk, then rhs_r -= u_rk x_k for r < k; solution overwrites the rhs column
+            double xk = KK[k * LD + ND] * PIV[k];
+            for (int r = tid; r < k; r += NT) KK[r * LD + ND] -= KK[r * LD + k] * xk;
+            if (tid == 0) XS[k] = xk;
+            __syncthreads();
         }
+        for (int e = tid; e < ND; e += NT) KK[e * LD + ND] = XS[e];
+        __syncthreads();
         // ---- direction: du, dlambda from the solve; dx = G du + dp; nu+ ; costate recursion for the dynamics multipliers
-        for (int e = lane; e < NR; e += 32) D[OU + e] = KK[e * LD + ND];
-        for (int e = lane; e < 7; e += 32) LAMN[6 * N + e] = KK[(NR + e) * LD + ND];
-        __syncwarp();
-        for (int e = 6 + lane; e < NX; e += 32) {
+        for (int e = tid; e < NR; e += NT) D[OU + e] = KK[e * LD + ND];
+        for (int e = tid; e < 7; e += NT) LAMN[6 * N + e] = KK[(NR + e) * LD + ND];
+        __syncthreads();
+        for (int e = 6 + tid; e < NX; e += NT) {
             double s = DP[e];
             for (int c = 0; c < NU; c++) s += G[(e - 6) * NU + c] * D[OU + c];
             D[e] = s;
         }
-        if (lane < 6) D[lane] = 0.0;
-        __syncwarp();
+        if (tid < 6) D[tid] = 0.0;
+        __syncthreads();
         // res_x = rhs_x - (K d)_x  -> KD
-        for (int e = 6 + lane; e < NX; e += 32) {
+        for (int e = 6 + tid; e < NX; e += NT) {
             int i = e / 6, a = e - 6 * i;
             double s = SIG[e] * D[e];
             for (int b = 0; b < 6; b++) s += df * (Q[6 * a + b] + Q[6 * b + a]) * D[6 * i + b];
             KD[e] = RHS[e] - s;
         }
-        __syncwarp();
-        for (int i = N; i >= 1; i--) {
-            if (lane < 6) {
-                double s = KD[6 * i + lane];
-                if (i < N) { for (int b = 0; b < 6; b++) s += Am[36 * i + 6 * b + lane] * LAMN[6 * i + b]; }
-                else s -= LAMN[6 * N + lane];
-                LAMN[6 * (i - 1) + lane] = s;
+        __syncthreads();
+        if (wid == 0) {
+            for (int i = N; i >= 1; i--) {
+                if (lane < 6) {
+                    double s = KD[6 * i + lane];
+                    if (i < N) { for (int b = 0; b < 6; b++) s += Am[36 * i + 6 * b + lane] * LAMN[6 * i + b]; }
+                    else s -= LAMN[6 * N + lane];
+                    LAMN[6 * (i - 1) + lane] = s;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
+        __syncthreads();
         // ---- step sizes, directional derivative
         double a_max = 1.0, a_z = 1.0, gphi = 0.0;
-        for (int e = 6 + lane; e < NW; e += 32) {
+        for (int e = 6 + tid; e < NW; e += NT) {
             double d = D[e], w = W[e];
             gphi += df * GF[e] * d;
             if (has_l(e)) {
@@ -461,10 +496,10 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
                 gphi += mu * d * rcp(du);
             }
         }
-        a_max = warp_min(a_max); a_z = warp_min(a_z); gphi = warp_sum(gphi);
+        a_max = bmin(a_max); a_z = bmin(a_z); gphi = bsum(gphi);
         double th = 0.0;
-        for (int e = lane; e < ME; e += 32) th += fabs(CEQ[e]);
-        th = warp_sum(th);
+        for (int e = tid; e < ME; e += NT) th += fabs(CEQ[e]);
+        th = bsum(th);
         double ph = df * objective(W, 0.0, false) - mu * barrier(0.0, false);
         double amin;
         if (gphi < 0.0 && th <= theta_min)
@@ -507,7 +542,7 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             if (nfilt < 64) nfilt++;
         }
         // ---- update
-        for (int e = 6 + lane; e < NW; e += 32) {
+        for (int e = 6 + tid; e < NW; e += NT) {
             double d = D[e], w = W[e], wn = w + a * d;
             if (has_l(e)) {
                 double dl = w - lbv(e), zl = ZL[e];
@@ -523,12 +558,12 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
             }
             W[e] = wn;
         }
-        for (int e = lane; e < ME; e += 32) LAM[e] += a * (LAMN[e] - LAM[e]);
-        __syncwarp();
+        for (int e = tid; e < ME; e += NT) LAM[e] += a * (LAMN[e] - LAM[e]);
+        __syncthreads();
         iter++;
     }
     double cost = objective(W, 0.0, false);
-    if (lane == 0) {
+    if (tid == 0) {
         b200mpc_record rc;
         rc.cost = cost;
         rc.u0[0] = W[OU];
@@ -537,13 +572,13 @@ __global__ void __launch_bounds__(32) lmpc_kernel(const __grid_constant__ LmpcKP
         rc.iters = iter;
         rec[inst] = rc;
     }
-    if (aux != nullptr && lane < 4) aux[(size_t)inst * 4 + lane] = (lane == 0) ? E0 : (lane == 3 ? (double)n_back : 0.0);
+    if (aux != nullptr && tid < 4) aux[(size_t)inst * 4 + tid] = (tid == 0) ? E0 : (tid == 3 ? (double)n_back : 0.0);
     if (xpred != nullptr)
-        for (int e = lane; e < NX; e += 32) xpred[(size_t)inst * NX + e] = W[e];
+        for (int e = tid; e < NX; e += NT) xpred[(size_t)inst * NX + e] = W[e];
     if (upred != nullptr)
-        for (int e = lane; e < NU; e += 32) upred[(size_t)inst * NU + e] = W[OU + e];
+        for (int e = tid; e < NU; e += NT) upred[(size_t)inst * NU + e] = W[OU + e];
     if (lambda_out != nullptr)
-        for (int e = lane; e < K; e += 32) lambda_out[(size_t)inst * K + e] = W[OL + e];
+        for (int e = tid; e < K; e += NT) lambda_out[(size_t)inst * K + e] = W[OL + e];
 }
 
 }  // namespace b200mpc
