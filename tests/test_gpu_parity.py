@@ -462,3 +462,65 @@ def test_sysid_chains_into_lmpc_records_and_drop_in(crb, oracle):
     assert len(Atv) == N and Atv[0].shape == (6, 6) and Btv[0].shape == (6, 2) and Ctv[0].shape == (6, 1) and len(used[0]) == 2
     assert np.abs(np.array(Atv) - g["A"][5]).max() < 1e-8 and np.abs(np.array(Ctv)[:, :, 0] - g["C"][5]).max() < 1e-8
     assert (used[3][1] == g["idx"][5, 3, 1]).all()
+
+
+def test_sysid_lmpc_chain_on_device(crb, oracle):
+    """Config 4 end to end on the device: sysid_kernel writes the model block of the LMPC records in HBM, lmpc_kernel
+    consumes them (device-pointer entry points, same stream); checked against restatement + oracle on the host."""
+    import ctypes as C
+    import torch
+    import sysid_numpy
+    from car_racing_b200 import _capi, batch
+    g = _sysid_gold()
+    N, K, Bn = 12, 44, 16
+    rng = np.random.default_rng(11)
+    lap = rng.integers(0, 2, Bn)
+    t0 = np.array([rng.integers(5, g["time_ss"][l] - 70) for l in lap])
+    lp = np.stack([g["ss"][t + 1:t + N + 2, :, l] for t, l in zip(t0, lap)])
+    li = np.stack([g["us"][t + 1:t + N + 1, :, l] for t, l in zip(t0, lap)])
+    x0 = np.stack([g["ss"][t, :, l] for t, l in zip(t0, lap)]) + rng.normal(scale=1e-3, size=(Bn, 6))
+    u_old = np.stack([g["us"][t, :, l] for t, l in zip(t0, lap)])
+    # safe set: 22 points ahead on each of the two stored laps (nearest in s), Qfun = time to go
+    SS = np.zeros((Bn, 6, K)); Qf = np.zeros((Bn, K))
+    for b in range(Bn):
+        for j in range(2):
+            m = int(np.argmin(np.abs(g["ss"][:g["time_ss"][j], 4, j] - x0[b, 4]))) + 4
+            SS[b, :, 22 * j:22 * j + 22] = g["ss"][m:m + 22, :, j].T
+            Qf[b, 22 * j:22 * j + 22] = (g["time_ss"][j] - np.arange(m, m + 22)) + 10.0 * j
+    prm = scenarios.default_lmpc_params(width=1.0)
+    zeros = np.zeros
+    rec, _ = batch.pack_lmpc(x0, u_old, zeros((Bn, N, 6, 6)), zeros((Bn, N, 6, 2)), zeros((Bn, N, 6)), SS, Qf, N)
+    stride = rec.shape[1]
+    laps, rows, lstride = batch.pack_laps(g["ss"], g["us"], g["time_ss"], [0, 1])
+    pat = g["point_and_tangent"]
+    dev = torch.device("cuda:0")
+    h = batch.default_handle()
+    d_rec = torch.from_numpy(rec).to(dev)
+    d_lin = torch.from_numpy(np.ascontiguousarray(np.concatenate([lp[:, :N], li], axis=2))).to(dev)
+    d_laps = torch.from_numpy(laps).to(dev)
+    d_seg = torch.from_numpy(np.ascontiguousarray(pat[:, 3:6])).to(dev)
+    d_out = torch.zeros((Bn, 4), dtype=torch.float64, device=dev)
+    d_x = torch.zeros((Bn, N + 1, 6), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    sp = _capi.SysidParams()
+    sp.N, sp.num_laps, sp.max_num_point, sp.num_segments, sp.lap_stride = N, 2, 40, pat.shape[0], lstride
+    sp.lap_rows[0], sp.lap_rows[1] = rows
+    sp.dt, sp.h, sp.lap_length = 0.1, 5.0, float(pat[-1, 3] + pat[-1, 4])
+    L = _capi.lib()
+    h.check(L.b200mpc_lmpc_sysid_device(h.ptr, C.byref(sp), Bn, d_lin.data_ptr(), d_laps.data_ptr(), d_seg.data_ptr(),
+                                        d_rec.data_ptr(), stride, 8, None, None), "sysid_device")
+    lpm = _capi.make_lmpc_params(prm, K)
+    opt = _capi.default_options()
+    h.check(L.b200mpc_lmpc_solve_device(h.ptr, C.byref(lpm), C.byref(opt), Bn, d_rec.data_ptr(), d_out.data_ptr(), None,
+                                        d_x.data_ptr(), None, None), "lmpc_solve_device")
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().reshape(-1).view(_capi.RECORD_DTYPE)
+    A, Bm, Cm, _ = sysid_numpy.estimate_abc(lp, li, g["ss"], g["us"], g["time_ss"], [0, 1], pat, 0.1)
+    model = d_rec.cpu().numpy()[:, 8:8 + 54 * N]
+    assert np.abs(model[:, :36 * N].reshape(Bn, N, 6, 6) - A).max() < 1e-8
+    r = oracle.solve_lmpc_batch(x0, u_old, A, Bm, Cm, SS, Qf, prm, nthreads=os.cpu_count() or 1)
+    both = (got["status"] == 0) & (r["status"] == 0)
+    print("chain: both converged", both.sum(), "of", Bn, "statuses", got["status"], r["status"])
+    assert both.sum() >= Bn // 2 and ((got["status"] == 0) == (r["status"] == 0)).mean() >= 0.9
+    assert np.abs(got["u0"][both] - r["u0"][both]).max() < TOL_U and np.abs(got["cost"][both] - r["cost"][both]).max() < TOL_C
+    assert np.abs(d_x.cpu().numpy()[both] - r["x"][both]).max() < 1e-4
