@@ -216,3 +216,18 @@ def install(control_module=None):
     for name in ("mpc_lti", "mpccbf", "mpc_multi_agents", "ilqr", "lmpc"):
         setattr(control_module, name, globals()[name])
     return control_module
+
+
+def install_all(control_module=None, base_module=None, planner_class=None):
+    """Everything on the control-step path: the five solve functions, LMPCRacingGame.estimate_ABC, the planner's
+    solve_optimization_problem and the rivals' sympy-free trajectory prediction."""
+    from . import planning, rivals
+    control_module = install(control_module)
+    if base_module is None:
+        from utils import base as base_module
+    base_module.LMPCRacingGame.estimate_ABC = estimate_ABC
+    rivals.install(base_module)
+    if planner_class is None:
+        from planning.overtake_traj_planner import OvertakeTrajPlanner as planner_class
+    planner_class.solve_optimization_problem = planning.solve_optimization_problem
+    return control_module, base_module, planner_class

@@ -1,0 +1,54 @@
+"""Rival trajectory prediction: drop-in for `NoDynamicsModel.get_trajectory_nsteps`
+(car_racing/utils/base.py:879-886).
+
+The reference evaluates the rival's sympy expressions s(t), ey(t) with four `subs`/`diff` calls per predicted step
+(`get_estimation`, base.py:860-877) -- 8.2 ms per rival and control step, i.e. several times the GPU
+solve it feeds.  Here the expressions and their time derivatives are compiled once per rival (`sympy.lambdify`) and
+evaluated for all n steps in one numpy call.  Every caller in the reference discards the second return value
+(control.py:103,296,509; overtake_traj_planner.py:78), so the global-frame block is only filled on request."""
+import numpy as np
+
+X_DIM = 6
+_CACHE_ATTR = "_b200_traj_fn"
+
+
+def _compiled(model):
+    import sympy as sp
+    key = (id(model.s_func), id(model.ey_func), id(model.t_symbol))
+    hit = getattr(model, _CACHE_ATTR, None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    t = model.t_symbol
+    exprs = [sp.diff(model.s_func, t), sp.diff(model.ey_func, t), model.s_func, model.ey_func]
+    fns = [sp.lambdify(t, e, "numpy") for e in exprs]
+    try:
+        setattr(model, _CACHE_ATTR, (key, fns))
+    except Exception:
+        pass
+    return fns
+
+
+def get_trajectory_nsteps(self, t0, delta_t, n, with_glob=False):
+    """Same first return value as the reference: (6, n) with rows (ds/dt, dey/dt, 0, 0, s, ey) at self.time + k*delta_t
+    (the reference ignores t0 and uses self.time, base.py:883).  Second value: zeros unless with_glob."""
+    fns = _compiled(self)
+    tt = self.time + np.arange(n) * delta_t
+    xcurv = np.zeros((X_DIM, n))
+    for row, fn in zip((0, 1, 4, 5), fns):
+        xcurv[row, :] = np.broadcast_to(np.asarray(fn(tt), dtype=float), (n,))
+    xglob = np.zeros((X_DIM, n))
+    if with_glob:
+        xglob[0:3, :] = xcurv[0:3, :]
+        for k in range(n):
+            X, Y = self.track.get_global_position(xcurv[4, k], xcurv[5, k])
+            xglob[3, k] = self.track.get_orientation(xcurv[4, k], xcurv[5, k])
+            xglob[4, k], xglob[5, k] = X, Y
+    return xcurv, xglob
+
+
+def install(base_module=None):
+    """Patch the reference's NoDynamicsModel in place."""
+    if base_module is None:
+        from utils import base as base_module
+    base_module.NoDynamicsModel.get_trajectory_nsteps = get_trajectory_nsteps
+    return base_module

@@ -84,3 +84,18 @@ def test_mpc_multi_agents_targets(monkeypatch):
     assert np.allclose(xt[0, :, 5], np.interp(s, traj[:, 4], traj[:, 5]))
     assert seen["obs"].shape[1] == 1 and seen["prm"]["alpha"] == 0.6 and seen["prm"]["margin"] == 0.15
     assert seen["prm"]["L"] == 0.4 and seen["prm"]["W"] == 0.2
+
+
+def test_install_all_patches_every_hook():
+    import types
+    import car_racing_b200 as crb
+    from car_racing_b200 import planning, rivals
+    ctrl = types.SimpleNamespace()
+    base = types.SimpleNamespace(LMPCRacingGame=type("LMPCRacingGame", (), {}), NoDynamicsModel=type("NoDynamicsModel", (), {}))
+    planner = type("OvertakeTrajPlanner", (), {})
+    crb.install_all(ctrl, base, planner)
+    for name in ("mpc_lti", "mpccbf", "mpc_multi_agents", "ilqr", "lmpc"):
+        assert getattr(ctrl, name) is getattr(crb.control, name)
+    assert base.LMPCRacingGame.estimate_ABC is crb.control.estimate_ABC
+    assert base.NoDynamicsModel.get_trajectory_nsteps is rivals.get_trajectory_nsteps
+    assert planner.solve_optimization_problem is planning.solve_optimization_problem
