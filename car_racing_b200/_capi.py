@@ -60,6 +60,15 @@ class SysidParams(C.Structure):
     ]
 
 
+class PlantParams(C.Structure):
+    _fields_ = [
+        ("n_sub", C.c_int32), ("num_segments", C.c_int32), ("wrap_lap", C.c_int32), ("reserved", C.c_int32),
+        ("delta_t", C.c_double), ("lap_length", C.c_double),
+        ("m", C.c_double), ("lf", C.c_double), ("lr", C.c_double), ("Iz", C.c_double), ("Df", C.c_double), ("Cf", C.c_double),
+        ("Bf", C.c_double), ("Dr", C.c_double), ("Cr", C.c_double), ("Br", C.c_double),
+    ]
+
+
 RECORD_DTYPE = np.dtype([("cost", "<f8"), ("u0", "<f8", (2,)), ("status", "<i4"), ("iters", "<i4")])
 assert RECORD_DTYPE.itemsize == 32
 
@@ -68,7 +77,7 @@ EXPORTS = [
     "b200mpc_stream", "b200mpc_launch_count", "b200mpc_cbf_record_doubles", "b200mpc_cbf_record_doubles_ex", "b200mpc_cbf_solve",
     "b200mpc_cbf_solve_device", "b200mpc_ilqr_record_doubles", "b200mpc_ilqr_solve", "b200mpc_ilqr_solve_device",
     "b200mpc_argmin_cost_device", "b200mpc_lmpc_record_doubles", "b200mpc_lmpc_solve", "b200mpc_lmpc_solve_device",
-    "b200mpc_lmpc_sysid", "b200mpc_lmpc_sysid_device",
+    "b200mpc_lmpc_sysid", "b200mpc_lmpc_sysid_device", "b200mpc_plant_step", "b200mpc_plant_step_device",
 ]
 
 _lib = None
@@ -114,6 +123,9 @@ def lib():
     sysid_args = [vp, C.POINTER(SysidParams), ip, dp, dp, dp, dp, ip, ip, dp, dp]
     L.b200mpc_lmpc_sysid.argtypes = sysid_args
     L.b200mpc_lmpc_sysid_device.argtypes = sysid_args
+    plant_args = [vp, C.POINTER(PlantParams), ip, dp, ip, ip, dp, dp, ip, dp, dp, dp]
+    L.b200mpc_plant_step.argtypes = plant_args
+    L.b200mpc_plant_step_device.argtypes = plant_args
     _lib = L
     return L
 
@@ -219,4 +231,19 @@ def make_lmpc_params(prm, K):
     _fill(p.Q, prm["Q"], 36); _fill(p.R, prm["R"], 4); _fill(p.dR, prm["dR"], 4); _fill(p.xtrk, prm["xtrk"], 6)
     _fill(p.umax, prm["umax"], 2)
     p.vmax, p.width = float(prm["vmax"]), float(prm["width"])
+    return p
+
+
+DEFAULT_DYN = (1.98, 0.125, 0.125, 0.024, 0.8 * 1.98 * 9.81 / 2.0, 1.25, 1.0, 0.8 * 1.98 * 9.81 / 2.0, 1.25, 1.0)   # base.py:659-672
+
+
+def make_plant_params(num_segments, lap_length, timestep=0.1, delta_t=0.001, dyn=DEFAULT_DYN, wrap_lap=False):
+    p = PlantParams()
+    i = 0
+    while (i + 1) * delta_t <= timestep:      # the reference's loop condition (base.py:909)
+        i += 1
+    p.n_sub, p.num_segments, p.wrap_lap = i, int(num_segments), int(bool(wrap_lap))
+    p.delta_t, p.lap_length = float(delta_t), float(lap_length)
+    for k, v in zip(("m", "lf", "lr", "Iz", "Df", "Cf", "Bf", "Dr", "Cr", "Br"), dyn):
+        setattr(p, k, float(v))
     return p

@@ -261,3 +261,21 @@ def estimate_abc_batch(lin_points, lin_input, ss_xcurv, u_ss, time_ss, used_laps
     if st is not None:
         res["status"] = st
     return res
+
+
+def plant_step_batch(xcurv, xglob, u, draws, point_and_tangent, timestep=0.1, dyn=_capi.DEFAULT_DYN, wrap_lap=False, handle=None):
+    """Batched DynamicBicycleModel.forward_dynamics (base.py:897-942).  xcurv, xglob (Bn,6); u (Bn,2); draws (Bn,3) standard
+    normal draws or None (zero_noise_flag).  Returns (xcurv_next, xglob_next[, laps])."""
+    hd = handle or default_handle()
+    xc = np.ascontiguousarray(np.atleast_2d(np.asarray(xcurv, dtype=np.float64))).copy()
+    xg = np.ascontiguousarray(np.atleast_2d(np.asarray(xglob, dtype=np.float64))).copy()
+    uu = np.ascontiguousarray(np.atleast_2d(np.asarray(u, dtype=np.float64)))
+    Bn = xc.shape[0]
+    dr = None if draws is None else np.ascontiguousarray(np.asarray(draws, dtype=np.float64).reshape(Bn, 3))
+    pat = np.asarray(point_and_tangent, dtype=np.float64)
+    seg = np.ascontiguousarray(pat[:, 3:6])
+    p = _capi.make_plant_params(seg.shape[0], pat[-1, 3] + pat[-1, 4], timestep=timestep, dyn=dyn, wrap_lap=wrap_lap)
+    laps = np.zeros(Bn, dtype=np.int32) if wrap_lap else None
+    rc = _capi.lib().b200mpc_plant_step(hd.ptr, C.byref(p), Bn, _ptr(xc), 6, 0, _ptr(xg), _ptr(uu), 2, _ptr(dr), _ptr(seg), _ptr(laps))
+    hd.check(rc, "b200mpc_plant_step")
+    return (xc, xg, laps) if wrap_lap else (xc, xg)

@@ -10,6 +10,7 @@
 #include "ilqr.cuh"
 #include "lmpc.cuh"
 #include "ocp_ipm.cuh"
+#include "plant.cuh"
 #include "sysid.cuh"
 
 using namespace b200mpc;
@@ -410,6 +411,66 @@ int b200mpc_lmpc_sysid(b200mpc_handle *h, const b200mpc_sysid_params *prm, int B
                             (size_t)54 * N * 8, B, cudaMemcpyDeviceToHost, h->stream));
     if (idx) CK(h, cudaMemcpyAsync(idx, h->d_idx, b_idx, cudaMemcpyDeviceToHost, h->stream));
     if (status) CK(h, cudaMemcpyAsync(status, h->d_stat, b_st, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+static int check_plant(b200mpc_handle *h, const b200mpc_plant_params *p, int B, const void *xc, int stride, int offset,
+                       const void *xg, const void *u, int u_stride, const void *seg) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!p || !xc || !xg || !u || !seg || B < 1) return fail(h, B200MPC_ERR_ARG, "b200mpc_plant_step: null argument or B < 1");
+    if (p->n_sub < 1 || p->n_sub > 100000 || p->num_segments < 1 || offset < 0 || stride < offset + 6 || u_stride < 2)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_plant_step: size out of range");
+    if (!(p->delta_t > 0.0) || !(p->lap_length > 0.0) || !(p->m > 0.0) || !(p->Iz > 0.0))
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_plant_step: bad parameter value");
+    return B200MPC_OK;
+}
+
+int b200mpc_plant_step_device(b200mpc_handle *h, const b200mpc_plant_params *prm, int B, double *d_xcurv, int xcurv_stride,
+                              int xcurv_offset, double *d_xglob, const double *d_u, int u_stride, const double *d_draws,
+                              const double *d_segments, int32_t *d_laps) {
+    int rc = check_plant(h, prm, B, d_xcurv, xcurv_stride, xcurv_offset, d_xglob, d_u, u_stride, d_segments);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    PlantKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.p = *prm;
+    kp.B = B;
+    kp.xcurv_stride = xcurv_stride;
+    kp.xcurv_offset = xcurv_offset;
+    plant_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(kp, d_xcurv, d_xglob, d_u, u_stride, d_draws, d_segments, d_laps);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+int b200mpc_plant_step(b200mpc_handle *h, const b200mpc_plant_params *prm, int B, double *xcurv, int xcurv_stride,
+                       int xcurv_offset, double *xglob, const double *u, int u_stride, const double *draws,
+                       const double *segments, int32_t *laps) {
+    int rc = check_plant(h, prm, B, xcurv, xcurv_stride, xcurv_offset, xglob, u, u_stride, segments);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    const size_t b_xc = (size_t)B * xcurv_stride * 8, b_xg = (size_t)B * 48, b_u = ((size_t)(B - 1) * u_stride + 2) * 8;
+    const size_t b_d = (size_t)B * 24, b_seg = (size_t)prm->num_segments * 24, b_l = (size_t)B * 4;
+    if ((rc = grow(h, &h->d_in, &h->c_in, b_xc))) return rc;
+    if ((rc = grow(h, &h->d_x, &h->c_x, b_xg))) return rc;
+    if ((rc = grow(h, &h->d_u, &h->c_u, b_u))) return rc;
+    if (draws && (rc = grow(h, &h->d_aux, &h->c_aux, b_d))) return rc;
+    if ((rc = grow(h, &h->d_seg, &h->c_seg, b_seg))) return rc;
+    if (laps && (rc = grow(h, &h->d_stat, &h->c_stat, b_l))) return rc;
+    CK(h, cudaMemcpyAsync(h->d_in, xcurv, b_xc, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_x, xglob, b_xg, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_u, u, b_u, cudaMemcpyHostToDevice, h->stream));
+    if (draws) CK(h, cudaMemcpyAsync(h->d_aux, draws, b_d, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_seg, segments, b_seg, cudaMemcpyHostToDevice, h->stream));
+    if (laps) CK(h, cudaMemcpyAsync(h->d_stat, laps, b_l, cudaMemcpyHostToDevice, h->stream));
+    rc = b200mpc_plant_step_device(h, prm, B, (double *)h->d_in, xcurv_stride, xcurv_offset, (double *)h->d_x,
+                                   (const double *)h->d_u, u_stride, draws ? (const double *)h->d_aux : nullptr,
+                                   (const double *)h->d_seg, laps ? (int32_t *)h->d_stat : nullptr);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(xcurv, h->d_in, b_xc, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(xglob, h->d_x, b_xg, cudaMemcpyDeviceToHost, h->stream));
+    if (laps) CK(h, cudaMemcpyAsync(laps, h->d_stat, b_l, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }

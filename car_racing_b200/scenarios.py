@@ -170,3 +170,28 @@ def lmpc_scenarios(B, N=12, num_ss_points=44, num_ss_iter=2, seed=1, ltv_noise=5
         SS[b] = np.concatenate(cols, axis=1)
         Qf[b] = np.concatenate(qs)
     return x0, u_old, A, Bm, C, SS, Qf
+
+
+def closed_loop_scenarios(B, N=20, M=3, seed=1, track="l_shape"):
+    """Closed-loop episodes in the style of car_racing/tests/mpccbf_test.py:15-36: the ego starts slowly near the centre
+    line, M slower rivals (0.1-0.3 m/s, the test uses 0.2) start 2-10 m ahead with small lateral offsets.
+    Returns x0 (B,6), xtarget (6,), rival s0 (B,M), ey (B,M), speed (B,M)."""
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((B, 6))
+    x0[:, 0] = rng.uniform(0.3, 0.9, B)
+    x0[:, 3] = rng.uniform(-0.05, 0.05, B)
+    x0[:, 4] = rng.uniform(0.0, 5.0, B)
+    x0[:, 5] = rng.uniform(-0.3, 0.3, B)
+    s0 = x0[:, 4, None] + rng.uniform(2.0, 4.0, (B, M)) + 3.0 * np.arange(M)[None, :]
+    ey = rng.uniform(-0.4, 0.4, (B, M))
+    v = rng.uniform(0.1, 0.3, (B, M))
+    return x0, np.array([0.8, 0.0, 0.0, 0.0, 0.0, 0.0]), s0, ey, v
+
+
+def rival_block(s0, ey, v, t, N, dt=0.1):
+    """Predicted rival rows (B,M,2,N+1) at time t: s_j(t + i dt) = s0 + v (t + i dt), ey constant (NoDynamicsModel, base.py:879-886)."""
+    tt = t + dt * np.arange(N + 1)
+    obs = np.zeros(s0.shape + (2, N + 1))
+    obs[:, :, 0, :] = s0[:, :, None] + v[:, :, None] * tt[None, None, :]
+    obs[:, :, 1, :] = ey[:, :, None]
+    return obs

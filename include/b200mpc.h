@@ -12,6 +12,7 @@
  *   b200mpc_ilqr_solve    <- control.ilqr             (control.py:64-195, ilqr_helper.py:4-55)
  *   b200mpc_lmpc_solve    <- control.lmpc             (control.py:610-730)
  *   b200mpc_lmpc_sysid    <- LMPCRacingGame.estimate_ABC (utils/base.py:585-622, control/lmpc_helper.py:26-264)
+ *   b200mpc_plant_step    <- DynamicBicycleModel.forward_dynamics (utils/base.py:897-942, system/vehicle_dynamics.py:4-49)
  *   b200mpc_argmin_cost   <- the argmin of OvertakeTrajPlanner.solve_optimization_problem
  *                            (car_racing/planning/overtake_traj_planner.py:244)
  *
@@ -202,6 +203,29 @@ int b200mpc_lmpc_sysid(b200mpc_handle *h, const b200mpc_sysid_params *prm, int B
 int b200mpc_lmpc_sysid_device(b200mpc_handle *h, const b200mpc_sysid_params *prm, int B, const double *d_lin,
                               const double *d_laps, const double *d_segments, double *d_out, int out_stride, int out_offset,
                               int32_t *d_idx, int32_t *d_status);
+
+/* Plant step: DynamicBicycleModel.forward_dynamics (utils/base.py:897-942) = n_sub Euler sub-steps of
+ * system/vehicle_dynamics.py:4-49 + clipped noise + the lap wrap of update_memory (base.py:804-809). */
+typedef struct {
+    int32_t n_sub;          /* sub-steps: the count of the loop `while (i+1)*0.001 <= timestep` (base.py:909) = 100 */
+    int32_t num_segments;   /* rows of `segments` */
+    int32_t wrap_lap;       /* 1: s -= lap_length when s > lap_length and laps[b]++ */
+    int32_t reserved;
+    double delta_t;         /* 0.001 (base.py:901) */
+    double lap_length;
+    double m, lf, lr, Iz, Df, Cf, Bf, Dr, Cr, Br;   /* BicycleDynamicsParam (base.py:659-696) */
+} b200mpc_plant_params;
+
+/* In place: xcurv (vehicle b at xcurv + b*xcurv_stride + xcurv_offset, 6 doubles: with stride = record doubles and
+ * offset 0 this is the x0 slot of the MPC records), xglob B x 6; u: delta, a of vehicle b at u + b*u_stride (u_stride = 4
+ * reads u0 out of b200mpc_record arrays starting at &rec[0].u0); draws: optional B x 3 standard-normal draws (NULL =
+ * zero_noise_flag); segments as in b200mpc_lmpc_sysid; laps: optional B lap counters. */
+int b200mpc_plant_step(b200mpc_handle *h, const b200mpc_plant_params *prm, int B, double *xcurv, int xcurv_stride,
+                       int xcurv_offset, double *xglob, const double *u, int u_stride, const double *draws,
+                       const double *segments, int32_t *laps);
+int b200mpc_plant_step_device(b200mpc_handle *h, const b200mpc_plant_params *prm, int B, double *d_xcurv, int xcurv_stride,
+                              int xcurv_offset, double *d_xglob, const double *d_u, int u_stride, const double *d_draws,
+                              const double *d_segments, int32_t *d_laps);
 
 /* argmin over records (device pointers): index of the smallest cost among status<=max_status,
  * lowest index wins ties (list.index(min(...)), overtake_traj_planner.py:244); *d_out = -1 if none. */

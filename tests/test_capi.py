@@ -39,6 +39,8 @@ def test_struct_layouts_and_record_sizes():
             for ps in (0, 1):
                 assert L.b200mpc_cbf_record_doubles(N, M, ps) == batch.cbf_record_doubles(N, M, ps)
         assert L.b200mpc_ilqr_record_doubles(N) == batch.ilqr_record_doubles(N)
+    assert C.sizeof(_capi.PlantParams) == 16 + 12 * 8
+    assert _capi.make_plant_params(9, 25.4).n_sub == 100
     assert C.sizeof(_capi.SysidParams) == 4 * 4 + 4 * 4 + 8 + 3 * 8
     assert C.sizeof(_capi.LmpcParams) == 8 + 8 * (36 + 4 + 4 + 6 + 2 + 2)
     for N, K in ((2, 1), (12, 44), (16, 64), (10, 33)):

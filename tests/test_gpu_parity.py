@@ -524,3 +524,46 @@ def test_sysid_lmpc_chain_on_device(crb, oracle):
     assert both.sum() >= Bn // 2 and ((got["status"] == 0) == (r["status"] == 0)).mean() >= 0.9
     assert np.abs(got["u0"][both] - r["u0"][both]).max() < TOL_U and np.abs(got["cost"][both] - r["cost"][both]).max() < TOL_C
     assert np.abs(d_x.cpu().numpy()[both] - r["x"][both]).max() < 1e-4
+
+
+def test_plant_step_matches_reference_golden(crb):
+    """Batched plant step against the reference's DynamicBicycleModel.forward_dynamics goldens."""
+    g = np.load(os.path.join(GOLD, "plant_golden.npz"))
+    for name in ("ellipse", "l_shape"):
+        xc, xg, us, dr = g["xcurv_" + name], g["xglob_" + name], g["u_" + name], g["draws_" + name]
+        worst = 0.0
+        for k in range(us.shape[1]):
+            nc, ng = crb.plant_step_batch(xc[:, k], xg[:, k], us[:, k], dr[:, k], g["pat_" + name], dyn=tuple(g["dyn"]))
+            worst = max(worst, np.abs(nc - xc[:, k + 1]).max(), np.abs(ng - xg[:, k + 1]).max())
+        print(name, "max |d state| over", us.shape[1], "steps:", worst)
+        assert worst < 1e-10          # 100 sub-steps of libm vs CUDA sin/cos/atan (1-2 ulp each)
+    # zero_noise_flag and the lap wrap
+    name = "ellipse"
+    xc0 = g["xcurv_" + name][:, 0].copy()
+    xc0[:, 4] = float(g["lap_length_" + name]) - 0.01
+    nc, ng, laps = crb.plant_step_batch(xc0, g["xglob_" + name][:, 0], g["u_" + name][:, 0], None, g["pat_" + name], wrap_lap=True)
+    assert (laps == 1).all() and (nc[:, 4] < 1.0).all() and (nc[:, 4] > 0.0).all()
+
+
+def test_closed_loop_chain_matches_cpu_chain(crb, oracle):
+    """Solve -> plant -> solve on the device (tools/closed_loop.py) against oracle + numpy plant on the host, 8 control steps."""
+    import sys
+    import plant_numpy
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), "..", "tools"))
+    import closed_loop
+    B, T, N = 12, 8, 20
+    res, traj = closed_loop.run(B, T, seed=4, noise=False, record_every=1)
+    g = np.load(os.path.join(GOLD, "plant_golden.npz"))
+    x0, xt, s0, ey, v = scenarios.closed_loop_scenarios(B, N=N, M=3, seed=4)
+    prm = scenarios.default_cbf_params(N=N)
+    xc = x0.copy(); xg = np.zeros((B, 6)); xg[:, 0:3] = x0[:, 0:3]
+    nfail = 0
+    for k in range(T):
+        r = oracle.solve_cbf_batch(xc, xt, scenarios.rival_block(s0, ey, v, 0.1 * k, N), np.zeros((B, 3)), prm,
+                                   nthreads=os.cpu_count() or 1)
+        nfail += int((r["status"] != 0).sum())
+        xc, xg = plant_numpy.plant_step(xc, xg, r["u0"], np.zeros((B, 3)), g["dyn"], g["pat_l_shape"], float(g["lap_length_l_shape"]))
+        d = np.abs(traj[k] - xc).max()
+        print("closed loop step", k, "max |dx|", d)
+        assert d < 1e-6
+    assert res["status_counts"].get(0, 0) == B * T - nfail
