@@ -78,6 +78,7 @@ EXPORTS = [
     "b200mpc_cbf_solve_device", "b200mpc_ilqr_record_doubles", "b200mpc_ilqr_solve", "b200mpc_ilqr_solve_device",
     "b200mpc_argmin_cost_device", "b200mpc_lmpc_record_doubles", "b200mpc_lmpc_solve", "b200mpc_lmpc_solve_device",
     "b200mpc_lmpc_sysid", "b200mpc_lmpc_sysid_device", "b200mpc_plant_step", "b200mpc_plant_step_device",
+    "b200mpc_cbf_solve_async", "b200mpc_synchronize", "b200mpc_host_alloc", "b200mpc_host_free",
 ]
 
 _lib = None
@@ -112,6 +113,12 @@ def lib():
     cbf_args = [vp, C.POINTER(CbfParams), C.POINTER(IpmOptions), ip, dp, dp, dp, dp, dp, dp]
     L.b200mpc_cbf_solve.argtypes = cbf_args
     L.b200mpc_cbf_solve_device.argtypes = cbf_args
+    L.b200mpc_cbf_solve_async.argtypes = cbf_args
+    L.b200mpc_synchronize.argtypes = [vp]
+    L.b200mpc_host_alloc.argtypes = [C.c_size_t]
+    L.b200mpc_host_alloc.restype = C.c_void_p
+    L.b200mpc_host_free.argtypes = [vp]
+    L.b200mpc_host_free.restype = None
     ilqr_args = [vp, C.POINTER(IlqrParams), ip, dp, dp, dp, dp]
     L.b200mpc_ilqr_solve.argtypes = ilqr_args
     L.b200mpc_ilqr_solve_device.argtypes = ilqr_args
@@ -164,6 +171,9 @@ class Handle:
     def stream(self):
         return int(lib().b200mpc_stream(self.ptr))
 
+    def synchronize(self):
+        self.check(lib().b200mpc_synchronize(self.ptr), "b200mpc_synchronize")
+
     @property
     def launch_count(self):
         return int(lib().b200mpc_launch_count(self.ptr))
@@ -185,6 +195,30 @@ class Handle:
     def __setstate__(self, st):
         self.device, self.max_batch = st["device"], st["max_batch"]
         self._h = None
+
+
+class PinnedArray:
+    """A numpy view of page-locked host memory (b200mpc_host_alloc) -- what the asynchronous calls need for their
+    copies to overlap with compute.  Keep the object alive while `.a` is in use."""
+
+    def __init__(self, shape, dtype=np.float64):
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        self._p = lib().b200mpc_host_alloc(max(n, 1))
+        if not self._p:
+            raise B200MPCError("b200mpc_host_alloc failed")
+        buf = (C.c_char * max(n, 1)).from_address(self._p)
+        self.a = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        self.a[...] = 0
+
+    def __del__(self):
+        try:
+            p, self._p = self._p, None
+            if p:
+                self.a = None
+                lib().b200mpc_host_free(p)
+        except Exception:
+            pass
 
 
 def default_options(**kw):

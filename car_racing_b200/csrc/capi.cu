@@ -202,8 +202,31 @@ int b200mpc_cbf_solve_device(b200mpc_handle *h, const b200mpc_cbf_params *prm, c
     return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: M out of range");
 }
 
+void *b200mpc_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void b200mpc_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int b200mpc_synchronize(b200mpc_handle *h) {
+    if (!h) return B200MPC_ERR_ARG;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
 int b200mpc_cbf_solve(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b200mpc_ipm_options *opt, int B,
                       const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *sigma) {
+    int rc = b200mpc_cbf_solve_async(h, prm, opt, B, in, rec, aux, xpred, upred, sigma);
+    if (rc) return rc;
+    return b200mpc_synchronize(h);
+}
+
+int b200mpc_cbf_solve_async(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b200mpc_ipm_options *opt, int B,
+                            const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *sigma) {
     int rc = check_cbf(h, prm, opt, B, in, rec);
     if (rc) return rc;
     CK(h, cudaSetDevice(h->device));
@@ -227,7 +250,6 @@ int b200mpc_cbf_solve(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b2
     if (xpred) CK(h, cudaMemcpyAsync(xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
     if (upred) CK(h, cudaMemcpyAsync(upred, h->d_u, b_u, cudaMemcpyDeviceToHost, h->stream));
     if (sigma && M > 0) CK(h, cudaMemcpyAsync(sigma, h->d_sig, b_sig, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }
 

@@ -135,6 +135,19 @@ int b200mpc_cbf_solve(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b2
 int b200mpc_cbf_solve_device(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b200mpc_ipm_options *opt, int B,
                              const double *d_in, b200mpc_record *d_rec, double *d_aux, double *d_xpred, double *d_upred,
                              double *d_sigma);
+/* The same call without the final stream synchronisation: H2D of the records, the kernel and the D2H of the
+ * results are only ENQUEUED on the handle's stream.  The host buffers must stay alive (and should be pinned, or
+ * the copies block) until b200mpc_synchronize(h) returns; a second call on the same handle before that reuses the
+ * handle's staging buffers in stream order, which is safe.  Several handles (= streams) driven round-robin keep
+ * several batches in flight: the reference's planner forks one process per candidate and joins them
+ * (planning/overtake_traj_planner.py:182-203); here the join is this call, and the stragglers of one batch
+ * overlap the next batch instead of idling the GPU (DESIGN.md "Batches in flight"). */
+int b200mpc_cbf_solve_async(b200mpc_handle *h, const b200mpc_cbf_params *prm, const b200mpc_ipm_options *opt, int B,
+                            const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *sigma);
+int b200mpc_synchronize(b200mpc_handle *h);
+/* page-locked host memory for the asynchronous calls (cudaHostAlloc / cudaFreeHost); NULL on failure */
+void *b200mpc_host_alloc(size_t bytes);
+void b200mpc_host_free(void *p);
 
 /* iLQR (control.py:64-195).  Shared data: */
 typedef struct {

@@ -567,3 +567,32 @@ def test_closed_loop_chain_matches_cpu_chain(crb, oracle):
         print("closed loop step", k, "max |dx|", d)
         assert d < 1e-6
     assert res["status_counts"].get(0, 0) == B * T - nfail
+
+
+def test_batches_in_flight_equal_the_blocking_call(crb):
+    """CbfPipeline (b200mpc_cbf_solve_async on several handles, pinned buffers) must return, batch by batch, exactly
+    what the blocking b200mpc_cbf_solve returns -- including when a slot is reused before the others are collected."""
+    from car_racing_b200 import batch
+    prm = scenarios.default_cbf_params(N=20)
+    B, depth, nb = 96, 3, 7
+    recs, refs = [], []
+    for k in range(nb):
+        x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=20, M=3, seed=100 + k)
+        rec, M, ps = crb.pack_cbf(x0, xt, obs, lap_off, 20)
+        recs.append(rec)
+        refs.append(crb.solve_cbf_packed(rec, prm, M, ps, want=())["record"])
+    pipe = batch.CbfPipeline(prm, M=3, B=B, depth=depth)
+    out, tickets = {}, []
+    for k in range(nb):
+        if k >= depth:
+            t = tickets[k - depth]
+            out[t] = pipe.result(t)
+        tickets.append(pipe.submit(recs[k]))
+    with pytest.raises(RuntimeError):
+        pipe.submit(recs[0])                     # the slot's previous batch has not been collected
+    for t in tickets[-depth:]:
+        out[t] = pipe.result(t)
+    for k in range(nb):
+        assert out[k].tobytes() == refs[k].tobytes()
+    assert pipe.launch_count == nb
+    pipe.close()
