@@ -129,16 +129,20 @@ __device__ __forceinline__ double p4(double a) { double b = a * a; return b * b;
 __device__ __forceinline__ double p5(double a) { double b = a * a; return b * b * a; }
 __device__ __forceinline__ double p6(double a) { double b = a * a; return b * b * b; }
 
-// sum of logs of positive numbers without one log() per term: multiply mantissas, add exponents
+// sum of logs of positive numbers without one log() per term: multiply the values (raw() -- a product of a few
+// terms cannot leave the double range), pull the exponent out of the running product once per group (norm(): integer
+// ops on the exponent field; the mantissa bits are those of the un-normalised product, so the result equals the
+// term-by-term frexp version bit for bit)
 struct LogAcc {
     double m = 1.0;
     int e = 0;
-    __device__ __forceinline__ void mul(double v) {
-        int ex;
-        m *= frexp(v, &ex);
-        e += ex;
-        if (m < 1e-200) { m = frexp(m, &ex); e += ex; }
+    __device__ __forceinline__ void raw(double v) { m *= v; }
+    __device__ __forceinline__ void norm() {   // m is positive and normal here
+        int hi = __double2hiint(m);
+        e += (hi >> 20) - 1022;
+        m = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(m));
     }
+    __device__ __forceinline__ void mul(double v) { raw(v); norm(); }
     __device__ __forceinline__ double value() const { return log(m) + (double)e * 0.693147180559945309417232; }
 };
 
@@ -461,9 +465,10 @@ struct Ipm {
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     double lb = xlb(k, c), ub = xub(k, c), w = c ? x[5] : x[0];
-                    if (has(lb)) la.mul(w - lb);
-                    if (has(ub)) la.mul(ub - w);
+                    if (has(lb)) la.raw(w - lb);
+                    if (has(ub)) la.raw(ub - w);
                 }
+                la.norm();
             }
             double sgk[MM];
 #pragma unroll
@@ -472,15 +477,17 @@ struct Ipm {
                 if (useD) sv += al * D[isg(j, k)];
                 sgk[j] = sv;
                 ss += sv;
-                la.mul(sv);                                          // sigma >= 0 (:559,561)
+                la.raw(sv);                                          // sigma >= 0 (:559,561)
             }
+            if (M > 0) la.norm();
             if (k < N) {
                 double xn[6], u[2];
                 load_x<useD>(k + 1, al, xn);
                 load_u<useD>(k, al, u);
                 f += input_cost(u);                                  // :578-579
-                la.mul(u[0] + kp.p.umax[0]); la.mul(kp.p.umax[0] - u[0]);
-                la.mul(u[1] + kp.p.umax[1]); la.mul(kp.p.umax[1] - u[1]);
+                la.raw(u[0] + kp.p.umax[0]); la.raw(kp.p.umax[0] - u[0]);
+                la.raw(u[1] + kp.p.umax[1]); la.raw(kp.p.umax[1] - u[1]);
+                la.norm();
                 th += dyn_res<useD, false>(k, al, x, u);
                 if (hwd) f += wdp[k] * (xn[5] - x[5]) * (xn[5] - x[5]);   // overtake_traj_planner.py:325-327
 #pragma unroll
@@ -497,8 +504,9 @@ struct Ipm {
                         tt += al * dt;
                     }
                     th += fabs(g + tt - s);
-                    la.mul(s);
-                    la.mul(tt);
+                    la.raw(s);
+                    la.raw(tt);
+                    la.norm();
                     tsum += tt;
                 }
             }
@@ -506,6 +514,19 @@ struct Ipm {
         f += kp.p.slack_w * ss;
         theta = warp_sum(th);
         phi = df * warp_sum(f) + rho * warp_sum(tsum) - mu * warp_sum(la.value());
+    }
+
+    // constraint violation at the start point: the rows start with s = g + t, i.e. zero residual, so only the
+    // dynamics count (the bound push may have moved the rolled-out states)
+    __device__ double theta0() const {
+        double th = 0.0;
+        for (int k = lane; k < N; k += 32) {
+            double x[6], u[2];
+            load_x<false>(k, 0.0, x);
+            load_u<false>(k, 0.0, u);
+            th += dyn_res<false, false>(k, 0.0, x, u);
+        }
+        return warp_sum(th);
     }
 
     // unscaled objective at W
@@ -637,44 +658,48 @@ struct Ipm {
         e.zsum = warp_sum(zsum);
         return e;
     }
-    __device__ double comp_err(double m) const {
-        double c = 0.0;
+    // complementarity error for m = 0 (-> c0) and m = mu (-> cm) in ONE pass over the iterate: one copy of the code in
+    // the instruction stream instead of two (the crowded kernel is instruction-fetch bound)
+    __device__ void comp_err2(double m, double &c0, double &cm) const {
+        double a0 = 0.0, am = 0.0;
+        auto acc = [&](double v) { a0 = fmax(a0, fabs(v)); am = fmax(am, fabs(v - m)); };
         for (int k = lane; k <= N; k += 32) {
             if (k >= 1) {
                 double vx = W[6 * k], ey = W[6 * k + 5];
                 double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
-                if (has(xlb(k, 0))) c = fmax(c, fabs((vx - xlb(k, 0)) * zl.x - m));
-                if (has(xub(k, 0))) c = fmax(c, fabs((xub(k, 0) - vx) * zu.x - m));
-                if (has(xlb(k, 1))) c = fmax(c, fabs((ey - xlb(k, 1)) * zl.y - m));
-                if (has(xub(k, 1))) c = fmax(c, fabs((xub(k, 1) - ey) * zu.y - m));
+                if (has(xlb(k, 0))) acc((vx - xlb(k, 0)) * zl.x);
+                if (has(xub(k, 0))) acc((xub(k, 0) - vx) * zu.x);
+                if (has(xlb(k, 1))) acc((ey - xlb(k, 1)) * zl.y);
+                if (has(xub(k, 1))) acc((xub(k, 1) - ey) * zu.y);
             }
 #pragma unroll
-            for (int j = 0; j < M; j++) c = fmax(c, fabs(W[isg(j, k)] * ZL[bss(j, k)] - m));
+            for (int j = 0; j < M; j++) acc(W[isg(j, k)] * ZL[bss(j, k)]);
             if (k < N) {
                 double u[2];
                 load_u<false>(k, 0.0, u);
                 double2 zl = ld2(ZL + bsu(k)), zu = ld2(ZU + bsu(k));
-                c = fmax(c, fabs((u[0] + kp.p.umax[0]) * zl.x - m));
-                c = fmax(c, fabs((kp.p.umax[0] - u[0]) * zu.x - m));
-                c = fmax(c, fabs((u[1] + kp.p.umax[1]) * zl.y - m));
-                c = fmax(c, fabs((kp.p.umax[1] - u[1]) * zu.y - m));
+                acc((u[0] + kp.p.umax[0]) * zl.x);
+                acc((kp.p.umax[0] - u[0]) * zu.x);
+                acc((u[1] + kp.p.umax[1]) * zl.y);
+                acc((kp.p.umax[1] - u[1]) * zu.y);
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
-                    c = fmax(c, fabs(S[r] * Z[r] - m));
-                    c = fmax(c, fabs(T[r] * V[r] - m));
+                    acc(S[r] * Z[r]);
+                    acc(T[r] * V[r]);
                 }
             }
         }
-        return warp_max(c);
+        c0 = warp_max(a0);
+        cm = warp_max(am);
     }
-    __device__ double total_err(const Err &e, double m) const {
+    __device__ double total_err(const Err &e, double comp) const {
         const double s_max = 100.0;
         int nb = nb_count;  // lower + upper bound multipliers + row (z, v)
         int nmul = 6 * N + R + nb;
         double sd = fmax(s_max, (e.ysum + e.zsum) / (double)(nmul > 0 ? nmul : 1)) / s_max;
         double sc = fmax(s_max, e.zsum / (double)(nb > 0 ? nb : 1)) / s_max;
-        return fmax(e.dual / sd, fmax(e.prim, comp_err(m) / sc));
+        return fmax(e.dual / sd, fmax(e.prim, comp / sc));
     }
 
     // ---- per-iteration assembly (lane = stage): HD (diag Hessian additions), base gradient (into D), SIGE, YHAT
@@ -1209,8 +1234,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         }
         __syncwarp();
     }
-    double th0, ph_dummy;
-    q.template theta_phi<false>(0.0, th0, ph_dummy);
+    double th0 = q.theta0();
     const double theta_max = 1e4 * fmax(1.0, th0), theta_min = 1e-4 * fmax(1.0, th0);
 
     // filter: entry f lives in lane f%32, slot f/32 (capacity 64; the oldest entry is overwritten)
@@ -1236,16 +1260,21 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         PCLK(7)
         q.eval_point();
         typename IP::Err eb = q.error_base();
-        E0 = q.total_err(eb, 0.0);
-        if (E0 <= o.tol) { status = B200MPC_SOLVED; break; }
-        if (E0 <= o.acceptable_tol) {
-            if (++n_acc >= o.acceptable_iter) { status = B200MPC_SOLVED; break; }
-        } else
-            n_acc = 0;
-        if (iter >= o.max_iter) { status = B200MPC_MAX_ITER; break; }
-        // ---- barrier parameter (monotone Fiacco-McCormick)
-        for (;;) {
-            double em = q.total_err(eb, q.mu);
+        bool stop = false;
+        // termination test (first pass) and the monotone Fiacco-McCormick barrier update share one evaluation site
+        for (bool first = true;; first = false) {
+            double c0, cm;
+            q.comp_err2(q.mu, c0, cm);
+            if (first) {
+                E0 = q.total_err(eb, c0);
+                if (E0 <= o.tol) { status = B200MPC_SOLVED; stop = true; break; }
+                if (E0 <= o.acceptable_tol) {
+                    if (++n_acc >= o.acceptable_iter) { status = B200MPC_SOLVED; stop = true; break; }
+                } else
+                    n_acc = 0;
+                if (iter >= o.max_iter) { status = B200MPC_MAX_ITER; stop = true; break; }
+            }
+            double em = q.total_err(eb, cm);
             if (em <= kappa_eps * q.mu && q.mu > o.tol / 11.0) {
                 q.mu = fmax(o.tol / 11.0, fmin(kappa_mu * q.mu, q.mu * sqrt(q.mu)));
                 nfilt = 0;
@@ -1253,6 +1282,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             } else
                 break;
         }
+        if (stop) break;
         const double mu = q.mu, rho = q.rho;
         const double tau = fmax(tau_min, 1.0 - mu);
         PCLK(0)
@@ -1388,29 +1418,31 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         a_z = warp_min(a_z);
         gphi = warp_sum(gphi);
         th = warp_sum(th);
-        double th_chk, ph;
-        q.template theta_phi<false>(0.0, th_chk, ph);
         PCLK(4)
-        // ---- filter line search
+        // ---- filter line search.  One evaluation site: the first pass (alpha = 0) yields phi at the current point,
+        //      the following passes are the trial points (same code, warm in the instruction cache).
+        double pw_g = 0.0, pw_t = 0.0;
+        if (gphi < 0.0) { pw_g = pow(-gphi, s_phi); pw_t = delta_sw * pow(th, s_theta); }
         double amin;
         if (gphi < 0.0 && th <= theta_min)
-            amin = gamma_alpha * fmin(gamma_theta, fmin(gamma_phi * th / (-gphi), delta_sw * pow(th, s_theta) / pow(-gphi, s_phi)));
+            amin = gamma_alpha * fmin(gamma_theta, fmin(gamma_phi * th / (-gphi), pw_t / pw_g));
         else if (gphi < 0.0)
             amin = gamma_alpha * fmin(gamma_theta, gamma_phi * th / (-gphi));
         else
             amin = gamma_alpha * gamma_theta;
-        double a = a_max;
+        double a = a_max, ph = 0.0;
         bool accepted = false, ftype = false;
         int nls = 0;
-        while (a >= amin || nls == 0) {
+        for (bool base = true;;) {
             double tht, pht;
-            q.template theta_phi<true>(a, tht, pht);
+            q.template theta_phi<true>(base ? 0.0 : a, tht, pht);
+            if (base) { ph = pht; base = false; continue; }
             bool dom = false;
             if (lane < nfilt && tht >= f_th0 && pht >= f_ph0) dom = true;
             if (lane + 32 < nfilt && tht >= f_th1 && pht >= f_ph1) dom = true;
             bool okf = (tht < theta_max) && !__any_sync(0xffffffffu, dom);
             if (okf) {
-                bool sw = gphi < 0.0 && a * pow(-gphi, s_phi) > delta_sw * pow(th, s_theta);
+                bool sw = gphi < 0.0 && a * pw_g > pw_t;
                 if (th <= theta_min && sw) {
                     if (pht <= ph + eta_phi * a * gphi) { accepted = true; ftype = true; }
                 } else if (tht <= (1.0 - gamma_theta) * th || pht <= ph - gamma_phi * th)
@@ -1420,6 +1452,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             a *= 0.5;
             nls++;
             n_back++;
+            if (!(a >= amin)) break;
         }
         if (!accepted) {
             // IPOPT would call its restoration phase; the rows are elastic, so remove their residual by
