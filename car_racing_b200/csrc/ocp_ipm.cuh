@@ -107,6 +107,22 @@ __device__ __forceinline__ double warp_min(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// max / min over the warp of NON-NEGATIVE doubles (error norms, step lengths): for those the IEEE bit pattern orders
+// like the value, so two hardware integer reductions (REDUX: high word, then the low words of the lanes that hold the
+// winning high word) replace five shuffle + DSETP/FSEL/SEL rounds.  A NaN anywhere wins the max (the caller's
+// comparisons then fail and the solve ends at max_iter), where fmax would have dropped it silently.
+__device__ __forceinline__ double warp_max_nn(double v) {
+    unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double warp_min_nn(double v) {
+    unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
+}
 // branch-free FP64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) + two Newton
 // steps (quadratic: 20 -> 40 -> 80 bits).  The compiler's IEEE division carries a slow-path call per site (~20 instructions, 2 branches); the
 // solver's operands are positive, finite and far from the denormal range, and 1-ulp differences are irrelevant here.
@@ -214,6 +230,9 @@ struct Ipm {
     const KParams &kp;
     const int lane;
     static constexpr bool kStaticN = NT > 0;
+    // stage loops: with a compile-time horizon below 32 every stage has its own lane and the loop runs once -- a step
+    // that overshoots any horizon lets the compiler drop the loop (back edge, loop-carried moves)
+    static constexpr int KSTEP = (NT > 0 && NT < 32) ? (1 << 20) : 32;
     const int N, R, NB, NW, OU, OS;
     double *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM, *CRES, *KFB, *KFF, *PT,
         *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC, *GX, *ABs;
@@ -457,7 +476,7 @@ struct Ipm {
     __device__ void theta_phi(double al, double &theta, double &phi) const {
         double th = 0.0, f = 0.0, tsum = 0.0, ss = 0.0;
         LogAcc la;
-        for (int k = lane; k <= N; k += 32) {
+        for (int k = lane; k <= N; k += KSTEP) {
             double x[6];
             load_x<useD>(k, al, x);
             f += stage_cost(k, x);                                   // control.py:588-591
@@ -513,14 +532,14 @@ struct Ipm {
         }
         f += kp.p.slack_w * ss;
         theta = warp_sum(th);
-        phi = df * warp_sum(f) + rho * warp_sum(tsum) - mu * warp_sum(la.value());
+        phi = warp_sum(df * f + rho * tsum - mu * la.value());   // lane-local partial of phi, one reduction
     }
 
     // constraint violation at the start point: the rows start with s = g + t, i.e. zero residual, so only the
     // dynamics count (the bound push may have moved the rolled-out states)
     __device__ double theta0() const {
         double th = 0.0;
-        for (int k = lane; k < N; k += 32) {
+        for (int k = lane; k < N; k += KSTEP) {
             double x[6], u[2];
             load_x<false>(k, 0.0, x);
             load_u<false>(k, 0.0, u);
@@ -532,7 +551,7 @@ struct Ipm {
     // unscaled objective at W
     __device__ double objective() const {
         double f = 0.0, ss = 0.0;
-        for (int k = lane; k <= N; k += 32) {
+        for (int k = lane; k <= N; k += KSTEP) {
             double x[6];
             load_x<false>(k, 0.0, x);
             f += stage_cost(k, x);
@@ -550,7 +569,7 @@ struct Ipm {
 
     // ---- evaluate rows (GR, JA) and dynamics residual at the current iterate (lane = stage)
     __device__ void eval_point() {
-        for (int k = lane; k < N; k += 32) {
+        for (int k = lane; k < N; k += KSTEP) {
             double x[6], xn[6], u[2];
             load_x<false>(k, 0.0, x);
             load_x<false>(k + 1, 0.0, xn);
@@ -578,7 +597,7 @@ struct Ipm {
     struct Err { double dual, prim, ysum, zsum; };
     __device__ Err error_base() const {
         double dual = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0;
-        for (int k = lane; k <= N; k += 32) {
+        for (int k = lane; k <= N; k += KSTEP) {
             double lamn[6];  // lam_{k+1} (multiplier of c_k), zero for k = N
             if (k < N) ld6(LAM + 6 * k, lamn);
             else {
@@ -652,8 +671,8 @@ struct Ipm {
             }
         }
         Err e;
-        e.dual = warp_max(dual);
-        e.prim = warp_max(prim);
+        e.dual = warp_max_nn(dual);
+        e.prim = warp_max_nn(prim);
         e.ysum = warp_sum(ysum);
         e.zsum = warp_sum(zsum);
         return e;
@@ -663,7 +682,7 @@ struct Ipm {
     __device__ void comp_err2(double m, double &c0, double &cm) const {
         double a0 = 0.0, am = 0.0;
         auto acc = [&](double v) { a0 = fmax(a0, fabs(v)); am = fmax(am, fabs(v - m)); };
-        for (int k = lane; k <= N; k += 32) {
+        for (int k = lane; k <= N; k += KSTEP) {
             if (k >= 1) {
                 double vx = W[6 * k], ey = W[6 * k + 5];
                 double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
@@ -690,8 +709,8 @@ struct Ipm {
                 }
             }
         }
-        c0 = warp_max(a0);
-        cm = warp_max(am);
+        c0 = warp_max_nn(a0);
+        cm = warp_max_nn(am);
     }
     __device__ double total_err(const Err &e, double comp) const {
         const double s_max = 100.0;
@@ -704,7 +723,7 @@ struct Ipm {
 
     // ---- per-iteration assembly (lane = stage): HD (diag Hessian additions), base gradient (into D), SIGE, YHAT
     __device__ void assemble() {
-        for (int k = lane; k <= N; k += 32) {
+        for (int k = lane; k <= N; k += KSTEP) {
             if (k >= 1) {
                 double x[6], g[6], hd[6];
                 load_x<false>(k, 0.0, x);
@@ -1096,7 +1115,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     Ipm<M, FL, NT> S_(kp, pl, sm, lane);
     Ipm<M, FL, NT> &q = S_;
     using IP = Ipm<M, FL, NT>;
-    constexpr int NXAP = IP::NXAP, NC = IP::NC;
+    constexpr int NXAP = IP::NXAP, NC = IP::NC, KSTEP = IP::KSTEP;
     const int N = q.N, R = q.R, NW = q.NW, OU = q.OU, OS = q.OS;
     const b200mpc_ipm_options &o = kp.o;
 
@@ -1138,7 +1157,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     }
     __syncwarp();
     int nbc = 0;
-    for (int k = lane; k <= N; k += 32) {
+    for (int k = lane; k <= N; k += KSTEP) {
         if (k >= 1) {   // bound_push / bound_frac on vx_k, ey_k
 #pragma unroll
             for (int c = 0; c < 2; c++) {
@@ -1190,7 +1209,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     // ---- gradient-based scaling at the start (nlp_scaling_max_gradient)
     {
         double gm = (M > 0) ? kp.p.slack_w : 0.0;
-        for (int k = lane; k <= N; k += 32) {
+        for (int k = lane; k <= N; k += KSTEP) {
             if (k >= 1) {
                 double x[6];
                 q.template load_x<false>(k, 0.0, x);
@@ -1203,10 +1222,10 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 gm = fmax(gm, fabs(q.R2(1, 0) * u[0] + q.R2(1, 1) * u[1]));
             }
         }
-        gm = warp_max(gm);
+        gm = warp_max_nn(gm);
         q.df = gm > o.max_grad ? o.max_grad / gm : 1.0;
         q.set_scaled_columns();
-        for (int k = lane; k < N; k += 32) {
+        for (int k = lane; k < N; k += KSTEP) {
             double x[6], xn[6];
             q.template load_x<false>(k, 0.0, x);
             q.template load_x<false>(k + 1, 0.0, xn);
@@ -1317,7 +1336,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         q.riccati_forward();
         PCLK(3)
         // ---- rows: J d, step bounds, directional derivative (lane = stage)
-        for (int k = lane; k < N; k += 32) {
+        for (int k = lane; k < N; k += KSTEP) {
             double dxk[6], dxn[6];
             ld6(q.D + 6 * k, dxk);
             ld6(q.D + 6 * (k + 1), dxn);
@@ -1333,7 +1352,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         }
         __syncwarp();
         double a_max = 1.0, a_z = 1.0, gphi = 0.0, th = 0.0;
-        for (int k = lane; k <= N; k += 32) {
+        for (int k = lane; k <= N; k += KSTEP) {
             if (k >= 1) {
                 double x[6], d[6];
                 q.template load_x<false>(k, 0.0, x);
@@ -1414,18 +1433,20 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 }
             }
         }
-        a_max = warp_min(a_max);
-        a_z = warp_min(a_z);
+        a_max = warp_min_nn(a_max);
+        a_z = warp_min_nn(a_z);
         gphi = warp_sum(gphi);
         th = warp_sum(th);
         PCLK(4)
         // ---- filter line search.  One evaluation site: the first pass (alpha = 0) yields phi at the current point,
         //      the following passes are the trial points (same code, warm in the instruction cache).
-        double pw_g = 0.0, pw_t = 0.0;
-        if (gphi < 0.0) { pw_g = pow(-gphi, s_phi); pw_t = delta_sw * pow(th, s_theta); }
+        // switching condition a (-gphi)^s_phi > delta th^s_theta and the a_min term delta th^s_theta / (-gphi)^s_phi in
+        // the log domain: lsw = s_phi log(-gphi) - log(delta) - s_theta log(th); a = a_max 2^-nls
+        double lsw = 0.0, la_max = 0.0;
+        if (gphi < 0.0) { lsw = s_phi * log(-gphi) - log(delta_sw) - s_theta * log(th); la_max = log(a_max); }
         double amin;
         if (gphi < 0.0 && th <= theta_min)
-            amin = gamma_alpha * fmin(gamma_theta, fmin(gamma_phi * th / (-gphi), pw_t / pw_g));
+            amin = gamma_alpha * fmin(gamma_theta, fmin(gamma_phi * th / (-gphi), exp(-lsw)));
         else if (gphi < 0.0)
             amin = gamma_alpha * fmin(gamma_theta, gamma_phi * th / (-gphi));
         else
@@ -1442,7 +1463,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             if (lane + 32 < nfilt && tht >= f_th1 && pht >= f_ph1) dom = true;
             bool okf = (tht < theta_max) && !__any_sync(0xffffffffu, dom);
             if (okf) {
-                bool sw = gphi < 0.0 && a * pw_g > pw_t;
+                bool sw = gphi < 0.0 && la_max - (double)nls * 0.693147180559945309417232 + lsw > 0.0;
                 if (th <= theta_min && sw) {
                     if (pht <= ph + eta_phi * a * gphi) { accepted = true; ftype = true; }
                 } else if (tht <= (1.0 - gamma_theta) * th || pht <= ph - gamma_phi * th)
@@ -1485,7 +1506,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         // ---- accept: multipliers of the dynamics by the costate recursion, from
         //      K d + Jc' lam+ = rhs  =>  lam+_i = (rhs - K d)_{x_i} + A' lam+_{i+1}
         // (a) residuals res_i = (rhs - K d)_{x_i} for all stages in parallel -> CRES (dead until the next eval)
-        for (int i = lane + 1; i <= N; i += 32) {
+        for (int i = lane + 1; i <= N; i += KSTEP) {
             double x[6], d[6], g[6];
             q.template load_x<false>(i, 0.0, x);
             ld6(q.D + 6 * i, d);
@@ -1543,7 +1564,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             }
         }
         // bound multipliers (old point), primal step, kappa_sigma safeguard (new point): lane = stage
-        for (int k = lane; k <= N; k += 32) {
+        for (int k = lane; k <= N; k += KSTEP) {
             if (k >= 1) {
                 double x[6], d[6];
                 q.template load_x<false>(k, 0.0, x);
@@ -1634,7 +1655,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     double cost = q.objective();
     double tm = 0.0;
     for (int r = lane; r < R; r += 32) tm = fmax(tm, q.T[r]);
-    tm = warp_max(tm);
+    tm = warp_max_nn(tm);
     if (lane == 0) {
         b200mpc_record rc;
         rc.cost = cost;
