@@ -244,6 +244,8 @@ struct Ipm {
     // lane = column role of the Riccati sweep (set once)
     bool isx, iss, isu, isp;
     int jrole, cmap;
+    int idx_base, idx_step, kmin;   // lane's diagonal / gradient slot at stage k: idx_base + k*idx_step, live for k >= kmin
+    double crow[MM], psel[MM];      // d(row j)/d(own sigma variable): (1-alpha) for sigma_k, -1 for sigma_{k+1}; one-hot of sigma_{k+1}
     double tcol[6], qqcol[6], rrcol[2];
     double arow[6], brow[2];   // row `lane` of A and B (lanes < 6), for the forward sweep
 
@@ -276,6 +278,14 @@ struct Ipm {
         isp = l >= NXA + 2 && l < NZ;
         jrole = iss ? l - 6 : (isp ? l - NXA - 2 : (isu ? l - NXA : 0));
         cmap = isx ? l : (isu ? 6 + (l - NXA) : (isp ? 8 + (l - NXA - 2) : NC));  // NC = the all-zero row of PT
+        idx_base = isx ? l : (iss ? OS + jrole * (N + 1) : (isu ? OU + jrole : 0));
+        idx_step = isx ? 6 : (iss ? 1 : (isu ? 2 : 0));
+        kmin = isx ? 1 : ((iss || isu) ? 0 : (1 << 30));
+#pragma unroll
+        for (int j = 0; j < MM; j++) {
+            crow[j] = (iss && jrole == j) ? a1 : ((isp && jrole == j) ? -1.0 : 0.0);
+            psel[j] = (isp && jrole == j) ? 1.0 : 0.0;
+        }
 #pragma unroll
         for (int q = 0; q < 6; q++) {
             double va = 0.0, vb = 0.0;
@@ -871,8 +881,8 @@ struct Ipm {
                 }
 #pragma unroll
                 for (int j = 0; j < M; j++) g[NXA + 2 + j] = colv[6 + j];
-                int idx = isx ? 6 * k + lane : (iss ? isg(jrole, k) : (isu ? OU + 2 * k + jrole : 0));
-                bool live = (isx && k > 0) || iss || isu;
+                int idx = idx_base + k * idx_step;
+                bool live = k >= kmin;
                 double dsg = live ? HD[idx] + dw : 0.0;
                 gv = live ? D[idx] : 0.0;
 #pragma unroll
@@ -880,7 +890,7 @@ struct Ipm {
 #pragma unroll
                 for (int q = 0; q < 6; q++) gv += tcol[q] * qvs[q];
 #pragma unroll
-                for (int j = 0; j < M; j++) gv += (isp && jrole == j) ? qvs[6 + j] : 0.0;
+                for (int j = 0; j < M; j++) gv += psel[j] * qvs[6 + j];
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
@@ -890,8 +900,7 @@ struct Ipm {
                     double own = tcol[4] * ja[2] + tcol[5] * ja[3];
                     own += (lane == 4) ? ja[0] : 0.0;
                     own += (lane == 5) ? ja[1] : 0.0;
-                    own += (iss && jrole == j) ? dgr * a1 : 0.0;
-                    own -= (isp && jrole == j) ? dgr : 0.0;
+                    own += crow[j] * dgr;
                     double w = sg * own;
 #pragma unroll
                     for (int a = 0; a < 6; a++) {
