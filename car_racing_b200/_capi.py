@@ -69,6 +69,14 @@ class PlantParams(C.Structure):
     ]
 
 
+class PlannerSelectParams(C.Structure):
+    _fields_ = [
+        ("C", C.c_int32), ("N", C.c_int32), ("num_veh", C.c_int32), ("old_direction_flag", C.c_int32),
+        ("N_ctrl", C.c_int32), ("M_ctrl", C.c_int32),
+        ("veh_length", C.c_double), ("veh_width", C.c_double), ("lap_length", C.c_double),
+    ]
+
+
 RECORD_DTYPE = np.dtype([("cost", "<f8"), ("u0", "<f8", (2,)), ("status", "<i4"), ("iters", "<i4")])
 assert RECORD_DTYPE.itemsize == 32
 
@@ -78,7 +86,7 @@ EXPORTS = [
     "b200mpc_cbf_solve_device", "b200mpc_ilqr_record_doubles", "b200mpc_ilqr_solve", "b200mpc_ilqr_solve_device",
     "b200mpc_argmin_cost_device", "b200mpc_lmpc_record_doubles", "b200mpc_lmpc_solve", "b200mpc_lmpc_solve_device",
     "b200mpc_lmpc_sysid", "b200mpc_lmpc_sysid_device", "b200mpc_plant_step", "b200mpc_plant_step_device",
-    "b200mpc_cbf_solve_async", "b200mpc_synchronize", "b200mpc_host_alloc", "b200mpc_host_free",
+    "b200mpc_cbf_solve_async", "b200mpc_synchronize", "b200mpc_host_alloc", "b200mpc_host_free", "b200mpc_planner_select_device", "b200mpc_plan_and_track",
 ]
 
 _lib = None
@@ -119,6 +127,9 @@ def lib():
     L.b200mpc_host_alloc.restype = C.c_void_p
     L.b200mpc_host_free.argtypes = [vp]
     L.b200mpc_host_free.restype = None
+    L.b200mpc_planner_select_device.argtypes = [vp, C.POINTER(PlannerSelectParams)] + [dp] * 10
+    L.b200mpc_plan_and_track.argtypes = [vp, C.POINTER(CbfParams), C.POINTER(CbfParams), C.POINTER(IpmOptions),
+                                         C.POINTER(PlannerSelectParams)] + [dp] * 14
     ilqr_args = [vp, C.POINTER(IlqrParams), ip, dp, dp, dp, dp]
     L.b200mpc_ilqr_solve.argtypes = ilqr_args
     L.b200mpc_ilqr_solve_device.argtypes = ilqr_args

@@ -11,6 +11,7 @@
 #include "lmpc.cuh"
 #include "ocp_ipm.cuh"
 #include "plant.cuh"
+#include "planner_select.cuh"
 #include "sysid.cuh"
 
 using namespace b200mpc;
@@ -23,8 +24,8 @@ struct b200mpc_handle {
     int max_smem_optin = 0;
     // staging buffers for the host-pointer API (grown on demand)
     void *d_in = nullptr, *d_rec = nullptr, *d_aux = nullptr, *d_x = nullptr, *d_u = nullptr, *d_sig = nullptr;
-    void *d_laps = nullptr, *d_seg = nullptr, *d_idx = nullptr, *d_stat = nullptr;
-    size_t c_in = 0, c_rec = 0, c_aux = 0, c_x = 0, c_u = 0, c_sig = 0, c_laps = 0, c_seg = 0, c_idx = 0, c_stat = 0;
+    void *d_laps = nullptr, *d_seg = nullptr, *d_idx = nullptr, *d_stat = nullptr, *d_chain = nullptr;
+    size_t c_in = 0, c_rec = 0, c_aux = 0, c_x = 0, c_u = 0, c_sig = 0, c_laps = 0, c_seg = 0, c_idx = 0, c_stat = 0, c_chain = 0;
     uint64_t launches = 0;
     std::string err;
 };
@@ -102,7 +103,7 @@ void b200mpc_destroy(b200mpc_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void *bufs[] = {h->d_in, h->d_rec, h->d_aux, h->d_x, h->d_u, h->d_sig, h->d_laps, h->d_seg, h->d_idx, h->d_stat};
+    void *bufs[] = {h->d_in, h->d_rec, h->d_aux, h->d_x, h->d_u, h->d_sig, h->d_laps, h->d_seg, h->d_idx, h->d_stat, h->d_chain};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -493,6 +494,91 @@ int b200mpc_plant_step(b200mpc_handle *h, const b200mpc_plant_params *prm, int B
     CK(h, cudaMemcpyAsync(xcurv, h->d_in, b_xc, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(xglob, h->d_x, b_xg, cudaMemcpyDeviceToHost, h->stream));
     if (laps) CK(h, cudaMemcpyAsync(laps, h->d_stat, b_l, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+int b200mpc_planner_select_device(b200mpc_handle *h, const b200mpc_planner_select_params *prm, const b200mpc_record *d_rec,
+                                  const double *d_xpred, const double *d_heur, const int32_t *d_ok0, const int32_t *d_region,
+                                  const double *d_rivals, double *d_sel_cost, int32_t *d_flag, double *d_traj,
+                                  double *d_track_rec) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!prm || !d_rec || !d_xpred || !d_heur || !d_ok0 || !d_region || !d_flag)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_planner_select: null argument");
+    if (prm->C < 1 || prm->N < 1 || prm->N > B200MPC_NMAX || prm->num_veh < 0 || (prm->num_veh > 0 && !d_rivals) ||
+        prm->N_ctrl < 1 || prm->N_ctrl > B200MPC_NMAX || prm->M_ctrl < 0 || prm->M_ctrl > B200MPC_MMAX)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_planner_select: bad parameter value");
+    CK(h, cudaSetDevice(h->device));
+    SelectKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.p = *prm;
+    kp.track_xt_off = cbf_hdr_doubles(prm->M_ctrl);
+    planner_select_kernel<<<1, SELECT_NT, 0, h->stream>>>(kp, d_rec, d_xpred, d_heur, d_ok0, d_region, d_rivals, d_sel_cost, d_flag,
+                                                         d_traj, d_track_rec);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+int b200mpc_plan_and_track(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
+                           const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel, const double *cand_in,
+                           const double *heur, const int32_t *ok0, const int32_t *region, const double *rivals,
+                           const double *track_in, b200mpc_record *cand_rec, double *cand_xpred, double *sel_cost, int32_t *flag,
+                           double *traj, b200mpc_record *track_rec, double *track_xpred, double *track_upred) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!plan_prm || !track_prm || !opt || !sel || !cand_in || !heur || !ok0 || !region || !track_in || !flag || !track_rec)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: null argument");
+    const int C_ = sel->C, N = plan_prm->N, Nc = track_prm->N, Mc = track_prm->M;
+    if (C_ < 1 || sel->N != N || sel->N_ctrl != Nc || sel->M_ctrl != Mc || !track_prm->xt_per_stage || track_prm->flags != 0 ||
+        (sel->num_veh > 0 && !rivals))
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: inconsistent parameters (the tracking record has per-stage targets)");
+    int rc = check_cbf(h, plan_prm, opt, C_, cand_in, flag);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    const size_t cs = (size_t)cbf_record_doubles(N, plan_prm->M, plan_prm->xt_per_stage, plan_prm->flags);
+    const size_t ts = (size_t)cbf_record_doubles(Nc, Mc, 1, 0);
+    const size_t b_in = cs * 8 * C_, b_rec = sizeof(b200mpc_record) * (size_t)C_, b_x = 48 * (size_t)(N + 1) * C_;
+    const size_t b_riv = 16 * (size_t)(N + 1) * (sel->num_veh > 0 ? sel->num_veh : 1), b_int = 4 * (size_t)C_;
+    // chain buffer: [flag 2 ints + pad][traj 6(N+1)][tracking record][tracking result record][x_pred][u_pred]
+    const size_t o_traj = 2, o_trk = o_traj + 6 * (size_t)(N + 1), o_out = o_trk + ts, o_tx = o_out + 4,
+                 o_tu = o_tx + 6 * (size_t)(Nc + 1), n_chain = o_tu + 2 * (size_t)Nc;
+    if ((rc = grow(h, &h->d_in, &h->c_in, b_in))) return rc;
+    if ((rc = grow(h, &h->d_rec, &h->c_rec, b_rec))) return rc;
+    if ((rc = grow(h, &h->d_x, &h->c_x, b_x))) return rc;
+    if ((rc = grow(h, &h->d_laps, &h->c_laps, b_x))) return rc;
+    if ((rc = grow(h, &h->d_seg, &h->c_seg, b_riv))) return rc;
+    if ((rc = grow(h, &h->d_idx, &h->c_idx, b_int))) return rc;
+    if ((rc = grow(h, &h->d_stat, &h->c_stat, b_int))) return rc;
+    if ((rc = grow(h, &h->d_aux, &h->c_aux, 8 * (size_t)C_))) return rc;
+    if ((rc = grow(h, &h->d_chain, &h->c_chain, 8 * n_chain))) return rc;
+    double *ch = (double *)h->d_chain;
+    CK(h, cudaMemcpyAsync(h->d_in, cand_in, b_in, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_laps, heur, b_x, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_idx, ok0, b_int, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_stat, region, b_int, cudaMemcpyHostToDevice, h->stream));
+    if (sel->num_veh > 0) CK(h, cudaMemcpyAsync(h->d_seg, rivals, b_riv, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(ch + o_trk, track_in, ts * 8, cudaMemcpyHostToDevice, h->stream));
+    // (1) all candidates, one launch
+    rc = b200mpc_cbf_solve_device(h, plan_prm, opt, C_, (const double *)h->d_in, (b200mpc_record *)h->d_rec, nullptr, (double *)h->d_x,
+                                  nullptr, nullptr);
+    if (rc) return rc;
+    // (2) selection cost, first argmin, chosen trajectory, per-stage targets of the tracking record
+    rc = b200mpc_planner_select_device(h, sel, (const b200mpc_record *)h->d_rec, (const double *)h->d_x, (const double *)h->d_laps,
+                                       (const int32_t *)h->d_idx, (const int32_t *)h->d_stat, (const double *)h->d_seg,
+                                       (double *)h->d_aux, (int32_t *)ch, ch + o_traj, ch + o_trk);
+    if (rc) return rc;
+    // (3) the tracking MPC on the record the selection kernel completed
+    rc = b200mpc_cbf_solve_device(h, track_prm, opt, 1, ch + o_trk, (b200mpc_record *)(ch + o_out), nullptr, ch + o_tx, ch + o_tu,
+                                  nullptr);
+    if (rc) return rc;
+    if (cand_rec) CK(h, cudaMemcpyAsync(cand_rec, h->d_rec, b_rec, cudaMemcpyDeviceToHost, h->stream));
+    if (cand_xpred) CK(h, cudaMemcpyAsync(cand_xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
+    if (sel_cost) CK(h, cudaMemcpyAsync(sel_cost, h->d_aux, 8 * (size_t)C_, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(flag, ch, 8, cudaMemcpyDeviceToHost, h->stream));
+    if (traj) CK(h, cudaMemcpyAsync(traj, ch + o_traj, 48 * (size_t)(N + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(track_rec, ch + o_out, sizeof(b200mpc_record), cudaMemcpyDeviceToHost, h->stream));
+    if (track_xpred) CK(h, cudaMemcpyAsync(track_xpred, ch + o_tx, 48 * (size_t)(Nc + 1), cudaMemcpyDeviceToHost, h->stream));
+    if (track_upred) CK(h, cudaMemcpyAsync(track_upred, ch + o_tu, 16 * (size_t)Nc, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }

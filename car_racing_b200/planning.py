@@ -18,9 +18,11 @@ Mapping of the candidate QP onto the batched MPC kernel (include/b200mpc.h, flag
     the predicted ego s is inside the rival's window (:286-324; same sign for both sides -- reference quirk)
     become per-stage lower bounds on ey_k.
 """
+import ctypes as C
+
 import numpy as np
 
-from . import batch
+from . import _capi, batch
 
 SAFETY_MARGIN = 0.15          # overtake_traj_planner.py:177,262
 W_EY_RATE, W_PROGRESS, W_TRACK = 30.0, 200.0, 20.0   # :327,328,333-334
@@ -169,3 +171,86 @@ def solve_optimization_problem(self, solver=None):
     traj_xcurv = solution_xvar[direction_flag, :, :].T
     solve_time = np.full(C, dt / C)
     return traj_xcurv, direction_flag, solve_time, solution_xvar
+
+
+def plan_and_track(self, xcurv, mpc_lti_param, track, system_param, vehicles=None, agent_name=None, sorted_vehicles=None,
+                   time=None, handle=None, region=None, extra=None):
+    """The whole overtaking step in ONE call on one CUDA stream (b200mpc_plan_and_track, include/b200mpc.h): candidate
+    QPs (overtake_traj_planner.py:248-379) -> selection cost + first argmin (:205-246) -> per-stage targets from the chosen
+    trajectory (control.py:277, 373-382) -> tracking MPC-CBF (control.py:251-473), without a host round trip in between.
+    The reference does this as solve_optimization_problem() followed by control.mpc_multi_agents() (utils/base.py:540-582).
+
+    `self` is the reference's planner object after get_local_traj prepared it.  Returns
+    ((traj_xcurv, direction_flag, solve_time, solution_xvar), (u0, x_pred)) -- the two reference return values.
+    `extra`: optional dict of additional candidates {"s_ref","ey_ref","xlb","xub","region"} appended to the reference's
+    num_veh+1 regions (BASELINE config 3 evaluates 64 candidates)."""
+    import time as _time
+    from . import control
+    h = handle or batch.default_handle()
+    sorted_vehicles = self.sorted_vehicles if sorted_vehicles is None else sorted_vehicles
+    vehicles = self.vehicles if vehicles is None else vehicles
+    agent_name = self.agent_name if agent_name is None else agent_name
+    obs_infos = self.obs_infos
+    N = self.racing_game_param.num_horizon_planner
+    num_veh = len(self.sorted_vehicles)
+    ego = vehicles[agent_name]
+    veh_length, veh_width = ego.param.length, ego.param.width
+    ego_x = np.asarray(ego.xcurv, float)
+    Cn = num_veh + 1
+    s_ref, ey_ref = np.zeros((Cn, N + 1)), np.zeros((Cn, N + 1))
+    xlb, xub = np.zeros((Cn, N + 1, 2)), np.zeros((Cn, N + 1, 2))
+    reg = np.arange(Cn, dtype=np.int32)
+    for c in range(Cn):
+        xlb[c], xub[c] = candidate_bounds(c, self.xcurv_ego, self.sorted_vehicles, obs_infos, veh_length, veh_width, track.width,
+                                          track.lap_length, N)
+        s_ref[c], ey_ref[c] = candidate_targets(c, ego_x, self.bezier_xcurvs, self.bezier_funcs, N)
+    heur = np.stack([heuristic_traj(c, self.xcurv_ego, self.bezier_xcurvs, self.bezier_funcs, N).T for c in range(Cn)])
+    if extra is not None:
+        s_ref, ey_ref = np.concatenate([s_ref, extra["s_ref"]]), np.concatenate([ey_ref, extra["ey_ref"]])
+        xlb, xub = np.concatenate([xlb, extra["xlb"]]), np.concatenate([xub, extra["xub"]])
+        reg = np.concatenate([reg, np.asarray(extra["region"], dtype=np.int32)])
+        heur = np.concatenate([heur, extra["heur"]])
+    Cn = s_ref.shape[0]
+    ok0 = np.array([x0_feasible(ego_x, xlb[c], xub[c]) for c in range(Cn)], dtype=np.int32)
+    pprm = planner_params(self.racing_game_param.matrix_A, self.racing_game_param.matrix_B, N)
+    kw, offset = pack_candidates(ego_x, s_ref, ey_ref, xlb, xub, N)
+    cand, M0, ps0 = batch.pack_cbf(kw["x0"], kw["xt"], kw["obs"], None, N, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"])
+    rivals = np.zeros((max(num_veh, 1), 2, N + 1))
+    for j, name in enumerate(self.sorted_vehicles):
+        rivals[j, 0], rivals[j, 1] = obs_infos[name][4, :N + 1], obs_infos[name][5, :N + 1]
+    # tracking MPC record (control.mpc_multi_agents): everything except the per-stage targets, which the device fills
+    Nc = mpc_lti_param.num_horizon_ctrl
+    xc = np.asarray(xcurv, float).reshape(6)
+    kept, num_cycle_ego = control._nearby_rivals(xc, sorted_vehicles, vehicles, agent_name, track.lap_length, time, 0.1, False, Nc + 1)
+    obs_t, lap_off_t = control._rival_block(kept, num_cycle_ego, track.lap_length, Nc)
+    tprm = control._limits(control._model(mpc_lti_param, Nc), system_param, track.width)
+    tprm.update(alpha=0.6, margin=0.15, L=veh_length, W=veh_width)            # control.py:285,311,316-319
+    trec, Mc, _ = batch.pack_cbf(xc.reshape(1, 6), np.zeros((1, Nc + 1, 6)), obs_t, lap_off_t, Nc)
+    p_plan = _capi.make_cbf_params(pprm, 0, True, _capi.FLAG_STAGE_BOUNDS | _capi.FLAG_EY_RATE)
+    p_track = _capi.make_cbf_params(tprm, Mc, True, 0)
+    o = _capi.default_options()
+    sel = _capi.PlannerSelectParams()
+    sel.C, sel.N, sel.num_veh, sel.N_ctrl, sel.M_ctrl = Cn, N, num_veh, Nc, Mc
+    sel.old_direction_flag = -1 if self.old_direction_flag is None else int(self.old_direction_flag)
+    sel.veh_length, sel.veh_width, sel.lap_length = veh_length, veh_width, track.lap_length
+    cand_rec = np.zeros(Cn, dtype=_capi.RECORD_DTYPE)
+    cand_x = np.zeros((Cn, N + 1, 6))
+    sel_cost = np.zeros(Cn)
+    flag = np.zeros(2, dtype=np.int32)
+    traj = np.zeros((N + 1, 6))
+    trk = np.zeros(1, dtype=_capi.RECORD_DTYPE)
+    trk_x, trk_u = np.zeros((Nc + 1, 6)), np.zeros((Nc, 2))
+    P = batch._ptr
+    heur = np.ascontiguousarray(heur)
+    t0 = _time.perf_counter()
+    rc = _capi.lib().b200mpc_plan_and_track(h.ptr, C.byref(p_plan), C.byref(p_track), C.byref(o), C.byref(sel), P(cand), P(heur),
+                                            P(ok0), P(reg), P(rivals), P(trec), P(cand_rec), P(cand_x), P(sel_cost), P(flag), P(traj),
+                                            P(trk), P(trk_x), P(trk_u))
+    h.check(rc, "b200mpc_plan_and_track")
+    dt = _time.perf_counter() - t0
+    solved = (ok0 != 0) & (cand_rec["status"] == 0)
+    solution_xvar = np.where(solved[:, None, None], cand_x, heur).transpose(0, 2, 1).copy()
+    self.candidate_costs = np.where(solved, cand_rec["cost"] + offset, np.inf)
+    self.selection_costs = sel_cost
+    self.tracking_status = int(trk["status"][0])
+    return (traj, int(flag[0]), np.full(Cn, dt / Cn), solution_xvar), (trk_u[0].copy(), trk_x)

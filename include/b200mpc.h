@@ -240,6 +240,52 @@ int b200mpc_plant_step_device(b200mpc_handle *h, const b200mpc_plant_params *prm
                               int xcurv_offset, double *d_xglob, const double *d_u, int u_stride, const double *d_draws,
                               const double *d_segments, int32_t *d_laps);
 
+/* Planner selection + hand-over to the tracking MPC: the part of
+ * OvertakeTrajPlanner.solve_optimization_problem after the candidates are gathered
+ * (planning/overtake_traj_planner.py:205-246) and the target construction of control.mpc_multi_agents
+ * (control/control.py:277, 373-382), on the device, so that candidate solve -> selection -> tracking solve
+ * chain on one stream. */
+typedef struct {
+    int32_t C;                  /* candidates (the reference: num_veh + 1 regions) */
+    int32_t N;                  /* num_horizon_planner (10) */
+    int32_t num_veh;            /* rivals, in sorted_vehicles order */
+    int32_t old_direction_flag; /* previous choice, -1 = None (:238-243) */
+    int32_t N_ctrl;             /* num_horizon_ctrl of the tracking MPC (stages of the target block to fill) */
+    int32_t M_ctrl;             /* rivals in the tracking record (fixes the offset of its target block) */
+    double veh_length, veh_width; /* ego.param.length / width (:209-210) */
+    double lap_length;
+} b200mpc_planner_select_params;
+
+/* All pointers are device pointers.
+ *   rec       : C records of the candidate solve;  xpred : C x (N+1) x 6 its trajectories
+ *   heur      : C x (N+1) x 6 heuristic trajectories used where ok0[c] == 0 or the solve failed (:365-374)
+ *   ok0       : C, 1 if x_0 satisfies the candidate's stage-0 rows;  region : C, region index of the candidate
+ *               (neighbours: rivals region-1 and region; the reference has region[c] = c)
+ *   rivals    : num_veh x 2 x (N+1): s and ey predictions (s is lap-wrapped here as :214-215 does)
+ * outputs:
+ *   sel_cost  : optional C selection costs;  flag : 2 ints {direction_flag = first argmin, its region}
+ *   traj      : optional (N+1) x 6 chosen trajectory (traj_xcurv of :245)
+ *   track_rec : optional packed record of the tracking MPC (layout of b200mpc_cbf_record_doubles(N_ctrl, M_ctrl, 1));
+ *               x0 must be filled in; its per-stage target block is written in place */
+int b200mpc_planner_select_device(b200mpc_handle *h, const b200mpc_planner_select_params *prm, const b200mpc_record *d_rec,
+                                  const double *d_xpred, const double *d_heur, const int32_t *d_ok0, const int32_t *d_region,
+                                  const double *d_rivals, double *d_sel_cost, int32_t *d_flag, double *d_traj,
+                                  double *d_track_rec);
+
+/* The whole overtaking step on one stream, host pointers in and out: H2D -> candidate solve (plan_prm: flags
+ * STAGE_BOUNDS|EY_RATE, M = 0; C packed records) -> b200mpc_planner_select_device -> tracking solve (track_prm: per-stage
+ * targets, alpha 0.6, margin 0.15 as control.py:285,311; track_in = ONE packed record with x0, lap offsets and the
+ * rival block filled in, its target block is completed on the device) -> D2H.  Replaces the reference's
+ * fork/join of one process per candidate + host selection + a second CasADi/IPOPT solve
+ * (overtake_traj_planner.py:162-246 followed by control.py:251-473, called from utils/base.py:540-582).
+ * Outputs: cand_rec C (optional), cand_xpred C x (N+1) x 6 (optional), sel_cost C (optional), flag 2 ints, traj (N+1) x 6
+ * (optional), track_rec 1 record (u0 = the control to apply), track_xpred (N_ctrl+1) x 6, track_upred N_ctrl x 2 (optional). */
+int b200mpc_plan_and_track(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
+                           const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel, const double *cand_in,
+                           const double *heur, const int32_t *ok0, const int32_t *region, const double *rivals,
+                           const double *track_in, b200mpc_record *cand_rec, double *cand_xpred, double *sel_cost, int32_t *flag,
+                           double *traj, b200mpc_record *track_rec, double *track_xpred, double *track_upred);
+
 /* argmin over records (device pointers): index of the smallest cost among status<=max_status,
  * lowest index wins ties (list.index(min(...)), overtake_traj_planner.py:244); *d_out = -1 if none. */
 int b200mpc_argmin_cost_device(b200mpc_handle *h, const b200mpc_record *d_rec, int B, int max_status, int32_t *d_out);

@@ -596,3 +596,37 @@ def test_batches_in_flight_equal_the_blocking_call(crb):
         assert out[k].tobytes() == refs[k].tobytes()
     assert pipe.launch_count == nb
     pipe.close()
+
+
+def test_plan_and_track_chain_matches_host_path(crb):
+    """candidate solve -> selection (overtake_traj_planner.py:205-246) -> per-stage targets
+    (control.py:373-382) -> tracking MPC on one stream (b200mpc_plan_and_track) must equal the two reference-shaped calls
+    with the host in between (planning.solve_optimization_problem, then control.mpc_multi_agents)."""
+    import types
+    from car_racing_b200 import control, planning
+    from planner_cases import make_planner
+    from test_shims_host import Rival
+    param = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 5.0, 0, 50.0]),
+                                  matrix_R=np.diag([0.1, 0.1]), num_horizon_ctrl=10)
+    sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+    flags = []
+    for seed, old in ((3, None), (7, None), (11, 0), (12, 2), (13, 1), (14, None)):
+        ps = [make_planner(seed, num_veh=2 + seed % 2) for _ in range(2)]
+        for p in ps:
+            p.old_direction_flag = old
+            for name in p.sorted_vehicles:
+                tr = p.obs_infos[name]
+                p.vehicles[name] = Rival(tr[4, 0], tr[0, 0], tr[5, 0])
+        p1, p2 = ps
+        x = np.asarray(p1.vehicles["ego"].xcurv, float).copy()
+        (t1, f1, st1, s1), (u1, x1) = planning.plan_and_track(p1, x, param, p1.track, sysp, time=None)
+        t2, f2, st2, s2 = planning.solve_optimization_problem(p2)
+        u2, x2 = control.mpc_multi_agents(x, param, p2.track, None, None, None, sysp, target_traj_xcurv=t2, vehicles=p2.vehicles,
+                                          agent_name="ego", direction_flag=f2, sorted_vehicles=p2.sorted_vehicles, time=None)
+        c2 = planning.selection_costs(s2, p2.sorted_vehicles, p2.obs_infos, 0.4, 0.2, p2.track.lap_length, old)
+        assert f1 == f2 and np.abs(p1.selection_costs - np.array(c2)).max() < 1e-9
+        assert np.abs(t1 - t2).max() < 1e-12 and np.abs(s1 - s2).max() < 1e-12
+        assert p1.tracking_status == 0
+        assert np.abs(u1 - u2).max() < 1e-7 and np.abs(x1 - x2).max() < 1e-7
+        flags.append(f1)
+    assert len(set(flags)) > 1          # the cases do not all pick the same region
