@@ -1271,6 +1271,10 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     int iter = 0, status = B200MPC_MAX_ITER, n_acc = 0, n_refac = 0, n_back = 0, n_reset = 0;
     double dw_last = 0.0, E0 = 0.0;
     bool last_needed = false;
+    // phi at the current point = phi of the trial point accepted by the previous iteration, as long as mu and the
+    // slacks were not touched in between (IPOPT caches it the same way)
+    bool ph_valid = false;
+    double ph_cache = 0.0;
 
     const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99;
     const double gamma_theta = 1e-5, gamma_phi = 1e-8, delta_sw = 1.0, s_theta = 1.1, s_phi = 2.3, eta_phi = 1e-8;
@@ -1307,6 +1311,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 q.mu = fmax(o.tol / 11.0, fmin(kappa_mu * q.mu, q.mu * sqrt(q.mu)));
                 nfilt = 0;
                 fpos = 0;
+                ph_valid = false;
             } else
                 break;
         }
@@ -1460,13 +1465,14 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             amin = gamma_alpha * fmin(gamma_theta, gamma_phi * th / (-gphi));
         else
             amin = gamma_alpha * gamma_theta;
-        double a = a_max, ph = 0.0;
+        double a = a_max, ph = ph_cache, ph_acc = 0.0;
         bool accepted = false, ftype = false;
         int nls = 0;
-        for (bool base = true;;) {
+        for (bool base = !ph_valid;;) {
             double tht, pht;
             q.template theta_phi<true>(base ? 0.0 : a, tht, pht);
             if (base) { ph = pht; base = false; continue; }
+            ph_acc = pht;
             bool dom = false;
             if (lane < nfilt && tht >= f_th0 && pht >= f_ph0) dom = true;
             if (lane + 32 < nfilt && tht >= f_th1 && pht >= f_ph1) dom = true;
@@ -1497,10 +1503,13 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             }
             nfilt = 0;
             fpos = 0;
+            ph_valid = false;
             iter++;
             __syncwarp();
             continue;
         }
+        ph_cache = ph_acc;
+        ph_valid = true;
         if (!ftype) {
             double nth = (1.0 - gamma_theta) * th, nph = ph - gamma_phi * th;
             int slot = fpos >> 5, ln = fpos & 31;
