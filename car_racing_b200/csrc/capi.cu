@@ -2,6 +2,7 @@
 // fallback: every entry point either launches the CUDA kernels or fails with an error code.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -138,6 +139,7 @@ static int launch_cbf(b200mpc_handle *h, const KParams &kp, const double *d_in, 
                       double *d_x, double *d_u, double *d_sig) {
     SmemPlan<M> pl(kp.p.N, kp.in_stride);
     size_t smem = pl.bytes();
+    if (const char *pad = getenv("B200MPC_SMEM_PAD")) smem += (size_t)atoi(pad);   // occupancy experiments only
     if ((int)smem > h->max_smem_optin)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: horizon too long for one CTA's shared memory");
     CK(h, cudaFuncSetAttribute(ocp_ipm_kernel<M, FL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -499,18 +499,9 @@ struct Ipm {
                 }
                 la.norm();
             }
-            double sgk[MM];
-#pragma unroll
-            for (int j = 0; j < M; j++) {
-                double sv = W[isg(j, k)];
-                if (useD) sv += al * D[isg(j, k)];
-                sgk[j] = sv;
-                ss += sv;
-                la.raw(sv);                                          // sigma >= 0 (:559,561)
-            }
-            if (M > 0) la.norm();
-            if (k < N) {
-                double xn[6], u[2];
+            const bool kn = k < N;
+            double xn[6], u[2];
+            if (kn) {
                 load_x<useD>(k + 1, al, xn);
                 load_u<useD>(k, al, u);
                 f += input_cost(u);                                  // :578-579
@@ -519,12 +510,19 @@ struct Ipm {
                 la.norm();
                 th += dyn_res<useD, false>(k, al, x, u);
                 if (hwd) f += wdp[k] * (xn[5] - x[5]) * (xn[5] - x[5]);   // overtake_traj_planner.py:325-327
-#pragma unroll
-                for (int j = 0; j < M; j++) {
+            }
+            // one rolled loop over the rivals (the kernel is instruction-fetch bound: code size counts)
+#pragma unroll 1
+            for (int j = 0; j < M; j++) {
+                double sv = W[isg(j, k)];
+                if (useD) sv += al * D[isg(j, k)];
+                ss += sv;
+                la.raw(sv);                                          // sigma >= 0 (:559,561)
+                if (kn) {
                     int r = j * N + k;
                     double sgn = W[isg(j, k + 1)];
                     if (useD) sgn += al * D[isg(j, k + 1)];
-                    double g = DG[r] * row_g(row_vals(j, k, x, xn, sgk[j], sgn));
+                    double g = DG[r] * row_g(row_vals(j, k, x, xn, sv, sgn));
                     double s = S[r], tt = T[r];
                     if (useD) {
                         double ds, dt, dy, dz, dv;
@@ -535,9 +533,9 @@ struct Ipm {
                     th += fabs(g + tt - s);
                     la.raw(s);
                     la.raw(tt);
-                    la.norm();
                     tsum += tt;
                 }
+                la.norm();
             }
         }
         f += kp.p.slack_w * ss;
@@ -586,7 +584,7 @@ struct Ipm {
             load_u<false>(k, 0.0, u);
             dyn_res<false, true>(k, 0.0, x, u);
             grad_x_store(k + 1, xn, GX + 6 * (k + 1));   // objective gradient of x_{k+1}, shared by the later phases
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < M; j++) {
                 int r = j * N + k;
                 RowV v = row_vals(j, k, x, xn, W[isg(j, k)], W[isg(j, k + 1)]);
@@ -616,7 +614,7 @@ struct Ipm {
             }
             if (k >= 1) {
                 double jy4 = 0.0, jy5 = 0.0;
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < M; j++) {  // J'y on (s, ey)
                     if (k < N) {
                         int r = j * N + k;
@@ -640,7 +638,7 @@ struct Ipm {
                     dual = fmax(dual, fabs(s));
                 }
             }
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < M; j++) {  // sigma_{j,k}
                 double zl = ZL[bss(j, k)];
                 double rw = df * kp.p.slack_w - zl;
@@ -669,7 +667,7 @@ struct Ipm {
                     prim = fmax(prim, fabs(c6[a]));
                     ysum += fabs(lamn[a]);
                 }
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     dual = fmax(dual, fabs(Y[r] - Z[r]));
@@ -701,7 +699,7 @@ struct Ipm {
                 if (has(xlb(k, 1))) acc((ey - xlb(k, 1)) * zl.y);
                 if (has(xub(k, 1))) acc((xub(k, 1) - ey) * zu.y);
             }
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < M; j++) acc(W[isg(j, k)] * ZL[bss(j, k)]);
             if (k < N) {
                 double u[2];
@@ -711,7 +709,7 @@ struct Ipm {
                 acc((kp.p.umax[0] - u[0]) * zu.x);
                 acc((u[1] + kp.p.umax[1]) * zl.y);
                 acc((kp.p.umax[1] - u[1]) * zu.y);
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     acc(S[r] * Z[r]);
@@ -753,7 +751,7 @@ struct Ipm {
                     hd[5] = zl.y * il + zu.y * iu;
                     g[5] += -mu * il + mu * iu;
                 }
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < M; j++) {  // Hessian of -y_r g_r: diagonal on (s, ey) (control.py:544-557, degree 6)
                     if (k < N) {
                         int r = j * N + k;
@@ -769,7 +767,7 @@ struct Ipm {
                 st6(HD + 6 * k, hd);
                 st6(D + 6 * k, g);  // base gradient of the barrier problem; D is overwritten by the forward pass
             }
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < M; j++) {
                 double is = rcp(W[isg(j, k)]);
                 HD[isg(j, k)] = ZL[bss(j, k)] * is;
@@ -784,7 +782,7 @@ struct Ipm {
                 st2(HD + OU + 2 * k, zl.x * il0 + zu.x * iu0, zl.y * il1 + zu.y * iu1);
                 st2(D + OU + 2 * k, df * (R2(0, 0) * u[0] + R2(0, 1) * u[1]) - mu * il0 + mu * iu0,
                     df * (R2(1, 0) * u[0] + R2(1, 1) * u[1]) - mu * il1 + mu * iu1);
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     double s = S[r], tt = T[r];
@@ -1323,14 +1321,10 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         q.assemble();
         PCLK(1)
         // grad(phi)'d needs the base gradient of this lane's stage, which the forward sweep overwrites in D
-        double gbx[6] = {0, 0, 0, 0, 0, 0}, gbu[2] = {0, 0}, gbs[IP::MM];
-#pragma unroll
-        for (int j = 0; j < IP::MM; j++) gbs[j] = 0.0;
+        double gbx[6] = {0, 0, 0, 0, 0, 0}, gbu[2] = {0, 0};
         if (one_round && lane <= N) {
             ld6(q.D + 6 * lane, gbx);
             if (lane < N) { double2 t2 = ld2(q.D + OU + 2 * lane); gbu[0] = t2.x; gbu[1] = t2.y; }
-#pragma unroll
-            for (int j = 0; j < M; j++) gbs[j] = q.D[q.isg(j, lane)];
         }
         // IPOPT always retries dw = 0 first; when the previous iteration needed a correction we start from
         // dw_last/3 instead (saves one full sweep per iteration on the non-convex stragglers)
@@ -1354,7 +1348,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             double dxk[6], dxn[6];
             ld6(q.D + 6 * k, dxk);
             ld6(q.D + 6 * (k + 1), dxn);
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < M; j++) {
                 int r = j * N + k;
                 double ja[4];
@@ -1402,13 +1396,13 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                     for (int a = 0; a < 6; a++) gphi += g[a] * d[a];
                 }
             }
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < M; j++) {
                 double w = q.W[q.isg(j, k)], dd = q.D[q.isg(j, k)], zlc = q.ZL[q.bss(j, k)];
                 double dzl = (mu - zlc * dd) * rcp(w) - zlc;
                 if (dd < 0.0) a_max = fmin(a_max, -tau * w * rcp(dd));
                 if (dzl < 0.0) a_z = fmin(a_z, -tau * zlc * rcp(dzl));
-                gphi += (one_round ? gbs[j] : (q.df * kp.p.slack_w - mu * rcp(w))) * dd;
+                gphi += (q.df * kp.p.slack_w - mu * rcp(w)) * dd;
             }
             if (k < N) {
                 double u[2];
@@ -1432,7 +1426,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 ld6(q.CRES + 6 * k, c6);
 #pragma unroll
                 for (int a = 0; a < 6; a++) th += fabs(c6[a]);
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     double ds, dt, dy, dz, dv;
@@ -1531,7 +1525,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             ld6(q.GX + 6 * i, g);
             q.barrier_grad_x(i, x, g);
             double r4 = 0.0, r5 = 0.0;
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < M; j++) {
                 if (i < N) {
                     int r = j * N + i;
@@ -1614,7 +1608,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 for (int a2 = 0; a2 < 6; a2++) x[a2] += a * d[a2];
                 st6(q.W + 6 * k, x);
             }
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < M; j++) {
                 double w = q.W[q.isg(j, k)], dd = q.D[q.isg(j, k)], zlc = q.ZL[q.bss(j, k)];
                 zlc += a_z * ((mu - zlc * dd) * rcp(w) - zlc);
@@ -1642,7 +1636,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 st2(q.ZL + q.bsu(k), zln[0], zln[1]);
                 st2(q.ZU + q.bsu(k), zun[0], zun[1]);
                 st2(q.W + OU + 2 * k, un[0], un[1]);
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     double ds, dt, dy, dz, dv;
