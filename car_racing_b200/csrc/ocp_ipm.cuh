@@ -1275,7 +1275,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     double ph_cache = 0.0;
 
     const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99;
-    const double gamma_theta = 1e-5, gamma_phi = 1e-8, delta_sw = 1.0, s_theta = 1.1, s_phi = 2.3, eta_phi = 1e-8;
+    const double gamma_theta = 1e-5, gamma_phi = 1e-8, s_theta = 1.1, s_phi = 2.3, eta_phi = 1e-8;
     const double gamma_alpha = 0.05, kappa_sigma = 1e10;
     const bool one_round = (N < 32);   // every stage has its own lane
 
@@ -1451,7 +1451,11 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         // switching condition a (-gphi)^s_phi > delta th^s_theta and the a_min term delta th^s_theta / (-gphi)^s_phi in
         // the log domain: lsw = s_phi log(-gphi) - log(delta) - s_theta log(th); a = a_max 2^-nls
         double lsw = 0.0, la_max = 0.0;
-        if (gphi < 0.0) { lsw = s_phi * log(-gphi) - log(delta_sw) - s_theta * log(th); la_max = log(a_max); }
+        if (gphi < 0.0) {   // the three logarithms through ONE call site: lane 0/1/2 take -gphi, th, a_max (delta_sw = 1)
+            double lg = log(lane == 0 ? -gphi : (lane == 1 ? th : a_max));
+            lsw = s_phi * __shfl_sync(0xffffffffu, lg, 0) - s_theta * __shfl_sync(0xffffffffu, lg, 1);
+            la_max = __shfl_sync(0xffffffffu, lg, 2);
+        }
         double amin;
         if (gphi < 0.0 && th <= theta_min)
             amin = gamma_alpha * fmin(gamma_theta, fmin(gamma_phi * th / (-gphi), exp(-lsw)));
@@ -1563,6 +1567,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
 #pragma unroll
             for (int a2 = 0; a2 < 6; a2++) ln[a2] = 0.0;
             const int comp = (lane < 6) ? lane : 0;
+#pragma unroll 1
             for (int i = N; i >= 1; i--) {
                 double sres = q.CRES[6 * (i - 1) + comp];
 #pragma unroll
