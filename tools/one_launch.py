@@ -19,7 +19,27 @@ from car_racing_b200 import scenarios              # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=8192)
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--kind", default="cbf", choices=["cbf", "lmpc", "ilqr"])
 a = ap.parse_args()
+if a.kind == "lmpc":     # BASELINE config 4: N=12, 44 safe-set points (ncu: -k regex:lmpc_kernel)
+    sc = scenarios.lmpc_scenarios(min(a.B, 512), seed=3)
+    if a.B > 512:
+        sc = tuple(np.tile(v, (a.B // 512,) + (1,) * (v.ndim - 1)) for v in sc)
+    lprm = scenarios.default_lmpc_params()
+    fn = lambda: crb.solve_lmpc_batch(*sc, lprm, want=())
+elif a.kind == "ilqr":   # BASELINE config 5: N=50 (ncu: -k regex:ilqr_kernel)
+    p = scenarios.default_cbf_params()
+    iprm = dict(A=p["A"], B=p["B"], Q=p["Q"], R=p["R"], N=50, max_iter=150, L=0.4, W=0.2)
+    x0, xt, obs, lo = scenarios.ilqr_scenarios(a.B, N=50, seed=1)
+    fn = lambda: crb.solve_ilqr_batch(x0, xt, obs, lo, iprm, want=())
+if a.kind != "cbf":
+    g = fn()
+    for _ in range(a.reps):
+        t0 = time.perf_counter()
+        g = fn()
+        dt = time.perf_counter() - t0
+        print(f"{a.kind} B={a.B} {dt * 1e3:.2f} ms  {a.B / dt:.0f} solves/s  iters mean {g['iters'].mean():.1f} max {g['iters'].max()}")
+    sys.exit(0)
 prm = scenarios.default_cbf_params(N=20)
 x0, xt, obs, lo = scenarios.mpccbf_scenarios(min(a.B, 8192), N=20, M=3, seed=1)
 if a.B > 8192:
