@@ -630,3 +630,54 @@ def test_plan_and_track_chain_matches_host_path(crb):
         assert np.abs(u1 - u2).max() < 1e-7 and np.abs(x1 - x2).max() < 1e-7
         flags.append(f1)
     assert len(set(flags)) > 1          # the cases do not all pick the same region
+
+
+def test_plan_and_track_with_64_candidates(crb):
+    """BASELINE config 3: 64 candidates per planner call -- the reference's num_veh+1 regions plus perturbed references
+    (scaled lateral targets x stretched progress), each mapped to its region for the neighbour test of the selection
+    cost.  The device chain must pick the candidate a host re-computation picks, and track its trajectory."""
+    import types
+    from car_racing_b200 import control, planning
+    from planner_cases import make_planner
+    from test_shims_host import Rival
+    param = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 5.0, 0, 50.0]),
+                                  matrix_R=np.diag([0.1, 0.1]), num_horizon_ctrl=10)
+    sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+    for seed in (5, 9):
+        p = make_planner(seed, num_veh=2)
+        for name in p.sorted_vehicles:
+            tr = p.obs_infos[name]
+            p.vehicles[name] = Rival(tr[4, 0], tr[0, 0], tr[5, 0])
+        N, ego = 10, p.vehicles["ego"]
+        x = np.asarray(ego.xcurv, float).copy()
+        ex = dict(s_ref=[], ey_ref=[], xlb=[], xub=[], region=[], heur=[])
+        for c in range(3):
+            xlb, xub = planning.candidate_bounds(c, p.xcurv_ego, p.sorted_vehicles, p.obs_infos, 0.4, 0.2, 1.0, p.track.lap_length, N)
+            s0, e0 = planning.candidate_targets(c, x, p.bezier_xcurvs, p.bezier_funcs, N)
+            h0 = planning.heuristic_traj(c, p.xcurv_ego, p.bezier_xcurvs, p.bezier_funcs, N).T
+            for scale in (0.4, 0.6, 0.8, 0.9, 1.1, 1.2, 1.4):
+                for stretch in (0.9, 1.0, 1.1):
+                    if len(ex["region"]) == 61:
+                        break
+                    ex["s_ref"].append(x[4] + stretch * (s0 - x[4]))
+                    ex["ey_ref"].append(x[5] + scale * (e0 - x[5]))
+                    ex["xlb"].append(xlb); ex["xub"].append(xub); ex["region"].append(c); ex["heur"].append(h0)
+        ex = {k: np.array(v) for k, v in ex.items()}
+        (traj, flag, st, sol), (u, xp) = planning.plan_and_track(p, x, param, p.track, sysp, time=None, extra=ex)
+        C = sol.shape[0]
+        assert C == 64 and len(p.selection_costs) == 64
+        # host re-computation of the selection cost with the region map (overtake_traj_planner.py:205-243)
+        region = np.concatenate([np.arange(3), ex["region"]])
+        cost = np.zeros(C)
+        for c in range(C):
+            cost[c] = -10 * (sol[c, 4, -1] - sol[c, 4, 0])
+            for side in (region[c] - 1, region[c]):
+                if 0 <= side < 2:
+                    o = p.obs_infos[p.sorted_vehicles[side]]
+                    d2 = (sol[c, 4] - o[4, :N + 1]) ** 2 + (sol[c, 5] - o[5, :N + 1]) ** 2
+                    cost[c] += 100 * (d2 - 0.4 ** 2 - 0.2 ** 2 < 0).sum()
+        assert np.abs(cost - p.selection_costs).max() < 1e-9 and flag == int(np.argmin(cost))
+        assert np.abs(traj - sol[flag].T).max() == 0.0
+        u2, x2 = control.mpc_multi_agents(x, param, p.track, None, None, None, sysp, target_traj_xcurv=traj, vehicles=p.vehicles,
+                                          agent_name="ego", direction_flag=flag, sorted_vehicles=p.sorted_vehicles, time=None)
+        assert p.tracking_status == 0 and np.abs(u - u2).max() < 1e-7 and np.abs(xp - x2).max() < 1e-7

@@ -78,6 +78,35 @@ def main():
     doc["config3_planner"] = ent
     print("config3", ent, flush=True)
 
+    # ---- overtaking step: planner + tracking MPC as two reference-shaped calls vs the fused device chain
+    import types
+    from planner_cases import make_planner
+    from test_shims_host import Rival
+    from car_racing_b200 import control, planning
+    mp = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 5.0, 0, 50.0]),
+                               matrix_R=np.diag([0.1, 0.1]), num_horizon_ctrl=10)
+    sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+
+    def mk():
+        pl = make_planner(7, num_veh=3)
+        for name in pl.sorted_vehicles:
+            tr = pl.obs_infos[name]
+            pl.vehicles[name] = Rival(tr[4, 0], tr[0, 0], tr[5, 0])
+        return pl
+    pl = mk()
+    xc = np.asarray(pl.vehicles["ego"].xcurv, float).copy()
+
+    def two_calls():
+        t2, f2, _, _ = planning.solve_optimization_problem(pl)
+        return control.mpc_multi_agents(xc, mp, pl.track, None, None, None, sysp, target_traj_xcurv=t2, vehicles=pl.vehicles,
+                                        agent_name="ego", direction_flag=f2, sorted_vehicles=pl.sorted_vehicles, time=None)
+    _, t_two, _, _ = timed(two_calls, reps=21, warm=3)
+    _, t_one, _, _ = timed(lambda: planning.plan_and_track(pl, xc, mp, pl.track, sysp, time=None), reps=21, warm=3)
+    doc["overtaking_step"] = dict(candidates=len(pl.sorted_vehicles) + 1, two_calls_ms=t_two * 1e3, fused_chain_ms=t_one * 1e3,
+                                  note="median wall time incl. host packing; two_calls = solve_optimization_problem + mpc_multi_agents shims, "
+                                       "fused = planning.plan_and_track (b200mpc_plan_and_track: one stream, no host round trip)")
+    print("overtaking_step", doc["overtaking_step"], flush=True)
+
     # ---- config 4: LMPC, 512 per GPU
     lprm = scenarios.default_lmpc_params()
     out4 = []
