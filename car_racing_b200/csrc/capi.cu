@@ -139,7 +139,9 @@ static int launch_cbf(b200mpc_handle *h, const KParams &kp, const double *d_in, 
                       double *d_x, double *d_u, double *d_sig) {
     SmemPlan<M> pl(kp.p.N, kp.in_stride);
     size_t smem = pl.bytes();
-    if (const char *pad = getenv("B200MPC_SMEM_PAD")) smem += (size_t)atoi(pad);   // occupancy experiments only
+    // B200MPC_SMEM_PAD=<bytes>: measurement hook only (occupancy sweep) -- pads the dynamic shared
+    // memory so that fewer CTAs fit an SM; results are unaffected
+    if (const char *pad = getenv("B200MPC_SMEM_PAD")) smem += (size_t)atoi(pad);
     if ((int)smem > h->max_smem_optin)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: horizon too long for one CTA's shared memory");
     CK(h, cudaFuncSetAttribute(ocp_ipm_kernel<M, FL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
