@@ -86,7 +86,7 @@ EXPORTS = [
     "b200mpc_cbf_solve_device", "b200mpc_ilqr_record_doubles", "b200mpc_ilqr_solve", "b200mpc_ilqr_solve_device",
     "b200mpc_argmin_cost_device", "b200mpc_lmpc_record_doubles", "b200mpc_lmpc_solve", "b200mpc_lmpc_solve_device",
     "b200mpc_lmpc_sysid", "b200mpc_lmpc_sysid_device", "b200mpc_plant_step", "b200mpc_plant_step_device",
-    "b200mpc_cbf_solve_async", "b200mpc_synchronize", "b200mpc_host_alloc", "b200mpc_host_free", "b200mpc_planner_select_device", "b200mpc_plan_and_track",
+    "b200mpc_cbf_solve_async", "b200mpc_synchronize", "b200mpc_host_alloc", "b200mpc_host_free", "b200mpc_planner_select_device", "b200mpc_plan_and_track", "b200mpc_ilqr_solve_async", "b200mpc_lmpc_solve_async",
 ]
 
 _lib = None
@@ -133,11 +133,13 @@ def lib():
     ilqr_args = [vp, C.POINTER(IlqrParams), ip, dp, dp, dp, dp]
     L.b200mpc_ilqr_solve.argtypes = ilqr_args
     L.b200mpc_ilqr_solve_device.argtypes = ilqr_args
+    L.b200mpc_ilqr_solve_async.argtypes = ilqr_args
     L.b200mpc_argmin_cost_device.argtypes = [vp, dp, ip, ip, dp]
     L.b200mpc_lmpc_record_doubles.argtypes = [ip, ip]
     lmpc_args = [vp, C.POINTER(LmpcParams), C.POINTER(IpmOptions), ip, dp, dp, dp, dp, dp, dp]
     L.b200mpc_lmpc_solve.argtypes = lmpc_args
     L.b200mpc_lmpc_solve_device.argtypes = lmpc_args
+    L.b200mpc_lmpc_solve_async.argtypes = lmpc_args
     sysid_args = [vp, C.POINTER(SysidParams), ip, dp, dp, dp, dp, ip, ip, dp, dp]
     L.b200mpc_lmpc_sysid.argtypes = sysid_args
     L.b200mpc_lmpc_sysid_device.argtypes = sysid_args

@@ -130,40 +130,36 @@ def solve_cbf_packed(records, prm, M, xt_per_stage, want=("aux", "x", "u", "sigm
     return out
 
 
-class CbfPipeline:
-    """Several MPC-CBF batches in flight: `depth` handles (one CUDA stream + staging buffers each) driven round-robin
-    through b200mpc_cbf_solve_async.  Iteration counts of the NLP are heavy-tailed (mean 37, max 200 on BASELINE
-    config 2), so a lone batch of 1024 leaves most SMs idle while its last few instances finish; with the next
-    batches already enqueued their instances take the vacated warp slots.  Per-batch latency is unchanged.
+class _Pipeline:
+    """`depth` handles (one CUDA stream + staging buffers each) driven round-robin through an *_async entry point, pinned
+    host buffers.  Iteration counts are heavy-tailed (MPC-CBF: mean 37, max 200; iLQR: mean 5, max 41), so a lone batch that
+    fills the GPU exactly once leaves most SMs idle while its last instances finish; with the next batches already enqueued
+    their instances take the vacated warp slots.  Per-batch latency is unchanged.
 
-        pipe = CbfPipeline(prm, M=3, B=1024, depth=4)
         t = pipe.submit(records)          # (B, stride) float64; copied into the slot's pinned buffer
         ...
         rec = pipe.result(t)              # structured (B,) array: cost, u0, status, iters (waits for that batch)
     """
 
-    def __init__(self, prm, M, B, depth=4, xt_per_stage=False, flags=0, device=-1, **opt):
-        self.N, self.M, self.B, self.depth = int(prm["N"]), int(M), int(B), int(depth)
-        self.stride = cbf_record_doubles(self.N, self.M, xt_per_stage, flags)
-        self.p = _capi.make_cbf_params(prm, M, xt_per_stage, flags)
-        self.o = _capi.default_options(**opt)
+    def __init__(self, B, stride, depth, device):
+        self.B, self.stride, self.depth = int(B), int(stride), int(depth)
         self.handles = [_capi.Handle(device=device, max_batch=B) for _ in range(self.depth)]
         self.pin_in = [_capi.PinnedArray((B, self.stride)) for _ in range(self.depth)]
         self.pin_out = [_capi.PinnedArray((B,), _capi.RECORD_DTYPE) for _ in range(self.depth)]
         self.busy = [False] * self.depth
         self.n_submitted = 0
 
+    def _enqueue(self, k):
+        raise NotImplementedError
+
     def submit(self, records, copy=True):
-        """Enqueue one batch; returns its ticket.  Blocks only if the slot's previous batch has not been collected."""
+        """Enqueue one batch; returns its ticket.  The slot's previous batch must have been collected."""
         k = self.n_submitted % self.depth
         if self.busy[k]:
-            raise RuntimeError("CbfPipeline: collect result(%d) before submitting again" % (self.n_submitted - self.depth))
-        h = self.handles[k]
+            raise RuntimeError("pipeline: collect result(%d) before submitting again" % (self.n_submitted - self.depth))
         if copy:
             self.pin_in[k].a[...] = records
-        rc = _capi.lib().b200mpc_cbf_solve_async(h.ptr, C.byref(self.p), C.byref(self.o), self.B, _ptr(self.pin_in[k].a),
-                                                 _ptr(self.pin_out[k].a), None, None, None, None)
-        h.check(rc, "b200mpc_cbf_solve_async")
+        self._enqueue(k)
         self.busy[k] = True
         self.n_submitted += 1
         return self.n_submitted - 1
@@ -181,6 +177,53 @@ class CbfPipeline:
     def close(self):
         for h in self.handles:
             h.close()
+
+
+class CbfPipeline(_Pipeline):
+    """Several MPC-CBF / MPC-LTI / planner-QP batches in flight (b200mpc_cbf_solve_async)."""
+
+    def __init__(self, prm, M, B, depth=4, xt_per_stage=False, flags=0, device=-1, **opt):
+        self.N, self.M = int(prm["N"]), int(M)
+        self.p = _capi.make_cbf_params(prm, M, xt_per_stage, flags)
+        self.o = _capi.default_options(**opt)
+        super().__init__(B, cbf_record_doubles(self.N, self.M, xt_per_stage, flags), depth, device)
+
+    def _enqueue(self, k):
+        h = self.handles[k]
+        rc = _capi.lib().b200mpc_cbf_solve_async(h.ptr, C.byref(self.p), C.byref(self.o), self.B, _ptr(self.pin_in[k].a),
+                                                 _ptr(self.pin_out[k].a), None, None, None, None)
+        h.check(rc, "b200mpc_cbf_solve_async")
+
+
+class IlqrPipeline(_Pipeline):
+    """Several iLQR batches in flight (b200mpc_ilqr_solve_async; records from pack_ilqr)."""
+
+    def __init__(self, prm, B, depth=4, device=-1):
+        self.N = int(prm["N"])
+        self.p = _capi.make_ilqr_params(prm)
+        super().__init__(B, ilqr_record_doubles(self.N), depth, device)
+
+    def _enqueue(self, k):
+        h = self.handles[k]
+        rc = _capi.lib().b200mpc_ilqr_solve_async(h.ptr, C.byref(self.p), self.B, _ptr(self.pin_in[k].a), _ptr(self.pin_out[k].a),
+                                                  None, None)
+        h.check(rc, "b200mpc_ilqr_solve_async")
+
+
+class LmpcPipeline(_Pipeline):
+    """Several LMPC batches in flight (b200mpc_lmpc_solve_async; records from pack_lmpc)."""
+
+    def __init__(self, prm, K, B, depth=4, device=-1, **opt):
+        self.N, self.K = int(prm["N"]), int(K)
+        self.p = _capi.make_lmpc_params(prm, K)
+        self.o = _capi.default_options(**opt)
+        super().__init__(B, lmpc_record_doubles(self.N, self.K), depth, device)
+
+    def _enqueue(self, k):
+        h = self.handles[k]
+        rc = _capi.lib().b200mpc_lmpc_solve_async(h.ptr, C.byref(self.p), C.byref(self.o), self.B, _ptr(self.pin_in[k].a),
+                                                  _ptr(self.pin_out[k].a), None, None, None, None)
+        h.check(rc, "b200mpc_lmpc_solve_async")
 
 
 def solve_cbf_batch(x0, xt, obs, lap_off, prm, want=("aux", "x", "u", "sigma"), handle=None, xlb=None, xub=None, wd=None,

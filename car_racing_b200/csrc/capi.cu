@@ -287,6 +287,13 @@ int b200mpc_ilqr_solve_device(b200mpc_handle *h, const b200mpc_ilqr_params *prm,
 
 int b200mpc_ilqr_solve(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B, const double *in, b200mpc_record *rec,
                        double *xpred, double *upred) {
+    int rc = b200mpc_ilqr_solve_async(h, prm, B, in, rec, xpred, upred);
+    if (rc) return rc;
+    return b200mpc_synchronize(h);
+}
+
+int b200mpc_ilqr_solve_async(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B, const double *in, b200mpc_record *rec,
+                             double *xpred, double *upred) {
     int rc = check_ilqr(h, prm, B, in, rec);
     if (rc) return rc;
     CK(h, cudaSetDevice(h->device));
@@ -304,7 +311,6 @@ int b200mpc_ilqr_solve(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B,
     CK(h, cudaMemcpyAsync(rec, h->d_rec, b_rec, cudaMemcpyDeviceToHost, h->stream));
     if (xpred) CK(h, cudaMemcpyAsync(xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
     if (upred) CK(h, cudaMemcpyAsync(upred, h->d_u, b_u, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }
 
@@ -344,6 +350,13 @@ int b200mpc_lmpc_solve_device(b200mpc_handle *h, const b200mpc_lmpc_params *prm,
 
 int b200mpc_lmpc_solve(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const b200mpc_ipm_options *opt, int B,
                        const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *lambda) {
+    int rc = b200mpc_lmpc_solve_async(h, prm, opt, B, in, rec, aux, xpred, upred, lambda);
+    if (rc) return rc;
+    return b200mpc_synchronize(h);
+}
+
+int b200mpc_lmpc_solve_async(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const b200mpc_ipm_options *opt, int B,
+                             const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *lambda) {
     int rc = check_lmpc(h, prm, opt, B, in, rec);
     if (rc) return rc;
     CK(h, cudaSetDevice(h->device));
@@ -366,7 +379,6 @@ int b200mpc_lmpc_solve(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const 
     if (xpred) CK(h, cudaMemcpyAsync(xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
     if (upred) CK(h, cudaMemcpyAsync(upred, h->d_u, b_u, cudaMemcpyDeviceToHost, h->stream));
     if (lambda) CK(h, cudaMemcpyAsync(lambda, h->d_sig, b_l, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }
 

@@ -163,6 +163,9 @@ int b200mpc_ilqr_solve(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B,
                        b200mpc_record *rec, double *xpred, double *upred);
 int b200mpc_ilqr_solve_device(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B, const double *d_in,
                               b200mpc_record *d_rec, double *d_xpred, double *d_upred);
+/* as b200mpc_cbf_solve_async: enqueue only, join with b200mpc_synchronize */
+int b200mpc_ilqr_solve_async(b200mpc_handle *h, const b200mpc_ilqr_params *prm, int B, const double *in,
+                             b200mpc_record *rec, double *xpred, double *upred);
 
 /* LMPC (control.py:610-730): the per-step QP over the LTV model and the convex hull of the selected safe set.
  * Replaces the CasADi `opti.solve()` at control.py:703.  Shared data: */
@@ -184,6 +187,8 @@ int b200mpc_lmpc_solve(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const 
 int b200mpc_lmpc_solve_device(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const b200mpc_ipm_options *opt, int B,
                               const double *d_in, b200mpc_record *d_rec, double *d_aux, double *d_xpred, double *d_upred,
                               double *d_lambda);
+int b200mpc_lmpc_solve_async(b200mpc_handle *h, const b200mpc_lmpc_params *prm, const b200mpc_ipm_options *opt, int B,
+                             const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred, double *lambda);
 
 /* LMPC model identification: LMPCRacingGame.estimate_ABC (utils/base.py:585-622) = per horizon stage
  * lmpc_helper.regression_and_linearization (control/lmpc_helper.py:26-201).  Replaces the N sequential calls (each

@@ -681,3 +681,29 @@ def test_plan_and_track_with_64_candidates(crb):
         u2, x2 = control.mpc_multi_agents(x, param, p.track, None, None, None, sysp, target_traj_xcurv=traj, vehicles=p.vehicles,
                                           agent_name="ego", direction_flag=flag, sorted_vehicles=p.sorted_vehicles, time=None)
         assert p.tracking_status == 0 and np.abs(u - u2).max() < 1e-7 and np.abs(xp - x2).max() < 1e-7
+
+
+def test_ilqr_and_lmpc_pipelines_equal_the_blocking_calls(crb):
+    from car_racing_b200 import batch
+    p = scenarios.default_cbf_params()
+    iprm = dict(A=p["A"], B=p["B"], Q=p["Q"], R=p["R"], N=50, max_iter=150, L=0.4, W=0.2)
+    B = 64
+    pipe = batch.IlqrPipeline(iprm, B=B, depth=2)
+    refs, tickets = [], []
+    for k in range(3):
+        x0, xt, obs, lo = scenarios.ilqr_scenarios(B, N=50, seed=40 + k)
+        refs.append(crb.solve_ilqr_batch(x0, xt, obs, lo, iprm, want=())["record"])
+        if k >= 2:
+            assert pipe.result(tickets[k - 2]).tobytes() == refs[k - 2].tobytes()
+        tickets.append(pipe.submit(batch.pack_ilqr(x0, xt, obs, lo, 50)))
+    for k in (1, 2):
+        assert pipe.result(tickets[k]).tobytes() == refs[k].tobytes()
+    pipe.close()
+    lprm = scenarios.default_lmpc_params()
+    sc = scenarios.lmpc_scenarios(32, seed=8)
+    ref = crb.solve_lmpc_batch(*sc, lprm, want=())["record"]
+    rec, K = batch.pack_lmpc(*sc, int(lprm["N"]))
+    lp = batch.LmpcPipeline(lprm, K, B=32, depth=2)
+    t0, t1 = lp.submit(rec), lp.submit(rec)
+    assert lp.result(t0).tobytes() == ref.tobytes() and lp.result(t1).tobytes() == ref.tobytes()
+    lp.close()

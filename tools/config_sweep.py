@@ -137,6 +137,34 @@ def main():
         out5.append(ent)
         print("config5", ent, flush=True)
     doc["config5_ilqr"] = out5
+    # ---- batches in flight for configs 4 and 5 (per-GPU batch of the BASELINE configs, 4 streams)
+    from car_racing_b200 import batch as _b
+
+    def pipelined(pipe, rec, nb=24):
+        for i in range(pipe.depth):
+            pipe.submit(rec)
+        for i in range(pipe.depth):
+            pipe.result(i)
+        base = pipe.n_submitted
+        t0 = time.perf_counter()
+        for i in range(nb):
+            if i >= pipe.depth:
+                pipe.result(base + i - pipe.depth, copy=False)
+            pipe.submit(rec, copy=True)
+        for i in range(nb - pipe.depth, nb):
+            pipe.result(base + i, copy=False)
+        dt = time.perf_counter() - t0
+        return nb * rec.shape[0] / dt
+    x0, xt, obs, lo = scenarios.ilqr_scenarios(1024, N=50, seed=1)
+    ip = _b.IlqrPipeline(iprm, B=1024, depth=4)
+    doc["config5_ilqr_in_flight"] = dict(B=1024, depth=4, solves_per_s=pipelined(ip, _b.pack_ilqr(x0, xt, obs, lo, 50)))
+    ip.close()
+    sc = scenarios.lmpc_scenarios(512, seed=3)
+    rec4, K4 = _b.pack_lmpc(*sc, int(lprm["N"]))
+    lp = _b.LmpcPipeline(lprm, K4, B=512, depth=4)
+    doc["config4_lmpc_in_flight"] = dict(B=512, depth=4, solves_per_s=pipelined(lp, rec4))
+    lp.close()
+    print("in flight", doc["config5_ilqr_in_flight"], doc["config4_lmpc_in_flight"], flush=True)
     doc["reference_python_ilqr_note"] = "SURVEY.md 8(d): the reference's own numpy iLQR measured p50 20.1 ms per solve (1 core)"
     s = json.dumps(doc, indent=1)
     if a.out:
