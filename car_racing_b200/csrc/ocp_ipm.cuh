@@ -250,6 +250,7 @@ struct Ipm {
     bool isx, iss, isu, isp;
     int jrole, cmap;
     int idx_base, idx_step, kmin;   // lane's diagonal / gradient slot at stage k: idx_base + k*idx_step, live for k >= kmin
+    double e4, e5;                  // one-hot of lanes 4 (s) and 5 (ey) as doubles
     double crow[MM], psel[MM];      // d(row j)/d(own sigma variable): (1-alpha) for sigma_k, -1 for sigma_{k+1}; one-hot of sigma_{k+1}
     double tcol[6], qqcol[6], rrcol[2];
     double arow[6], brow[2];   // row `lane` of A and B (lanes < 6), for the forward sweep
@@ -286,6 +287,8 @@ struct Ipm {
         idx_base = isx ? l : (iss ? OS + jrole * (N + 1) : (isu ? OU + jrole : 0));
         idx_step = isx ? 6 : (iss ? 1 : (isu ? 2 : 0));
         kmin = isx ? 1 : ((iss || isu) ? 0 : (1 << 30));
+        e4 = (l == 4) ? 1.0 : 0.0;
+        e5 = (l == 5) ? 1.0 : 0.0;
 #pragma unroll
         for (int j = 0; j < MM; j++) {
             crow[j] = (iss && jrole == j) ? a1 : ((isp && jrole == j) ? -1.0 : 0.0);
@@ -901,8 +904,7 @@ struct Ipm {
                     ldv<4>(JA + 4 * r, ja);
                     double dgr = DG[r], sg = SIGE[r], yh = YHAT[r];
                     double own = tcol[4] * ja[2] + tcol[5] * ja[3];
-                    own += (lane == 4) ? ja[0] : 0.0;
-                    own += (lane == 5) ? ja[1] : 0.0;
+                    own += e4 * ja[0] + e5 * ja[1];
                     own += crow[j] * dgr;
                     double w = sg * own;
 #pragma unroll
