@@ -7,8 +7,9 @@ Problem statement follows car_racing/control/control.py:476-607 (mpccbf) /
 Math. Prog. 106(1) 2006), the solver bundled with the CasADi 3.5.5 wheel pinned in the
 reference's requirements.txt:6.
 
-PARITY UNPINNED: CasADi/IPOPT cannot be installed here (no network) and the reference
-holds no golden vector for this path.  Only tests/ may import this file.
+PARITY: the solver algorithm is UNPINNED -- CasADi/IPOPT cannot be installed here (no network) and the
+reference holds no golden vector for this path; the problem functions below (f, c, g, bounds)
+ARE pinned to the reference's own code (tests/test_reference_statement.py).  Only tests/ may import this file.
 See DESIGN.md "Solver definition" for the conventions (start point, bounds-as-bounds).
 """
 import numpy as np

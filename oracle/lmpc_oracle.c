@@ -10,7 +10,9 @@
  * and solves it with the interior-point definition of DESIGN.md section 2 (IPOPT conventions; the QP is convex, so no
  * inertia correction and no elastic rows are involved).  Linear algebra is deliberately not the product's: the full
  * KKT matrix is assembled densely and solved by LU with partial pivoting.
- * PARITY UNPINNED for the same reason as ocp_oracle.c (no CasADi/IPOPT here, no golden vectors in the reference).
+ * PARITY: solver algorithm UNPINNED for the same reason as ocp_oracle.c (no CasADi/IPOPT here, no golden vectors in the
+ * reference); the problem statement is pinned to the reference's own code (tests/test_reference_statement.py); the QP is
+ * convex, so any correct solver returns the reference's optimum.
  */
 #include "ocp_oracle.h"
 #include <math.h>

@@ -7,9 +7,12 @@
  * 2006) -- the solver inside the CasADi 3.5.5 wheel the reference pins (requirements.txt:6);
  * neither is present under /root/reference nor installable here.
  *
- * PARITY UNPINNED: the reference holds no golden vector / asserting test for this path
- *  and CasADi/IPOPT cannot be run here.  The iLQR restatement
- * (ilqr_oracle.c) IS pinned against the reference's own control.ilqr (tests/golden/).
+ * PARITY: the SOLVER ALGORITHM is UNPINNED -- the reference holds no golden vector / asserting test for
+ * this path and CasADi/IPOPT cannot be run here.  The PROBLEM STATEMENT is pinned: the reference's
+ * own functions, run under a recording stand-in for casadi, give the cost / constraint values of
+ * tests/golden/nlp_golden.npz, and tests/test_reference_statement.py checks the oracle's problem functions and the
+ * packed problem data against them.  The iLQR restatement (ilqr_oracle.c) IS pinned end to end against the
+ * reference's own control.ilqr (tests/golden/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
  * may link or call this library.  The product (car_racing_b200/) never does.
