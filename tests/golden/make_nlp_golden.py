@@ -97,6 +97,31 @@ def single_variable_bounds(opti):
     return boxes
 
 
+def at_solution(opti, values, cost_reported):
+    """The reference's own cost / constraints at a solver's returned point (values in the reference's variable layout)."""
+    ctx = {v: np.asarray(a, float).reshape(v.shape) for v, a in zip(opti.variables, values)}
+    e, i = opti.eval_constraints(ctx)
+    return dict(sol_cost_ref=opti.eval_cost(ctx), sol_cost_reported=float(cost_reported), sol_eq_max=float(np.abs(e).max()),
+                sol_ineq_min=float(i.min()))
+
+
+class OracleSolve:
+    """Routes the drop-in shims' batch calls to the CPU oracle (as the tests do) and keeps the last result."""
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        self.orc, self.last = oracle, None
+
+    def cbf(self, x0, xt, obs, lap_off, prm, want=None, handle=None, **kw):
+        self.last = self.orc.solve_cbf_batch(x0, xt, obs, lap_off, prm, **kw)
+        return self.last
+
+    def lmpc(self, *a, want=None, handle=None, **kw):
+        self.last = self.orc.solve_lmpc_batch(*a, **kw)
+        return self.last
+
+
 def put(store, prefix, d):
     for k, v in d.items():
         store["%s/%s" % (prefix, k)] = np.asarray(v)
@@ -107,6 +132,10 @@ def main():
     from planner_cases import make_planner
     from test_shims_host import Rival
     ref_control, ref_planner = import_reference()
+    from car_racing_b200 import control as our_control, planning as our_planning
+    osolve = OracleSolve()
+    our_control.batch.solve_cbf_batch = osolve.cbf
+    our_control.batch.solve_lmpc_batch = osolve.lmpc
     rng = np.random.default_rng(2024)
     store = {}
     lap = scenarios.LAP_LENGTH["l_shape"]
@@ -124,6 +153,9 @@ def main():
         except RuntimeError:
             pass
         d = evaluate(rec.LAST[-1], rng)
+        our_control.mpc_lti(x0, xt, prm, sysp, track)
+        r = osolve.last
+        d.update(at_solution(rec.LAST[-1], [r["x"][0].T, r["u"][0].T], r["cost"][0]))
         d.update(x0=x0, xtarget=xt.ravel(), N=10, width=0.8)
         put(store, "mpc_lti%d" % k, d)
 
@@ -158,6 +190,10 @@ def main():
         ec = [opti.eval_constraints(c) for c in ctxs]
         near["eq"], near["ineq"] = np.array([e for e, _ in ec]), np.array([i for _, i in ec])
         d.update({"near_" + kk: vv for kk, vv in near.items()})
+        our_control.mpccbf(x0, xt, prm, vehicles, "ego", lap, 0.3, 0.1, False, track, sysp)
+        r = osolve.last
+        d.update(at_solution(opti, [r["x"][0].T, r["u"][0].T, r["sigma"][0]], r["cost"][0]))
+        d.update(sol_status=int(r["status"][0]), sol_elastic=float(r["elastic_max"][0]))
         d.update(x0=x0, xtarget=xt.ravel(), N=20, alpha=cs["alpha"], time=0.3, rivals=np.array(cs["rivals"]),
                  num_slack_rows=opti.variables[2].shape[0])
         put(store, "mpccbf%d" % k, d)
@@ -179,6 +215,11 @@ def main():
                                      sorted_vehicles=["car1", "car2", "car3"], time=None)
         opti = rec.LAST[-1]
         d = evaluate(opti, rng)
+        our_control.mpc_multi_agents(x0, prm, track, None, None, None, sysp, target_traj_xcurv=traj, vehicles=vehicles,
+                                     agent_name="ego", direction_flag=0, sorted_vehicles=["car1", "car2", "car3"], time=None)
+        r = osolve.last
+        d.update(at_solution(opti, [r["x"][0].T, r["u"][0].T, r["sigma"][0]], r["cost"][0]))
+        d.update(sol_status=int(r["status"][0]), sol_elastic=float(r["elastic_max"][0]))
         d.update(x0=x0, traj=traj, N=10, rivals=np.array([(5.0 + k, 1.0, -0.5), (5.6, 0.9, 0.2), (30.0, 1.0, 0.0)]),
                  num_slack_rows=opti.variables[2].shape[0])
         put(store, "multi%d" % k, d)
@@ -210,6 +251,11 @@ def main():
         out = ref_control.lmpc(x0, lp_prm, Atv, Btv, Ctv, ss, Qf, 3, 25.0, 0.9, u_old, sysp)
         opti = rec.LAST[-1]
         d = evaluate(opti, rng, zero=(3,))        # slack is forced to 0 by :693-694; evaluate there
+        lp2 = types.SimpleNamespace(**{kk: vv for kk, vv in lp_prm.__dict__.items() if kk != "matrix_Qslack"})
+        our_control.lmpc(x0, lp2, Atv, Btv, Ctv, ss, Qf, 3, 25.0, 0.9, u_old, sysp)
+        r = osolve.last
+        d.update(at_solution(opti, [r["x"][0].T, r["u"][0].T, r["lam"][0], np.zeros(6)], r["cost"][0]))
+        d.update(sol_status=int(r["status"][0]))
         d.update(x0=x0, ss=ss, Qfun=Qf, it=3, Atv=np.array(Atv), Btv=np.array(Btv), Ctv=np.array(Ctv), u_old=np.asarray(u_old).ravel(),
                  matrix_Q=lp_prm.matrix_Q, lap_width=0.9, ss_sel=out[2], Qfun_sel=out[3])
         put(store, "lmpc%d" % k, d)
@@ -246,6 +292,16 @@ def main():
             ref_planner.OvertakeTrajPlanner.generate_traj_per_region(p, c, dt, ds, dc)
             fallback[c] = dt[c].copy()                # the reference's heuristic trajectory (solve() raised)
             d = evaluate(rec.LAST[-1], rng)
+            N_ = p.racing_game_param.num_horizon_planner
+            ego_x = np.asarray(p.vehicles["ego"].xcurv, float)
+            xlb, xub = our_planning.candidate_bounds(c, p.xcurv_ego, p.sorted_vehicles, p.obs_infos, 0.4, 0.2, p.track.width,
+                                                     p.track.lap_length, N_)
+            s_ref, ey_ref = our_planning.candidate_targets(c, ego_x, p.bezier_xcurvs, p.bezier_funcs, N_)
+            kw, off = our_planning.pack_candidates(ego_x, s_ref[None], ey_ref[None], xlb[None], xub[None], N_)
+            pprm = our_planning.planner_params(p.racing_game_param.matrix_A, p.racing_game_param.matrix_B, N_)
+            r = osolve.orc.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, pprm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"])
+            d.update(sol_status=int(r["status"][0]), sol_x0_feasible=int(our_planning.x0_feasible(ego_x, xlb, xub)))
+            d.update(at_solution(rec.LAST[-1], [r["x"][0].T, r["u"][0].T], r["cost"][0] + off[0]))
             bx = single_variable_bounds(rec.LAST[-1])
             d.update(x_lb=bx[0][0], x_ub=bx[0][1], u_lb=bx[1][0], u_ub=bx[1][1])
             put(store, "plan%d/cand%d" % (nplan, c), d)

@@ -290,3 +290,42 @@ def test_selection_kernel_matches_reference_selection():
         h.synchronize()
         assert int(d_flag[0].item()) == int(G[key + "/sel_flag"])
         assert np.abs(d_traj.cpu().numpy() - G[key + "/sel_traj"]).max() == 0.0
+
+
+def test_oracle_solutions_satisfy_the_reference_statement(oracle, monkeypatch):
+    """make_nlp_golden.py evaluated the REFERENCE's recorded cost and constraints at the point the oracle returns for the
+    same inputs (through our shims): wherever the oracle converged, that point satisfies every row of the reference's
+    own problem and the reported cost is the reference's cost there.  The oracle is re-run here so that a drift of the
+    oracle away from the stored solutions is caught as well."""
+    n_ok = 0
+    for key in sorted({k[:-len("sol_cost_ref")] for k in G.files if k.endswith("sol_cost_ref")}):
+        status = int(G[key + "sol_status"]) if key + "sol_status" in G else 0
+        if key + "sol_x0_feasible" in G and not int(G[key + "sol_x0_feasible"]):
+            assert status != 0          # x_0 violates a stage-0 row: the reference's IPOPT fails, ours reports failure too
+            continue
+        if status != 0:
+            continue
+        ref, rep = float(G[key + "sol_cost_ref"]), float(G[key + "sol_cost_reported"])
+        assert abs(ref - rep) < 1e-8 * (1 + abs(ref)), (key, ref, rep)
+        assert float(G[key + "sol_eq_max"]) < 1e-9 and float(G[key + "sol_ineq_min"]) > -1e-9, key
+        n_ok += 1
+    assert n_ok >= 16
+    assert abs(float(G["mpc_lti0/sol_cost_ref"]) - 22.71576162) < 1e-6        # SURVEY 8(c) anchor, now the reference's own cost
+    # re-solve the MPC-CBF cases with the current oracle
+    lap = scenarios.LAP_LENGTH["l_shape"]
+    for k in range(3):
+        key = "mpccbf%d" % k
+        got = {}
+
+        def solve(x0, xt, obs, lap_off, prm, want=None, handle=None, **kw):
+            got["r"] = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, **kw)
+            return got["r"]
+        monkeypatch.setattr(control.batch, "solve_cbf_batch", solve)
+        vehicles = {"ego": Rival(0, 0, 0)}
+        for j, (s0, v, ey) in enumerate(G[key + "/rivals"]):
+            vehicles["car%d" % (j + 1)] = Rival(s0, v, ey)
+        prm = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 4.0, 0, 40.0]),
+                                    matrix_R=np.diag([0.1, 0.1]), num_horizon=20, alpha=float(G[key + "/alpha"]))
+        control.mpccbf(G[key + "/x0"], G[key + "/xtarget"].reshape(6, 1), prm, vehicles, "ego", lap, float(G[key + "/time"]), 0.1, False,
+                       types.SimpleNamespace(width=1.0, lap_length=lap), SYSP)
+        assert abs(got["r"]["cost"][0] - float(G[key + "/sol_cost_reported"])) < 1e-9
