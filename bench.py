@@ -29,6 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+OUT = sys.stdout
 METRIC = "MPC-CBF solves/sec (N=20, 6-state, 3 obs)"
 ALG_BYTES_PER_SOLVE = 1136 + 536      # 1136 B in (one packed record) + 536 B out
 N_H, M_OBS = 20, 3
@@ -123,7 +124,16 @@ def run_reference(args, rank, world):
                              "sample": "%d instances per step, %d pthreads" % (B, cores)},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
+
+
+def _claim_stdout():
+    """Rank 0 must print ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter) is
+    sent to stderr; the returned file object is the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -140,6 +150,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    global OUT
+    OUT = _claim_stdout()
     if args.impl == "reference":
         return run_reference(args, rank, world)
     if args.warmup < 3:
@@ -155,6 +167,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     D = max(1, args.inflight)
@@ -329,7 +342,7 @@ def main():
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
