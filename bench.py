@@ -184,17 +184,38 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     torch.cuda.synchronize()
 
+    # N>1: the exchange step (all-gather of the 32-byte records + argmin) runs on its own stream.  NCCL completes collectives
+    # in issue order, so an all-gather enqueued on a solver stream would hold that stream until every EARLIER batch's
+    # stragglers have finished on every rank; here the solver stream only records an event and moves on to its next batch
+    # (result buffers are double-buffered per slot).
+    hc = _capi.Handle(device=local_rank, max_batch=B) if world > 1 else None
+    ext_c = torch.cuda.ExternalStream(hc.stream, device=dev) if world > 1 else None
+    d_rec2 = [[d_rec[k], torch.zeros_like(d_rec[k])] for k in range(D)]
+    ag_done = [[None, None] for _ in range(D)]
+    n_issued = [0] * D
+
     def step_device(k):
-        """One step = one batch of B instances: L2 flush, the solve kernel, (N>1) all-gather of the 32-byte records +
-        argmin; everything enqueued on slot k's stream."""
+        """One step = one batch of B instances: L2 flush, the solve kernel on slot k's stream; (N>1) all-gather of the
+        32-byte records + argmin on the exchange stream."""
         h = hs[k]
+        b = n_issued[k] & 1
+        n_issued[k] += 1
         with torch.cuda.stream(exts[k]):
             flush.zero_()
-            rc = L.b200mpc_cbf_solve_device(h.ptr, C.byref(p), C.byref(o), B, d_in.data_ptr(), d_rec[k].data_ptr(), None, None, None, None)
+            if ag_done[k][b] is not None:
+                exts[k].wait_event(ag_done[k][b])          # the exchange that last read this result buffer
+            rc = L.b200mpc_cbf_solve_device(h.ptr, C.byref(p), C.byref(o), B, d_in.data_ptr(), d_rec2[k][b].data_ptr(), None, None, None, None)
             h.check(rc, "b200mpc_cbf_solve_device")
             if world > 1:
-                dist.all_gather_into_tensor(d_all[k], d_rec[k])
-                h.check(L.b200mpc_argmin_cost_device(h.ptr, d_all[k].data_ptr(), world * B, 0, d_arg[k].data_ptr()), "argmin")
+                ev = torch.cuda.Event()
+                ev.record(exts[k])
+        if world > 1:
+            with torch.cuda.stream(ext_c):
+                ext_c.wait_event(ev)
+                dist.all_gather_into_tensor(d_all[k], d_rec2[k][b])
+                hc.check(L.b200mpc_argmin_cost_device(hc.ptr, d_all[k].data_ptr(), world * B, 0, d_arg[k].data_ptr()), "argmin")
+                ag_done[k][b] = torch.cuda.Event()
+                ag_done[k][b].record(ext_c)
 
     def barrier():
         torch.cuda.synchronize()
@@ -203,7 +224,7 @@ def main():
             torch.cuda.synchronize()
 
     def launches():
-        return sum(h.launch_count for h in hs)
+        return sum(h.launch_count for h in hs) + (hc.launch_count if hc is not None else 0)
 
     for i in range(max(args.warmup, D)):
         step_device(i % D)
@@ -241,10 +262,14 @@ def main():
         step_device(i % D)
     for k in range(D):
         ends[k].record(exts[k])
+    if world > 1:
+        end_c = torch.cuda.Event(enable_timing=True)
+        end_c.record(ext_c)
+        ends.append(end_c)
     barrier()
     wall = time.perf_counter() - wall0
     launches_dev = launches() - launches0
-    t_dev = max(starts[a].elapsed_time(ends[b]) for a in range(D) for b in range(D)) * 1e-3
+    t_dev = max(sa.elapsed_time(eb) for sa in starts for eb in ends) * 1e-3
     status = sharding.tensor_to_records(d_rec[0])["status"]
     conv = float((status == 0).mean())
 
@@ -313,7 +338,7 @@ def main():
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 per GPU (BASELINE config 2)" % B,
-                   "global_batch": B * world, "parallelism": "dp%d (independent scenario shards + 1 all-gather of 32-B records)" % world,
+                   "global_batch": B * world, "parallelism": "dp%d (independent scenario shards + 1 all-gather of 32-B records and argmin per step, on an exchange stream)" % world,
                    "l2": "256 MiB buffer written before every timed step, on the step's stream (inputs are 1.1 MB << L2)",
                    "batches_in_flight": D,
                    "pipelining": ("steps are issued round-robin on %d streams (one handle each): the stragglers of one 1024-instance "
