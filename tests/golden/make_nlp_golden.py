@@ -105,6 +105,64 @@ def at_solution(opti, values, cost_reported):
                 sol_ineq_min=float(i.min()))
 
 
+def _ctx_from_w(opti, w):
+    ctx, o = {}, 0
+    for v in opti.variables:
+        n = v.shape[0] * v.shape[1]
+        ctx[v] = np.asarray(w[o:o + n], float).reshape(v.shape)
+        o += n
+    return ctx
+
+
+def independent_qp_solution(opti, fixed_zero=()):
+    """For the CONVEX problems (quadratic cost, linear rows): read H, g and the row matrices off the reference's recorded
+    closures (exact for quadratics: second differences at unit vectors) and solve the reference's own QP with scipy's
+    trust-constr from a cold start -- an optimum of the reference's problem that owes nothing to our solver.
+    Returns (w*, cost*)."""
+    from scipy.optimize import minimize
+    sizes = [v.shape[0] * v.shape[1] for v in opti.variables]
+    n = sum(sizes)
+    f = lambda w: opti.eval_cost(_ctx_from_w(opti, w))
+    z = np.zeros(n)
+    f0 = f(z)
+    E = np.eye(n)
+    fi = np.array([f(E[i]) for i in range(n)])
+    H = np.zeros((n, n))
+    for i in range(n):
+        H[i, i] = f(2 * E[i]) - 2 * fi[i] + f0
+    # off-diagonal terms only where both variables carry curvature or the cost couples them: brute force over pairs
+    for i in range(n):
+        for j in range(i + 1, n):
+            hij = f(E[i] + E[j]) - fi[i] - fi[j] + f0
+            if abs(hij) > 1e-12:
+                H[i, j] = H[j, i] = hij
+    g = fi - f0 - 0.5 * np.diag(H)
+    e0, i0 = opti.eval_constraints(_ctx_from_w(opti, z))
+    Aeq = np.zeros((e0.size, n))
+    Ain = np.zeros((i0.size, n))
+    for i in range(n):
+        e1, i1 = opti.eval_constraints(_ctx_from_w(opti, E[i]))
+        Aeq[:, i], Ain[:, i] = e1 - e0, i1 - i0
+    # eliminate the equality rows (x_0 and the dynamics fix the states): w = w_p + Z y, then SLSQP on the reduced, well
+    # conditioned QP in the inputs (and lambda) with exact gradients
+    from scipy.linalg import null_space
+    w_p = np.linalg.lstsq(Aeq, -e0, rcond=None)[0]
+    Z = null_space(Aeq)
+    Hr, gr = Z.T @ H @ Z, Z.T @ (H @ w_p + g)
+    Ar, br = Ain @ Z, Ain @ w_p + i0
+    fun = lambda y: 0.5 * y @ Hr @ y + gr @ y
+    best = None
+    for y0 in (np.zeros(Z.shape[1]),):
+        res = minimize(fun, y0, jac=lambda y: Hr @ y + gr, method="SLSQP",
+                       constraints=[{"type": "ineq", "fun": lambda y: Ar @ y + br, "jac": lambda y: Ar}],
+                       options=dict(maxiter=2000, ftol=1e-15))
+        if best is None or res.fun < best.fun:
+            best = res
+    w = w_p + Z @ best.x
+    viol = max(np.abs(Aeq @ w + e0).max(), max(0.0, -(Ain @ w + i0).min()))
+    return w, float(f(w)), float(viol), int(best.status)
+
+
 class OracleSolve:
     """Routes the drop-in shims' batch calls to the CPU oracle (as the tests do) and keeps the last result."""
 
@@ -156,6 +214,10 @@ def main():
         our_control.mpc_lti(x0, xt, prm, sysp, track)
         r = osolve.last
         d.update(at_solution(rec.LAST[-1], [r["x"][0].T, r["u"][0].T], r["cost"][0]))
+        w, c, viol, st = independent_qp_solution(rec.LAST[-1])
+        ctx = _ctx_from_w(rec.LAST[-1], w)
+        d.update(scipy_u0=ctx[rec.LAST[-1].variables[1]][:, 0], scipy_cost=c, scipy_viol=viol, scipy_status=st, oracle_u0=r["u0"][0])
+        print("mpc_lti", k, "scipy cost", c, "oracle cost", r["cost"][0], "du0", np.abs(d["scipy_u0"] - r["u0"][0]).max(), "viol", viol, flush=True)
         d.update(x0=x0, xtarget=xt.ravel(), N=10, width=0.8)
         put(store, "mpc_lti%d" % k, d)
 
@@ -255,7 +317,12 @@ def main():
         our_control.lmpc(x0, lp2, Atv, Btv, Ctv, ss, Qf, 3, 25.0, 0.9, u_old, sysp)
         r = osolve.last
         d.update(at_solution(opti, [r["x"][0].T, r["u"][0].T, r["lam"][0], np.zeros(6)], r["cost"][0]))
-        d.update(sol_status=int(r["status"][0]))
+        d.update(sol_status=int(r["status"][0]), oracle_u0=r["u0"][0])
+        if int(r["status"][0]) == 0:
+            w, c, viol, st = independent_qp_solution(opti)
+            ctx = _ctx_from_w(opti, w)
+            d.update(scipy_u0=ctx[opti.variables[1]][:, 0], scipy_cost=c, scipy_viol=viol, scipy_status=st)
+            print("lmpc", k, "scipy cost", c, "oracle cost", r["cost"][0], "du0", np.abs(d["scipy_u0"] - r["u0"][0]).max(), "viol", viol, flush=True)
         d.update(x0=x0, ss=ss, Qfun=Qf, it=3, Atv=np.array(Atv), Btv=np.array(Btv), Ctv=np.array(Ctv), u_old=np.asarray(u_old).ravel(),
                  matrix_Q=lp_prm.matrix_Q, lap_width=0.9, ss_sel=out[2], Qfun_sel=out[3])
         put(store, "lmpc%d" % k, d)
@@ -302,6 +369,12 @@ def main():
             r = osolve.orc.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, pprm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"])
             d.update(sol_status=int(r["status"][0]), sol_x0_feasible=int(our_planning.x0_feasible(ego_x, xlb, xub)))
             d.update(at_solution(rec.LAST[-1], [r["x"][0].T, r["u"][0].T], r["cost"][0] + off[0]))
+            d.update(oracle_x=r["x"][0])
+            if int(r["status"][0]) == 0:
+                w, cst, viol, st = independent_qp_solution(rec.LAST[-1])
+                ctx = _ctx_from_w(rec.LAST[-1], w)
+                d.update(scipy_x=ctx[rec.LAST[-1].variables[0]].T, scipy_cost=cst, scipy_viol=viol, scipy_status=st)
+                print("plan", nplan, c, "scipy cost", cst, "oracle cost", r["cost"][0] + off[0], "dx", np.abs(d["scipy_x"] - r["x"][0]).max(), flush=True)
             bx = single_variable_bounds(rec.LAST[-1])
             d.update(x_lb=bx[0][0], x_ub=bx[0][1], u_lb=bx[1][0], u_ub=bx[1][1])
             put(store, "plan%d/cand%d" % (nplan, c), d)

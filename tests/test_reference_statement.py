@@ -329,3 +329,67 @@ def test_oracle_solutions_satisfy_the_reference_statement(oracle, monkeypatch):
         control.mpccbf(G[key + "/x0"], G[key + "/xtarget"].reshape(6, 1), prm, vehicles, "ego", lap, float(G[key + "/time"]), 0.1, False,
                        types.SimpleNamespace(width=1.0, lap_length=lap), SYSP)
         assert abs(got["r"]["cost"][0] - float(G[key + "/sol_cost_reported"])) < 1e-9
+
+
+def test_convex_paths_against_an_independent_solve_of_the_reference_qp(oracle, monkeypatch):
+    """For the convex problems the optimum is unique, so any correct solver pins it.  make_nlp_golden.py read H, g and the
+    row matrices off the reference's recorded closures and solved the REFERENCE's own QP with scipy (equalities
+    eliminated, SLSQP from a cold start).  The oracle -- re-run here through our shims for MPC-LTI, stored for LMPC and
+    the planner candidates -- must land on the same optimum: |du0| < 1e-5, |dcost| < 1e-6 (the oracle's cost sits ~1e-7
+    above scipy's: the barrier residual at tol 1e-8)."""
+    n = 0
+    for key in sorted({k[:-len("scipy_cost")] for k in G.files if k.endswith("scipy_cost")}):
+        assert float(G[key + "scipy_viol"]) < 1e-9
+        dc = float(G[key + "sol_cost_reported"]) - float(G[key + "scipy_cost"])
+        assert -1e-7 < dc < 1e-6, (key, dc)
+        if key + "scipy_u0" in G:
+            assert np.abs(G[key + "scipy_u0"] - G[key + "oracle_u0"]).max() < 1e-5, key
+        else:
+            assert np.abs(G[key + "scipy_x"] - G[key + "oracle_x"]).max() < 1e-4, key
+        n += 1
+    assert n >= 10
+    for k in range(2):
+        key = "mpc_lti%d" % k
+        got = {}
+
+        def solve(x0, xt, obs, lap_off, prm, want=None, handle=None, **kw):
+            got["r"] = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, **kw)
+            return got["r"]
+        monkeypatch.setattr(control.batch, "solve_cbf_batch", solve)
+        prm = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 4.0, 0, 40.0]),
+                                    matrix_R=np.diag([0.1, 0.1]), num_horizon=10)
+        track = types.SimpleNamespace(width=0.8, lap_length=scenarios.LAP_LENGTH["l_shape"])
+        u = control.mpc_lti(G[key + "/x0"], G[key + "/xtarget"].reshape(6, 1), prm, SYSP, track)
+        assert np.abs(u - G[key + "/scipy_u0"]).max() < 1e-5
+        assert abs(got["r"]["cost"][0] - float(G[key + "/scipy_cost"])) < 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_solutions_against_the_independent_solve_of_the_reference_qp():
+    """The CUDA path itself (through the drop-in shims) on the convex cases: MPC-LTI, LMPC and the planner candidates land
+    on the optimum scipy found for the REFERENCE's own recorded QP."""
+    for k in range(2):
+        key = "mpc_lti%d" % k
+        prm = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 4.0, 0, 40.0]),
+                                    matrix_R=np.diag([0.1, 0.1]), num_horizon=10)
+        track = types.SimpleNamespace(width=0.8, lap_length=scenarios.LAP_LENGTH["l_shape"])
+        u = control.mpc_lti(G[key + "/x0"], G[key + "/xtarget"].reshape(6, 1), prm, SYSP, track)
+        assert np.abs(u - G[key + "/scipy_u0"]).max() < 1e-5
+    key = "lmpc1"
+    lp = types.SimpleNamespace(num_horizon=12, num_ss_iter=2, num_ss_points=44, shift=0, matrix_Q=G[key + "/matrix_Q"],
+                               matrix_R=np.diag([1.0, 0.25]), matrix_dR=np.diag([4.0, 0.0]))
+    out = control.lmpc(G[key + "/x0"], lp, list(G[key + "/Atv"]), list(G[key + "/Btv"]), list(G[key + "/Ctv"]), G[key + "/ss"],
+                       G[key + "/Qfun"], int(G[key + "/it"]), 25.0, float(G[key + "/lap_width"]), G[key + "/u_old"], SYSP)
+    assert np.abs(out[0][0] - G[key + "/scipy_u0"]).max() < 1e-5
+    checked = 0
+    for n in range(int(G["num_plans"])):
+        key = "plan%d" % n
+        p = _planner(int(G[key + "/seed"]), int(G[key + "/num_veh"]), int(G[key + "/old"]), G[key + "/obs"])
+        traj, flag, st, sol = planning.solve_optimization_problem(p)
+        for c in range(sol.shape[0]):
+            ck = f"{key}/cand{c}/scipy_x"
+            if ck in G:
+                assert np.abs(sol[c].T - G[ck]).max() < 1e-4, ck
+                assert abs(p.candidate_costs[c] - float(G[f"{key}/cand{c}/scipy_cost"])) < 1e-6
+                checked += 1
+    assert checked >= 7
