@@ -359,6 +359,18 @@ def main():
                      "traffic": traffic, "peak_source": peak_src,
                      "note": "algorithmic bytes = 1672 B/solve x %d; the kernel is FP64-latency/shared-memory bound, see profiles/ and DESIGN.md" % B},
     }
+    # what actually bounds the kernel (ncu, crowded launch; measured once per kernel version, not live): see DESIGN.md section 5
+    sp = os.path.join(ROOT, "profiles", "r01x_ncu_crowded_b8192_summary.json")
+    if os.path.exists(sp):
+        m = json.load(open(sp))["metrics"]
+        g = lambda k: float(m[k]["value"]) if k in m else None
+        line["roofline"]["ncu_crowded_launch"] = {
+            "source": "profiles/r01x_ncu_crowded_b8192_summary.json",
+            "issue_slots_busy_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "fp64_pipe_busy_pct": g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            "dram_pct_of_peak": g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "icache_hit_pct": g("sm__icc_request_hit_rate.pct"),
+            "bound": "dependent-issue latency (stall_wait 45 %), after the instruction-fetch bound was removed"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         v, dt = cpu_port_rate(min(B, 1024), cores)
