@@ -77,6 +77,15 @@ class PlannerSelectParams(C.Structure):
     ]
 
 
+class PlannerPrepareParams(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("num_veh", C.c_int32), ("num_opt", C.c_int32), ("reserved", C.c_int32),
+        ("prediction_factor", C.c_double), ("track_width", C.c_double), ("lap_length", C.c_double),
+        ("veh_length", C.c_double), ("veh_width", C.c_double), ("safety_margin", C.c_double), ("vx_max", C.c_double),
+        ("w_ey_rate", C.c_double), ("w_progress", C.c_double), ("w_track", C.c_double),
+    ]
+
+
 RECORD_DTYPE = np.dtype([("cost", "<f8"), ("u0", "<f8", (2,)), ("status", "<i4"), ("iters", "<i4")])
 assert RECORD_DTYPE.itemsize == 32
 
@@ -87,6 +96,7 @@ EXPORTS = [
     "b200mpc_argmin_cost_device", "b200mpc_lmpc_record_doubles", "b200mpc_lmpc_solve", "b200mpc_lmpc_solve_device",
     "b200mpc_lmpc_sysid", "b200mpc_lmpc_sysid_device", "b200mpc_plant_step", "b200mpc_plant_step_device",
     "b200mpc_cbf_solve_async", "b200mpc_synchronize", "b200mpc_host_alloc", "b200mpc_host_free", "b200mpc_planner_select_device", "b200mpc_plan_and_track", "b200mpc_ilqr_solve_async", "b200mpc_lmpc_solve_async",
+    "b200mpc_planner_prepare_device", "b200mpc_planner_prepare", "b200mpc_plan_and_track_prepared",
 ]
 
 _lib = None
@@ -130,6 +140,12 @@ def lib():
     L.b200mpc_planner_select_device.argtypes = [vp, C.POINTER(PlannerSelectParams)] + [dp] * 10
     L.b200mpc_plan_and_track.argtypes = [vp, C.POINTER(CbfParams), C.POINTER(CbfParams), C.POINTER(IpmOptions),
                                          C.POINTER(PlannerSelectParams)] + [dp] * 14
+    prep_args = [vp, C.POINTER(PlannerPrepareParams)] + [dp] * 13
+    L.b200mpc_planner_prepare_device.argtypes = prep_args
+    L.b200mpc_planner_prepare.argtypes = prep_args
+    L.b200mpc_plan_and_track_prepared.argtypes = [vp, C.POINTER(CbfParams), C.POINTER(CbfParams), C.POINTER(IpmOptions),
+                                                  C.POINTER(PlannerSelectParams), C.POINTER(PlannerPrepareParams)] + \
+        [dp] * 5 + [ip] + [dp] * 18
     ilqr_args = [vp, C.POINTER(IlqrParams), ip, dp, dp, dp, dp]
     L.b200mpc_ilqr_solve.argtypes = ilqr_args
     L.b200mpc_ilqr_solve_device.argtypes = ilqr_args

@@ -12,6 +12,7 @@
 #include "lmpc.cuh"
 #include "ocp_ipm.cuh"
 #include "plant.cuh"
+#include "planner_prepare.cuh"
 #include "planner_select.cuh"
 #include "sysid.cuh"
 
@@ -536,47 +537,118 @@ int b200mpc_planner_select_device(b200mpc_handle *h, const b200mpc_planner_selec
     return B200MPC_OK;
 }
 
-int b200mpc_plan_and_track(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
-                           const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel, const double *cand_in,
-                           const double *heur, const int32_t *ok0, const int32_t *region, const double *rivals,
-                           const double *track_in, b200mpc_record *cand_rec, double *cand_xpred, double *sel_cost, int32_t *flag,
-                           double *traj, b200mpc_record *track_rec, double *track_xpred, double *track_upred) {
+static int check_prepare(b200mpc_handle *h, const b200mpc_planner_prepare_params *prm, const void *ego, const void *rivals,
+                         const void *rival_vx, const void *insertion, const void *opt_traj) {
     if (!h) return B200MPC_ERR_ARG;
-    if (!plan_prm || !track_prm || !opt || !sel || !cand_in || !heur || !ok0 || !region || !track_in || !flag || !track_rec)
-        return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: null argument");
-    const int C_ = sel->C, N = plan_prm->N, Nc = track_prm->N, Mc = track_prm->M;
-    if (C_ < 1 || sel->N != N || sel->N_ctrl != Nc || sel->M_ctrl != Mc || !track_prm->xt_per_stage || track_prm->flags != 0 ||
-        (sel->num_veh > 0 && !rivals))
-        return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: inconsistent parameters (the tracking record has per-stage targets)");
-    int rc = check_cbf(h, plan_prm, opt, C_, cand_in, flag);
+    if (!prm || !ego || !rivals || !rival_vx || !insertion || !opt_traj)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_planner_prepare: null argument");
+    if (prm->N < 3 || prm->N > B200MPC_NMAX || prm->num_veh < 1 || prm->num_opt < 2 || !(prm->lap_length > 0.0) ||
+        !(prm->w_track > 0.0) || !(prm->veh_width > 0.0) || !(prm->veh_length > 0.0))
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_planner_prepare: bad parameter value");
+    return B200MPC_OK;
+}
+
+int b200mpc_planner_prepare_device(b200mpc_handle *h, const b200mpc_planner_prepare_params *prm, const double *d_ego,
+                                   const double *d_rivals, const double *d_rival_vx, const int32_t *d_insertion,
+                                   const double *d_opt_traj, double *d_cand, double *d_heur, int32_t *d_ok0, int32_t *d_region,
+                                   double *d_offset, double *d_ctrl, double *d_bezier, int32_t *d_err) {
+    int rc = check_prepare(h, prm, d_ego, d_rivals, d_rival_vx, d_insertion, d_opt_traj);
     if (rc) return rc;
+    if (!d_cand || !d_heur || !d_ok0 || !d_region) return fail(h, B200MPC_ERR_ARG, "b200mpc_planner_prepare: null output");
     CK(h, cudaSetDevice(h->device));
-    const size_t cs = (size_t)cbf_record_doubles(N, plan_prm->M, plan_prm->xt_per_stage, plan_prm->flags);
-    const size_t ts = (size_t)cbf_record_doubles(Nc, Mc, 1, 0);
-    const size_t b_in = cs * 8 * C_, b_rec = sizeof(b200mpc_record) * (size_t)C_, b_x = 48 * (size_t)(N + 1) * C_;
-    const size_t b_riv = 16 * (size_t)(N + 1) * (sel->num_veh > 0 ? sel->num_veh : 1), b_int = 4 * (size_t)C_;
-    // chain buffer: [flag 2 ints + pad][traj 6(N+1)][tracking record][tracking result record][x_pred][u_pred]
-    const size_t o_traj = 2, o_trk = o_traj + 6 * (size_t)(N + 1), o_out = o_trk + ts, o_tx = o_out + 4,
-                 o_tu = o_tx + 6 * (size_t)(Nc + 1), n_chain = o_tu + 2 * (size_t)Nc;
+    PrepareKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.p = *prm;
+    const int fl = B200MPC_FLAG_STAGE_BOUNDS | B200MPC_FLAG_EY_RATE;
+    kp.stride = cbf_record_doubles(prm->N, 0, 1, fl);
+    kp.xt_off = cbf_hdr_doubles(0);
+    kp.bnd_off = cbf_base_doubles(prm->N, 0, 1);
+    kp.wd_off = kp.bnd_off + 4 * (prm->N + 1);
+    planner_prepare_kernel<<<1, PREPARE_NT, 0, h->stream>>>(kp, d_ego, d_rivals, d_rival_vx, d_insertion, d_opt_traj, d_cand, d_heur,
+                                                           d_ok0, d_region, d_offset, d_ctrl, d_bezier, d_err);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+// staging of the raw planner inputs: d_u = [ego 12][rival_vx nv][opt 2 num_opt][insertion nv ints], d_seg = rivals
+struct PrepStage {
+    const double *ego, *rival_vx, *opt;
+    const int32_t *insertion;
+};
+static int stage_prepare_inputs(b200mpc_handle *h, const b200mpc_planner_prepare_params *prm, const double *ego,
+                                const double *rivals, const double *rival_vx, const int32_t *insertion, const double *opt_traj,
+                                PrepStage *st) {
+    const int nv = prm->num_veh, N1 = prm->N + 1;
+    const size_t n_d = 12 + (size_t)nv + 2 * (size_t)prm->num_opt;
+    int rc;
+    if ((rc = grow(h, &h->d_u, &h->c_u, 8 * n_d + 4 * (size_t)nv))) return rc;
+    if ((rc = grow(h, &h->d_seg, &h->c_seg, 16 * (size_t)N1 * nv))) return rc;
+    double *d = (double *)h->d_u;
+    CK(h, cudaMemcpyAsync(d, ego, 96, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(d + 12, rival_vx, 8 * (size_t)nv, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(d + 12 + nv, opt_traj, 16 * (size_t)prm->num_opt, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(d + n_d, insertion, 4 * (size_t)nv, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_seg, rivals, 16 * (size_t)N1 * nv, cudaMemcpyHostToDevice, h->stream));
+    st->ego = d;
+    st->rival_vx = d + 12;
+    st->opt = d + 12 + nv;
+    st->insertion = (const int32_t *)(d + n_d);
+    return B200MPC_OK;
+}
+
+int b200mpc_planner_prepare(b200mpc_handle *h, const b200mpc_planner_prepare_params *prm, const double *ego,
+                            const double *rivals, const double *rival_vx, const int32_t *insertion, const double *opt_traj,
+                            double *cand, double *heur, int32_t *ok0, int32_t *region, double *offset, double *ctrl,
+                            double *bezier, int32_t *err) {
+    int rc = check_prepare(h, prm, ego, rivals, rival_vx, insertion, opt_traj);
+    if (rc) return rc;
+    if (!cand || !heur || !ok0 || !region) return fail(h, B200MPC_ERR_ARG, "b200mpc_planner_prepare: null output");
+    CK(h, cudaSetDevice(h->device));
+    const int C_ = prm->num_veh + 1, N1 = prm->N + 1;
+    const size_t cs = (size_t)cbf_record_doubles(prm->N, 0, 1, B200MPC_FLAG_STAGE_BOUNDS | B200MPC_FLAG_EY_RATE);
+    const size_t b_in = cs * 8 * C_, b_x = 48 * (size_t)N1 * C_, b_int = 4 * (size_t)C_;
+    // d_sig: [offset C][ctrl 8 C][bezier 2 N1 C][err]
+    const size_t o_ctrl = (size_t)C_, o_bez = o_ctrl + 8 * (size_t)C_, o_err = o_bez + 2 * (size_t)N1 * C_;
+    PrepStage st;
+    if ((rc = stage_prepare_inputs(h, prm, ego, rivals, rival_vx, insertion, opt_traj, &st))) return rc;
     if ((rc = grow(h, &h->d_in, &h->c_in, b_in))) return rc;
-    if ((rc = grow(h, &h->d_rec, &h->c_rec, b_rec))) return rc;
-    if ((rc = grow(h, &h->d_x, &h->c_x, b_x))) return rc;
     if ((rc = grow(h, &h->d_laps, &h->c_laps, b_x))) return rc;
-    if ((rc = grow(h, &h->d_seg, &h->c_seg, b_riv))) return rc;
     if ((rc = grow(h, &h->d_idx, &h->c_idx, b_int))) return rc;
     if ((rc = grow(h, &h->d_stat, &h->c_stat, b_int))) return rc;
-    if ((rc = grow(h, &h->d_aux, &h->c_aux, 8 * (size_t)C_))) return rc;
-    if ((rc = grow(h, &h->d_chain, &h->c_chain, 8 * n_chain))) return rc;
+    if ((rc = grow(h, &h->d_sig, &h->c_sig, 8 * (o_err + 1)))) return rc;
+    double *sg = (double *)h->d_sig;
+    rc = b200mpc_planner_prepare_device(h, prm, st.ego, (const double *)h->d_seg, st.rival_vx, st.insertion, st.opt, (double *)h->d_in,
+                                        (double *)h->d_laps, (int32_t *)h->d_idx, (int32_t *)h->d_stat, sg, sg + o_ctrl, sg + o_bez,
+                                        (int32_t *)(sg + o_err));
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(cand, h->d_in, b_in, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(heur, h->d_laps, b_x, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(ok0, h->d_idx, b_int, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(region, h->d_stat, b_int, cudaMemcpyDeviceToHost, h->stream));
+    if (offset) CK(h, cudaMemcpyAsync(offset, sg, 8 * (size_t)C_, cudaMemcpyDeviceToHost, h->stream));
+    if (ctrl) CK(h, cudaMemcpyAsync(ctrl, sg + o_ctrl, 64 * (size_t)C_, cudaMemcpyDeviceToHost, h->stream));
+    if (bezier) CK(h, cudaMemcpyAsync(bezier, sg + o_bez, 16 * (size_t)N1 * C_, cudaMemcpyDeviceToHost, h->stream));
+    if (err) CK(h, cudaMemcpyAsync(err, sg + o_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+// candidate solve -> selection -> tracking solve -> D2H on the handle's stream; the candidates (d_in), heuristic
+// trajectories (d_laps), ok0 (d_idx), regions (d_stat), rivals (d_seg) and the tracking record (chain buffer) are in place
+static int plan_chain(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
+                      const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel, b200mpc_record *cand_rec,
+                      double *cand_xpred, double *sel_cost, int32_t *flag, double *traj, b200mpc_record *track_rec,
+                      double *track_xpred, double *track_upred) {
+    const int C_ = sel->C, N = plan_prm->N, Nc = track_prm->N, Mc = track_prm->M;
+    const size_t ts = (size_t)cbf_record_doubles(Nc, Mc, 1, 0);
+    const size_t b_rec = sizeof(b200mpc_record) * (size_t)C_, b_x = 48 * (size_t)(N + 1) * C_;
+    const size_t o_traj = 2, o_trk = o_traj + 6 * (size_t)(N + 1), o_out = o_trk + ts, o_tx = o_out + 4,
+                 o_tu = o_tx + 6 * (size_t)(Nc + 1);
     double *ch = (double *)h->d_chain;
-    CK(h, cudaMemcpyAsync(h->d_in, cand_in, b_in, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(h->d_laps, heur, b_x, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(h->d_idx, ok0, b_int, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(h->d_stat, region, b_int, cudaMemcpyHostToDevice, h->stream));
-    if (sel->num_veh > 0) CK(h, cudaMemcpyAsync(h->d_seg, rivals, b_riv, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(ch + o_trk, track_in, ts * 8, cudaMemcpyHostToDevice, h->stream));
     // (1) all candidates, one launch
-    rc = b200mpc_cbf_solve_device(h, plan_prm, opt, C_, (const double *)h->d_in, (b200mpc_record *)h->d_rec, nullptr, (double *)h->d_x,
-                                  nullptr, nullptr);
+    int rc = b200mpc_cbf_solve_device(h, plan_prm, opt, C_, (const double *)h->d_in, (b200mpc_record *)h->d_rec, nullptr,
+                                      (double *)h->d_x, nullptr, nullptr);
     if (rc) return rc;
     // (2) selection cost, first argmin, chosen trajectory, per-stage targets of the tracking record
     rc = b200mpc_planner_select_device(h, sel, (const b200mpc_record *)h->d_rec, (const double *)h->d_x, (const double *)h->d_laps,
@@ -595,6 +667,116 @@ int b200mpc_plan_and_track(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm
     CK(h, cudaMemcpyAsync(track_rec, ch + o_out, sizeof(b200mpc_record), cudaMemcpyDeviceToHost, h->stream));
     if (track_xpred) CK(h, cudaMemcpyAsync(track_xpred, ch + o_tx, 48 * (size_t)(Nc + 1), cudaMemcpyDeviceToHost, h->stream));
     if (track_upred) CK(h, cudaMemcpyAsync(track_upred, ch + o_tu, 16 * (size_t)Nc, cudaMemcpyDeviceToHost, h->stream));
+    return B200MPC_OK;
+}
+
+static int plan_chain_buffers(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
+                              const b200mpc_planner_select_params *sel, const double *track_in) {
+    const int C_ = sel->C, N = plan_prm->N, Nc = track_prm->N, Mc = track_prm->M;
+    const size_t cs = (size_t)cbf_record_doubles(N, plan_prm->M, plan_prm->xt_per_stage, plan_prm->flags);
+    const size_t ts = (size_t)cbf_record_doubles(Nc, Mc, 1, 0);
+    const size_t b_in = cs * 8 * C_, b_rec = sizeof(b200mpc_record) * (size_t)C_, b_x = 48 * (size_t)(N + 1) * C_;
+    const size_t b_riv = 16 * (size_t)(N + 1) * (sel->num_veh > 0 ? sel->num_veh : 1), b_int = 4 * (size_t)C_;
+    // chain buffer: [flag 2 ints + pad][traj 6(N+1)][tracking record][tracking result record][x_pred][u_pred]
+    const size_t o_traj = 2, o_trk = o_traj + 6 * (size_t)(N + 1), o_out = o_trk + ts, o_tx = o_out + 4,
+                 o_tu = o_tx + 6 * (size_t)(Nc + 1), n_chain = o_tu + 2 * (size_t)Nc;
+    int rc;
+    if ((rc = grow(h, &h->d_in, &h->c_in, b_in))) return rc;
+    if ((rc = grow(h, &h->d_rec, &h->c_rec, b_rec))) return rc;
+    if ((rc = grow(h, &h->d_x, &h->c_x, b_x))) return rc;
+    if ((rc = grow(h, &h->d_laps, &h->c_laps, b_x))) return rc;
+    if ((rc = grow(h, &h->d_seg, &h->c_seg, b_riv))) return rc;
+    if ((rc = grow(h, &h->d_idx, &h->c_idx, b_int))) return rc;
+    if ((rc = grow(h, &h->d_stat, &h->c_stat, b_int))) return rc;
+    if ((rc = grow(h, &h->d_aux, &h->c_aux, 8 * (size_t)C_))) return rc;
+    if ((rc = grow(h, &h->d_chain, &h->c_chain, 8 * n_chain))) return rc;
+    CK(h, cudaMemcpyAsync((double *)h->d_chain + o_trk, track_in, ts * 8, cudaMemcpyHostToDevice, h->stream));
+    return B200MPC_OK;
+}
+
+static int check_plan(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
+                      const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel, const void *track_in,
+                      const void *flag, const void *track_rec) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!plan_prm || !track_prm || !opt || !sel || !track_in || !flag || !track_rec)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: null argument");
+    if (sel->C < 1 || sel->N != plan_prm->N || sel->N_ctrl != track_prm->N || sel->M_ctrl != track_prm->M ||
+        !track_prm->xt_per_stage || track_prm->flags != 0)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: inconsistent parameters (the tracking record has per-stage targets)");
+    return check_cbf(h, plan_prm, opt, sel->C, track_in, flag);
+}
+
+int b200mpc_plan_and_track(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
+                           const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel, const double *cand_in,
+                           const double *heur, const int32_t *ok0, const int32_t *region, const double *rivals,
+                           const double *track_in, b200mpc_record *cand_rec, double *cand_xpred, double *sel_cost, int32_t *flag,
+                           double *traj, b200mpc_record *track_rec, double *track_xpred, double *track_upred) {
+    int rc = check_plan(h, plan_prm, track_prm, opt, sel, track_in, flag, track_rec);
+    if (rc) return rc;
+    if (!cand_in || !heur || !ok0 || !region || (sel->num_veh > 0 && !rivals))
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: null argument");
+    CK(h, cudaSetDevice(h->device));
+    const int C_ = sel->C, N = plan_prm->N;
+    const size_t cs = (size_t)cbf_record_doubles(N, plan_prm->M, plan_prm->xt_per_stage, plan_prm->flags);
+    const size_t b_in = cs * 8 * C_, b_x = 48 * (size_t)(N + 1) * C_, b_int = 4 * (size_t)C_;
+    const size_t b_riv = 16 * (size_t)(N + 1) * (sel->num_veh > 0 ? sel->num_veh : 1);
+    if ((rc = plan_chain_buffers(h, plan_prm, track_prm, sel, track_in))) return rc;
+    CK(h, cudaMemcpyAsync(h->d_in, cand_in, b_in, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_laps, heur, b_x, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_idx, ok0, b_int, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_stat, region, b_int, cudaMemcpyHostToDevice, h->stream));
+    if (sel->num_veh > 0) CK(h, cudaMemcpyAsync(h->d_seg, rivals, b_riv, cudaMemcpyHostToDevice, h->stream));
+    rc = plan_chain(h, plan_prm, track_prm, opt, sel, cand_rec, cand_xpred, sel_cost, flag, traj, track_rec, track_xpred, track_upred);
+    if (rc) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+int b200mpc_plan_and_track_prepared(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
+                                    const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel,
+                                    const b200mpc_planner_prepare_params *prep, const double *ego, const double *rivals,
+                                    const double *rival_vx, const int32_t *insertion, const double *opt_traj, int n_extra,
+                                    const double *extra_cand, const double *extra_heur, const int32_t *extra_ok0,
+                                    const int32_t *extra_region, const double *track_in, b200mpc_record *cand_rec,
+                                    double *cand_xpred, double *sel_cost, int32_t *flag, double *traj, b200mpc_record *track_rec,
+                                    double *track_xpred, double *track_upred, double *heur_out, int32_t *ok0_out, double *offset,
+                                    double *bezier, int32_t *err) {
+    int rc = check_plan(h, plan_prm, track_prm, opt, sel, track_in, flag, track_rec);
+    if (rc) return rc;
+    if ((rc = check_prepare(h, prep, ego, rivals, rival_vx, insertion, opt_traj))) return rc;
+    const int fl = B200MPC_FLAG_STAGE_BOUNDS | B200MPC_FLAG_EY_RATE;
+    const int C0 = prep->num_veh + 1, C_ = sel->C, N = plan_prm->N, N1 = N + 1;
+    if (n_extra < 0 || C_ != C0 + n_extra || prep->N != N || sel->num_veh != prep->num_veh || plan_prm->M != 0 ||
+        !plan_prm->xt_per_stage || plan_prm->flags != fl || (n_extra > 0 && (!extra_cand || !extra_heur || !extra_ok0 || !extra_region)))
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track_prepared: inconsistent parameters (C = num_veh + 1 + n_extra, "
+                                        "planner records: M = 0, per-stage targets, STAGE_BOUNDS|EY_RATE)");
+    CK(h, cudaSetDevice(h->device));
+    const size_t cs = (size_t)cbf_record_doubles(N, 0, 1, fl);
+    if ((rc = plan_chain_buffers(h, plan_prm, track_prm, sel, track_in))) return rc;
+    PrepStage st;
+    if ((rc = stage_prepare_inputs(h, prep, ego, rivals, rival_vx, insertion, opt_traj, &st))) return rc;
+    // d_sig: [offset C0][bezier 2 N1 C0][err]
+    const size_t o_bez = (size_t)C0, o_err = o_bez + 2 * (size_t)N1 * C0;
+    if ((rc = grow(h, &h->d_sig, &h->c_sig, 8 * (o_err + 1)))) return rc;
+    double *sg = (double *)h->d_sig;
+    rc = b200mpc_planner_prepare_device(h, prep, st.ego, (const double *)h->d_seg, st.rival_vx, st.insertion, st.opt, (double *)h->d_in,
+                                        (double *)h->d_laps, (int32_t *)h->d_idx, (int32_t *)h->d_stat, sg, nullptr, sg + o_bez,
+                                        (int32_t *)(sg + o_err));
+    if (rc) return rc;
+    if (n_extra > 0) {   // additional candidates behind the reference's regions
+        CK(h, cudaMemcpyAsync((double *)h->d_in + cs * C0, extra_cand, cs * 8 * n_extra, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync((double *)h->d_laps + 6 * (size_t)N1 * C0, extra_heur, 48 * (size_t)N1 * n_extra, cudaMemcpyHostToDevice,
+                              h->stream));
+        CK(h, cudaMemcpyAsync((int32_t *)h->d_idx + C0, extra_ok0, 4 * (size_t)n_extra, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync((int32_t *)h->d_stat + C0, extra_region, 4 * (size_t)n_extra, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = plan_chain(h, plan_prm, track_prm, opt, sel, cand_rec, cand_xpred, sel_cost, flag, traj, track_rec, track_xpred, track_upred);
+    if (rc) return rc;
+    if (heur_out) CK(h, cudaMemcpyAsync(heur_out, h->d_laps, 48 * (size_t)N1 * C_, cudaMemcpyDeviceToHost, h->stream));
+    if (ok0_out) CK(h, cudaMemcpyAsync(ok0_out, h->d_idx, 4 * (size_t)C_, cudaMemcpyDeviceToHost, h->stream));
+    if (offset) CK(h, cudaMemcpyAsync(offset, sg, 8 * (size_t)C0, cudaMemcpyDeviceToHost, h->stream));
+    if (bezier) CK(h, cudaMemcpyAsync(bezier, sg + o_bez, 16 * (size_t)N1 * C0, cudaMemcpyDeviceToHost, h->stream));
+    if (err) CK(h, cudaMemcpyAsync(err, sg + o_err, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }

@@ -173,6 +173,20 @@ def solve_optimization_problem(self, solver=None):
     return traj_xcurv, direction_flag, solve_time, solution_xvar
 
 
+def _tracking_record(xcurv, mpc_lti_param, track, system_param, vehicles, agent_name, sorted_vehicles, time, veh_length, veh_width):
+    """Packed record of the tracking MPC (control.mpc_multi_agents, control.py:251-473): everything except the per-stage
+    targets, which the selection kernel fills on the device."""
+    from . import control
+    Nc = mpc_lti_param.num_horizon_ctrl
+    xc = np.asarray(xcurv, float).reshape(6)
+    kept, num_cycle_ego = control._nearby_rivals(xc, sorted_vehicles, vehicles, agent_name, track.lap_length, time, 0.1, False, Nc + 1)
+    obs_t, lap_off_t = control._rival_block(kept, num_cycle_ego, track.lap_length, Nc)
+    tprm = control._limits(control._model(mpc_lti_param, Nc), system_param, track.width)
+    tprm.update(alpha=0.6, margin=0.15, L=veh_length, W=veh_width)            # control.py:285,311,316-319
+    trec, Mc, _ = batch.pack_cbf(xc.reshape(1, 6), np.zeros((1, Nc + 1, 6)), obs_t, lap_off_t, Nc)
+    return trec, tprm, Nc, Mc
+
+
 def plan_and_track(self, xcurv, mpc_lti_param, track, system_param, vehicles=None, agent_name=None, sorted_vehicles=None,
                    time=None, handle=None, region=None, extra=None):
     """The whole overtaking step in ONE call on one CUDA stream (b200mpc_plan_and_track, include/b200mpc.h): candidate
@@ -185,7 +199,6 @@ def plan_and_track(self, xcurv, mpc_lti_param, track, system_param, vehicles=Non
     `extra`: optional dict of additional candidates {"s_ref","ey_ref","xlb","xub","region"} appended to the reference's
     num_veh+1 regions (BASELINE config 3 evaluates 64 candidates)."""
     import time as _time
-    from . import control
     h = handle or batch.default_handle()
     sorted_vehicles = self.sorted_vehicles if sorted_vehicles is None else sorted_vehicles
     vehicles = self.vehicles if vehicles is None else vehicles
@@ -218,14 +231,8 @@ def plan_and_track(self, xcurv, mpc_lti_param, track, system_param, vehicles=Non
     rivals = np.zeros((max(num_veh, 1), 2, N + 1))
     for j, name in enumerate(self.sorted_vehicles):
         rivals[j, 0], rivals[j, 1] = obs_infos[name][4, :N + 1], obs_infos[name][5, :N + 1]
-    # tracking MPC record (control.mpc_multi_agents): everything except the per-stage targets, which the device fills
-    Nc = mpc_lti_param.num_horizon_ctrl
-    xc = np.asarray(xcurv, float).reshape(6)
-    kept, num_cycle_ego = control._nearby_rivals(xc, sorted_vehicles, vehicles, agent_name, track.lap_length, time, 0.1, False, Nc + 1)
-    obs_t, lap_off_t = control._rival_block(kept, num_cycle_ego, track.lap_length, Nc)
-    tprm = control._limits(control._model(mpc_lti_param, Nc), system_param, track.width)
-    tprm.update(alpha=0.6, margin=0.15, L=veh_length, W=veh_width)            # control.py:285,311,316-319
-    trec, Mc, _ = batch.pack_cbf(xc.reshape(1, 6), np.zeros((1, Nc + 1, 6)), obs_t, lap_off_t, Nc)
+    trec, tprm, Nc, Mc = _tracking_record(xcurv, mpc_lti_param, track, system_param, vehicles, agent_name, sorted_vehicles, time,
+                                          veh_length, veh_width)
     p_plan = _capi.make_cbf_params(pprm, 0, True, _capi.FLAG_STAGE_BOUNDS | _capi.FLAG_EY_RATE)
     p_track = _capi.make_cbf_params(tprm, Mc, True, 0)
     o = _capi.default_options()
@@ -251,6 +258,164 @@ def plan_and_track(self, xcurv, mpc_lti_param, track, system_param, vehicles=Non
     solved = (ok0 != 0) & (cand_rec["status"] == 0)
     solution_xvar = np.where(solved[:, None, None], cand_x, heur).transpose(0, 2, 1).copy()
     self.candidate_costs = np.where(solved, cand_rec["cost"] + offset, np.inf)
+    self.selection_costs = sel_cost
+    self.tracking_status = int(trk["status"][0])
+    return (traj, int(flag[0]), np.full(Cn, dt / Cn), solution_xvar), (trk_u[0].copy(), trk_x)
+
+
+# ---------------------------------------------------------------- candidate preparation on the device
+def sort_rivals(eys):
+    """Order of `sorted_vehicles` as indices into the iteration order of vehicles_interest
+    (overtake_traj_planner.py:69-77): a rival goes to the front when its ey is >= the current first one's, to the back
+    otherwise -- not a full sort for more than two rivals, reproduced as it is."""
+    order = []
+    for i, ey in enumerate(eys):
+        if not order:
+            order.append(i)
+        elif ey >= eys[order[0]]:
+            order.insert(0, i)
+        elif ey <= eys[order[0]]:
+            order.append(i)
+    return order
+
+
+def _prepare_params(N, num_veh, num_opt, prediction_factor, track_width, lap_length, veh_length, veh_width):
+    p = _capi.PlannerPrepareParams()
+    p.N, p.num_veh, p.num_opt = int(N), int(num_veh), int(num_opt)
+    p.prediction_factor, p.track_width, p.lap_length = float(prediction_factor), float(track_width), float(lap_length)
+    p.veh_length, p.veh_width, p.safety_margin, p.vx_max = float(veh_length), float(veh_width), SAFETY_MARGIN, VX_MAX_PLAN
+    p.w_ey_rate, p.w_progress, p.w_track = W_EY_RATE, W_PROGRESS, W_TRACK
+    return p
+
+
+def _prepare_inputs(ego_x, xcurv_ego, obs_sorted, insertion, rival_vx, opt_traj, N):
+    ego = np.concatenate([np.asarray(ego_x, float).reshape(6), np.asarray(xcurv_ego, float).reshape(6)])
+    rivals = np.ascontiguousarray(obs_sorted, dtype=np.float64)
+    if rivals.ndim != 3 or rivals.shape[1:] != (2, N + 1) or rivals.shape[0] < 1:
+        raise ValueError("obs_sorted must be (num_veh >= 1, 2, N+1): rows s, ey of each rival's prediction")
+    num_veh = rivals.shape[0]
+    ins = np.ascontiguousarray(insertion, dtype=np.int32).reshape(num_veh)
+    if sorted(ins.tolist()) != list(range(num_veh)):
+        raise ValueError("insertion must be a permutation of range(num_veh)")
+    vx = np.ascontiguousarray(rival_vx, dtype=np.float64).reshape(num_veh)
+    opt = np.ascontiguousarray(opt_traj, dtype=np.float64)
+    if opt.ndim != 2 or opt.shape[1] != 2 or opt.shape[0] < 2 or not (np.diff(opt[:, 0]) > 0).all():
+        raise ValueError("opt_traj must be (T >= 2, 2): s (ascending), ey of the optimal trajectory")
+    return ego, rivals, ins, vx, opt
+
+
+def prepare_candidates(ego_x, xcurv_ego, obs_sorted, insertion, rival_vx, opt_traj, N, prediction_factor=0.5, track_width=1.0,
+                       lap_length=None, veh_length=0.4, veh_width=0.2, handle=None):
+    """What get_local_traj computes between the rivals' predictions and the candidate solves
+    (overtake_traj_planner.py:87-117, planner_helper.py:46-153, 177-205) plus the data part of generate_traj_per_region
+    (:276-334, 365-374), on the device (b200mpc_planner_prepare, include/b200mpc.h).
+
+    obs_sorted (num_veh,2,N+1): s, ey predictions in sorted_vehicles order; insertion[i] = position in sorted_vehicles of
+    the i-th rival of vehicles_interest; rival_vx (num_veh,) in sorted order; opt_traj (T,2) = s, ey of the optimal
+    trajectory.  Returns the packed candidate records and everything the host path computes for them."""
+    h = handle or batch.default_handle()
+    ego, rivals, ins, vx, opt = _prepare_inputs(ego_x, xcurv_ego, obs_sorted, insertion, rival_vx, opt_traj, N)
+    num_veh = rivals.shape[0]
+    Cn = num_veh + 1
+    p = _prepare_params(N, num_veh, opt.shape[0], prediction_factor, track_width, lap_length, veh_length, veh_width)
+    stride = batch.cbf_record_doubles(N, 0, True, _capi.FLAG_STAGE_BOUNDS | _capi.FLAG_EY_RATE)
+    cand = np.zeros((Cn, stride))
+    heur = np.zeros((Cn, N + 1, 6))
+    ok0, region = np.zeros(Cn, dtype=np.int32), np.zeros(Cn, dtype=np.int32)
+    offset, ctrl, bez = np.zeros(Cn), np.zeros((Cn, 4, 2)), np.zeros((Cn, N + 1, 2))
+    err = np.zeros(1, dtype=np.int32)
+    P = batch._ptr
+    rc = _capi.lib().b200mpc_planner_prepare(h.ptr, C.byref(p), P(ego), P(rivals), P(vx), P(ins), P(opt), P(cand), P(heur), P(ok0),
+                                             P(region), P(offset), P(ctrl), P(bez), P(err))
+    h.check(rc, "b200mpc_planner_prepare")
+    if err[0]:   # interp1d's bounds_error in get_bezier_control_points (planner_helper.py:57, 92-135)
+        raise ValueError("A value in x_new is outside the interpolation range.")
+    return dict(records=cand, heur=heur, ok0=ok0, region=region, offset=offset, ctrl=ctrl, bezier=bez)
+
+
+def plan_and_track_from_predictions(self, xcurv_ego, time, vehicles_interest, xcurv, mpc_lti_param, track, system_param,
+                                    old_direction_flag=None, handle=None, extra=None):
+    """The overtaking step from the rivals' predictions on: get_local_traj (overtake_traj_planner.py:44-161, without the
+    global-frame copies it makes for plotting) followed by control.mpc_multi_agents (utils/base.py:540-582) as ONE call on one
+    CUDA stream (b200mpc_plan_and_track_prepared): preparation -> candidate QPs -> selection -> tracking MPC-CBF.  The host
+    only predicts the rivals (their own get_trajectory_nsteps), orders them (:69-77) and packs the tracking record.
+
+    `self` is the reference's planner object (vehicles, agent_name, track, opti_traj_xcurv, racing_game_param set).  Leaves
+    sorted_vehicles / obs_infos / bezier_xcurvs / bezier_funcs / xcurv_ego / old_direction_flag on `self` as get_local_traj
+    does.  Returns ((traj_xcurv, direction_flag, solve_time, solution_xvar), (u0, x_pred)).
+    `extra`: optional additional candidates as in plan_and_track."""
+    import time as _time
+    from scipy.interpolate import interp1d
+    h = handle or batch.default_handle()
+    prm = self.racing_game_param
+    N = prm.num_horizon_planner
+    vehicles, agent_name = self.vehicles, self.agent_name
+    ego = vehicles[agent_name]
+    veh_length, veh_width = ego.param.length, ego.param.width
+    names = list(vehicles_interest)
+    order = sort_rivals([vehicles_interest[n].xcurv[5] for n in names])
+    sorted_vehicles = [names[i] for i in order]
+    obs_infos = {}
+    for name in names:                                                        # :78-86
+        if vehicles[name].no_dynamics:
+            obs_traj, _ = vehicles[name].get_trajectory_nsteps(time, prm.timestep, N + 1)
+        else:
+            obs_traj, _ = vehicles[name].get_trajectory_nsteps(N + 1)
+        obs_infos[name] = obs_traj
+    obs_sorted = np.array([obs_infos[n][4:6, :N + 1] for n in sorted_vehicles])
+    insertion = [sorted_vehicles.index(n) for n in names]
+    rival_vx = [vehicles[n].xcurv[0] for n in sorted_vehicles]
+    opt_traj = np.asarray(self.opti_traj_xcurv, float)[:, 4:6]
+    ego_x = np.asarray(ego.xcurv, float)
+    egov, rivals, ins, vx, opt = _prepare_inputs(ego_x, xcurv_ego, obs_sorted, insertion, rival_vx, opt_traj, N)
+    num_veh = len(names)
+    C0 = num_veh + 1
+    n_extra = 0 if extra is None else int(np.asarray(extra["region"]).shape[0])
+    Cn = C0 + n_extra
+    pp = _prepare_params(N, num_veh, opt.shape[0], prm.planning_prediction_factor, track.width, track.lap_length, veh_length, veh_width)
+    self.sorted_vehicles, self.obs_infos, self.xcurv_ego, self.old_direction_flag = sorted_vehicles, obs_infos, xcurv_ego, old_direction_flag
+    trec, tprm, Nc, Mc = _tracking_record(xcurv, mpc_lti_param, track, system_param, vehicles, agent_name, sorted_vehicles, None,
+                                          veh_length, veh_width)
+    pprm = planner_params(prm.matrix_A, prm.matrix_B, N)
+    fl = _capi.FLAG_STAGE_BOUNDS | _capi.FLAG_EY_RATE
+    p_plan = _capi.make_cbf_params(pprm, 0, True, fl)
+    p_track = _capi.make_cbf_params(tprm, Mc, True, 0)
+    o = _capi.default_options()
+    sel = _capi.PlannerSelectParams()
+    sel.C, sel.N, sel.num_veh, sel.N_ctrl, sel.M_ctrl = Cn, N, num_veh, Nc, Mc
+    sel.old_direction_flag = -1 if old_direction_flag is None else int(old_direction_flag)
+    sel.veh_length, sel.veh_width, sel.lap_length = veh_length, veh_width, track.lap_length
+    x_cand = x_heur = x_ok0 = x_reg = None
+    x_off = np.zeros(0)
+    if n_extra:
+        kw, x_off = pack_candidates(ego_x, extra["s_ref"], extra["ey_ref"], extra["xlb"], extra["xub"], N)
+        x_cand, _, _ = batch.pack_cbf(kw["x0"], kw["xt"], kw["obs"], None, N, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"])
+        x_heur = np.ascontiguousarray(extra["heur"], dtype=np.float64)
+        x_ok0 = np.array([x0_feasible(ego_x, kw["xlb"][c], kw["xub"][c]) for c in range(n_extra)], dtype=np.int32)
+        x_reg = np.ascontiguousarray(extra["region"], dtype=np.int32)
+    cand_rec = np.zeros(Cn, dtype=_capi.RECORD_DTYPE)
+    cand_x, heur = np.zeros((Cn, N + 1, 6)), np.zeros((Cn, N + 1, 6))
+    sel_cost, ok0 = np.zeros(Cn), np.zeros(Cn, dtype=np.int32)
+    flag = np.zeros(2, dtype=np.int32)
+    traj = np.zeros((N + 1, 6))
+    trk = np.zeros(1, dtype=_capi.RECORD_DTYPE)
+    trk_x, trk_u = np.zeros((Nc + 1, 6)), np.zeros((Nc, 2))
+    off0, bez, err = np.zeros(C0), np.zeros((C0, N + 1, 2)), np.zeros(1, dtype=np.int32)
+    P = batch._ptr
+    t0 = _time.perf_counter()
+    rc = _capi.lib().b200mpc_plan_and_track_prepared(
+        h.ptr, C.byref(p_plan), C.byref(p_track), C.byref(o), C.byref(sel), C.byref(pp), P(egov), P(rivals), P(vx), P(ins), P(opt),
+        n_extra, P(x_cand), P(x_heur), P(x_ok0), P(x_reg), P(trec), P(cand_rec), P(cand_x), P(sel_cost), P(flag), P(traj), P(trk),
+        P(trk_x), P(trk_u), P(heur), P(ok0), P(off0), P(bez), P(err))
+    h.check(rc, "b200mpc_plan_and_track_prepared")
+    dt = _time.perf_counter() - t0
+    if err[0]:
+        raise ValueError("A value in x_new is outside the interpolation range.")
+    self.bezier_xcurvs = bez
+    self.bezier_funcs = [interp1d(bez[c, :, 0], bez[c, :, 1]) for c in range(C0)]
+    solved = (ok0 != 0) & (cand_rec["status"] == 0)
+    solution_xvar = np.where(solved[:, None, None], cand_x, heur).transpose(0, 2, 1).copy()
+    self.candidate_costs = np.where(solved, cand_rec["cost"] + np.concatenate([off0, x_off]), np.inf)
     self.selection_costs = sel_cost
     self.tracking_status = int(trk["status"][0])
     return (traj, int(flag[0]), np.full(Cn, dt / Cn), solution_xvar), (trk_u[0].copy(), trk_x)

@@ -291,6 +291,62 @@ int b200mpc_plan_and_track(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm
                            const double *track_in, b200mpc_record *cand_rec, double *cand_xpred, double *sel_cost, int32_t *flag,
                            double *traj, b200mpc_record *track_rec, double *track_xpred, double *track_upred);
 
+/* Candidate preparation on the device: what OvertakeTrajPlanner.get_local_traj computes between the
+ * rivals' predictions and the candidate solves (planning/overtake_traj_planner.py:87-117: veh_infos, get_agent_info,
+ * get_bezier_control_points, the sampled Bezier curves -- planning/planner_helper.py:46-153, 177-205) and the data part of
+ * generate_traj_per_region (:276-334 targets and bounds, :365-374 heuristic trajectory), written as the packed candidate
+ * records of the solver (M = 0, per-stage targets, flags STAGE_BOUNDS|EY_RATE). */
+typedef struct {
+    int32_t N;                  /* num_horizon_planner */
+    int32_t num_veh;            /* rivals of interest >= 1; regions C = num_veh + 1 */
+    int32_t num_opt;            /* rows of the optimal-trajectory table (>= 2, s ascending) */
+    int32_t reserved;
+    double prediction_factor;   /* racing_game_param.planning_prediction_factor (utils/base.py:391) */
+    double track_width, lap_length;
+    double veh_length, veh_width;            /* ego.param.length / width */
+    double safety_margin;                    /* 0.15 (overtake_traj_planner.py:262) */
+    double vx_max;                           /* 5 (:276) */
+    double w_ey_rate, w_progress, w_track;   /* 30, 200, 20 (:327, 328, 333-334) */
+} b200mpc_planner_prepare_params;
+
+/* All pointers are device pointers.
+ *   ego       : 12 doubles: vehicles["ego"].xcurv, then the xcurv_ego argument of get_local_traj
+ *   rivals    : num_veh x 2 x (N+1): s and ey predictions in sorted_vehicles order (s not wrapped)
+ *   rival_vx  : num_veh current vx (sorted order);  insertion : num_veh, insertion[i] = position in sorted_vehicles of the
+ *               i-th rival of vehicles_interest (the reference fills veh_infos in that order and reads it by region)
+ *   opt_traj  : num_opt x 2 (s, ey) of the optimal trajectory
+ * outputs:
+ *   cand      : C x b200mpc_cbf_record_doubles_ex(N, 0, 1, STAGE_BOUNDS|EY_RATE) packed records
+ *   heur      : C x (N+1) x 6;  ok0, region : C ints (as b200mpc_planner_select_device takes them)
+ *   offset    : optional C, reference cost = solver cost + offset
+ *   ctrl      : optional C x 4 x 2 control points;  bezier : optional C x (N+1) x 2 curve samples
+ *   err       : optional 1 int, nonzero if a look-up left the optimal trajectory's range (the reference raises ValueError) */
+int b200mpc_planner_prepare_device(b200mpc_handle *h, const b200mpc_planner_prepare_params *prm, const double *d_ego,
+                                   const double *d_rivals, const double *d_rival_vx, const int32_t *d_insertion,
+                                   const double *d_opt_traj, double *d_cand, double *d_heur, int32_t *d_ok0, int32_t *d_region,
+                                   double *d_offset, double *d_ctrl, double *d_bezier, int32_t *d_err);
+/* The same with host pointers (H2D, kernel, D2H, synchronised). */
+int b200mpc_planner_prepare(b200mpc_handle *h, const b200mpc_planner_prepare_params *prm, const double *ego,
+                            const double *rivals, const double *rival_vx, const int32_t *insertion, const double *opt_traj,
+                            double *cand, double *heur, int32_t *ok0, int32_t *region, double *offset, double *ctrl,
+                            double *bezier, int32_t *err);
+
+/* b200mpc_plan_and_track with the candidates prepared on the device: H2D of the raw planner inputs ->
+ * b200mpc_planner_prepare_device -> candidate solve -> selection -> tracking solve -> D2H, one stream.  sel->C must be
+ * prep->num_veh + 1 + n_extra; the n_extra additional candidates (BASELINE config 3 evaluates 64) come packed from the
+ * host as in b200mpc_plan_and_track (extra_* may be NULL when n_extra = 0).  Outputs as b200mpc_plan_and_track plus
+ * heur_out C x (N+1) x 6, ok0_out C, offset C (first num_veh + 1 entries filled), bezier (num_veh+1) x (N+1) x 2 (all optional)
+ * and err (1 int, see above). */
+int b200mpc_plan_and_track_prepared(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
+                                    const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel,
+                                    const b200mpc_planner_prepare_params *prep, const double *ego, const double *rivals,
+                                    const double *rival_vx, const int32_t *insertion, const double *opt_traj, int n_extra,
+                                    const double *extra_cand, const double *extra_heur, const int32_t *extra_ok0,
+                                    const int32_t *extra_region, const double *track_in, b200mpc_record *cand_rec,
+                                    double *cand_xpred, double *sel_cost, int32_t *flag, double *traj, b200mpc_record *track_rec,
+                                    double *track_xpred, double *track_upred, double *heur_out, int32_t *ok0_out, double *offset,
+                                    double *bezier, int32_t *err);
+
 /* argmin over records (device pointers): index of the smallest cost among status<=max_status,
  * lowest index wins ties (list.index(min(...)), overtake_traj_planner.py:244); *d_out = -1 if none. */
 int b200mpc_argmin_cost_device(b200mpc_handle *h, const b200mpc_record *d_rec, int B, int max_status, int32_t *d_out);

@@ -102,9 +102,24 @@ def main():
                                         agent_name="ego", direction_flag=f2, sorted_vehicles=pl.sorted_vehicles, time=None)
     _, t_two, _, _ = timed(two_calls, reps=21, warm=3)
     _, t_one, _, _ = timed(lambda: planning.plan_and_track(pl, xc, mp, pl.track, sysp, time=None), reps=21, warm=3)
+    # the same step from the rivals' predictions on, candidates prepared on the device
+    pl3 = mk()
+    for name in pl3.sorted_vehicles:
+        pl3.vehicles[name].no_dynamics = True
+    pl3.racing_game_param.timestep, pl3.racing_game_param.planning_prediction_factor = 0.1, 0.5
+    s_tab = np.linspace(0.0, pl3.track.lap_length + 1.0, 64)
+    pl3.opti_traj_xcurv = np.zeros((64, 6))
+    pl3.opti_traj_xcurv[:, 4], pl3.opti_traj_xcurv[:, 5] = s_tab, 0.2 * np.sin(s_tab)
+    interest = {n: pl3.vehicles[n] for n in pl3.sorted_vehicles}
+    _, t_prep, _, _ = timed(lambda: planning.plan_and_track_from_predictions(pl3, xc, 0.0, interest, xc, mp, pl3.track, sysp),
+                            reps=21, warm=3)
     doc["overtaking_step"] = dict(candidates=len(pl.sorted_vehicles) + 1, two_calls_ms=t_two * 1e3, fused_chain_ms=t_one * 1e3,
+                                  from_predictions_ms=t_prep * 1e3,
                                   note="median wall time incl. host packing; two_calls = solve_optimization_problem + mpc_multi_agents shims, "
-                                       "fused = planning.plan_and_track (b200mpc_plan_and_track: one stream, no host round trip)")
+                                       "fused = planning.plan_and_track (b200mpc_plan_and_track: one stream, no host round trip); "
+                                       "from_predictions = planning.plan_and_track_from_predictions (b200mpc_plan_and_track_prepared: also "
+                                       "the Bezier references, targets, bounds and candidate records are made on the device; the time "
+                                       "includes the rivals' predictions, which the other two get ready-made)")
     print("overtaking_step", doc["overtaking_step"], flush=True)
 
     # ---- config 4: LMPC, 512 per GPU
