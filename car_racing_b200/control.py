@@ -220,7 +220,8 @@ def install(control_module=None):
 
 def install_all(control_module=None, base_module=None, planner_class=None):
     """Everything on the control-step path: the five solve functions, LMPCRacingGame.estimate_ABC, the planner's
-    solve_optimization_problem and the rivals' sympy-free trajectory prediction."""
+    solve_optimization_problem and get_local_traj (candidate preparation on the device) and the rivals' sympy-free
+    trajectory prediction."""
     from . import planning, rivals
     control_module = install(control_module)
     if base_module is None:
@@ -230,4 +231,5 @@ def install_all(control_module=None, base_module=None, planner_class=None):
     if planner_class is None:
         from planning.overtake_traj_planner import OvertakeTrajPlanner as planner_class
     planner_class.solve_optimization_problem = planning.solve_optimization_problem
+    planner_class.get_local_traj = planning.get_local_traj
     return control_module, base_module, planner_class

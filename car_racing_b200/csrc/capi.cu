@@ -523,13 +523,13 @@ int b200mpc_planner_select_device(b200mpc_handle *h, const b200mpc_planner_selec
     if (!prm || !d_rec || !d_xpred || !d_heur || !d_ok0 || !d_region || !d_flag)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_planner_select: null argument");
     if (prm->C < 1 || prm->N < 1 || prm->N > B200MPC_NMAX || prm->num_veh < 0 || (prm->num_veh > 0 && !d_rivals) ||
-        prm->N_ctrl < 1 || prm->N_ctrl > B200MPC_NMAX || prm->M_ctrl < 0 || prm->M_ctrl > B200MPC_MMAX)
+        (d_track_rec && (prm->N_ctrl < 1 || prm->N_ctrl > B200MPC_NMAX || prm->M_ctrl < 0 || prm->M_ctrl > B200MPC_MMAX)))
         return fail(h, B200MPC_ERR_ARG, "b200mpc_planner_select: bad parameter value");
     CK(h, cudaSetDevice(h->device));
     SelectKParams kp;
     memset(&kp, 0, sizeof(kp));
     kp.p = *prm;
-    kp.track_xt_off = cbf_hdr_doubles(prm->M_ctrl);
+    kp.track_xt_off = d_track_rec ? cbf_hdr_doubles(prm->M_ctrl) : 0;
     planner_select_kernel<<<1, SELECT_NT, 0, h->stream>>>(kp, d_rec, d_xpred, d_heur, d_ok0, d_region, d_rivals, d_sel_cost, d_flag,
                                                          d_traj, d_track_rec);
     CK(h, cudaGetLastError());
@@ -640,8 +640,9 @@ static int plan_chain(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, con
                       const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel, b200mpc_record *cand_rec,
                       double *cand_xpred, double *sel_cost, int32_t *flag, double *traj, b200mpc_record *track_rec,
                       double *track_xpred, double *track_upred) {
-    const int C_ = sel->C, N = plan_prm->N, Nc = track_prm->N, Mc = track_prm->M;
-    const size_t ts = (size_t)cbf_record_doubles(Nc, Mc, 1, 0);
+    const bool tracking = track_prm != nullptr;
+    const int C_ = sel->C, N = plan_prm->N, Nc = tracking ? track_prm->N : 0, Mc = tracking ? track_prm->M : 0;
+    const size_t ts = tracking ? (size_t)cbf_record_doubles(Nc, Mc, 1, 0) : 0;
     const size_t b_rec = sizeof(b200mpc_record) * (size_t)C_, b_x = 48 * (size_t)(N + 1) * C_;
     const size_t o_traj = 2, o_trk = o_traj + 6 * (size_t)(N + 1), o_out = o_trk + ts, o_tx = o_out + 4,
                  o_tu = o_tx + 6 * (size_t)(Nc + 1);
@@ -653,28 +654,33 @@ static int plan_chain(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, con
     // (2) selection cost, first argmin, chosen trajectory, per-stage targets of the tracking record
     rc = b200mpc_planner_select_device(h, sel, (const b200mpc_record *)h->d_rec, (const double *)h->d_x, (const double *)h->d_laps,
                                        (const int32_t *)h->d_idx, (const int32_t *)h->d_stat, (const double *)h->d_seg,
-                                       (double *)h->d_aux, (int32_t *)ch, ch + o_traj, ch + o_trk);
+                                       (double *)h->d_aux, (int32_t *)ch, ch + o_traj, tracking ? ch + o_trk : nullptr);
     if (rc) return rc;
     // (3) the tracking MPC on the record the selection kernel completed
-    rc = b200mpc_cbf_solve_device(h, track_prm, opt, 1, ch + o_trk, (b200mpc_record *)(ch + o_out), nullptr, ch + o_tx, ch + o_tu,
-                                  nullptr);
-    if (rc) return rc;
+    if (tracking) {
+        rc = b200mpc_cbf_solve_device(h, track_prm, opt, 1, ch + o_trk, (b200mpc_record *)(ch + o_out), nullptr, ch + o_tx,
+                                      ch + o_tu, nullptr);
+        if (rc) return rc;
+    }
     if (cand_rec) CK(h, cudaMemcpyAsync(cand_rec, h->d_rec, b_rec, cudaMemcpyDeviceToHost, h->stream));
     if (cand_xpred) CK(h, cudaMemcpyAsync(cand_xpred, h->d_x, b_x, cudaMemcpyDeviceToHost, h->stream));
     if (sel_cost) CK(h, cudaMemcpyAsync(sel_cost, h->d_aux, 8 * (size_t)C_, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(flag, ch, 8, cudaMemcpyDeviceToHost, h->stream));
     if (traj) CK(h, cudaMemcpyAsync(traj, ch + o_traj, 48 * (size_t)(N + 1), cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaMemcpyAsync(track_rec, ch + o_out, sizeof(b200mpc_record), cudaMemcpyDeviceToHost, h->stream));
-    if (track_xpred) CK(h, cudaMemcpyAsync(track_xpred, ch + o_tx, 48 * (size_t)(Nc + 1), cudaMemcpyDeviceToHost, h->stream));
-    if (track_upred) CK(h, cudaMemcpyAsync(track_upred, ch + o_tu, 16 * (size_t)Nc, cudaMemcpyDeviceToHost, h->stream));
+    if (tracking) {
+        CK(h, cudaMemcpyAsync(track_rec, ch + o_out, sizeof(b200mpc_record), cudaMemcpyDeviceToHost, h->stream));
+        if (track_xpred) CK(h, cudaMemcpyAsync(track_xpred, ch + o_tx, 48 * (size_t)(Nc + 1), cudaMemcpyDeviceToHost, h->stream));
+        if (track_upred) CK(h, cudaMemcpyAsync(track_upred, ch + o_tu, 16 * (size_t)Nc, cudaMemcpyDeviceToHost, h->stream));
+    }
     return B200MPC_OK;
 }
 
 static int plan_chain_buffers(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
                               const b200mpc_planner_select_params *sel, const double *track_in) {
-    const int C_ = sel->C, N = plan_prm->N, Nc = track_prm->N, Mc = track_prm->M;
+    const bool tracking = track_prm != nullptr;
+    const int C_ = sel->C, N = plan_prm->N, Nc = tracking ? track_prm->N : 0, Mc = tracking ? track_prm->M : 0;
     const size_t cs = (size_t)cbf_record_doubles(N, plan_prm->M, plan_prm->xt_per_stage, plan_prm->flags);
-    const size_t ts = (size_t)cbf_record_doubles(Nc, Mc, 1, 0);
+    const size_t ts = tracking ? (size_t)cbf_record_doubles(Nc, Mc, 1, 0) : 0;
     const size_t b_in = cs * 8 * C_, b_rec = sizeof(b200mpc_record) * (size_t)C_, b_x = 48 * (size_t)(N + 1) * C_;
     const size_t b_riv = 16 * (size_t)(N + 1) * (sel->num_veh > 0 ? sel->num_veh : 1), b_int = 4 * (size_t)C_;
     // chain buffer: [flag 2 ints + pad][traj 6(N+1)][tracking record][tracking result record][x_pred][u_pred]
@@ -690,16 +696,22 @@ static int plan_chain_buffers(b200mpc_handle *h, const b200mpc_cbf_params *plan_
     if ((rc = grow(h, &h->d_stat, &h->c_stat, b_int))) return rc;
     if ((rc = grow(h, &h->d_aux, &h->c_aux, 8 * (size_t)C_))) return rc;
     if ((rc = grow(h, &h->d_chain, &h->c_chain, 8 * n_chain))) return rc;
-    CK(h, cudaMemcpyAsync((double *)h->d_chain + o_trk, track_in, ts * 8, cudaMemcpyHostToDevice, h->stream));
+    if (tracking) CK(h, cudaMemcpyAsync((double *)h->d_chain + o_trk, track_in, ts * 8, cudaMemcpyHostToDevice, h->stream));
     return B200MPC_OK;
 }
 
 static int check_plan(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
                       const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel, const void *track_in,
-                      const void *flag, const void *track_rec) {
+                      const void *flag, const void *track_rec, bool allow_plan_only) {
     if (!h) return B200MPC_ERR_ARG;
-    if (!plan_prm || !track_prm || !opt || !sel || !track_in || !flag || !track_rec)
-        return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: null argument");
+    if (!plan_prm || !opt || !sel || !flag) return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: null argument");
+    if (!track_prm) {   // planning only: no tracking record, no tracking outputs
+        if (!allow_plan_only || track_in) return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: null argument");
+        if (sel->C < 1 || sel->N != plan_prm->N)
+            return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: inconsistent parameters");
+        return check_cbf(h, plan_prm, opt, sel->C, flag, flag);
+    }
+    if (!track_in || !track_rec) return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: null argument");
     if (sel->C < 1 || sel->N != plan_prm->N || sel->N_ctrl != track_prm->N || sel->M_ctrl != track_prm->M ||
         !track_prm->xt_per_stage || track_prm->flags != 0)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: inconsistent parameters (the tracking record has per-stage targets)");
@@ -711,7 +723,7 @@ int b200mpc_plan_and_track(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm
                            const double *heur, const int32_t *ok0, const int32_t *region, const double *rivals,
                            const double *track_in, b200mpc_record *cand_rec, double *cand_xpred, double *sel_cost, int32_t *flag,
                            double *traj, b200mpc_record *track_rec, double *track_xpred, double *track_upred) {
-    int rc = check_plan(h, plan_prm, track_prm, opt, sel, track_in, flag, track_rec);
+    int rc = check_plan(h, plan_prm, track_prm, opt, sel, track_in, flag, track_rec, false);
     if (rc) return rc;
     if (!cand_in || !heur || !ok0 || !region || (sel->num_veh > 0 && !rivals))
         return fail(h, B200MPC_ERR_ARG, "b200mpc_plan_and_track: null argument");
@@ -741,7 +753,7 @@ int b200mpc_plan_and_track_prepared(b200mpc_handle *h, const b200mpc_cbf_params 
                                     double *cand_xpred, double *sel_cost, int32_t *flag, double *traj, b200mpc_record *track_rec,
                                     double *track_xpred, double *track_upred, double *heur_out, int32_t *ok0_out, double *offset,
                                     double *bezier, int32_t *err) {
-    int rc = check_plan(h, plan_prm, track_prm, opt, sel, track_in, flag, track_rec);
+    int rc = check_plan(h, plan_prm, track_prm, opt, sel, track_in, flag, track_rec, true);
     if (rc) return rc;
     if ((rc = check_prepare(h, prep, ego, rivals, rival_vx, insertion, opt_traj))) return rc;
     const int fl = B200MPC_FLAG_STAGE_BOUNDS | B200MPC_FLAG_EY_RATE;

@@ -333,23 +333,15 @@ def prepare_candidates(ego_x, xcurv_ego, obs_sorted, insertion, rival_vx, opt_tr
     return dict(records=cand, heur=heur, ok0=ok0, region=region, offset=offset, ctrl=ctrl, bezier=bez)
 
 
-def plan_and_track_from_predictions(self, xcurv_ego, time, vehicles_interest, xcurv, mpc_lti_param, track, system_param,
-                                    old_direction_flag=None, handle=None, extra=None):
-    """The overtaking step from the rivals' predictions on: get_local_traj (overtake_traj_planner.py:44-161, without the
-    global-frame copies it makes for plotting) followed by control.mpc_multi_agents (utils/base.py:540-582) as ONE call on one
-    CUDA stream (b200mpc_plan_and_track_prepared): preparation -> candidate QPs -> selection -> tracking MPC-CBF.  The host
-    only predicts the rivals (their own get_trajectory_nsteps), orders them (:69-77) and packs the tracking record.
-
-    `self` is the reference's planner object (vehicles, agent_name, track, opti_traj_xcurv, racing_game_param set).  Leaves
-    sorted_vehicles / obs_infos / bezier_xcurvs / bezier_funcs / xcurv_ego / old_direction_flag on `self` as get_local_traj
-    does.  Returns ((traj_xcurv, direction_flag, solve_time, solution_xvar), (u0, x_pred)).
-    `extra`: optional additional candidates as in plan_and_track."""
+def _from_predictions(self, xcurv_ego, time, vehicles_interest, old_direction_flag, handle, extra, tracking):
+    """prediction -> preparation -> candidate solve -> selection [-> tracking solve] through
+    b200mpc_plan_and_track_prepared; `tracking` = (xcurv, mpc_lti_param, track, system_param) or None."""
     import time as _time
     from scipy.interpolate import interp1d
     h = handle or batch.default_handle()
     prm = self.racing_game_param
     N = prm.num_horizon_planner
-    vehicles, agent_name = self.vehicles, self.agent_name
+    vehicles, agent_name, track = self.vehicles, self.agent_name, self.track
     ego = vehicles[agent_name]
     veh_length, veh_width = ego.param.length, ego.param.width
     names = list(vehicles_interest)
@@ -374,17 +366,24 @@ def plan_and_track_from_predictions(self, xcurv_ego, time, vehicles_interest, xc
     Cn = C0 + n_extra
     pp = _prepare_params(N, num_veh, opt.shape[0], prm.planning_prediction_factor, track.width, track.lap_length, veh_length, veh_width)
     self.sorted_vehicles, self.obs_infos, self.xcurv_ego, self.old_direction_flag = sorted_vehicles, obs_infos, xcurv_ego, old_direction_flag
-    trec, tprm, Nc, Mc = _tracking_record(xcurv, mpc_lti_param, track, system_param, vehicles, agent_name, sorted_vehicles, None,
-                                          veh_length, veh_width)
-    pprm = planner_params(prm.matrix_A, prm.matrix_B, N)
-    fl = _capi.FLAG_STAGE_BOUNDS | _capi.FLAG_EY_RATE
-    p_plan = _capi.make_cbf_params(pprm, 0, True, fl)
-    p_track = _capi.make_cbf_params(tprm, Mc, True, 0)
-    o = _capi.default_options()
     sel = _capi.PlannerSelectParams()
-    sel.C, sel.N, sel.num_veh, sel.N_ctrl, sel.M_ctrl = Cn, N, num_veh, Nc, Mc
+    sel.C, sel.N, sel.num_veh = Cn, N, num_veh
     sel.old_direction_flag = -1 if old_direction_flag is None else int(old_direction_flag)
     sel.veh_length, sel.veh_width, sel.lap_length = veh_length, veh_width, track.lap_length
+    trec = trk = trk_x = trk_u = p_track_ref = None
+    if tracking is not None:
+        xcurv, mpc_lti_param, trk_track, system_param = tracking
+        # control.mpc_multi_agents is called without `time` (utils/base.py:558-572)
+        trec, tprm, Nc, Mc = _tracking_record(xcurv, mpc_lti_param, trk_track, system_param, vehicles, agent_name, sorted_vehicles, None,
+                                              veh_length, veh_width)
+        sel.N_ctrl, sel.M_ctrl = Nc, Mc
+        p_track = _capi.make_cbf_params(tprm, Mc, True, 0)
+        p_track_ref = C.byref(p_track)
+        trk = np.zeros(1, dtype=_capi.RECORD_DTYPE)
+        trk_x, trk_u = np.zeros((Nc + 1, 6)), np.zeros((Nc, 2))
+    pprm = planner_params(prm.matrix_A, prm.matrix_B, N)
+    p_plan = _capi.make_cbf_params(pprm, 0, True, _capi.FLAG_STAGE_BOUNDS | _capi.FLAG_EY_RATE)
+    o = _capi.default_options()
     x_cand = x_heur = x_ok0 = x_reg = None
     x_off = np.zeros(0)
     if n_extra:
@@ -398,18 +397,16 @@ def plan_and_track_from_predictions(self, xcurv_ego, time, vehicles_interest, xc
     sel_cost, ok0 = np.zeros(Cn), np.zeros(Cn, dtype=np.int32)
     flag = np.zeros(2, dtype=np.int32)
     traj = np.zeros((N + 1, 6))
-    trk = np.zeros(1, dtype=_capi.RECORD_DTYPE)
-    trk_x, trk_u = np.zeros((Nc + 1, 6)), np.zeros((Nc, 2))
     off0, bez, err = np.zeros(C0), np.zeros((C0, N + 1, 2)), np.zeros(1, dtype=np.int32)
     P = batch._ptr
     t0 = _time.perf_counter()
     rc = _capi.lib().b200mpc_plan_and_track_prepared(
-        h.ptr, C.byref(p_plan), C.byref(p_track), C.byref(o), C.byref(sel), C.byref(pp), P(egov), P(rivals), P(vx), P(ins), P(opt),
+        h.ptr, C.byref(p_plan), p_track_ref, C.byref(o), C.byref(sel), C.byref(pp), P(egov), P(rivals), P(vx), P(ins), P(opt),
         n_extra, P(x_cand), P(x_heur), P(x_ok0), P(x_reg), P(trec), P(cand_rec), P(cand_x), P(sel_cost), P(flag), P(traj), P(trk),
         P(trk_x), P(trk_u), P(heur), P(ok0), P(off0), P(bez), P(err))
     h.check(rc, "b200mpc_plan_and_track_prepared")
     dt = _time.perf_counter() - t0
-    if err[0]:
+    if err[0]:   # interp1d's bounds_error in get_bezier_control_points (planner_helper.py:57, 92-135)
         raise ValueError("A value in x_new is outside the interpolation range.")
     self.bezier_xcurvs = bez
     self.bezier_funcs = [interp1d(bez[c, :, 0], bez[c, :, 1]) for c in range(C0)]
@@ -417,5 +414,58 @@ def plan_and_track_from_predictions(self, xcurv_ego, time, vehicles_interest, xc
     solution_xvar = np.where(solved[:, None, None], cand_x, heur).transpose(0, 2, 1).copy()
     self.candidate_costs = np.where(solved, cand_rec["cost"] + np.concatenate([off0, x_off]), np.inf)
     self.selection_costs = sel_cost
+    plan = (traj, int(flag[0]), np.full(Cn, dt / Cn), solution_xvar)
+    if tracking is None:
+        return plan, None
     self.tracking_status = int(trk["status"][0])
-    return (traj, int(flag[0]), np.full(Cn, dt / Cn), solution_xvar), (trk_u[0].copy(), trk_x)
+    return plan, (trk_u[0].copy(), trk_x)
+
+
+def plan_and_track_from_predictions(self, xcurv_ego, time, vehicles_interest, xcurv, mpc_lti_param, track, system_param,
+                                    old_direction_flag=None, handle=None, extra=None):
+    """The overtaking step from the rivals' predictions on: get_local_traj (overtake_traj_planner.py:44-161, without the
+    global-frame copies it makes for plotting) followed by control.mpc_multi_agents (utils/base.py:540-582) as ONE call on one
+    CUDA stream (b200mpc_plan_and_track_prepared): preparation -> candidate QPs -> selection -> tracking MPC-CBF.  The host
+    only predicts the rivals (their own get_trajectory_nsteps), orders them (:69-77) and packs the tracking record.
+
+    `self` is the reference's planner object (vehicles, agent_name, track, opti_traj_xcurv, racing_game_param set).  Leaves
+    sorted_vehicles / obs_infos / bezier_xcurvs / bezier_funcs / xcurv_ego / old_direction_flag on `self` as get_local_traj
+    does.  Returns ((traj_xcurv, direction_flag, solve_time, solution_xvar), (u0, x_pred)).
+    `extra`: optional additional candidates as in plan_and_track."""
+    return _from_predictions(self, xcurv_ego, time, vehicles_interest, old_direction_flag, handle, extra,
+                             (xcurv, mpc_lti_param, track, system_param))
+
+
+def _traj_xglob(traj_xcurv, track):
+    """planner_helper.get_traj_xglob (planning/planner_helper.py:208-220): only columns 4, 5 (global x, y) are filled."""
+    out = np.zeros((traj_xcurv.shape[0], 6))
+    for i in range(traj_xcurv.shape[0]):
+        s_i = float(traj_xcurv[i, 4])
+        while s_i > track.lap_length:
+            s_i = s_i - track.lap_length
+        out[i, 4], out[i, 5] = track.get_global_position(s_i, traj_xcurv[i, 5])
+    return out
+
+
+def get_local_traj(self, xcurv_ego, time, vehicles_interest, matrix_Atv, matrix_Btv, matrix_Ctv, old_ey, old_direction_flag):
+    """Drop-in for OvertakeTrajPlanner.get_local_traj (overtake_traj_planner.py:44-161; assign to the class): same arguments,
+    same 8-tuple.  Rival predictions and ordering on the host, then ONE call (b200mpc_plan_and_track_prepared without the
+    tracking stage): Bezier references, candidate records, candidate QPs, selection on the device; the global-frame copies
+    for plotting go through the reference's own track.get_global_position."""
+    self.matrix_Atv, self.matrix_Btv, self.matrix_Ctv = matrix_Atv, matrix_Btv, matrix_Ctv
+    self.old_ey = old_ey
+    (traj, flag, solve_time, sol), _ = _from_predictions(self, xcurv_ego, time, vehicles_interest, old_direction_flag, None, None, None)
+    N = self.racing_game_param.num_horizon_planner
+    C0 = sol.shape[0]
+    track = self.track
+    target_traj_xglob = _traj_xglob(traj, track)
+    line = np.zeros((N + 1, 6))
+    line[:, 4:6] = self.bezier_xcurvs[flag]
+    bezier_xglob = _traj_xglob(line, track)
+    all_bezier_xglob, all_local_traj_xglob = np.zeros((C0, N + 1, 6)), np.zeros((C0, N + 1, 6))
+    for c in range(C0):
+        line = np.zeros((N + 1, 6))
+        line[:, 4:6] = self.bezier_xcurvs[c]
+        all_bezier_xglob[c] = _traj_xglob(line, track)
+        all_local_traj_xglob[c] = _traj_xglob(sol[c].T, track)
+    return traj, target_traj_xglob, flag, self.sorted_vehicles, bezier_xglob, solve_time, all_bezier_xglob, all_local_traj_xglob

@@ -336,7 +336,8 @@ int b200mpc_planner_prepare(b200mpc_handle *h, const b200mpc_planner_prepare_par
  * prep->num_veh + 1 + n_extra; the n_extra additional candidates (BASELINE config 3 evaluates 64) come packed from the
  * host as in b200mpc_plan_and_track (extra_* may be NULL when n_extra = 0).  Outputs as b200mpc_plan_and_track plus
  * heur_out C x (N+1) x 6, ok0_out C, offset C (first num_veh + 1 entries filled), bezier (num_veh+1) x (N+1) x 2 (all optional)
- * and err (1 int, see above). */
+ * and err (1 int, see above).  track_prm = NULL (with track_in = NULL) stops after the selection: the device form of
+ * get_local_traj alone (planning/overtake_traj_planner.py:44-161); the tracking outputs are then not written. */
 int b200mpc_plan_and_track_prepared(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm, const b200mpc_cbf_params *track_prm,
                                     const b200mpc_ipm_options *opt, const b200mpc_planner_select_params *sel,
                                     const b200mpc_planner_prepare_params *prep, const double *ego, const double *rivals,

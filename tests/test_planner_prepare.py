@@ -220,5 +220,15 @@ def test_prepared_chain_matches_host_prepared_chain(crb):
         assert (fin == np.isfinite(p2.candidate_costs)).all()      # all False when x_0 violates a stage-0 row of every region
         assert not fin.any() or np.abs(p1.candidate_costs[fin] - p2.candidate_costs[fin]).max() < 1e-6
         n_solved += int(fin.sum())
+        # the get_local_traj drop-in (no tracking stage): same plan, the reference's 8-tuple
+        p3 = planner()
+        p3.track.get_global_position = lambda s, ey: (s + 100.0, ey - 100.0)
+        out = planning.get_local_traj(p3, x, 0.0, {n: p3.vehicles[n] for n in names}, None, None, None, None, None)
+        assert len(out) == 8 and out[2] == f1 and out[3] == p1.sorted_vehicles
+        assert np.abs(out[0] - t1).max() < 1e-12 and out[5].shape == (nv + 1,)
+        assert out[6].shape == (nv + 1, 11, 6) and out[7].shape == (nv + 1, 11, 6) and out[4].shape == (11, 6)
+        s_wrapped = np.where(t1[:, 4] > lap, t1[:, 4] - lap, t1[:, 4])
+        assert np.abs(out[1][:, 4] - (s_wrapped + 100.0)).max() < 1e-12 and np.abs(out[1][:, 5] - (t1[:, 5] - 100.0)).max() < 1e-12
+        assert np.abs(out[7][f1][:, 5] - (t1[:, 5] - 100.0)).max() < 1e-12
         flags.append(f1)
     assert len(flags) == 10 and n_solved >= 5 and len(set(flags)) > 1

@@ -99,3 +99,4 @@ def test_install_all_patches_every_hook():
     assert base.LMPCRacingGame.estimate_ABC is crb.control.estimate_ABC
     assert base.NoDynamicsModel.get_trajectory_nsteps is rivals.get_trajectory_nsteps
     assert planner.solve_optimization_problem is planning.solve_optimization_problem
+    assert planner.get_local_traj is planning.get_local_traj
