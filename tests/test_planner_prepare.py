@@ -232,3 +232,67 @@ def test_prepared_chain_matches_host_prepared_chain(crb):
         assert np.abs(out[7][f1][:, 5] - (t1[:, 5] - 100.0)).max() < 1e-12
         flags.append(f1)
     assert len(flags) == 10 and n_solved >= 5 and len(set(flags)) > 1
+
+
+@pytest.mark.gpu
+def test_prepared_chain_with_64_candidates_equals_host_prepared_chain(crb):
+    """BASELINE config 3 (64 candidates): the reference's regions prepared on the device + 61 host-packed extra candidates
+    behind them (b200mpc_plan_and_track_prepared, n_extra > 0) against planning.plan_and_track with everything packed on
+    the host."""
+    from scipy.interpolate import interp1d
+    from test_shims_host import Rival
+    param = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 5.0, 0, 50.0]),
+                                  matrix_R=np.diag([0.1, 0.1]), num_horizon_ctrl=10)
+    sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+    done = 0
+    for ci, c, opt, lap in _cases():
+        nv = int(c["num_veh"])
+        if nv != 2:
+            continue
+        ins, N = c["insertion"].tolist(), 10
+        names = ["car%d" % (i + 1) for i in range(nv)]
+        opt6 = np.zeros((opt.shape[0], 6))
+        opt6[:, 4:6] = opt
+
+        def planner():
+            veh = {"ego": types.SimpleNamespace(param=types.SimpleNamespace(length=0.4, width=0.2), xcurv=c["ego_x"].copy())}
+            for i, n in enumerate(names):
+                o = c["obs"][ins[i]]
+                veh[n] = Rival(o[0, 0], c["rival_vx"][ins[i]], o[1, 0])
+                veh[n].no_dynamics = True
+            rg = types.SimpleNamespace(num_horizon_planner=N, matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, timestep=0.1,
+                                       planning_prediction_factor=0.5)
+            return types.SimpleNamespace(vehicles=veh, agent_name="ego", track=types.SimpleNamespace(width=1.0, lap_length=lap),
+                                         opti_traj_xcurv=opt6, racing_game_param=rg, old_direction_flag=None)
+        p1, p2 = planner(), planner()
+        x = c["ego_x"].copy()
+        # host preparation (restatement) -> extras as tests/test_gpu_parity.py::test_plan_and_track_with_64_candidates builds them
+        order = planning.sort_rivals([p2.vehicles[n].xcurv[5] for n in names])
+        p2.sorted_vehicles = [names[i] for i in order]
+        p2.obs_infos = {n: p2.vehicles[n].get_trajectory_nsteps(0.0, 0.1, N + 1)[0] for n in names}
+        obs_sorted = np.array([p2.obs_infos[n][4:6] for n in p2.sorted_vehicles])
+        r = planner_numpy.prepare(x, x, obs_sorted, [p2.sorted_vehicles.index(n) for n in names],
+                                  [p2.vehicles[n].xcurv[0] for n in p2.sorted_vehicles], 0.5, 1.0, lap, 0.2, opt, N)
+        p2.bezier_xcurvs, p2.xcurv_ego = r["bezier"], x
+        p2.bezier_funcs = [interp1d(r["bezier"][i, :, 0], r["bezier"][i, :, 1]) for i in range(nv + 1)]
+        ex = dict(s_ref=[], ey_ref=[], xlb=[], xub=[], region=[], heur=[])
+        for reg in range(3):
+            xlb, xub = planning.candidate_bounds(reg, x, p2.sorted_vehicles, p2.obs_infos, 0.4, 0.2, 1.0, lap, N)
+            s0, e0 = planning.candidate_targets(reg, x, p2.bezier_xcurvs, p2.bezier_funcs, N)
+            h0 = planning.heuristic_traj(reg, x, p2.bezier_xcurvs, p2.bezier_funcs, N).T
+            for scale in (0.4, 0.6, 0.8, 0.9, 1.1, 1.2, 1.4):
+                for stretch in (0.9, 1.0, 1.1):
+                    if len(ex["region"]) == 61:
+                        break
+                    ex["s_ref"].append(x[4] + stretch * (s0 - x[4]))
+                    ex["ey_ref"].append(x[5] + scale * (e0 - x[5]))
+                    ex["xlb"].append(xlb); ex["xub"].append(xub); ex["region"].append(reg); ex["heur"].append(h0)
+        ex = {k: np.array(v) for k, v in ex.items()}
+        (t2, f2, st2, s2), (u2, x2) = planning.plan_and_track(p2, x, param, p2.track, sysp, time=None, extra=ex)
+        (t1, f1, st1, s1), (u1, x1) = planning.plan_and_track_from_predictions(p1, x, 0.0, {n: p1.vehicles[n] for n in names}, x, param,
+                                                                               p1.track, sysp, extra=ex)
+        assert s1.shape[0] == 64 and f1 == f2 and np.abs(p1.selection_costs - p2.selection_costs).max() < 1e-9
+        assert np.abs(s1 - s2).max() < 1e-8 and np.abs(t1 - t2).max() < 1e-8
+        assert np.abs(u1 - u2).max() < 1e-7 and np.abs(x1 - x2).max() < 1e-7
+        done += 1
+    assert done >= 3
