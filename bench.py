@@ -118,7 +118,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 (config 2)" % B,
+            "config": {"workload": "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 per GPU (BASELINE config 2)" % B,
                        "note": "CasADi/IPOPT not installable offline; CPU port of the same NLP + interior point (oracle/ocp_oracle.c)"},
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
                              "sample": "%d instances per step, %d pthreads" % (B, cores)},
