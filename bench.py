@@ -84,16 +84,21 @@ def workload(B, seed):
 
 
 def cpu_port_rate(B_sample, nthreads, seed=1):
-    """The CPU restatement (oracle/ocp_oracle.c) on `nthreads` host threads; returns (solves/s, seconds)."""
+    """The CPU restatement (oracle/ocp_oracle.c) on `nthreads` host threads; returns (solves/s, seconds, passes)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     from car_racing_b200 import scenarios
     (x0, xt, obs, lap_off), prm, _ = workload(B_sample, seed)
     orc.lib()
     t = time.perf_counter()
-    orc.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=nthreads)
-    dt = time.perf_counter() - t
-    return B_sample / dt, dt
+    passes = 0
+    while True:       # bounded sample: whole passes over the batch until ~10 s of wall time (at most 16 passes)
+        orc.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=nthreads)
+        passes += 1
+        dt = time.perf_counter() - t
+        if dt >= 10.0 or passes >= 16:
+            break
+    return B_sample * passes / dt, dt, passes
 
 
 def run_reference(args, rank, world):
@@ -373,9 +378,9 @@ def main():
             "bound": "dependent-issue latency (stall_wait 45 %), after the instruction-fetch bound was removed"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, dt = cpu_port_rate(min(B, 1024), cores)
+        v, dt, passes = cpu_port_rate(min(B, 1024), cores)
         line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
-                                "sample": "the same %d scenarios, once, %d pthreads (%.1f s)" % (min(B, 1024), cores, dt)}
+                                "sample": "the same %d scenarios, %d passes, %d pthreads (%.1f s)" % (min(B, 1024), passes, cores, dt)}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
