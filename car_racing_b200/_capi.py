@@ -77,6 +77,10 @@ class PlannerSelectParams(C.Structure):
     ]
 
 
+class RolloutParams(C.Structure):
+    _fields_ = [("n", C.c_int32), ("num_segments", C.c_int32), ("timestep", C.c_double), ("lap_length", C.c_double)]
+
+
 class PlannerPrepareParams(C.Structure):
     _fields_ = [
         ("N", C.c_int32), ("num_veh", C.c_int32), ("num_opt", C.c_int32), ("reserved", C.c_int32),
@@ -97,6 +101,7 @@ EXPORTS = [
     "b200mpc_lmpc_sysid", "b200mpc_lmpc_sysid_device", "b200mpc_plant_step", "b200mpc_plant_step_device",
     "b200mpc_cbf_solve_async", "b200mpc_synchronize", "b200mpc_host_alloc", "b200mpc_host_free", "b200mpc_planner_select_device", "b200mpc_plan_and_track", "b200mpc_ilqr_solve_async", "b200mpc_lmpc_solve_async",
     "b200mpc_planner_prepare_device", "b200mpc_planner_prepare", "b200mpc_plan_and_track_prepared",
+    "b200mpc_rival_rollout", "b200mpc_rival_rollout_device",
 ]
 
 _lib = None
@@ -140,6 +145,9 @@ def lib():
     L.b200mpc_planner_select_device.argtypes = [vp, C.POINTER(PlannerSelectParams)] + [dp] * 10
     L.b200mpc_plan_and_track.argtypes = [vp, C.POINTER(CbfParams), C.POINTER(CbfParams), C.POINTER(IpmOptions),
                                          C.POINTER(PlannerSelectParams)] + [dp] * 14
+    roll_args = [vp, C.POINTER(RolloutParams), ip] + [dp] * 5
+    L.b200mpc_rival_rollout.argtypes = roll_args
+    L.b200mpc_rival_rollout_device.argtypes = roll_args
     prep_args = [vp, C.POINTER(PlannerPrepareParams)] + [dp] * 13
     L.b200mpc_planner_prepare_device.argtypes = prep_args
     L.b200mpc_planner_prepare.argtypes = prep_args

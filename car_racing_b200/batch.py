@@ -375,3 +375,22 @@ def plant_step_batch(xcurv, xglob, u, draws, point_and_tangent, timestep=0.1, dy
     rc = _capi.lib().b200mpc_plant_step(hd.ptr, C.byref(p), Bn, _ptr(xc), 6, 0, _ptr(xg), _ptr(uu), 2, _ptr(dr), _ptr(seg), _ptr(laps))
     hd.check(rc, "b200mpc_plant_step")
     return (xc, xg, laps) if wrap_lap else (xc, xg)
+
+
+def rival_rollout_batch(xcurv, xglob, point_and_tangent, lap_length, timestep, n, with_glob=False, handle=None):
+    """Batched offboard.DynamicBicycleModel.get_trajectory_nsteps (racing/offboard.py:80-94): zero-input Frenet rollout of Bn
+    rivals over n steps in one launch.  xcurv, xglob (Bn,6).  Returns xcurv_nsteps (Bn,6,n) and, on request, xglob_nsteps."""
+    hd = handle or default_handle()
+    xc = np.ascontiguousarray(np.atleast_2d(np.asarray(xcurv, dtype=np.float64)))
+    xg = np.ascontiguousarray(np.atleast_2d(np.asarray(xglob, dtype=np.float64)))
+    if xc.shape != xg.shape or xc.shape[1] != 6:
+        raise ValueError("xcurv and xglob must both be (B, 6)")
+    Bn = xc.shape[0]
+    seg = np.ascontiguousarray(np.asarray(point_and_tangent, dtype=np.float64)[:, 3:6])
+    p = _capi.RolloutParams()
+    p.n, p.num_segments, p.timestep, p.lap_length = int(n), seg.shape[0], float(timestep), float(lap_length)
+    out_c = np.zeros((Bn, 6, int(n)))
+    out_g = np.zeros((Bn, 6, int(n))) if with_glob else None
+    rc = _capi.lib().b200mpc_rival_rollout(hd.ptr, C.byref(p), Bn, _ptr(xc), _ptr(xg), _ptr(seg), _ptr(out_c), _ptr(out_g))
+    hd.check(rc, "b200mpc_rival_rollout")
+    return (out_c, out_g) if with_glob else out_c

@@ -14,6 +14,7 @@
 #include "plant.cuh"
 #include "planner_prepare.cuh"
 #include "planner_select.cuh"
+#include "rival_rollout.cuh"
 #include "sysid.cuh"
 
 using namespace b200mpc;
@@ -534,6 +535,49 @@ int b200mpc_planner_select_device(b200mpc_handle *h, const b200mpc_planner_selec
                                                          d_traj, d_track_rec);
     CK(h, cudaGetLastError());
     h->launches++;
+    return B200MPC_OK;
+}
+
+int b200mpc_rival_rollout_device(b200mpc_handle *h, const b200mpc_rollout_params *prm, int B, const double *d_xcurv,
+                                 const double *d_xglob, const double *d_segments, double *d_xcurv_n, double *d_xglob_n) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!prm || !d_xcurv || !d_xglob || !d_segments || !d_xcurv_n || B < 1)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_rival_rollout: null argument or B < 1");
+    if (prm->n < 1 || prm->num_segments < 1 || !(prm->lap_length > 0.0) || !(prm->timestep > 0.0))
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_rival_rollout: bad parameter value");
+    CK(h, cudaSetDevice(h->device));
+    RolloutKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.p = *prm;
+    kp.B = B;
+    rival_rollout_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(kp, d_xcurv, d_xglob, d_segments, d_xcurv_n, d_xglob_n);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+int b200mpc_rival_rollout(b200mpc_handle *h, const b200mpc_rollout_params *prm, int B, const double *xcurv, const double *xglob,
+                          const double *segments, double *xcurv_n, double *xglob_n) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!prm || !xcurv || !xglob || !segments || !xcurv_n || B < 1 || prm->n < 1 || prm->num_segments < 1)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_rival_rollout: null argument, B < 1 or bad parameter value");
+    CK(h, cudaSetDevice(h->device));
+    const size_t b_in = 48 * (size_t)B, b_seg = 24 * (size_t)prm->num_segments, b_out = 48 * (size_t)B * prm->n;
+    int rc;
+    if ((rc = grow(h, &h->d_in, &h->c_in, 2 * b_in))) return rc;
+    if ((rc = grow(h, &h->d_seg, &h->c_seg, b_seg))) return rc;
+    if ((rc = grow(h, &h->d_x, &h->c_x, b_out))) return rc;
+    if (xglob_n && (rc = grow(h, &h->d_laps, &h->c_laps, b_out))) return rc;
+    double *din = (double *)h->d_in;
+    CK(h, cudaMemcpyAsync(din, xcurv, b_in, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(din + 6 * (size_t)B, xglob, b_in, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_seg, segments, b_seg, cudaMemcpyHostToDevice, h->stream));
+    rc = b200mpc_rival_rollout_device(h, prm, B, din, din + 6 * (size_t)B, (const double *)h->d_seg, (double *)h->d_x,
+                                      xglob_n ? (double *)h->d_laps : nullptr);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(xcurv_n, h->d_x, b_out, cudaMemcpyDeviceToHost, h->stream));
+    if (xglob_n) CK(h, cudaMemcpyAsync(xglob_n, h->d_laps, b_out, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }
 

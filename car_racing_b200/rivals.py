@@ -4,7 +4,9 @@
 The reference evaluates the rival's sympy expressions s(t), ey(t) with four `subs`/`diff` calls per predicted step
 (`get_estimation`, base.py:860-877) -- 8.2 ms per rival and control step, i.e. several times the GPU
 solve it feeds.  Here the expressions and their time derivatives are compiled once per rival (`sympy.lambdify`) and
-evaluated for all n steps in one numpy call.  Every caller in the reference discards the second return value
+evaluated for all n steps in one numpy call.  Rivals WITH dynamics (`offboard.DynamicBicycleModel.get_trajectory_nsteps`,
+car_racing/racing/offboard.py:80-94: a zero-input Frenet rollout) are predicted on the device, see
+`dynamic_get_trajectory_nsteps` below.  Every caller in the reference discards the second return value
 (control.py:103,296,509; overtake_traj_planner.py:78), so the global-frame block is only filled on request."""
 import numpy as np
 
@@ -46,9 +48,22 @@ def get_trajectory_nsteps(self, t0, delta_t, n, with_glob=False):
     return xcurv, xglob
 
 
-def install(base_module=None):
-    """Patch the reference's NoDynamicsModel in place."""
+def dynamic_get_trajectory_nsteps(self, n):
+    """Drop-in for offboard.DynamicBicycleModel.get_trajectory_nsteps (car_racing/racing/offboard.py:80-94): the zero-input
+    Frenet rollout of a rival with dynamics, n steps in one kernel launch (b200mpc_rival_rollout).  Same return value:
+    (xcurv_nsteps (6,n), xglob_nsteps (6,n)), incl. the reference's global-frame quirks (offboard.py:71-76).  Many rivals
+    or scenarios at once: car_racing_b200.batch.rival_rollout_batch."""
+    from . import batch
+    xc, xg = batch.rival_rollout_batch(self.xcurv, self.xglob, self.point_and_tangent, self.lap_length, self.timestep, n,
+                                       with_glob=True)
+    return xc[0], xg[0]
+
+
+def install(base_module=None, offboard_module=None):
+    """Patch the reference's NoDynamicsModel (and, when its module is given, offboard.DynamicBicycleModel) in place."""
     if base_module is None:
         from utils import base as base_module
     base_module.NoDynamicsModel.get_trajectory_nsteps = get_trajectory_nsteps
+    if offboard_module is not None:
+        offboard_module.DynamicBicycleModel.get_trajectory_nsteps = dynamic_get_trajectory_nsteps
     return base_module

@@ -291,6 +291,24 @@ int b200mpc_plan_and_track(b200mpc_handle *h, const b200mpc_cbf_params *plan_prm
                            const double *track_in, b200mpc_record *cand_rec, double *cand_xpred, double *sel_cost, int32_t *flag,
                            double *traj, b200mpc_record *track_rec, double *track_xpred, double *track_upred);
 
+/* Prediction of rivals that have dynamics: offboard.DynamicBicycleModel.get_trajectory_nsteps
+ * (racing/offboard.py:80-94) = n Euler steps of the zero-input Frenet kinematics (get_estimation, :51-77), curvature from
+ * the track segments (utils/racing_env.py:225-246), s wrapped into the lap after every step. */
+typedef struct {
+    int32_t n;              /* predicted steps (N + 1) */
+    int32_t num_segments;   /* rows of `segments` */
+    double timestep;        /* the model's timestep (0.1) */
+    double lap_length;
+} b200mpc_rollout_params;
+
+/* xcurv, xglob: B x 6 current states; segments: num_segments x 3 (start s, length, curvature) = point_and_tangent[:, 3:6];
+ * xcurv_n, xglob_n: B x 6 x n, the reference's (6, n) blocks per rival (xglob_n optional: every caller in the reference
+ * discards it). */
+int b200mpc_rival_rollout(b200mpc_handle *h, const b200mpc_rollout_params *prm, int B, const double *xcurv, const double *xglob,
+                          const double *segments, double *xcurv_n, double *xglob_n);
+int b200mpc_rival_rollout_device(b200mpc_handle *h, const b200mpc_rollout_params *prm, int B, const double *d_xcurv,
+                                 const double *d_xglob, const double *d_segments, double *d_xcurv_n, double *d_xglob_n);
+
 /* Candidate preparation on the device: what OvertakeTrajPlanner.get_local_traj computes between the
  * rivals' predictions and the candidate solves (planning/overtake_traj_planner.py:87-117: veh_infos, get_agent_info,
  * get_bezier_control_points, the sampled Bezier curves -- planning/planner_helper.py:46-153, 177-205) and the data part of

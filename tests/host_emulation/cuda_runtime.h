@@ -13,7 +13,7 @@
 #define __shared__ static
 #define __launch_bounds__(x)
 struct EmuIdx { int x; };
-static EmuIdx threadIdx = {0};
+static EmuIdx threadIdx = {0}, blockIdx = {0}, blockDim = {1};
 static inline void __syncthreads() {}
 static inline int atomicOr(int *p, int v) { int o = *p; *p |= v; return o; }
 /* compiled with -ffp-contract=off: plain operators are the separately rounded operations */
