@@ -218,16 +218,21 @@ def install(control_module=None):
     return control_module
 
 
-def install_all(control_module=None, base_module=None, planner_class=None):
+def install_all(control_module=None, base_module=None, planner_class=None, offboard_module=None):
     """Everything on the control-step path: the five solve functions, LMPCRacingGame.estimate_ABC, the planner's
-    solve_optimization_problem and get_local_traj (candidate preparation on the device) and the rivals' sympy-free
-    trajectory prediction."""
+    solve_optimization_problem and get_local_traj (candidate preparation on the device) and the rivals' trajectory
+    prediction (sympy-free for NoDynamicsModel, on the device for offboard.DynamicBicycleModel)."""
     from . import planning, rivals
     control_module = install(control_module)
     if base_module is None:
         from utils import base as base_module
     base_module.LMPCRacingGame.estimate_ABC = estimate_ABC
-    rivals.install(base_module)
+    if offboard_module is None:
+        try:
+            from racing import offboard as offboard_module     # rivals with dynamics (racing/offboard.py:80-94)
+        except ImportError:
+            offboard_module = None
+    rivals.install(base_module, offboard_module)
     if planner_class is None:
         from planning.overtake_traj_planner import OvertakeTrajPlanner as planner_class
     planner_class.solve_optimization_problem = planning.solve_optimization_problem

@@ -93,7 +93,9 @@ def test_install_all_patches_every_hook():
     ctrl = types.SimpleNamespace()
     base = types.SimpleNamespace(LMPCRacingGame=type("LMPCRacingGame", (), {}), NoDynamicsModel=type("NoDynamicsModel", (), {}))
     planner = type("OvertakeTrajPlanner", (), {})
-    crb.install_all(ctrl, base, planner)
+    offboard = types.SimpleNamespace(DynamicBicycleModel=type("DynamicBicycleModel", (), {}))
+    crb.install_all(ctrl, base, planner, offboard)
+    assert offboard.DynamicBicycleModel.get_trajectory_nsteps is rivals.dynamic_get_trajectory_nsteps
     for name in ("mpc_lti", "mpccbf", "mpc_multi_agents", "ilqr", "lmpc"):
         assert getattr(ctrl, name) is getattr(crb.control, name)
     assert base.LMPCRacingGame.estimate_ABC is crb.control.estimate_ABC
