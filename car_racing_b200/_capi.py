@@ -101,7 +101,7 @@ EXPORTS = [
     "b200mpc_lmpc_sysid", "b200mpc_lmpc_sysid_device", "b200mpc_plant_step", "b200mpc_plant_step_device",
     "b200mpc_cbf_solve_async", "b200mpc_synchronize", "b200mpc_host_alloc", "b200mpc_host_free", "b200mpc_planner_select_device", "b200mpc_plan_and_track", "b200mpc_ilqr_solve_async", "b200mpc_lmpc_solve_async",
     "b200mpc_planner_prepare_device", "b200mpc_planner_prepare", "b200mpc_plan_and_track_prepared",
-    "b200mpc_rival_rollout", "b200mpc_rival_rollout_device",
+    "b200mpc_rival_rollout", "b200mpc_rival_rollout_device", "b200mpc_curv_to_glob", "b200mpc_curv_to_glob_device",
 ]
 
 _lib = None
@@ -145,6 +145,9 @@ def lib():
     L.b200mpc_planner_select_device.argtypes = [vp, C.POINTER(PlannerSelectParams)] + [dp] * 10
     L.b200mpc_plan_and_track.argtypes = [vp, C.POINTER(CbfParams), C.POINTER(CbfParams), C.POINTER(IpmOptions),
                                          C.POINTER(PlannerSelectParams)] + [dp] * 14
+    c2g_args = [vp, ip, ip, C.c_double, dp, dp, ip, dp, ip, dp]
+    L.b200mpc_curv_to_glob.argtypes = c2g_args
+    L.b200mpc_curv_to_glob_device.argtypes = c2g_args
     roll_args = [vp, C.POINTER(RolloutParams), ip] + [dp] * 5
     L.b200mpc_rival_rollout.argtypes = roll_args
     L.b200mpc_rival_rollout_device.argtypes = roll_args

@@ -394,3 +394,20 @@ def rival_rollout_batch(xcurv, xglob, point_and_tangent, lap_length, timestep, n
     rc = _capi.lib().b200mpc_rival_rollout(hd.ptr, C.byref(p), Bn, _ptr(xc), _ptr(xg), _ptr(seg), _ptr(out_c), _ptr(out_g))
     hd.check(rc, "b200mpc_rival_rollout")
     return (out_c, out_g) if with_glob else out_c
+
+
+def curv_to_glob_batch(s, ey, point_and_tangent, lap_length, handle=None):
+    """Batched racing_env.get_global_position / get_orientation (utils/racing_env.py:6-127): s, ey of any (equal) shape ->
+    (x, y, psi) arrays of that shape, one launch.  The controllers' global-frame logs (utils/base.py:500-509, 573-580) and
+    the planner's plot copies (planner_helper.py:208-220) call the scalar reference functions once per point."""
+    hd = handle or default_handle()
+    sa = np.ascontiguousarray(np.asarray(s, dtype=np.float64))
+    ea = np.ascontiguousarray(np.asarray(ey, dtype=np.float64))
+    if sa.shape != ea.shape or sa.size < 1:
+        raise ValueError("s and ey must have the same non-empty shape")
+    pat = np.ascontiguousarray(np.asarray(point_and_tangent, dtype=np.float64)[:, :6])
+    out = np.zeros((sa.size, 3))
+    rc = _capi.lib().b200mpc_curv_to_glob(hd.ptr, sa.size, pat.shape[0], float(lap_length), _ptr(pat), _ptr(sa), 1, _ptr(ea), 1,
+                                          _ptr(out))
+    hd.check(rc, "b200mpc_curv_to_glob")
+    return out[:, 0].reshape(sa.shape), out[:, 1].reshape(sa.shape), out[:, 2].reshape(sa.shape)

@@ -8,6 +8,7 @@
 #include <string>
 
 #include "../../include/b200mpc.h"
+#include "frenet.cuh"
 #include "ilqr.cuh"
 #include "lmpc.cuh"
 #include "ocp_ipm.cuh"
@@ -535,6 +536,42 @@ int b200mpc_planner_select_device(b200mpc_handle *h, const b200mpc_planner_selec
                                                          d_traj, d_track_rec);
     CK(h, cudaGetLastError());
     h->launches++;
+    return B200MPC_OK;
+}
+
+int b200mpc_curv_to_glob_device(b200mpc_handle *h, int P, int num_segments, double lap_length, const double *d_track,
+                                const double *d_s, int s_stride, const double *d_ey, int ey_stride, double *d_out) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!d_track || !d_s || !d_ey || !d_out || P < 1 || num_segments < 1 || s_stride < 1 || ey_stride < 1 || !(lap_length > 0.0))
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_curv_to_glob: bad arguments");
+    CK(h, cudaSetDevice(h->device));
+    curv_to_glob_kernel<<<(P + 127) / 128, 128, 0, h->stream>>>(P, num_segments, lap_length, d_track, d_s, s_stride, d_ey, ey_stride,
+                                                              d_out);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+int b200mpc_curv_to_glob(b200mpc_handle *h, int P, int num_segments, double lap_length, const double *track, const double *s,
+                         int s_stride, const double *ey, int ey_stride, double *out) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!track || !s || !ey || !out || P < 1 || num_segments < 1 || s_stride < 1 || ey_stride < 1)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_curv_to_glob: bad arguments");
+    CK(h, cudaSetDevice(h->device));
+    const size_t n_s = (size_t)(P - 1) * s_stride + 1, n_e = (size_t)(P - 1) * ey_stride + 1;
+    int rc;
+    if ((rc = grow(h, &h->d_in, &h->c_in, 8 * (n_s + n_e)))) return rc;
+    if ((rc = grow(h, &h->d_seg, &h->c_seg, 48 * (size_t)num_segments))) return rc;
+    if ((rc = grow(h, &h->d_x, &h->c_x, 24 * (size_t)P))) return rc;
+    double *din = (double *)h->d_in;
+    CK(h, cudaMemcpyAsync(din, s, 8 * n_s, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(din + n_s, ey, 8 * n_e, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_seg, track, 48 * (size_t)num_segments, cudaMemcpyHostToDevice, h->stream));
+    rc = b200mpc_curv_to_glob_device(h, P, num_segments, lap_length, (const double *)h->d_seg, din, s_stride, din + n_s, ey_stride,
+                                     (double *)h->d_x);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(out, h->d_x, 24 * (size_t)P, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }
 

@@ -436,14 +436,22 @@ def plan_and_track_from_predictions(self, xcurv_ego, time, vehicles_interest, xc
                              (xcurv, mpc_lti_param, track, system_param))
 
 
-def _traj_xglob(traj_xcurv, track):
-    """planner_helper.get_traj_xglob (planning/planner_helper.py:208-220): only columns 4, 5 (global x, y) are filled."""
-    out = np.zeros((traj_xcurv.shape[0], 6))
-    for i in range(traj_xcurv.shape[0]):
-        s_i = float(traj_xcurv[i, 4])
+def _traj_xglob(trajs_xcurv, track):
+    """planner_helper.get_traj_xglob (planning/planner_helper.py:208-220) for a stack of trajectories (..., 6): only columns
+    4, 5 (global x, y) are filled.  One launch for all points (b200mpc_curv_to_glob) when the track carries the reference's
+    point_and_tangent table; a duck-typed track without it is asked point by point, as the reference does."""
+    trajs_xcurv = np.asarray(trajs_xcurv, float)
+    out = np.zeros(trajs_xcurv.shape)
+    if hasattr(track, "point_and_tangent"):
+        x, y, _ = batch.curv_to_glob_batch(trajs_xcurv[..., 4], trajs_xcurv[..., 5], track.point_and_tangent, track.lap_length)
+        out[..., 4], out[..., 5] = x, y
+        return out
+    flat_in, flat_out = trajs_xcurv.reshape(-1, 6), out.reshape(-1, 6)
+    for i in range(flat_in.shape[0]):
+        s_i = float(flat_in[i, 4])
         while s_i > track.lap_length:
             s_i = s_i - track.lap_length
-        out[i, 4], out[i, 5] = track.get_global_position(s_i, traj_xcurv[i, 5])
+        flat_out[i, 4], flat_out[i, 5] = track.get_global_position(s_i, flat_in[i, 5])
     return out
 
 
@@ -451,21 +459,18 @@ def get_local_traj(self, xcurv_ego, time, vehicles_interest, matrix_Atv, matrix_
     """Drop-in for OvertakeTrajPlanner.get_local_traj (overtake_traj_planner.py:44-161; assign to the class): same arguments,
     same 8-tuple.  Rival predictions and ordering on the host, then ONE call (b200mpc_plan_and_track_prepared without the
     tracking stage): Bezier references, candidate records, candidate QPs, selection on the device; the global-frame copies
-    for plotting go through the reference's own track.get_global_position."""
+    for plotting are one more launch (b200mpc_curv_to_glob) instead of one get_global_position call per point."""
     self.matrix_Atv, self.matrix_Btv, self.matrix_Ctv = matrix_Atv, matrix_Btv, matrix_Ctv
     self.old_ey = old_ey
     (traj, flag, solve_time, sol), _ = _from_predictions(self, xcurv_ego, time, vehicles_interest, old_direction_flag, None, None, None)
     N = self.racing_game_param.num_horizon_planner
     C0 = sol.shape[0]
     track = self.track
-    target_traj_xglob = _traj_xglob(traj, track)
-    line = np.zeros((N + 1, 6))
-    line[:, 4:6] = self.bezier_xcurvs[flag]
-    bezier_xglob = _traj_xglob(line, track)
-    all_bezier_xglob, all_local_traj_xglob = np.zeros((C0, N + 1, 6)), np.zeros((C0, N + 1, 6))
-    for c in range(C0):
-        line = np.zeros((N + 1, 6))
-        line[:, 4:6] = self.bezier_xcurvs[c]
-        all_bezier_xglob[c] = _traj_xglob(line, track)
-        all_local_traj_xglob[c] = _traj_xglob(sol[c].T, track)
+    # the reference converts target, chosen curve, all curves and all candidates point by point (:124-147); here one launch
+    lines = np.zeros((C0, N + 1, 6))
+    lines[:, :, 4:6] = self.bezier_xcurvs
+    stack = np.concatenate([traj[None], lines, sol.transpose(0, 2, 1)])          # (1 + 2 C0, N+1, 6)
+    glob = _traj_xglob(stack, track)
+    target_traj_xglob, all_bezier_xglob, all_local_traj_xglob = glob[0], glob[1:1 + C0], glob[1 + C0:]
+    bezier_xglob = all_bezier_xglob[flag].copy()
     return traj, target_traj_xglob, flag, self.sorted_vehicles, bezier_xglob, solve_time, all_bezier_xglob, all_local_traj_xglob

@@ -309,6 +309,15 @@ int b200mpc_rival_rollout(b200mpc_handle *h, const b200mpc_rollout_params *prm, 
 int b200mpc_rival_rollout_device(b200mpc_handle *h, const b200mpc_rollout_params *prm, int B, const double *d_xcurv,
                                  const double *d_xglob, const double *d_segments, double *d_xcurv_n, double *d_xglob_n);
 
+/* Curvilinear -> global frame: racing_env.get_global_position / get_orientation
+ * (utils/racing_env.py:6-127) for P points at once.  track: num_segments x 6 = ClosedTrack.point_and_tangent
+ * (x, y, psi, start s, length, curvature).  s, ey: P values read with the given strides (doubles) -- stride 6 reads
+ * columns 4, 5 of (.., 6) state trajectories in place.  out: P x 3 (x, y, psi). */
+int b200mpc_curv_to_glob(b200mpc_handle *h, int P, int num_segments, double lap_length, const double *track, const double *s,
+                         int s_stride, const double *ey, int ey_stride, double *out);
+int b200mpc_curv_to_glob_device(b200mpc_handle *h, int P, int num_segments, double lap_length, const double *d_track,
+                                const double *d_s, int s_stride, const double *d_ey, int ey_stride, double *d_out);
+
 /* Candidate preparation on the device: what OvertakeTrajPlanner.get_local_traj computes between the
  * rivals' predictions and the candidate solves (planning/overtake_traj_planner.py:87-117: veh_infos, get_agent_info,
  * get_bezier_control_points, the sampled Bezier curves -- planning/planner_helper.py:46-153, 177-205) and the data part of
