@@ -151,6 +151,9 @@ def main():
     ap.add_argument("--inflight", type=int, default=6,
                     help="batches in flight (streams driven round-robin); 1 = strictly one batch at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange-priority", default="normal", choices=["high", "normal"],
+                    help="N>1: stream priority of the exchange step (NCCL all-gather + argmin); measured on 2 B200: high is "
+                         "slower (profiles/r03e_exchange_priority.json)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,7 +176,13 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # The exchange is 32 KB per rank and step, but its kernels share the SMs with up to D in-flight solver grids (7 resident
+        # CTAs per SM).  Tried: exchange on high-priority streams (NCCL's and the argmin handle's) so that the block scheduler
+        # places its CTAs first -- measured SLOWER on 2 B200 (696-703 k against 733-750 k solves/s, r03e), so normal is the default.
+        pg_opts = None
+        if args.exchange_priority == "high":
+            pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
     B = args.batch
     D = max(1, args.inflight)
     _, prm, rec_host = workload(B, seed=1 + rank)            # each rank: its own shard of scenarios
@@ -193,7 +202,7 @@ def main():
     # in issue order, so an all-gather enqueued on a solver stream would hold that stream until every EARLIER batch's
     # stragglers have finished on every rank; here the solver stream only records an event and moves on to its next batch
     # (result buffers are double-buffered per slot).
-    hc = _capi.Handle(device=local_rank, max_batch=B) if world > 1 else None
+    hc = _capi.Handle(device=local_rank, max_batch=B, high_priority=args.exchange_priority == "high") if world > 1 else None
     ext_c = torch.cuda.ExternalStream(hc.stream, device=dev) if world > 1 else None
     d_rec2 = [[d_rec[k], torch.zeros_like(d_rec[k])] for k in range(D)]
     ag_done = [[None, None] for _ in range(D)]
@@ -343,7 +352,7 @@ def main():
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 per GPU (BASELINE config 2)" % B,
-                   "global_batch": B * world, "parallelism": "dp%d (independent scenario shards + 1 all-gather of 32-B records and argmin per step, on an exchange stream)" % world,
+                   "global_batch": B * world, "parallelism": "dp%d (independent scenario shards + 1 all-gather of 32-B records and argmin per step, on an exchange stream%s)" % (world, ", high priority" if world > 1 and args.exchange_priority == "high" else ""),
                    "l2": "256 MiB buffer written before every timed step, on the step's stream (inputs are 1.1 MB << L2)",
                    "batches_in_flight": D,
                    "pipelining": ("steps are issued round-robin on %d streams (one handle each): the stragglers of one 1024-instance "

@@ -94,7 +94,7 @@ RECORD_DTYPE = np.dtype([("cost", "<f8"), ("u0", "<f8", (2,)), ("status", "<i4")
 assert RECORD_DTYPE.itemsize == 32
 
 EXPORTS = [
-    "b200mpc_version", "b200mpc_default_ipm_options", "b200mpc_create", "b200mpc_destroy", "b200mpc_last_error",
+    "b200mpc_version", "b200mpc_default_ipm_options", "b200mpc_create", "b200mpc_create_ex", "b200mpc_destroy", "b200mpc_last_error",
     "b200mpc_stream", "b200mpc_launch_count", "b200mpc_cbf_record_doubles", "b200mpc_cbf_record_doubles_ex", "b200mpc_cbf_solve",
     "b200mpc_cbf_solve_device", "b200mpc_ilqr_record_doubles", "b200mpc_ilqr_solve", "b200mpc_ilqr_solve_device",
     "b200mpc_argmin_cost_device", "b200mpc_lmpc_record_doubles", "b200mpc_lmpc_solve", "b200mpc_lmpc_solve_device",
@@ -122,6 +122,7 @@ def lib():
     L.b200mpc_default_ipm_options.argtypes = [C.POINTER(IpmOptions)]
     L.b200mpc_default_ipm_options.restype = None
     L.b200mpc_create.argtypes = [ip, ip, C.POINTER(vp)]
+    L.b200mpc_create_ex.argtypes = [ip, ip, ip, C.POINTER(vp)]
     L.b200mpc_destroy.argtypes = [vp]
     L.b200mpc_destroy.restype = None
     L.b200mpc_last_error.argtypes = [vp]
@@ -186,14 +187,14 @@ class Handle:
     native handle and re-creates it lazily (controller objects are pickled with the simulator,
     car_racing/tests/mpccbf_test.py:45-46)."""
 
-    def __init__(self, device=-1, max_batch=1024):
-        self.device, self.max_batch = device, max_batch
+    def __init__(self, device=-1, max_batch=1024, high_priority=False):
+        self.device, self.max_batch, self.high_priority = device, max_batch, bool(high_priority)
         self._h = None
 
     def _ensure(self):
         if self._h is None:
             h = C.c_void_p()
-            rc = lib().b200mpc_create(self.device, self.max_batch, C.byref(h))
+            rc = lib().b200mpc_create_ex(self.device, self.max_batch, int(getattr(self, "high_priority", False)), C.byref(h))
             if rc != 0:
                 raise B200MPCError(f"b200mpc_create failed ({rc}): {lib().b200mpc_last_error(None).decode()}")
             self._h = h
@@ -230,10 +231,10 @@ class Handle:
             pass
 
     def __getstate__(self):
-        return {"device": self.device, "max_batch": self.max_batch}
+        return {"device": self.device, "max_batch": self.max_batch, "high_priority": getattr(self, "high_priority", False)}
 
     def __setstate__(self, st):
-        self.device, self.max_batch = st["device"], st["max_batch"]
+        self.device, self.max_batch, self.high_priority = st["device"], st["max_batch"], st.get("high_priority", False)
         self._h = None
 
 

@@ -75,7 +75,9 @@ void b200mpc_default_ipm_options(b200mpc_ipm_options *o) {
     o->max_grad = 100.0;
 }
 
-int b200mpc_create(int device, int max_batch, b200mpc_handle **out) {
+int b200mpc_create(int device, int max_batch, b200mpc_handle **out) { return b200mpc_create_ex(device, max_batch, 0, out); }
+
+int b200mpc_create_ex(int device, int max_batch, int high_priority, b200mpc_handle **out) {
     if (!out || max_batch < 1) return fail(nullptr, B200MPC_ERR_ARG, "b200mpc_create: bad arguments");
     *out = nullptr;
     int ndev = 0;
@@ -92,7 +94,9 @@ int b200mpc_create(int device, int max_batch, b200mpc_handle **out) {
     if (!h) return fail(nullptr, B200MPC_ERR_NOMEM, "out of host memory");
     h->device = device;
     h->max_batch = max_batch;
-    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    int prio_lo = 0, prio_hi = 0;   // numerically lower = higher priority; pending blocks of a high-priority stream are placed first
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, high_priority ? prio_hi : 0)) != cudaSuccess) {
         std::string m = cudaGetErrorString(e);
         delete h;
         return fail(nullptr, B200MPC_ERR_CUDA, "b200mpc_create: " + m);

@@ -106,6 +106,9 @@ void b200mpc_default_ipm_options(b200mpc_ipm_options *opt);
 
 /* device < 0: current CUDA device.  max_batch bounds the staging buffers of the host-pointer API. */
 int b200mpc_create(int device, int max_batch, b200mpc_handle **out);
+/* The same with the handle's stream created at the device's highest priority when high_priority != 0: for short kernels
+ * that must not queue behind the pending blocks of other handles' batches (the planner's exchange / argmin step). */
+int b200mpc_create_ex(int device, int max_batch, int high_priority, b200mpc_handle **out);
 void b200mpc_destroy(b200mpc_handle *h);
 const char *b200mpc_last_error(const b200mpc_handle *h); /* h may be NULL: last create() error */
 /* the handle's CUDA stream (cudaStream_t) as an integer, for event timing by the caller */
