@@ -133,7 +133,11 @@ __device__ __forceinline__ double warp_min_nn(double v) {
 // solver's operands are positive, finite and far from the denormal range, and 1-ulp differences are irrelevant here.
 __device__ __forceinline__ double rcp(double x) {
     double r;
+#ifdef B200MPC_HOST_EMULATION   // tests/host_emulation: the kernel source compiled by g++; the seed is exact there
+    r = 1.0 / x;
+#else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
@@ -141,7 +145,11 @@ __device__ __forceinline__ double rcp(double x) {
 }
 __device__ __forceinline__ double rsq(double x) {
     double y;
+#ifdef B200MPC_HOST_EMULATION
+    y = 1.0 / sqrt(x);
+#else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#endif
     double h = 0.5 * x;
     y = y * fma(-h * y, y, 1.5);   // seed 1e-6 -> 1.3e-12 -> 4e-16 (measured over 60 binades, profiles/r01k_rsq_accuracy.txt)
     return y * fma(-h * y, y, 1.5);
@@ -198,6 +206,13 @@ __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_ca
 __device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 
 // ---------------------------------------------------------------- TMA (bulk async copy) + mbarrier
+#ifdef B200MPC_HOST_EMULATION
+// tests/host_emulation: the issuing lane copies synchronously; the __syncwarp() that follows mbar_wait() publishes the data
+__device__ __forceinline__ void mbar_init(uint64_t *, int) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *, uint32_t) {}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t *, uint32_t) {}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -225,6 +240,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
         "r"(phase)
         : "memory");
 }
+#endif
 
 // ---------------------------------------------------------------- the solver
 // NT > 0: horizon known at compile time (all shared-memory offsets become immediates); NT == 0: runtime horizon
