@@ -5,12 +5,21 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #define __device__
+#define __host__
 #define __global__
 #define __forceinline__ inline
 #define __restrict__
 #define __grid_constant__
+#ifdef EMU_DYNAMIC_SMEM_ONLY
+/* translation units whose kernels use `extern __shared__ double sm[]`: the declaration becomes `extern double sm[]` and the
+ * harness defines b200mpc::sm (one block in flight at a time) */
+#define __shared__
+#define __align__(x)
+#else
 #define __shared__ static
+#endif
 #define __launch_bounds__(x)
 struct EmuIdx { int x; };
 /* one host thread per CUDA thread of a block (emu_launch below); single-threaded callers leave the defaults */
@@ -31,6 +40,58 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 #include <functional>
 #include <thread>
 #include <vector>
+#endif
+
+#ifdef EMU_WARPS
+/* warp collectives for kernels whose CTA is one or more full warps executing convergently: every lane is a host thread,
+ * a collective = publish, barrier, read, barrier on the warp's own std::barrier.  A collective inside divergent code would
+ * dead-lock here (the tests run under a timeout); on the GPU the same code would be undefined behaviour with a full mask. */
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+struct EmuWarp {
+    std::barrier<> bar{32};
+    uint64_t xch[32];
+};
+static EmuWarp *emu_warps = nullptr;    // one per warp of the block in flight
+static inline EmuWarp &emu_warp() { return emu_warps[threadIdx.x >> 5]; }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp().bar.arrive_and_wait(); }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    EmuWarp &w = emu_warp();
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    w.xch[threadIdx.x & 31] = raw;
+    w.bar.arrive_and_wait();
+    raw = w.xch[src & 31];
+    w.bar.arrive_and_wait();
+    T r;
+    memcpy(&r, &raw, sizeof(T));
+    return r;
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned m, T v, int lanemask) { return __shfl_sync(m, v, (threadIdx.x & 31) ^ lanemask); }
+template <typename F> static inline uint64_t emu_warp_fold(uint64_t mine, F f) {
+    EmuWarp &w = emu_warp();
+    w.xch[threadIdx.x & 31] = mine;
+    w.bar.arrive_and_wait();
+    uint64_t acc = w.xch[0];
+    for (int l = 1; l < 32; l++) acc = f(acc, w.xch[l]);
+    w.bar.arrive_and_wait();
+    return acc;
+}
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return (unsigned)emu_warp_fold(v, [](uint64_t a, uint64_t b) { return a > b ? a : b; }); }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) { return (unsigned)emu_warp_fold(v, [](uint64_t a, uint64_t b) { return a < b ? a : b; }); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    return (unsigned)emu_warp_fold(pred ? (1ull << (threadIdx.x & 31)) : 0ull, [](uint64_t a, uint64_t b) { return a | b; });
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __double2hiint(double d) { uint64_t r; memcpy(&r, &d, 8); return (int)(r >> 32); }
+static inline int __double2loint(double d) { uint64_t r; memcpy(&r, &d, 8); return (int)(r & 0xffffffffu); }
+static inline double __hiloint2double(int hi, int lo) { uint64_t r = ((uint64_t)(unsigned)hi << 32) | (unsigned)lo; double d; memcpy(&d, &r, 8); return d; }
+#endif
+
+#ifdef EMU_WITH_LAUNCH
 /* blocks run one after the other; the threads of a block are real host threads, __syncthreads() is a std::barrier and
  * __shared__ variables are function-local statics (shared by the block's threads, reused by the next block) */
 static std::barrier<> *emu_block_barrier = nullptr;
@@ -42,6 +103,10 @@ static inline void emu_launch(int grid, int block, const std::function<void()> &
         std::barrier<> bar(block);
         emu_block_barrier = &bar;
         emu_barrier_fn = emu_barrier_wait;
+#ifdef EMU_WARPS
+        std::vector<EmuWarp> warps((block + 31) / 32);
+        emu_warps = warps.data();
+#endif
         std::vector<std::thread> ts;
         for (int t = 0; t < block; t++)
             ts.emplace_back([&, t]() {
@@ -56,3 +121,4 @@ static inline void emu_launch(int grid, int block, const std::function<void()> &
     blockDim.x = 1;
 }
 #endif
+
