@@ -20,7 +20,7 @@ pytestmark = pytest.mark.timeout(600)
 
 
 def _lib():
-    lib = os.path.join(EMU, "_build", "libocp_emu.so")
+    lib = os.path.join(EMU, "_build", "libocp_ipm_emu.so")
     src = [os.path.join(EMU, "ocp_ipm_host.cpp"), os.path.join(EMU, "cuda_runtime.h"),
            os.path.join(HERE, "..", "car_racing_b200", "csrc", "ocp_ipm.cuh"), os.path.join(HERE, "..", "include", "b200mpc.h")]
     if not os.path.exists(lib) or any(os.path.getmtime(f) > os.path.getmtime(lib) for f in src):

@@ -1,0 +1,157 @@
+"""The whole C-ABI library on the host: car_racing_b200/csrc/capi.cu and every kernel header compiled by g++
+(tests/host_emulation/build_emu_library.py: launches become emu_launch, "device" memory is host memory, one host thread
+per CUDA thread with barriers for __syncthreads / __syncwarp / shuffles), loaded INTO THE TESTS ONLY in place of
+libb200mpc.so, so that the product's own Python API -- packers, parameter structs, dispatch, kernels -- is exercised end
+to end without a GPU at small sizes: MPC-CBF, iLQR (against the reference's own golden outputs), LMPC, model
+identification (reference golden), the planner chain, rival rollout, frame conversion.  This is a checker of logic; the CUDA
+build of the same sources is what `-m gpu` and bench.py run, and nothing on the product path can load the emulated
+library."""
+import importlib.util
+import os
+import types
+
+import numpy as np
+import pytest
+
+import car_racing_b200 as crb
+from car_racing_b200 import _capi, batch, planning, scenarios
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+pytestmark = pytest.mark.timeout(900)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    spec = importlib.util.spec_from_file_location("build_emu_library", os.path.join(HERE, "host_emulation", "build_emu_library.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    path = mod.build()
+    saved = (_capi.LIB_PATH, _capi._lib, batch._default_handle)
+    _capi.LIB_PATH, _capi._lib, batch._default_handle = path, None, None
+    try:
+        yield path
+    finally:
+        if batch._default_handle is not None:
+            batch._default_handle.close()
+        _capi.LIB_PATH, _capi._lib, batch._default_handle = saved
+
+
+def test_mpccbf_through_the_product_api(emu, oracle):
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(2, N=20, M=3, seed=1)
+    prm = scenarios.default_cbf_params(N=20)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    assert (g["status"] == r["status"]).all() and (g["iters"] == r["iters"]).all()
+    ok = g["status"] == 0
+    assert ok.any() and np.abs(g["u0"] - r["u0"])[ok].max() < 1e-4 and np.abs(g["cost"] - r["cost"])[ok].max() < 1e-5
+    assert batch.default_handle().launch_count == 1
+
+
+def test_ilqr_against_the_reference_golden(emu):
+    """ilqr_kernel against vectors produced by the unmodified reference control.ilqr (a subset of the -m gpu test)."""
+    gold = np.load(os.path.join(GOLD, "ilqr_golden.npz"))
+    done = 0
+    for N in sorted(set(gold["N"].tolist())):
+        idx = np.where(gold["N"] == N)[0][:3]
+        x0, xt, obs, lap = gold["x0"][idx], gold["xt"][idx], gold["obs"][idx][:, :, :N + 1], gold["lap"][idx]
+        lap_off = (np.trunc(x0[:, 4] / lap) - np.trunc(obs[:, 0, 0] / lap)) * lap
+        prm = dict(A=gold["A"], B=gold["B"], Q=gold["Q"], R=gold["R"], N=int(N), max_iter=int(gold["max_iter"]), L=0.4, W=0.2)
+        g = crb.solve_ilqr_batch(x0, xt, obs, lap_off, prm)
+        assert np.abs(g["u0"] - gold["u0"][idx]).max() < 1e-9
+        done += len(idx)
+    assert done >= 3
+
+
+def test_lmpc_against_the_oracle(emu, oracle):
+    sc = scenarios.lmpc_scenarios(2, seed=5)
+    prm = scenarios.default_lmpc_params()
+    g = crb.solve_lmpc_batch(*sc, prm)
+    r = oracle.solve_lmpc_batch(*sc, prm)
+    assert (g["status"] == r["status"]).all()
+    ok = g["status"] == 0
+    assert ok.any() and np.abs(g["u0"] - r["u0"])[ok].max() < 1e-4 and np.abs(g["cost"] - r["cost"])[ok].max() < 1e-5
+    assert np.abs(g["x"][ok] - r["x"][ok]).max() < 1e-4 and np.abs(g["lambda"][ok] - r["lam"][ok]).max() < 1e-4
+
+
+def test_model_identification_against_the_reference_golden(emu):
+    g = np.load(os.path.join(GOLD, "sysid_golden.npz"))
+    r = crb.estimate_abc_batch(g["lin_points"][:1], g["lin_input"][:1], g["ss"], g["us"], g["time_ss"], [0, 1], g["point_and_tangent"],
+                               float(g["dt"]), int(g["max_num_point"]))
+    assert (r["status"] == 0).all() and (r["idx"] == g["idx"][:1]).all()
+    assert np.abs(r["A"] - g["A"][:1]).max() < 1e-8 and np.abs(r["B"] - g["B"][:1]).max() < 1e-8 and np.abs(r["C"] - g["C"][:1]).max() < 1e-8
+
+
+def test_overtaking_step_from_predictions(emu):
+    """b200mpc_plan_and_track_prepared (preparation, candidate QPs, selection, tracking MPC-CBF in one call) against the same
+    step with the candidates packed on the host, both through the library on the host; plus the get_local_traj drop-in."""
+    from scipy.interpolate import interp1d
+    import planner_numpy
+    from test_shims_host import Rival
+    g = np.load(os.path.join(GOLD, "planner_prep_golden.npz"))
+    fg = np.load(os.path.join(GOLD, "frenet_golden.npz"))
+    c = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith("case1/")}
+    opt, lap = g["opt_traj"], float(fg["goggle/lap_length"])
+    nv, ins = int(c["num_veh"]), c["insertion"].tolist()
+    names = ["car%d" % (i + 1) for i in range(nv)]
+    opt6 = np.zeros((opt.shape[0], 6))
+    opt6[:, 4:6] = opt
+    param = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 5.0, 0, 50.0]),
+                                  matrix_R=np.diag([0.1, 0.1]), num_horizon_ctrl=10)
+    sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+
+    def planner():
+        veh = {"ego": types.SimpleNamespace(param=types.SimpleNamespace(length=0.4, width=0.2), xcurv=c["ego_x"].copy())}
+        for i, n in enumerate(names):
+            o = c["obs"][ins[i]]
+            veh[n] = Rival(o[0, 0], c["rival_vx"][ins[i]], o[1, 0])
+            veh[n].no_dynamics = True
+        rg = types.SimpleNamespace(num_horizon_planner=10, matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, timestep=0.1,
+                                   planning_prediction_factor=0.5)
+        track = types.SimpleNamespace(width=1.0, lap_length=lap, point_and_tangent=fg["goggle/pat"])
+        return types.SimpleNamespace(vehicles=veh, agent_name="ego", track=track, opti_traj_xcurv=opt6, racing_game_param=rg,
+                                     old_direction_flag=None)
+    p1, p2, p3 = planner(), planner(), planner()
+    x = c["ego_x"].copy()
+    (t1, f1, _, s1), (u1, x1) = planning.plan_and_track_from_predictions(p1, x, 0.0, {n: p1.vehicles[n] for n in names}, x, param,
+                                                                         p1.track, sysp)
+    order = planning.sort_rivals([p2.vehicles[n].xcurv[5] for n in names])
+    p2.sorted_vehicles = [names[i] for i in order]
+    p2.obs_infos = {n: p2.vehicles[n].get_trajectory_nsteps(0.0, 0.1, 11)[0] for n in names}
+    obs_sorted = np.array([p2.obs_infos[n][4:6] for n in p2.sorted_vehicles])
+    r = planner_numpy.prepare(x, x, obs_sorted, [p2.sorted_vehicles.index(n) for n in names],
+                              [p2.vehicles[n].xcurv[0] for n in p2.sorted_vehicles], 0.5, 1.0, lap, 0.2, opt, 10)
+    p2.bezier_xcurvs, p2.xcurv_ego = r["bezier"], x
+    p2.bezier_funcs = [interp1d(r["bezier"][i, :, 0], r["bezier"][i, :, 1]) for i in range(nv + 1)]
+    (t2, f2, _, s2), (u2, x2) = planning.plan_and_track(p2, x, param, p2.track, sysp, time=None)
+    assert f1 == f2 and np.abs(p1.selection_costs - p2.selection_costs).max() < 1e-9
+    assert np.abs(t1 - t2).max() < 1e-8 and np.abs(s1 - s2).max() < 1e-8 and np.abs(u1 - u2).max() < 1e-7 and np.abs(x1 - x2).max() < 1e-7
+    assert p1.tracking_status == 0 and np.abs(p1.bezier_xcurvs - r["bezier"]).max() < 1e-12
+    out = planning.get_local_traj(p3, x, 0.0, {n: p3.vehicles[n] for n in names}, None, None, None, None, None)
+    assert len(out) == 8 and out[2] == f1 and np.abs(out[0] - t1).max() < 1e-12
+    import frenet_numpy
+    for j in range(11):
+        gx, gy, _ = frenet_numpy.curv_to_glob(lap, fg["goggle/pat"], t1[j, 4], t1[j, 5])
+        assert abs(out[1][j, 4] - gx) < 1e-12 and abs(out[1][j, 5] - gy) < 1e-12
+
+
+def test_small_kernels_through_the_product_api(emu):
+    """rival_rollout_kernel, curv_to_glob_kernel, planner_prepare_kernel, plant_kernel through their batch functions against
+    the reference goldens."""
+    g = np.load(os.path.join(GOLD, "rollout_golden.npz"))
+    oc, og = crb.rival_rollout_batch(g["l_shape/n21/xcurv0"], g["l_shape/n21/xglob0"], g["l_shape/pat"], float(g["l_shape/lap_length"]),
+                                     0.1, 21, with_glob=True)
+    assert np.abs(oc - g["l_shape/n21/xcurv"]).max() < 1e-12 and np.abs(og - g["l_shape/n21/xglob"]).max() < 1e-12
+    f = np.load(os.path.join(GOLD, "frenet_golden.npz"))
+    x, y, psi = crb.curv_to_glob_batch(f["m_shape/s"], f["m_shape/ey"], f["m_shape/pat"], float(f["m_shape/lap_length"]))
+    assert np.abs(x - f["m_shape/xy"][:, 0]).max() < 1e-12 and np.abs(y - f["m_shape/xy"][:, 1]).max() < 1e-12
+    assert np.abs(psi - f["m_shape/psi"]).max() < 1e-12
+    pg = np.load(os.path.join(GOLD, "planner_prep_golden.npz"))
+    k = lambda n: pg["case9/" + n]     # noqa: E731  (4 rivals)
+    r = planning.prepare_candidates(k("ego_x"), k("ego_x"), k("obs"), k("insertion"), k("rival_vx"), pg["opt_traj"], 10,
+                                    lap_length=float(pg["lap_length"]))
+    assert np.abs(r["ctrl"] - k("ctrl")).max() < 1e-12 and np.abs(r["bezier"] - k("bezier_xcurvs")).max() < 1e-12
+    pl = np.load(os.path.join(GOLD, "plant_golden.npz"))
+    nc, ng = crb.plant_step_batch(pl["xcurv_ellipse"][:, 0], pl["xglob_ellipse"][:, 0], pl["u_ellipse"][:, 0], pl["draws_ellipse"][:, 0],
+                                  pl["pat_ellipse"], dyn=tuple(pl["dyn"]))
+    assert np.abs(nc - pl["xcurv_ellipse"][:, 1]).max() < 1e-12 and np.abs(ng - pl["xglob_ellipse"][:, 1]).max() < 1e-12
