@@ -1,6 +1,7 @@
-"""Driver of tools/tsan_kernels.sh: runs the host-emulated kernels (built with -fsanitize=thread into $B200MPC_EMU_LIBDIR)
-on a few instances each and prints one line per kernel; ThreadSanitizer's own reports go to stderr."""
-import ctypes as C
+"""Driver of tools/tsan_kernels.sh: builds the host-compiled C-ABI library with -fsanitize=thread (B200MPC_EMU_TSAN=1), points
+car_racing_b200._capi at it and runs every kernel on a few instances through the product's batch API; ThreadSanitizer's
+reports go to stderr.  Test infrastructure: never used by the product."""
+import importlib.util
 import os
 import sys
 import time
@@ -10,26 +11,63 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-LIBDIR = os.environ.get("B200MPC_EMU_LIBDIR", os.path.join(ROOT, "tests", "host_emulation", "_build"))
+GOLD = os.path.join(ROOT, "tests", "golden")
 
 
 def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-    from car_racing_b200 import scenarios
-    import test_hot_kernel_on_host as hk
-    L = C.CDLL(os.path.join(LIBDIR, "libocp_ipm_emu.so"))
-    L.emu_cbf_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
-    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=20, M=3, seed=0)
-    prm = scenarios.default_cbf_params(N=20)
-    t = time.time()
-    r = hk._solve(L, x0, xt, obs, lap_off, prm, specialised=1)
-    print("kernel ocp_ipm_kernel<3,0,20>: %d instances, iterations %s, status %s, %.1f s" % (B, r["iters"].tolist(), r["status"].tolist(),
-                                                                                              time.time() - t), flush=True)
-    for name, fn in (("ilqr", "run_ilqr"), ("lmpc", "run_lmpc"), ("sysid", "run_sysid")):
-        path = os.path.join(LIBDIR, "lib%s_emu.so" % name)
-        if os.path.exists(path):
-            import test_warp_kernels_on_host as wk
-            print(getattr(wk, fn)(C.CDLL(path), B), flush=True)
+    spec = importlib.util.spec_from_file_location("build_emu_library", os.path.join(ROOT, "tests", "host_emulation", "build_emu_library.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.LIB = os.path.join(mod.OUT, "libb200mpc_emu_tsan.so")
+    path = mod.build(force=True)
+    import car_racing_b200 as crb
+    from car_racing_b200 import _capi, batch, planning, scenarios
+    _capi.LIB_PATH, _capi._lib, batch._default_handle = path, None, None
+
+    def report(name, fn):
+        t = time.time()
+        info = fn()
+        print("kernel %s: %s, %.1f s" % (name, info, time.time() - t), flush=True)
+
+    def cbf():
+        x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(2, N=20, M=3, seed=0)
+        r = crb.solve_cbf_batch(x0, xt, obs, lap_off, scenarios.default_cbf_params(N=20))
+        return "2 instances, iterations %s, status %s" % (r["iters"].tolist(), r["status"].tolist())
+
+    def ilqr():
+        p = scenarios.default_cbf_params()
+        x0, xt, obs, lap_off = scenarios.ilqr_scenarios(2, N=50, seed=2)
+        r = crb.solve_ilqr_batch(x0, xt, obs, lap_off, dict(A=p["A"], B=p["B"], Q=p["Q"], R=p["R"], N=50, max_iter=150, L=0.4, W=0.2))
+        return "2 instances, iterations %s" % r["iters"].tolist()
+
+    def lmpc():
+        r = crb.solve_lmpc_batch(*scenarios.lmpc_scenarios(1, seed=5), scenarios.default_lmpc_params())
+        return "1 instance (128 threads), iterations %s, status %s" % (r["iters"].tolist(), r["status"].tolist())
+
+    def sysid():
+        g = np.load(os.path.join(GOLD, "sysid_golden.npz"))
+        r = crb.estimate_abc_batch(g["lin_points"][:1], g["lin_input"][:1], g["ss"], g["us"], g["time_ss"], [0, 1], g["point_and_tangent"],
+                                   float(g["dt"]), int(g["max_num_point"]))
+        return "1 instance x 12 stages, status %s" % r["status"].tolist()
+
+    def planner():
+        from planner_cases import make_planner
+        from test_shims_host import Rival
+        import types
+        p = make_planner(7, num_veh=2)
+        for name in p.sorted_vehicles:
+            tr = p.obs_infos[name]
+            p.vehicles[name] = Rival(tr[4, 0], tr[0, 0], tr[5, 0])
+        prm = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.diag([10.0, 0, 0, 5.0, 0, 50.0]),
+                                    matrix_R=np.diag([0.1, 0.1]), num_horizon_ctrl=10)
+        sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
+        x = np.asarray(p.vehicles["ego"].xcurv, float).copy()
+        (_, flag, _, _), _ = planning.plan_and_track(p, x, prm, p.track, sysp, time=None)
+        return "3 candidates + selection + tracking solve, region %d, tracking status %d" % (flag, p.tracking_status)
+
+    for name, fn in (("ocp_ipm_kernel<3,0,20>", cbf), ("ilqr_kernel", ilqr), ("lmpc_kernel", lmpc), ("sysid_kernel", sysid),
+                     ("ocp_ipm_kernel<0,3,0> + planner_select_kernel + ocp_ipm_kernel<M,0,0>", planner)):
+        report(name, fn)
     print("summary: done")
 
 
