@@ -12,7 +12,7 @@ extern "C" void emu_planner_select(const b200mpc_planner_select_params *prm, int
     b200mpc::SelectKParams kp;
     kp.p = *prm;
     kp.track_xt_off = track_xt_off;
-    emu_launch(1, b200mpc::SELECT_NT, [&]() {
+    emu_launch(1, b200mpc::SELECT_NT, 0, [&]() {
         b200mpc::planner_select_kernel(kp, rec, xpred, heur, ok0, region, rivals, sel_cost, flag, traj, track_rec);
     });
 }
@@ -25,5 +25,5 @@ extern "C" void emu_plant_step(const b200mpc_plant_params *prm, int B, double *x
     kp.B = B;
     kp.xcurv_stride = xcurv_stride;
     kp.xcurv_offset = xcurv_offset;
-    emu_launch((B + 127) / 128, 128, [&]() { b200mpc::plant_kernel(kp, xcurv, xglob, u, u_stride, draws, segments, laps); });
+    emu_launch((B + 127) / 128, 128, 0, [&]() { b200mpc::plant_kernel(kp, xcurv, xglob, u, u_stride, draws, segments, laps); });
 }

@@ -4,7 +4,7 @@ so that the product's own Python API can be exercised end to end on a machine wi
 thread per CUDA thread, "device" memory is host memory.
 
 The sources are used as they are, except for two mechanical substitutions made on copies under _build/src/:
-  * `kernel<<<grid, block, smem, stream>>>(args);`            ->  `emu_launch(grid, block, [&]() { kernel(args); });`
+  * `kernel<<<grid, block, smem, stream>>>(args);`            ->  `emu_launch(grid, block, smem, [&]() { kernel(args); });`
   * `extern __shared__ __align__(16) double sm[];`            ->  `double *sm = emu_dynamic_smem;`
 Nothing on the product path knows about this library: only tests load it (by pointing car_racing_b200._capi at it inside a
 fixture).  It is a checker of the kernels' logic, not a fallback."""
@@ -38,8 +38,9 @@ def _split_top(s):
 
 
 def _rewrite_launch(m):
-    grid, block = _split_top(m.group(2))[:2]
-    return "emu_launch(%s, %s, [&]() { %s(%s); });" % (grid, block, m.group(1), m.group(3))
+    cfg = _split_top(m.group(2))
+    grid, block, smem = cfg[0], cfg[1], (cfg[2] if len(cfg) > 2 else "0")
+    return "emu_launch(%s, %s, %s, [&]() { %s(%s); });" % (grid, block, smem, m.group(1), m.group(3))
 
 
 def transform(text):
@@ -70,6 +71,8 @@ def build(force=False):
            os.path.join(sdir, "capi.cpp"), "-o", LIB]
     if os.environ.get("B200MPC_EMU_TSAN"):
         cmd[1:1] = ["-g", "-fsanitize=thread"]
+    if os.environ.get("B200MPC_EMU_ASAN"):      # "device" buffers are malloc'ed: out-of-bounds global accesses of a kernel are caught
+        cmd[1:1] = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
     subprocess.run(cmd, check=True)
     return LIB
 

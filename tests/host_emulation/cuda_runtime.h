@@ -37,6 +37,7 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 
 #ifdef EMU_WITH_LAUNCH
 #include <barrier>
+#include <cstdlib>
 #include <functional>
 #include <thread>
 #include <vector>
@@ -96,10 +97,17 @@ static inline double __hiloint2double(int hi, int lo) { uint64_t r = ((uint64_t)
  * __shared__ variables are function-local statics (shared by the block's threads, reused by the next block) */
 static std::barrier<> *emu_block_barrier = nullptr;
 static void emu_barrier_wait() { emu_block_barrier->arrive_and_wait(); }
-static inline void emu_launch(int grid, int block, const std::function<void()> &kernel) {
+/* dynamic shared memory of the block in flight: allocated per block with exactly the launch's size (AddressSanitizer then
+ * sees out-of-bounds shared-memory accesses) and filled with 0xFF bytes = NaN doubles, so that a kernel that reads shared
+ * memory it has not written -- garbage on the GPU -- cannot pass a parity test here by luck */
+static double *emu_dynamic_smem = nullptr;
+static inline void emu_launch(int grid, int block, size_t smem_bytes, const std::function<void()> &kernel) {
     gridDim.x = grid;
     blockDim.x = block;
     for (int b = 0; b < grid; b++) {
+        const size_t bytes = (smem_bytes + 15) & ~(size_t)15;
+        emu_dynamic_smem = bytes ? (double *)aligned_alloc(16, bytes) : nullptr;
+        if (emu_dynamic_smem) memset(emu_dynamic_smem, 0xFF, bytes);
         std::barrier<> bar(block);
         emu_block_barrier = &bar;
         emu_barrier_fn = emu_barrier_wait;
@@ -116,6 +124,8 @@ static inline void emu_launch(int grid, int block, const std::function<void()> &
             });
         for (auto &th : ts) th.join();
         emu_barrier_fn = nullptr;
+        free(emu_dynamic_smem);
+        emu_dynamic_smem = nullptr;
     }
     gridDim.x = 1;
     blockDim.x = 1;
@@ -159,7 +169,6 @@ static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dpitch, const void *
     return cudaSuccess;
 }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
-/* `extern __shared__ double sm[]` of the kernels is rewritten to `double *sm = emu_dynamic_smem;` by build_emu_library.py:
- * one block in flight at a time; like real shared memory it is NOT cleared between blocks */
-alignas(16) static double emu_dynamic_smem[32768];
+/* `extern __shared__ double sm[]` of the kernels is rewritten to `double *sm = emu_dynamic_smem;` by build_emu_library.py
+ * (emu_launch above allocates it per block) */
 #endif

@@ -10,7 +10,7 @@
 #include "cuda_runtime.h"
 #include "../../include/b200mpc.h"
 namespace b200mpc {
-double sm[32768];   // the dynamic shared memory of the one block in flight (256 KB)
+alignas(16) double sm[32768];   // the dynamic shared memory of the one block in flight (256 KB), NOT cleared between blocks
 }
 #include "../../car_racing_b200/csrc/ocp_ipm.cuh"
 
@@ -37,7 +37,7 @@ static KParams make_kp(const b200mpc_cbf_params *p, const b200mpc_ipm_options *o
 template <int M, int FL, int NT>
 static void run(const KParams &kp, int B, const double *in, b200mpc_record *rec, double *aux, double *xpred, double *upred,
                 double *sigma) {
-    emu_launch(B, 32, [&]() { ocp_ipm_kernel<M, FL, NT>(kp, in, rec, aux, xpred, upred, sigma); });
+    emu_launch(B, 32, 0, [&]() { ocp_ipm_kernel<M, FL, NT>(kp, in, rec, aux, xpred, upred, sigma); });
 }
 
 // the dispatch of b200mpc_cbf_solve_device; `specialised` = 0 forces the runtime-horizon instantiation

@@ -1,4 +1,4 @@
-"""Driver of tools/tsan_kernels.sh: builds the host-compiled C-ABI library with -fsanitize=thread (B200MPC_EMU_TSAN=1), points
+"""Driver of tools/sanitize_kernels.sh: builds the host-compiled C-ABI library with -fsanitize=thread or =address (B200MPC_EMU_TSAN / _ASAN), points
 car_racing_b200._capi at it and runs every kernel on a few instances through the product's batch API; ThreadSanitizer's
 reports go to stderr.  Test infrastructure: never used by the product."""
 import importlib.util
@@ -18,7 +18,7 @@ def main():
     spec = importlib.util.spec_from_file_location("build_emu_library", os.path.join(ROOT, "tests", "host_emulation", "build_emu_library.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    mod.LIB = os.path.join(mod.OUT, "libb200mpc_emu_tsan.so")
+    mod.LIB = os.path.join(mod.OUT, "libb200mpc_emu_%s.so" % ("asan" if os.environ.get("B200MPC_EMU_ASAN") else "tsan"))
     path = mod.build(force=True)
     import car_racing_b200 as crb
     from car_racing_b200 import _capi, batch, planning, scenarios
