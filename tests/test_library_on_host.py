@@ -2,8 +2,7 @@
 (tests/host_emulation/build_emu_library.py: launches become emu_launch, "device" memory is host memory, one host thread
 per CUDA thread with barriers for __syncthreads / __syncwarp / shuffles), loaded INTO THE TESTS ONLY in place of
 libb200mpc.so, so that the product's own Python API -- packers, parameter structs, dispatch, kernels -- is exercised end
-to end without a GPU at small sizes: MPC-CBF, iLQR (against the reference's own golden outputs), LMPC, model
-identification (reference golden), the planner chain, rival rollout, frame conversion.  This is a checker of logic; the CUDA
+to end without a GPU at small sizes, including the -m gpu tests that fit (GPU_TESTS_ON_HOST below).  This is a checker of logic; the CUDA
 build of the same sources is what `-m gpu` and bench.py run, and nothing on the product path can load the emulated
 library."""
 import importlib.util
@@ -48,21 +47,6 @@ def test_mpccbf_through_the_product_api(emu, oracle):
     assert batch.default_handle().launch_count == 1
 
 
-def test_ilqr_against_the_reference_golden(emu):
-    """ilqr_kernel against vectors produced by the unmodified reference control.ilqr (a subset of the -m gpu test)."""
-    gold = np.load(os.path.join(GOLD, "ilqr_golden.npz"))
-    done = 0
-    for N in sorted(set(gold["N"].tolist())):
-        idx = np.where(gold["N"] == N)[0][:3]
-        x0, xt, obs, lap = gold["x0"][idx], gold["xt"][idx], gold["obs"][idx][:, :, :N + 1], gold["lap"][idx]
-        lap_off = (np.trunc(x0[:, 4] / lap) - np.trunc(obs[:, 0, 0] / lap)) * lap
-        prm = dict(A=gold["A"], B=gold["B"], Q=gold["Q"], R=gold["R"], N=int(N), max_iter=int(gold["max_iter"]), L=0.4, W=0.2)
-        g = crb.solve_ilqr_batch(x0, xt, obs, lap_off, prm)
-        assert np.abs(g["u0"] - gold["u0"][idx]).max() < 1e-9
-        done += len(idx)
-    assert done >= 3
-
-
 def test_lmpc_against_the_oracle(emu, oracle):
     sc = scenarios.lmpc_scenarios(2, seed=5)
     prm = scenarios.default_lmpc_params()
@@ -72,14 +56,6 @@ def test_lmpc_against_the_oracle(emu, oracle):
     ok = g["status"] == 0
     assert ok.any() and np.abs(g["u0"] - r["u0"])[ok].max() < 1e-4 and np.abs(g["cost"] - r["cost"])[ok].max() < 1e-5
     assert np.abs(g["x"][ok] - r["x"][ok]).max() < 1e-4 and np.abs(g["lambda"][ok] - r["lam"][ok]).max() < 1e-4
-
-
-def test_model_identification_against_the_reference_golden(emu):
-    g = np.load(os.path.join(GOLD, "sysid_golden.npz"))
-    r = crb.estimate_abc_batch(g["lin_points"][:1], g["lin_input"][:1], g["ss"], g["us"], g["time_ss"], [0, 1], g["point_and_tangent"],
-                               float(g["dt"]), int(g["max_num_point"]))
-    assert (r["status"] == 0).all() and (r["idx"] == g["idx"][:1]).all()
-    assert np.abs(r["A"] - g["A"][:1]).max() < 1e-8 and np.abs(r["B"] - g["B"][:1]).max() < 1e-8 and np.abs(r["C"] - g["C"][:1]).max() < 1e-8
 
 
 def test_overtaking_step_from_predictions(emu):
@@ -155,3 +131,34 @@ def test_small_kernels_through_the_product_api(emu):
     nc, ng = crb.plant_step_batch(pl["xcurv_ellipse"][:, 0], pl["xglob_ellipse"][:, 0], pl["u_ellipse"][:, 0], pl["draws_ellipse"][:, 0],
                                   pl["pat_ellipse"], dyn=tuple(pl["dyn"]))
     assert np.abs(nc - pl["xcurv_ellipse"][:, 1]).max() < 1e-12 and np.abs(ng - pl["xglob_ellipse"][:, 1]).max() < 1e-12
+
+
+GPU_TESTS_ON_HOST = [
+    ("test_gpu_parity", "test_mpc_lti_anchor_on_gpu"), ("test_gpu_parity", "test_capi_argument_validation"),
+    ("test_gpu_parity", "test_drop_in_shims_on_gpu"), ("test_gpu_parity", "test_planner_drop_in_on_gpu"),
+    ("test_gpu_parity", "test_lmpc_drop_in_on_gpu"), ("test_gpu_parity", "test_sysid_chains_into_lmpc_records_and_drop_in"),
+    ("test_gpu_parity", "test_moving_rivals_lap_offsets_per_stage_targets"), ("test_gpu_parity", "test_kkt_certificate_on_gpu_solutions"),
+    ("test_gpu_parity", "test_blocked_lane_elastic_rows"), ("test_gpu_parity", "test_plan_and_track_chain_matches_host_path"),
+    ("test_gpu_parity", "test_plan_and_track_with_64_candidates"), ("test_gpu_parity", "test_plant_step_matches_reference_golden"),
+    ("test_gpu_parity", "test_sysid_matches_reference_golden"), ("test_gpu_parity", "test_ilqr_matches_reference_golden"),
+    ("test_planner_prepare", "test_device_preparation_matches_reference_golden_and_host_packing"),
+    ("test_planner_prepare", "test_device_preparation_flags_out_of_range_lookup"),
+    ("test_planner_prepare", "test_prepared_chain_matches_host_prepared_chain"),
+    ("test_rival_rollout", "test_device_rollout_matches_reference_golden"),
+    ("test_rival_rollout", "test_device_rollout_large_batch_and_bad_arguments"),
+    ("test_frenet", "test_device_conversion_matches_reference_golden"), ("test_frenet", "test_planner_plot_copies_use_one_launch"),
+]
+
+
+@pytest.mark.parametrize("module,name", GPU_TESTS_ON_HOST)
+def test_gpu_tests_also_pass_on_the_host_library(emu, oracle, module, name):
+    """The -m gpu tests that need neither torch.cuda nor large batches, run UNCHANGED against the library on the host (the
+    others stay GPU-only: full BASELINE batches, torch device tensors, batches in flight): the SURVEY 8(c) anchor (MPC-LTI
+    N=10: u0 = [0.0033384, 1.0], cost 22.71576162), C-ABI argument validation, the reference-signature shims, moving rivals
+    with lap offsets, the KKT certificate, the blocked lane, the fused overtaking step (incl. 64 candidates), the reference
+    goldens of iLQR / model identification / plant / rollout / frame conversion / candidate preparation."""
+    import importlib
+    import inspect
+    fn = getattr(importlib.import_module(module), name)
+    args = {"crb": crb, "oracle": oracle}
+    fn(**{k: args[k] for k in inspect.signature(fn).parameters})
