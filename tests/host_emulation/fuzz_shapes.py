@@ -1,9 +1,9 @@
-"""Shape sweep of the C-ABI under AddressSanitizer on the host-compiled library (tools/sanitize_kernels.sh builds it the same
+"""Shape sweep of the C-ABI under AddressSanitizer on the host-compiled library (tests/host_emulation/sanitize_kernels.sh builds it the same
 way): every (N, M, per-stage target) combination at the corners of the supported ranges, odd batches, the iLQR and LMPC
 size limits.  Out-of-bounds shared / global accesses of a kernel show up as AddressSanitizer errors; the solves must also
 agree with the oracle where both converge.  Test infrastructure: never used by the product.
 
-    ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 LD_PRELOAD=$(g++ -print-file-name=libasan.so) B200MPC_EMU_ASAN=1 python tools/fuzz_shapes.py
+    ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 LD_PRELOAD=$(g++ -print-file-name=libasan.so) B200MPC_EMU_ASAN=1 python tests/host_emulation/fuzz_shapes.py
 """
 import importlib.util
 import os
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -1,4 +1,4 @@
-"""Driver of tools/sanitize_kernels.sh: builds the host-compiled C-ABI library with -fsanitize=thread or =address (B200MPC_EMU_TSAN / _ASAN), points
+"""Driver of tests/host_emulation/sanitize_kernels.sh: builds the host-compiled C-ABI library with -fsanitize=thread or =address (B200MPC_EMU_TSAN / _ASAN), points
 car_racing_b200._capi at it and runs every kernel on a few instances through the product's batch API; ThreadSanitizer's
 reports go to stderr.  Test infrastructure: never used by the product."""
 import importlib.util
@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 GOLD = os.path.join(ROOT, "tests", "golden")

@@ -7,17 +7,17 @@
 #  * AddressSanitizer: "device" buffers are malloc'ed and the dynamic shared memory of each block is allocated with exactly
 #    the launch's size, so out-of-bounds global and shared accesses are caught; shared memory starts as NaN bytes, so a read
 #    of unwritten shared memory cannot go unnoticed in the results.
-# Usage: tools/sanitize_kernels.sh            (writes profiles/sanitize_kernels.txt)
+# Usage: tests/host_emulation/sanitize_kernels.sh            (writes profiles/sanitize_kernels.txt)
 set -e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=/tmp/b200mpc_tsan_log.txt
 A=/tmp/b200mpc_asan_log.txt
 TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=2" LD_PRELOAD=$(g++ -print-file-name=libtsan.so) \
-  B200MPC_EMU_TSAN=1 python tools/sanitize_kernels.py > $T 2>&1 || true
+  B200MPC_EMU_TSAN=1 python tests/host_emulation/sanitize_kernels.py > $T 2>&1 || true
 ASAN_OPTIONS="detect_leaks=0:halt_on_error=0" LD_PRELOAD=$(g++ -print-file-name=libasan.so) \
-  B200MPC_EMU_ASAN=1 python tools/sanitize_kernels.py > $A 2>&1 || true
+  B200MPC_EMU_ASAN=1 python tests/host_emulation/sanitize_kernels.py > $A 2>&1 || true
 {
-  echo "tools/sanitize_kernels.sh  ($(date -u +%Y-%m-%d)): libb200mpc_emu.so = capi.cu + every kernel header compiled by g++, one host thread per CUDA thread"
+  echo "tests/host_emulation/sanitize_kernels.sh  ($(date -u +%Y-%m-%d)): libb200mpc_emu.so = capi.cu + every kernel header compiled by g++, one host thread per CUDA thread"
   echo "--- -fsanitize=thread"
   grep -E "^kernel|^summary" $T
   echo "ThreadSanitizer data-race reports: $(grep -c 'WARNING: ThreadSanitizer: data race' $T || true)"
