@@ -362,7 +362,9 @@ def main():
         "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(rec_host.nbytes),
                 "d2h_bytes_per_step": int(B * 32), "ms_per_step": 1e3 * t_e2e / args.steps,
                 "batches_in_flight": D, "p50_latency_ms_batch1": float(np.median(lat)), "p10_p90_latency_ms_batch1": [float(np.percentile(lat, 10)), float(np.percentile(lat, 90))],
-                "p50_latency_ms_one_batch": float(np.median(lat_b))},
+                "p50_latency_ms_one_batch": float(np.median(lat_b)),
+                "note": ("per rank: host records -> H2D -> solve -> D2H -> host read; the cross-rank exchange step (all-gather + argmin) is part of "
+                         "`value` only") if world > 1 else "host records -> H2D -> solve -> D2H -> host read"},
         "one_batch_at_a_time": {"value": B * world / (kernel_ms * 1e-3), "unit": "solves/s", "ms_per_step": kernel_ms,
                                 "note": "the same kernel, steps serialised on one stream (per-step CUDA events); its launch duration is the roofline's"},
         "gpu_launches": int(launches_dev),
