@@ -53,6 +53,8 @@ def build(force=False):
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
     deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, "cuda_runtime.h"), os.path.join(ROOT, "include", "b200mpc.h"),
                                                     os.path.abspath(__file__)]
+    if os.environ.get("B200MPC_EMU_CXXFLAGS"):
+        force = True                                                # variants are never served from the cache
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     sdir = os.path.join(OUT, "src", "car_racing_b200", "csrc")
@@ -69,6 +71,9 @@ def build(force=False):
     cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
            "-DB200MPC_HOST_EMULATION", "-DEMU_WITH_LAUNCH", "-DEMU_WARPS", "-DEMU_RUNTIME_API", "-I", HERE,
            os.path.join(sdir, "capi.cpp"), "-o", LIB]
+    extra = os.environ.get("B200MPC_EMU_CXXFLAGS", "").split()     # e.g. the -D flags of a kernel variant (tools/variants.sh)
+    if extra:
+        cmd[-2:-2] = extra
     if os.environ.get("B200MPC_EMU_TSAN"):
         cmd[1:1] = ["-g", "-fsanitize=thread"]
     if os.environ.get("B200MPC_EMU_ASAN"):      # "device" buffers are malloc'ed: out-of-bounds global accesses of a kernel are caught
