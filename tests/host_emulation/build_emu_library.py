@@ -53,10 +53,11 @@ def build(force=False):
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
     deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, "cuda_runtime.h"), os.path.join(ROOT, "include", "b200mpc.h"),
                                                     os.path.abspath(__file__)]
-    if os.environ.get("B200MPC_EMU_CXXFLAGS"):
-        force = True                                                # variants are never served from the cache
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
-        return LIB
+    lib = LIB
+    if os.environ.get("B200MPC_EMU_CXXFLAGS"):                      # a variant: its own file, never served from the cache
+        lib, force = LIB[:-3] + "_variant.so", True
+    if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
+        return lib
     sdir = os.path.join(OUT, "src", "car_racing_b200", "csrc")
     os.makedirs(sdir, exist_ok=True)
     os.makedirs(os.path.join(OUT, "src", "include"), exist_ok=True)
@@ -70,7 +71,7 @@ def build(force=False):
     assert launches >= 10 and smem >= 4, (launches, smem)
     cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
            "-DB200MPC_HOST_EMULATION", "-DEMU_WITH_LAUNCH", "-DEMU_WARPS", "-DEMU_RUNTIME_API", "-I", HERE,
-           os.path.join(sdir, "capi.cpp"), "-o", LIB]
+           os.path.join(sdir, "capi.cpp"), "-o", lib]
     extra = os.environ.get("B200MPC_EMU_CXXFLAGS", "").split()     # e.g. the -D flags of a kernel variant (tools/variants.sh)
     if extra:
         cmd[-2:-2] = extra
@@ -79,7 +80,7 @@ def build(force=False):
     if os.environ.get("B200MPC_EMU_ASAN"):      # "device" buffers are malloc'ed: out-of-bounds global accesses of a kernel are caught
         cmd[1:1] = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
