@@ -79,7 +79,10 @@ def build(force=False):
         cmd[1:1] = ["-g", "-fsanitize=thread"]
     if os.environ.get("B200MPC_EMU_ASAN"):      # "device" buffers are malloc'ed: out-of-bounds global accesses of a kernel are caught
         cmd[1:1] = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
+    tmp = lib + ".tmp%d" % os.getpid()                              # atomic: a concurrent reader never sees a half-written library
+    cmd[cmd.index("-o") + 1] = tmp
     subprocess.run(cmd, check=True)
+    os.replace(tmp, lib)
     return lib
 
 

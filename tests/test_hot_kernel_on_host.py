@@ -20,13 +20,8 @@ pytestmark = pytest.mark.timeout(600)
 
 
 def _lib():
-    lib = os.path.join(EMU, "_build", "libocp_ipm_emu.so")
-    src = [os.path.join(EMU, "ocp_ipm_host.cpp"), os.path.join(EMU, "cuda_runtime.h"),
-           os.path.join(HERE, "..", "car_racing_b200", "csrc", "ocp_ipm.cuh"), os.path.join(HERE, "..", "include", "b200mpc.h")]
-    if not os.path.exists(lib) or any(os.path.getmtime(f) > os.path.getmtime(lib) for f in src):
-        os.makedirs(os.path.dirname(lib), exist_ok=True)
-        subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
-                        "-I", EMU, src[0], "-o", lib], check=True)
+    from conftest import wait_prebuilt          # g++ -std=c++20 -O1 -ffp-contract=off -pthread on ocp_ipm_host.cpp (tests/conftest.py)
+    lib = wait_prebuilt("ocp_ipm_emu")
     L = C.CDLL(lib)
     L.emu_cbf_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
     return L

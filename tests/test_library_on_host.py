@@ -22,10 +22,8 @@ pytestmark = pytest.mark.timeout(900)
 
 @pytest.fixture(scope="module")
 def emu():
-    spec = importlib.util.spec_from_file_location("build_emu_library", os.path.join(HERE, "host_emulation", "build_emu_library.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    path = mod.build()
+    from conftest import wait_prebuilt          # tests/host_emulation/build_emu_library.py, started in the background at session start
+    path = wait_prebuilt("b200mpc_emu")
     saved = (_capi.LIB_PATH, _capi._lib, batch._default_handle)
     _capi.LIB_PATH, _capi._lib, batch._default_handle = path, None, None
     try:
