@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--lib", choices=["emu", "product", "auto"], default="auto")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--track-layout", default="l_shape", help="data/track_layout/<name>.csv of the reference (the test scripts' --track-layout)")
     ap.add_argument("--only-ilqr", action="store_true", help="stop after the reference-vs-drop-in iLQR closed loop")
     ap.add_argument("--racing-game", action="store_true", help="only the LMPC + overtaking scenario")
     ap.add_argument("--lmpc-steps", type=int, default=30)
@@ -236,9 +237,9 @@ def main():
         _capi.LIB_PATH, _capi._lib, batch._default_handle = mod.build(), None, None
     control, offboard, base, racing_env = import_reference()
     native = {n: getattr(control, n) for n in ("ilqr", "mpccbf", "mpc_lti", "mpc_multi_agents", "lmpc")}
-    out = {"library": lib, "steps": args.steps, "seed": args.seed, "scenarios": {}}
+    out = {"library": lib, "steps": args.steps, "seed": args.seed, "track_layout": args.track_layout, "scenarios": {}}
     if args.racing_game:
-        r = racing_game(crb, control, offboard, base, racing_env, args.lmpc_steps, args.overtake_steps, args.seed)
+        r = racing_game(crb, control, offboard, base, racing_env, args.lmpc_steps, args.overtake_steps, args.seed, args.track_layout)
         out["scenarios"]["racing_game"] = r
         print("[racing_game]", json.dumps(r), flush=True)
         if args.out:
@@ -248,13 +249,13 @@ def main():
 
     # --- iLQR: unmodified reference vs drop-in, same closed loop (car_racing/tests/ilqr_test.py) -------------------------
     rivals = [(4.0, 0.2, 0.1)]
-    sim, ego, track = build_sim(offboard, base, racing_env, "ilqr", rivals)
+    sim, ego, track = build_sim(offboard, base, racing_env, "ilqr", rivals, args.track_layout)
     xr, ur, tr = run(sim, ego, args.steps, args.seed)
     crb.install(control)
-    sim, ego, track = build_sim(offboard, base, racing_env, "ilqr", rivals)
+    sim, ego, track = build_sim(offboard, base, racing_env, "ilqr", rivals, args.track_layout)
     xg, ug, tg = run(sim, ego, args.steps, args.seed)
     out["scenarios"]["ilqr_test"] = {
-        "what": "car_racing/tests/ilqr_test.py, l_shape, 1 rival; reference control.ilqr (numpy) vs car_racing_b200.install()",
+        "what": "car_racing/tests/ilqr_test.py, 1 rival; reference control.ilqr (numpy) vs car_racing_b200.install()",
         "max_abs_dx": float(np.abs(xr - xg).max()), "max_abs_du": float(np.abs(ur - ug).max()),
         "s_final_reference": float(xr[-1, 4]), "s_final_dropin": float(xg[-1, 4]),
         "wall_s_reference": tr, "wall_s_dropin": tg}
@@ -277,11 +278,11 @@ def main():
         return u
     control.mpccbf = mpccbf_logged
     rivals = [(4.0, 0.2, 0.1), (10.0, 0.2, -0.1)]
-    sim, ego, track = build_sim(offboard, base, racing_env, "mpccbf", rivals)
+    sim, ego, track = build_sim(offboard, base, racing_env, "mpccbf", rivals, args.track_layout)
     xg, ug, tg = run(sim, ego, args.steps, args.seed)
     st = np.array(statuses)
     out["scenarios"]["mpccbf_test"] = {
-        "what": "car_racing/tests/mpccbf_test.py, l_shape, 2 rivals; car_racing_b200.install() only (no CasADi here)",
+        "what": "car_racing/tests/mpccbf_test.py, 2 rivals; car_racing_b200.install() only (no CasADi here)",
         "s_final": float(xg[-1, 4]), "laps": int(ego.laps), "min_barrier_h": barrier(xg, rivals, track.lap_length),
         "max_abs_ey": float(np.abs(xg[:, 5]).max()), "track_half_width": float(track.width),
         "steps_converged": int((st[:, 0] == 0).sum()), "steps_total": int(len(st)), "iters_mean": float(st[:, 1].mean()),
@@ -292,10 +293,10 @@ def main():
         st[:, 1].mean(), st[:, 1].max()), flush=True)
     control.mpccbf = shim
 
-    sim, ego, track = build_sim(offboard, base, racing_env, "mpc_lti", [])
+    sim, ego, track = build_sim(offboard, base, racing_env, "mpc_lti", [], args.track_layout)
     xg, ug, tg = run(sim, ego, args.steps, args.seed)
     out["scenarios"]["control_test_mpc_lti"] = {
-        "what": "car_racing/tests/control_test.py --ctrl-policy mpc-lti, l_shape, no rivals; drop-in only (raises if a solve does not converge)",
+        "what": "car_racing/tests/control_test.py --ctrl-policy mpc-lti, no rivals; drop-in only (raises if a solve does not converge)",
         "s_final": float(xg[-1, 4]), "vx_final": float(xg[-1, 0]), "max_abs_ey": float(np.abs(xg[:, 5]).max()), "wall_s_dropin": tg}
     print("[control_test mpc-lti] %d steps: s_final %.3f vx_final %.3f max|ey| %.3f" % (args.steps, xg[-1, 4], xg[-1, 0], np.abs(xg[:, 5]).max()), flush=True)
     for n, f in native.items():
