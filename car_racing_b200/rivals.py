@@ -11,22 +11,21 @@ car_racing/racing/offboard.py:80-94: a zero-input Frenet rollout) are predicted 
 import numpy as np
 
 X_DIM = 6
-_CACHE_ATTR = "_b200_traj_fn"
+_COMPILED = {}      # (t, s(t), ey(t)) -> compiled functions.  Kept here, NOT on the rival: the reference pickles the simulator with its vehicles
+                    # after every run (car_racing/tests/mpccbf_test.py:45-46, tests/auto_mpccbf_test.py:42-43) and lambdified functions do not pickle
 
 
 def _compiled(model):
     import sympy as sp
-    key = (id(model.s_func), id(model.ey_func), id(model.t_symbol))
-    hit = getattr(model, _CACHE_ATTR, None)
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    t = model.t_symbol
-    exprs = [sp.diff(model.s_func, t), sp.diff(model.ey_func, t), model.s_func, model.ey_func]
-    fns = [sp.lambdify(t, e, "numpy") for e in exprs]
-    try:
-        setattr(model, _CACHE_ATTR, (key, fns))
-    except Exception:
-        pass
+    key = (model.t_symbol, model.s_func, model.ey_func)          # sympy expressions hash and compare structurally
+    fns = _COMPILED.get(key)
+    if fns is None:
+        t = model.t_symbol
+        exprs = [sp.diff(model.s_func, t), sp.diff(model.ey_func, t), model.s_func, model.ey_func]
+        fns = [sp.lambdify(t, e, "numpy") for e in exprs]
+        if len(_COMPILED) >= 256:
+            _COMPILED.clear()
+        _COMPILED[key] = fns
     return fns
 
 

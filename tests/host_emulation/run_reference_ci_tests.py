@@ -15,12 +15,14 @@ Build container only (needs /root/reference).  TEST INFRASTRUCTURE: without a GP
     python tests/host_emulation/run_reference_ci_tests.py --tests test_tracking test_racing test_racing_overtake --out profiles/r04b_reference_ci_tests.json
 """
 import argparse
+import builtins
 import contextlib
 import importlib.util
 import io
 import json
 import os
 import sys
+import tempfile
 import time
 
 import numpy as np
@@ -73,15 +75,29 @@ def main():
         sims.append(self)
     offboard.CarRacingSim.__init__ = recording_init
     out = {"library": lib, "tests": {}}
+    real_open = builtins.open
+    scratch_dir = tempfile.mkdtemp(prefix="b200mpc_ref_ci_")
     for test in args.tests:
         spec = importlib.util.spec_from_file_location("ref_" + test, os.path.join(dropin_sim.REF, "tests", FILES[test]))
         module = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(module)
         del sims[:]
         buf = io.StringIO()
+        written = {}
+
+        def guarded_open(file, mode="r", *a, **k):          # the tests pickle the simulator into data/simulator/ of the reference checkout, which
+            if isinstance(file, str) and any(c in mode for c in "wax+") and (not os.path.isabs(file) or file.startswith(dropin_sim.REF)):
+                dst = os.path.join(scratch_dir, os.path.basename(file))               # must stay untouched: written to a scratch directory instead
+                written[file] = dst
+                return real_open(dst, mode, *a, **k)
+            return real_open(file, mode, *a, **k)
+        builtins.open = guarded_open
         t0 = time.time()
-        with contextlib.redirect_stdout(buf):
-            getattr(module, test)()                                                   # the reference's test function, as it is
+        try:
+            with contextlib.redirect_stdout(buf):
+                getattr(module, test)()                                               # the reference's test function, as it is
+        finally:
+            builtins.open = real_open
         wall = time.time() - t0
         sim = sims[-1]
         ego = sim.vehicles["ego"]
@@ -90,7 +106,8 @@ def main():
         r = {"file": "tests/" + FILES[test], "passed": True, "wall_s": wall, "ego_laps": int(ego.laps), "ego_time_s": float(ego.time),
              "ego_s_final": float(ego.xcurv[4]), "ego_vx_final": float(ego.xcurv[0]), "ego_ey_final": float(ego.xcurv[5]),
              "lap_times_printed_by_the_test": [ln for ln in text.splitlines() if ln.startswith("lap time")],
-             "non_convergence_messages": text.count("solver fail")}
+             "non_convergence_messages": text.count("solver fail"),
+             "files_the_test_pickled": {k: os.path.getsize(v) for k, v in written.items()}}
         ego_log = [x for lp in ego.xcurvs for x in lp] + list(ego.lap_xcurvs)            # completed laps + the lap in progress (base.py:76-93)
         r["max_abs_ey"] = float(max(abs(x[5]) for x in ego_log)) if ego_log else None
         r["track_half_width"] = float(sim.track.width)

@@ -44,3 +44,17 @@ def test_with_glob_uses_the_track_object():
     m = types.SimpleNamespace(t_symbol=t, s_func=cases[0][0], ey_func=cases[0][1], time=0.5, track=trk)
     xc, xg = rivals.get_trajectory_nsteps(m, 0, 0.1, 5, with_glob=True)
     assert np.allclose(xg[4], 2.0 * xc[4]) and np.allclose(xg[5], xc[5]) and np.allclose(xg[3], 0.25) and np.allclose(xg[0], xc[0])
+
+
+def test_rival_still_pickles_after_a_prediction():
+    """The reference pickles the simulator with its vehicles after a run (car_racing/tests/mpccbf_test.py:45-46): the drop-in
+    must not leave compiled functions on the rival."""
+    import pickle
+    from car_racing_b200 import rivals
+    t, cases = _cases()
+    m = types.SimpleNamespace(t_symbol=t, s_func=cases[1][0], ey_func=cases[1][1], time=0.3)
+    before = set(vars(m))
+    xc, _ = rivals.get_trajectory_nsteps(m, 0, 0.1, 11)
+    assert set(vars(m)) == before
+    m2 = pickle.loads(pickle.dumps(m))
+    assert np.array_equal(rivals.get_trajectory_nsteps(m2, 0, 0.1, 11)[0], xc)
