@@ -35,13 +35,16 @@ FILES = {"test_tracking": "auto_control_test.py", "test_racing": "auto_mpccbf_te
 
 
 def _clearance(ego_log, car_log, lap):
-    """Smallest box distance max(|ds| - length, |dey| - width) over the steps both vehicles logged (0.4 x 0.2 cars, base.py:700)."""
+    """Over the steps both vehicles logged (0.4 x 0.2 cars, base.py:700): the smallest box distance max(|ds| - length, |dey| - width), and the
+    smallest value of the reference's own degree-6 shape (ds / 0.4)^6 + (dey / 0.2)^6 - 1 (control.py:527-557 without margin and slack; >= 0 = no contact
+    in the reference's sense -- the shape's corners are rounded, so it can be positive where the box distance is slightly negative)."""
     n = min(len(ego_log), len(car_log))
-    best = np.inf
+    box, shape = np.inf, np.inf
     for a, b in zip(ego_log[-n:], car_log[-n:]):
         ds = (a[4] - b[4] + lap / 2) % lap - lap / 2
-        best = min(best, max(abs(ds) - 0.4, abs(a[5] - b[5]) - 0.2))
-    return float(best)
+        box = min(box, max(abs(ds) - 0.4, abs(a[5] - b[5]) - 0.2))
+        shape = min(shape, (ds / 0.4) ** 6 + ((a[5] - b[5]) / 0.2) ** 6 - 1.0)
+    return float(box), float(shape)
 
 
 def main():
@@ -117,7 +120,10 @@ def main():
                 continue
             ds = float((ego.xcurv[4] - car.xcurv[4] + lap / 2) % lap - lap / 2)      # position on the track relative to the rival (> 0: ahead)
             car_log = [x for lp in car.xcurvs for x in lp] + list(car.lap_xcurvs)
-            rivals[name] = {"ego_ahead_of_rival_at_end_m": ds, "min_clearance_m": _clearance(ego_log, car_log, lap) if car_log else None}
+            rivals[name] = {"ego_ahead_of_rival_on_track_at_end_m": ds,
+                            "ego_total_s_minus_rival_total_s_at_end_m": float(ego.xcurv[4] + ego.laps * lap - car.xcurv[4]),   # rivals' s is not lap-wrapped
+ "min_box_clearance_m": _clearance(ego_log, car_log, lap)[0] if car_log else None,
+                            "min_degree6_shape_minus_1": _clearance(ego_log, car_log, lap)[1] if car_log else None}
         r["rivals"] = rivals
         out["tests"][test] = r
         print("[%s] ran to the end in %.0f s: laps %d, ego s %.2f vx %.2f, max|ey| %s, rivals %s, non-convergence messages %d" % (
