@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mpc.so")
-NMAX, MMAX = 64, 4
+NMAX, MMAX = 64, 8
 
 
 class CbfParams(C.Structure):
@@ -29,7 +29,13 @@ class IpmOptions(C.Structure):
         ("tol", C.c_double), ("max_iter", C.c_int32), ("acceptable_iter", C.c_int32),
         ("acceptable_tol", C.c_double), ("mu_init", C.c_double), ("rho", C.c_double),
         ("bound_push", C.c_double), ("bound_frac", C.c_double), ("max_grad", C.c_double),
+        ("start", C.c_int32), ("max_reset", C.c_int32),
     ]
+
+
+START_ROLLOUT, START_ZERO = 0, 1
+STATUS_NAMES = {0: "solved", 1: "max_iter", 2: "line search failed", 3: "inertia correction failed",
+                4: "x0 violates its stage-0 bound rows (the reference's NLP is infeasible)"}
 
 
 class IlqrParams(C.Structure):
@@ -279,7 +285,7 @@ def _fill(dst, src, n):
     C.memmove(dst, a.ctypes.data, a.nbytes)
 
 
-FLAG_STAGE_BOUNDS, FLAG_EY_RATE = 1, 2
+FLAG_STAGE_BOUNDS, FLAG_EY_RATE, FLAG_RIVAL_SIZE = 1, 2, 4
 
 
 def make_cbf_params(prm, M, xt_per_stage, flags=0):

@@ -27,6 +27,8 @@ def cbf_record_doubles(N, M, xt_per_stage, flags=0):
         n += 4 * (N + 1)
     if flags & _capi.FLAG_EY_RATE:
         n += (N + 1) & ~1
+    if flags & _capi.FLAG_RIVAL_SIZE:
+        n += 2 * M
     return n
 
 
@@ -41,11 +43,23 @@ def lmpc_record_doubles(N, K):
 NO_BOUND = 1e300
 
 
-def pack_cbf(x0, xt, obs, lap_off, N, out=None, xlb=None, xub=None, wd=None):
+def cbf_flags(M, xlb=None, xub=None, wd=None, sizes=None):
+    """Flags of the packed record from which optional blocks are given.  The kernel has the planner blocks (per-stage
+    bounds + ey-rate weights) as ONE code path, so either of them switches both on (the missing one is packed as
+    "no bound" / zero weights); per-rival sizes only exist with rivals."""
+    if (xlb is None) != (xub is None):
+        raise ValueError("xlb and xub must be given together")
+    planner = xlb is not None or wd is not None
+    return ((_capi.FLAG_STAGE_BOUNDS | _capi.FLAG_EY_RATE) if planner else 0) | \
+        (_capi.FLAG_RIVAL_SIZE if (sizes is not None and M > 0) else 0)
+
+
+def pack_cbf(x0, xt, obs, lap_off, N, out=None, xlb=None, xub=None, wd=None, sizes=None):
     """x0 (B,6); xt (6,), (B,6) or (B,N+1,6); obs (B,M,2,N+1) = rows 4,5 of each rival's predicted
     trajectory (control.py:509-511); lap_off (B,M) or None.  Optional planner blocks: xlb/xub (B,N+1,2)
-    per-stage bounds on (vx, ey) (+-inf = none), wd (B,N) ey-rate weights.
-    Returns (records (B,stride), M, xt_per_stage) -- flags follow from which optional blocks are given."""
+    per-stage bounds on (vx, ey) (+-inf = none), wd (B,N) ey-rate weights.  Optional sizes (B,M,2) or (M,2):
+    (l_agent+l_obs, w_agent+w_obs) of every rival (control.py:530-535) -- without it prm["L"], prm["W"] apply to all.
+    Returns (records (B,stride), M, xt_per_stage) -- flags follow from which optional blocks are given (cbf_flags)."""
     x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)))
     B = x0.shape[0]
     obs = np.asarray(obs, dtype=np.float64)
@@ -55,7 +69,7 @@ def pack_cbf(x0, xt, obs, lap_off, N, out=None, xlb=None, xub=None, wd=None):
         raise ValueError(f"at most {_capi.MMAX} rivals per instance are supported, got {M}")
     xt = np.asarray(xt, dtype=np.float64)
     per_stage = xt.ndim == 3
-    flags = (_capi.FLAG_STAGE_BOUNDS if xlb is not None else 0) | (_capi.FLAG_EY_RATE if wd is not None else 0)
+    flags = cbf_flags(M, xlb, xub, wd, sizes)
     stride = cbf_record_doubles(N, M, per_stage, flags)
     rec = np.zeros((B, stride)) if out is None else out
     hdr = (6 + M + 1) & ~1
@@ -71,13 +85,23 @@ def pack_cbf(x0, xt, obs, lap_off, N, out=None, xlb=None, xub=None, wd=None):
     if M:
         rec[:, o:o + 2 * M * (N + 1)] = obs.reshape(B, 2 * M * (N + 1))
     o = cbf_record_doubles(N, M, per_stage, 0)
-    if xlb is not None:
-        lo = np.clip(np.asarray(xlb, dtype=np.float64).reshape(B, N + 1, 2), -NO_BOUND, NO_BOUND)
-        hi = np.clip(np.asarray(xub, dtype=np.float64).reshape(B, N + 1, 2), -NO_BOUND, NO_BOUND)
+    if flags & _capi.FLAG_STAGE_BOUNDS:
+        if xlb is None:                       # only wd given: no per-stage bounds at all
+            lo, hi = np.full((B, N + 1, 2), -NO_BOUND), np.full((B, N + 1, 2), NO_BOUND)
+        else:
+            lo = np.clip(np.asarray(xlb, dtype=np.float64).reshape(B, N + 1, 2), -NO_BOUND, NO_BOUND)
+            hi = np.clip(np.asarray(xub, dtype=np.float64).reshape(B, N + 1, 2), -NO_BOUND, NO_BOUND)
         rec[:, o:o + 4 * (N + 1)] = np.concatenate([lo, hi], axis=2).reshape(B, 4 * (N + 1))
         o += 4 * (N + 1)
-    if wd is not None:
-        rec[:, o:o + N] = np.asarray(wd, dtype=np.float64).reshape(B, N)
+    if flags & _capi.FLAG_EY_RATE:
+        if wd is not None:
+            rec[:, o:o + N] = np.asarray(wd, dtype=np.float64).reshape(B, N)
+        o += (N + 1) & ~1
+    if flags & _capi.FLAG_RIVAL_SIZE:
+        sz = np.broadcast_to(np.asarray(sizes, dtype=np.float64), (B, M, 2))
+        if not (sz > 0).all():
+            raise ValueError("rival sizes must be positive")
+        rec[:, o:o + 2 * M] = sz.reshape(B, 2 * M)
     return rec, M, per_stage
 
 
@@ -227,11 +251,11 @@ class LmpcPipeline(_Pipeline):
 
 
 def solve_cbf_batch(x0, xt, obs, lap_off, prm, want=("aux", "x", "u", "sigma"), handle=None, xlb=None, xub=None, wd=None,
-                    **opt):
+                    sizes=None, **opt):
     """Batched control.mpccbf / mpc_lti / mpc_multi_agents solve (control.py:476-607,198-248,251-473); with
     xlb/xub/wd also the planner's candidate QP (planning/overtake_traj_planner.py:248-379)."""
-    records, M, per_stage = pack_cbf(x0, xt, obs, lap_off, int(prm["N"]), xlb=xlb, xub=xub, wd=wd)
-    flags = (_capi.FLAG_STAGE_BOUNDS if xlb is not None else 0) | (_capi.FLAG_EY_RATE if wd is not None else 0)
+    records, M, per_stage = pack_cbf(x0, xt, obs, lap_off, int(prm["N"]), xlb=xlb, xub=xub, wd=wd, sizes=sizes)
+    flags = cbf_flags(M, xlb, xub, wd, sizes)
     return solve_cbf_packed(records, prm, M, per_stage, want=want, handle=handle, flags=flags, **opt)
 
 

@@ -11,10 +11,12 @@ Each shim does the reference's host-side packing in numpy (proximity filter, lap
 per-stage targets) and calls the C-ABI with a batch of one.  The solve itself always runs on
 the GPU: there is no CasADi/IPOPT and no CPU fallback here.
 """
+import warnings
+
 import numpy as np
 from scipy.interpolate import interp1d
 
-from . import batch
+from . import _capi, batch
 
 X_DIM, U_DIM = 6, 2
 _SLACK_W = 10000.0          # control.py:560
@@ -66,12 +68,66 @@ def _rival_block(kept, num_cycle_ego, lap_length, N):
     return obs, lap_off
 
 
-def _common_size(pairs):
-    L = {round(p[0], 12) for p in pairs}
-    W = {round(p[1], 12) for p in pairs}
-    if len(L) > 1 or len(W) > 1:
-        raise NotImplementedError("rivals of different size inside one solve are not supported by the batched kernel")
-    return (L.pop(), W.pop()) if pairs else (0.4, 0.2)
+def _nearest(kept, xcurv, lap_length):
+    """The kernel takes at most _capi.MMAX rivals per solve (one warp lane per column of the stage Hessian).  The reference
+    has no limit; with more rivals inside the +-2*vx window the MMAX nearest along s are kept (a CBF row only binds near its
+    rival) and a warning says so."""
+    if len(kept) <= _capi.MMAX:
+        return kept
+    dist_ego = xcurv[4] - int(xcurv[4] / lap_length) * lap_length
+    gap = [abs((t[4, 0] - int(t[4, 0] / lap_length) * lap_length) - dist_ego) for _, t in kept]
+    order = sorted(np.argsort(gap, kind="stable")[:_capi.MMAX])          # keep the reference's rival order
+    warnings.warn("b200mpc: %d rivals inside the proximity window, the %d nearest are used" % (len(kept), _capi.MMAX))
+    return [kept[i] for i in order]
+
+
+def _sizes(pairs):
+    """(L, W, sizes): one (l_agent+l_obs, w_agent+w_obs) pair for all rivals -> kernel constants; different rivals
+    (control.py:530-535 reads every rival's own length / width) -> the per-rival block of the record."""
+    if not pairs:
+        return 0.4, 0.2, None
+    if len({(round(p[0], 12), round(p[1], 12)) for p in pairs}) == 1:
+        return pairs[0][0], pairs[0][1], None
+    return pairs[0][0], pairs[0][1], np.asarray(pairs, float)
+
+
+# what the last single-instance solve did (status, iterations, retries, elastic_max, ...): the drop-ins return only u, as the
+# reference does; this is where a caller can look
+last_solve = {}
+ELASTIC_TOL = 1e-6      # elastic_max above this: a CBF row is not met exactly, the point is the rho-penalised one
+IPOPT_MAX_ITER = 3000   # IPOPT's default max_iter (the reference sets no solver option but printing, control.py:593)
+
+
+def _solve_one(xcurv, xt, obs, lap_off, prm, sizes=None):
+    """One instance through the batch API, with the second chances a single control step can afford (a batch cannot: its
+    stragglers set the step time, so the kernel's defaults are max_iter 200 and a fixed elastic weight):
+      * MAX_ITER at 200 iterations -> once more with IPOPT's own limit of 3000;
+      * converged with elastic_max > ELASTIC_TOL (the l1-elastic CBF row undercut the price of the reference's own slack,
+        DESIGN.md section 2 deviation 2) -> once more with rho x 100 and 3000 iterations; that result is used if it converges
+        with the rows met, otherwise the first one stands and a warning is issued.
+    Returns the batch result dict; `last_solve` records what happened."""
+    M = obs.shape[1]
+    r = batch.solve_cbf_batch(xcurv.reshape(1, 6), xt, obs, lap_off, prm, sizes=sizes)
+    info = dict(M=M, retries=[], status=int(r["status"][0]), iters=int(r["iters"][0]))
+    if r["status"][0] == 1:
+        r2 = batch.solve_cbf_batch(xcurv.reshape(1, 6), xt, obs, lap_off, prm, sizes=sizes, max_iter=IPOPT_MAX_ITER)
+        info["retries"].append(("max_iter=%d" % IPOPT_MAX_ITER, int(r2["status"][0]), int(r2["iters"][0])))
+        r = r2
+    if M > 0 and r["status"][0] == 0 and r["elastic_max"][0] > ELASTIC_TOL:
+        rho = _capi.default_options().rho * 100.0
+        r2 = batch.solve_cbf_batch(xcurv.reshape(1, 6), xt, obs, lap_off, prm, sizes=sizes, rho=rho, max_iter=IPOPT_MAX_ITER)
+        info["retries"].append(("rho=%g" % rho, int(r2["status"][0]), int(r2["iters"][0])))
+        if r2["status"][0] == 0 and r2["elastic_max"][0] <= ELASTIC_TOL:
+            r = r2
+        else:
+            warnings.warn("b200mpc: CBF rows met only elastically (elastic_max %.3g): the rival cannot be cleared within the "
+                          "horizon; the returned input is the penalised solution" % r["elastic_max"][0])
+    info.update(status=int(r["status"][0]), iters=int(r["iters"][0]), cost=float(r["cost"][0]),
+                elastic_max=float(r["elastic_max"][0]), kkt_err=float(r["kkt_err"][0]),
+                status_text=_capi.STATUS_NAMES.get(int(r["status"][0]), "?"))
+    last_solve.clear()
+    last_solve.update(info)
+    return r
 
 
 def pid(xcurv, xtarget):
@@ -89,10 +145,9 @@ def mpc_lti(xcurv, xtarget, mpc_lti_param, system_param, track):
     prm = _limits(_model(mpc_lti_param, N), system_param, track.width)
     prm.update(alpha=0.8, margin=0.2, L=0.4, W=0.2)
     xt = np.asarray(xtarget, float).reshape(X_DIM)
-    r = batch.solve_cbf_batch(np.asarray(xcurv, float).reshape(1, 6), xt, np.zeros((1, 0, 2, N + 1)), None, prm,
-                              want=("u",))
-    if r["status"][0] != 0:
-        raise RuntimeError("b200mpc: mpc_lti did not converge (status %d)" % r["status"][0])
+    r = _solve_one(np.asarray(xcurv, float).reshape(X_DIM), xt, np.zeros((1, 0, 2, N + 1)), None, prm)
+    if r["status"][0] != 0:      # incl. status 4: x0 outside the v / ey rows of stage 0 -- IPOPT reports infeasibility there
+        raise RuntimeError("b200mpc: mpc_lti failed: %s" % last_solve["status_text"])
     return r["u"][0, 0, :]
 
 
@@ -103,14 +158,17 @@ def mpccbf(xcurv, xtarget, mpc_cbf_param, vehicles, agent_name, lap_length, time
     xcurv = np.asarray(xcurv, float).reshape(X_DIM)
     kept, num_cycle_ego = _nearby_rivals(xcurv, list(vehicles), vehicles, agent_name, lap_length, time, timestep,
                                          realtime_flag, N + 1)
+    kept = _nearest(kept, xcurv, lap_length)
     obs, lap_off = _rival_block(kept, num_cycle_ego, lap_length, N)
     ego = vehicles[agent_name].param
-    L, W = _common_size([(ego.length / 2 + vehicles[n].param.length / 2, ego.width / 2 + vehicles[n].param.width / 2)
-                         for n, _ in kept])
+    L, W, sizes = _sizes([(ego.length / 2 + vehicles[n].param.length / 2, ego.width / 2 + vehicles[n].param.width / 2)
+                          for n, _ in kept])
     prm = _limits(_model(mpc_cbf_param, N), system_param, track.width)
     prm.update(alpha=mpc_cbf_param.alpha, margin=0.2, L=L, W=W)
     xt = np.asarray(xtarget, float).reshape(X_DIM)
-    r = batch.solve_cbf_batch(xcurv.reshape(1, 6), xt, obs, lap_off, prm)
+    r = _solve_one(xcurv, xt, obs, lap_off, prm, sizes)
+    if r["status"][0] != 0:
+        print("solver failed.")                   # control.py:601; the iterate is used, as opti.debug.value is there
     if return_details:
         return r["u"][0, 0, :], r
     return r["u"][0, 0, :]
@@ -128,6 +186,7 @@ def mpc_multi_agents(xcurv, mpc_lti_param, track, matrix_Atv, matrix_Btv, matrix
     veh_len, veh_width = vehicles["ego"].param.length, vehicles["ego"].param.width
     kept, num_cycle_ego = _nearby_rivals(xcurv, sorted_vehicles, vehicles, agent_name, track.lap_length, time, 0.1,
                                          False, N + 1)
+    kept = _nearest(kept, xcurv, track.lap_length)
     obs, lap_off = _rival_block(kept, num_cycle_ego, track.lap_length, N)
     xt = np.zeros((1, N + 1, 6))
     for i in range(N + 1):                        # control.py:373-378
@@ -137,8 +196,10 @@ def mpc_multi_agents(xcurv, mpc_lti_param, track, matrix_Atv, matrix_Btv, matrix
             s_tmp = target_traj_xcurv[-1, 4]
         xt[0, i] = [vx, 0, 0, 0, 0, float(f_traj(s_tmp))]
     prm = _limits(_model(mpc_lti_param, N), system_param, track.width)
-    prm.update(alpha=0.6, margin=0.15, L=veh_len, W=veh_width)   # control.py:285,311,316-319
-    r = batch.solve_cbf_batch(xcurv.reshape(1, 6), xt, obs, lap_off, prm)
+    prm.update(alpha=0.6, margin=0.15, L=veh_len, W=veh_width)   # control.py:285,311,316-319: the EGO's full length / width
+    r = _solve_one(xcurv, xt, obs, lap_off, prm)
+    if r["status"][0] != 0:
+        print("solver fail")                      # control.py:459; the iterate is used, as opti.debug.value is there
     return r["u"][0, 0, :], r["x"][0]
 
 

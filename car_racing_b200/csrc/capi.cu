@@ -11,7 +11,11 @@
 #include "frenet.cuh"
 #include "ilqr.cuh"
 #include "lmpc.cuh"
-#include "ocp_ipm.cuh"
+#include "ocp_launch.cuh"
+#ifdef B200MPC_HOST_EMULATION   // tests/host_emulation compiles one translation unit: a reduced instantiation list inline
+#define OCP_INST_EMU
+#include "ocp_inst.cuh"
+#endif
 #include "plant.cuh"
 #include "planner_prepare.cuh"
 #include "planner_select.cuh"
@@ -26,6 +30,7 @@ struct b200mpc_handle {
     int max_batch = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
+    size_t smem_pad = 0;   // B200MPC_SMEM_PAD, read once at create (occupancy sweeps only)
     // staging buffers for the host-pointer API (grown on demand)
     void *d_in = nullptr, *d_rec = nullptr, *d_aux = nullptr, *d_x = nullptr, *d_u = nullptr, *d_sig = nullptr;
     void *d_laps = nullptr, *d_seg = nullptr, *d_idx = nullptr, *d_stat = nullptr, *d_chain = nullptr;
@@ -73,6 +78,8 @@ void b200mpc_default_ipm_options(b200mpc_ipm_options *o) {
     o->bound_push = 1e-2;
     o->bound_frac = 1e-2;
     o->max_grad = 100.0;
+    o->start = B200MPC_START_ROLLOUT;
+    o->max_reset = 5;
 }
 
 int b200mpc_create(int device, int max_batch, b200mpc_handle **out) { return b200mpc_create_ex(device, max_batch, 0, out); }
@@ -103,6 +110,9 @@ int b200mpc_create_ex(int device, int max_batch, int high_priority, b200mpc_hand
     }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    // B200MPC_SMEM_PAD=<bytes>: measurement hook only (DESIGN.md section 5, occupancy sweep) -- pads the dynamic shared
+    // memory of ocp_ipm_kernel so that fewer CTAs fit an SM; results are unaffected
+    if (const char *pad = getenv("B200MPC_SMEM_PAD")) h->smem_pad = (size_t)atoi(pad);
     *out = h;
     return B200MPC_OK;
 }
@@ -141,30 +151,14 @@ int b200mpc_lmpc_record_doubles(int N, int K) {
 
 }  // extern "C"
 
-template <int M, int FL, int NT>
-static int launch_cbf(b200mpc_handle *h, const KParams &kp, const double *d_in, b200mpc_record *d_rec, double *d_aux,
-                      double *d_x, double *d_u, double *d_sig) {
-    SmemPlan<M> pl(kp.p.N, kp.in_stride);
-    size_t smem = pl.bytes();
-    // B200MPC_SMEM_PAD=<bytes>: measurement hook only (DESIGN.md section 5, occupancy sweep) -- pads the dynamic shared
-    // memory so that fewer CTAs fit an SM; results are unaffected
-    if (const char *pad = getenv("B200MPC_SMEM_PAD")) smem += (size_t)atoi(pad);
-    if ((int)smem > h->max_smem_optin)
-        return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: horizon too long for one CTA's shared memory");
-    CK(h, cudaFuncSetAttribute(ocp_ipm_kernel<M, FL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ocp_ipm_kernel<M, FL, NT><<<kp.B, 32, smem, h->stream>>>(kp, d_in, d_rec, d_aux, d_x, d_u, d_sig);
-    CK(h, cudaGetLastError());
-    h->launches++;
-    return B200MPC_OK;
-}
-
 static int check_cbf(b200mpc_handle *h, const b200mpc_cbf_params *p, const b200mpc_ipm_options *o, int B, const void *in,
                      const void *rec) {
     if (!h) return B200MPC_ERR_ARG;
     if (!p || !o || !in || !rec || B < 1) return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: null argument or B < 1");
     if (p->N < 1 || p->N > B200MPC_NMAX || p->M < 0 || p->M > B200MPC_MMAX)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: N or M out of range");
-    if (!(p->alpha >= 0.0 && p->alpha <= 1.0) || !(p->L > 0.0) || !(p->W > 0.0) || !(o->tol > 0.0) || o->max_iter < 1)
+    if (!(p->alpha >= 0.0 && p->alpha <= 1.0) || !(p->L > 0.0) || !(p->W > 0.0) || !(o->tol > 0.0) || o->max_iter < 1 ||
+        o->max_reset < 0 || (o->start != B200MPC_START_ROLLOUT && o->start != B200MPC_START_ZERO))
         return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: bad parameter value");
     return B200MPC_OK;
 }
@@ -180,6 +174,7 @@ static KParams make_kp(const b200mpc_cbf_params *p, const b200mpc_ipm_options *o
     kp.obs_off = kp.hdr + (p->xt_per_stage ? 6 * (p->N + 1) : 6);
     kp.bnd_off = cbf_base_doubles(p->N, p->M, p->xt_per_stage);
     kp.wd_off = kp.bnd_off + ((p->flags & B200MPC_FLAG_STAGE_BOUNDS) ? 4 * (p->N + 1) : 0);
+    kp.sz_off = kp.wd_off + ((p->flags & B200MPC_FLAG_EY_RATE) ? ((p->N + 1) & ~1) : 0);
     double L2 = p->L * p->L, W2 = p->W * p->W;
     kp.iL6 = 1.0 / (L2 * L2 * L2);
     kp.iW6 = 1.0 / (W2 * W2 * W2);
@@ -195,23 +190,26 @@ int b200mpc_cbf_solve_device(b200mpc_handle *h, const b200mpc_cbf_params *prm, c
     if (rc) return rc;
     CK(h, cudaSetDevice(h->device));
     KParams kp = make_kp(prm, opt, B);
-    // the planner-candidate blocks are compiled in only where the reference uses them (no rival rows there)
-    if (prm->flags == (B200MPC_FLAG_STAGE_BOUNDS | B200MPC_FLAG_EY_RATE) && prm->M == 0)
-        return launch_cbf<0, 3, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-    if (prm->flags != 0)
-        return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: flags are supported as STAGE_BOUNDS|EY_RATE with M = 0 only");
-    // horizon-specialised instantiation of the BASELINE.json north-star configuration (per-stage xtarget excluded:
-    // the record stride differs)
-    if (prm->N == 20 && prm->M == 3 && !prm->xt_per_stage)
-        return launch_cbf<3, 0, 20>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-    switch (prm->M) {
-        case 0: return launch_cbf<0, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-        case 1: return launch_cbf<1, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-        case 2: return launch_cbf<2, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-        case 3: return launch_cbf<3, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-        case 4: return launch_cbf<4, 0, 0>(h, kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma);
-    }
-    return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: M out of range");
+    // which instantiation <M, FLAGS, NT> (ocp_launch.cuh): the planner-candidate blocks are compiled in only where the reference
+    // uses them (no rival rows there); the per-rival sizes only with rival rows; the BASELINE.json north-star shape (N = 20,
+    // M = 3, one target) has a horizon-specialised instantiation (per-stage xtarget excluded: the record stride differs)
+    int M = prm->M, FL = prm->flags, NT = 0;
+    if (M == 0) FL &= ~B200MPC_FLAG_RIVAL_SIZE;
+    if (FL == (B200MPC_FLAG_STAGE_BOUNDS | B200MPC_FLAG_EY_RATE)) {
+        if (M != 0) return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: STAGE_BOUNDS|EY_RATE is supported with M = 0 only");
+    } else if (FL != 0 && FL != B200MPC_FLAG_RIVAL_SIZE)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: flags must be 0, STAGE_BOUNDS|EY_RATE (M = 0) or RIVAL_SIZE");
+    if (FL == 0 && prm->N == 20 && M == 3 && !prm->xt_per_stage) NT = 20;
+    CbfLaunch l{h->stream, h->device, h->max_smem_optin, h->smem_pad, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma};
+    int e = (FL == B200MPC_FLAG_RIVAL_SIZE) ? (M <= 4 ? launch_cbf_set3(l, kp, M, FL, NT) : launch_cbf_set4(l, kp, M, FL, NT))
+            : (M == 0 || NT) ? launch_cbf_set0(l, kp, M, FL, NT)
+            : (M <= 4)       ? launch_cbf_set1(l, kp, M, FL, NT)
+                             : launch_cbf_set2(l, kp, M, FL, NT);
+    if (e == CBF_LAUNCH_SMEM) return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: horizon too long for one CTA's shared memory");
+    if (e == CBF_LAUNCH_NOT_HERE) return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: no kernel instantiation for this (M, flags)");
+    if (e != 0) return fail(h, B200MPC_ERR_CUDA, std::string("ocp_ipm_kernel launch: ") + cudaGetErrorString((cudaError_t)e));
+    h->launches++;
+    return B200MPC_OK;
 }
 
 void *b200mpc_host_alloc(size_t bytes) {

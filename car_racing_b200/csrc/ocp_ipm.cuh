@@ -45,6 +45,7 @@ struct KParams {
     int32_t obs_off;    // offset of the rival block inside the record
     int32_t bnd_off;    // offset of the per-stage bound block (flag STAGE_BOUNDS)
     int32_t wd_off;     // offset of the ey-rate weights (flag EY_RATE)
+    int32_t sz_off;     // offset of the per-rival (L_j, W_j) block (flag RIVAL_SIZE)
     double iL6, iW6;    // 1/L^6, 1/W^6
 };
 
@@ -54,6 +55,7 @@ __host__ __device__ inline int cbf_record_doubles(int N, int M, int xt_per_stage
     n = (n + 1) & ~1;
     if (flags & B200MPC_FLAG_STAGE_BOUNDS) n += 4 * (N + 1);
     if (flags & B200MPC_FLAG_EY_RATE) n += (N + 1) & ~1;
+    if (flags & B200MPC_FLAG_RIVAL_SIZE) n += 2 * M;
     return n;
 }
 __host__ __device__ inline int cbf_base_doubles(int N, int M, int xt_per_stage) {
@@ -257,9 +259,12 @@ struct Ipm {
     const int N, R, NB, NW, OU, OS;
     double *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM, *CRES, *KFB, *KFF, *PT,
         *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC, *GX, *ABs;
-    const double *xt, *obs, *lapoff, *bnd, *wdp;
+    const double *xt, *obs, *lapoff, *bnd, *wdp, *szp;
     // per-stage bounds / ey-rate cost present (planner QP): compile-time so that the MPC-CBF path pays nothing
     static constexpr bool psb = (FL & B200MPC_FLAG_STAGE_BOUNDS) != 0, hwd = (FL & B200MPC_FLAG_EY_RATE) != 0;
+    // per-rival sizes (control.py:530-535 reads length / width of every rival): the record carries (L_j, W_j), the kernel
+    // turns them into 1/L_j^6, 1/W_j^6 in place once after staging; without the flag they are kernel-parameter constants
+    static constexpr bool prs = (FL & B200MPC_FLAG_RIVAL_SIZE) != 0;
     int nb_count;        // number of bound + row multipliers (for the error scaling)
     double df, mu, rho, a1;  // a1 = 1 - alpha
     // lane = column role of the Riccati sweep (set once)
@@ -285,6 +290,7 @@ struct Ipm {
         ABs = sm + pl.oAB;
         bnd = IN + kp.bnd_off;
         wdp = IN + kp.wd_off;
+        szp = IN + kp.sz_off;
         nb_count = 0;
         lapoff = IN + 6;
         xt = IN + kp.hdr;
@@ -387,7 +393,9 @@ struct Ipm {
     __device__ __forceinline__ int bss(int j, int i) const { return 4 * N + j * (N + 1) + i; }
 
     // ---- stage evaluation helpers (lane = stage)
-    struct RowV { double ds, de, dsn, den, sg, sgn; };
+    struct RowV { double ds, de, dsn, den, sg, sgn, iL, iW; };
+    __device__ __forceinline__ double iL6(int j) const { return prs ? szp[2 * j] : kp.iL6; }
+    __device__ __forceinline__ double iW6(int j) const { return prs ? szp[2 * j + 1] : kp.iW6; }
     __device__ __forceinline__ RowV row_vals(int j, int i, const double (&x)[6], const double (&xn)[6], double sg, double sgn) const {
         RowV v;
         v.sg = sg;
@@ -396,11 +404,13 @@ struct Ipm {
         v.de = x[5] - obs_e(j, i);
         v.dsn = xn[4] - obs_s(j, i + 1);         // control.py:542 (quirk: no lap offset)
         v.den = xn[5] - obs_e(j, i + 1);
+        v.iL = iL6(j);
+        v.iW = iW6(j);
         return v;
     }
     __device__ __forceinline__ double row_g(const RowV &v) const {  // unscaled h_next - (1-alpha) h  (control.py:558)
-        double h = p6(v.ds) * kp.iL6 + p6(v.de) * kp.iW6 - 1.0 - kp.p.margin - v.sg;
-        double hn = p6(v.dsn) * kp.iL6 + p6(v.den) * kp.iW6 - 1.0 - kp.p.margin - v.sgn;
+        double h = p6(v.ds) * v.iL + p6(v.de) * v.iW - 1.0 - kp.p.margin - v.sg;
+        double hn = p6(v.dsn) * v.iL + p6(v.den) * v.iW - 1.0 - kp.p.margin - v.sgn;
         return hn - a1 * h;
     }
     // x_k, u_k at W + al*D
@@ -615,10 +625,10 @@ struct Ipm {
                 double sc = DG[r];
                 GR[r] = sc * row_g(v);
                 double ja[4];
-                ja[0] = sc * (-a1 * 6.0 * p5(v.ds) * kp.iL6);
-                ja[1] = sc * (-a1 * 6.0 * p5(v.de) * kp.iW6);
-                ja[2] = sc * (6.0 * p5(v.dsn) * kp.iL6);
-                ja[3] = sc * (6.0 * p5(v.den) * kp.iW6);
+                ja[0] = sc * (-a1 * 6.0 * p5(v.ds) * v.iL);
+                ja[1] = sc * (-a1 * 6.0 * p5(v.de) * v.iW);
+                ja[2] = sc * (6.0 * p5(v.dsn) * v.iL);
+                ja[3] = sc * (6.0 * p5(v.den) * v.iW);
                 stv<4>(JA + 4 * r, ja);
             }
         }
@@ -780,13 +790,13 @@ struct Ipm {
                     if (k < N) {
                         int r = j * N + k;
                         double yd = Y[r] * DG[r] * a1 * 30.0;
-                        hd[4] += yd * p4(x[4] - obs_s(j, k) - lapoff[j]) * kp.iL6;
-                        hd[5] += yd * p4(x[5] - obs_e(j, k)) * kp.iW6;
+                        hd[4] += yd * p4(x[4] - obs_s(j, k) - lapoff[j]) * iL6(j);
+                        hd[5] += yd * p4(x[5] - obs_e(j, k)) * iW6(j);
                     }
                     int r = j * N + k - 1;
                     double yd = Y[r] * DG[r] * 30.0;
-                    hd[4] -= yd * p4(x[4] - obs_s(j, k)) * kp.iL6;
-                    hd[5] -= yd * p4(x[5] - obs_e(j, k)) * kp.iW6;
+                    hd[4] -= yd * p4(x[4] - obs_s(j, k)) * iL6(j);
+                    hd[5] -= yd * p4(x[5] - obs_e(j, k)) * iW6(j);
                 }
                 st6(HD + 6 * k, hd);
                 st6(D + 6 * k, g);  // base gradient of the barrier problem; D is overwritten by the forward pass
@@ -1164,14 +1174,22 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     for (int e = lane; e < 48; e += 32) { int r_ = e >> 3, c_ = e & 7; q.ABs[e] = (c_ < 6) ? kp.p.A[6 * r_ + c_] : kp.p.B[2 * r_ + (c_ - 6)]; }
     mbar_wait(bar, 0);
     __syncwarp();
+    if (IP::prs) {   // (L_j, W_j) -> (1/L_j^6, 1/W_j^6), in place in the staged record
+        if (lane < 2 * M) {
+            double v = q.IN[kp.sz_off + lane];
+            q.IN[kp.sz_off + lane] = 1.0 / p6(v);
+        }
+        __syncwarp();
+    }
 
-    // ---- start point: u = 0 roll-out from x_0 (every lane redundantly, constants as immediates), sigma = 0,
-    //      pushed into the bounds
+    // ---- start point.  start = B200MPC_START_ROLLOUT: u = 0 roll-out from x_0 (every lane redundantly, constants as
+    //      immediates); B200MPC_START_ZERO: x_1..x_N = 0, what Opti/IPOPT start from (the reference never calls
+    //      opti.set_initial in control.py:476-607).  u = 0, sigma = 0; everything is then pushed into the bounds.
     {
         double x[6];
         ld6(q.IN, x);
         if (lane == 0) st6(q.W, x);
-        for (int i = 1; i <= N; i++) {
+        for (int i = 1; o.start == B200MPC_START_ROLLOUT && i <= N; i++) {
             double xn[6];
 #pragma unroll
             for (int a = 0; a < 6; a++) {
@@ -1264,8 +1282,8 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 int r = j * N + k;
                 typename IP::RowV v = q.row_vals(j, k, x, xn, q.W[q.isg(j, k)], q.W[q.isg(j, k + 1)]);
                 double rm = fmax(q.a1, 1.0);  // |d/dsigma_i| = (1-alpha), |d/dsigma_{i+1}| = 1
-                rm = fmax(rm, fmax(fabs(6.0 * p5(v.dsn) * kp.iL6), fabs(6.0 * p5(v.den) * kp.iW6)));
-                if (k > 0) rm = fmax(rm, q.a1 * fmax(fabs(6.0 * p5(v.ds) * kp.iL6), fabs(6.0 * p5(v.de) * kp.iW6)));
+                rm = fmax(rm, fmax(fabs(6.0 * p5(v.dsn) * v.iL), fabs(6.0 * p5(v.den) * v.iW)));
+                if (k > 0) rm = fmax(rm, q.a1 * fmax(fabs(6.0 * p5(v.ds) * v.iL), fabs(6.0 * p5(v.de) * v.iW)));
                 double dgr = rm > o.max_grad ? o.max_grad / rm : 1.0;
                 q.DG[r] = dgr;
                 double g = dgr * q.row_g(v);
@@ -1514,7 +1532,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         if (!accepted) {
             // IPOPT would call its restoration phase; the rows are elastic, so remove their residual by
             // enlarging the slacks (t' = max(t, s-g), s' = g+t') and restart the filter.
-            if (n_reset >= 5) { status = B200MPC_LINESEARCH; break; }
+            if (n_reset >= o.max_reset) { status = B200MPC_LINESEARCH; break; }
             n_reset++;
             for (int r = lane; r < R; r += 32) {
                 double g = q.GR[r];
@@ -1692,6 +1710,14 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
 #endif
 
     // ---- results
+    // control.py:582-586 (and :228-232) impose the bound rows on stage 0 as well, where x_0 is fixed (:497): an x_0 outside
+    // them (beyond IPOPT's constr_viol_tol, 1e-4) makes the reference's NLP infeasible.  What was solved above is the problem
+    // without the stage-0 rows; its solution is returned, flagged.
+    {
+        const double ctol = 1e-4, vx0 = q.IN[0], ey0 = q.IN[5];
+        if (vx0 < q.xlb(0, 0) - ctol || vx0 > q.xub(0, 0) + ctol || ey0 < q.xlb(0, 1) - ctol || ey0 > q.xub(0, 1) + ctol)
+            status = B200MPC_INFEASIBLE_X0;
+    }
     double cost = q.objective();
     double tm = 0.0;
     for (int r = lane; r < R; r += 32) tm = fmax(tm, q.T[r]);

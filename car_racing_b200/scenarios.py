@@ -195,3 +195,42 @@ def rival_block(s0, ey, v, t, N, dt=0.1):
     obs[:, :, 0, :] = s0[:, :, None] + v[:, :, None] * tt[None, None, :]
     obs[:, :, 1, :] = ey[:, :, None]
     return obs
+
+
+def planner_scenarios(C=64, N=10, seed=1, track="goggle", time=2.0):
+    """Config 3: one overtaking-planner call with C candidate QPs.  Two moving rivals as in
+    car_racing/tests/overtake_planner_test.py:151-155 (s_j(t) = (1.2 + 0.02 j) t + 10.5 + 1.5 j, ey_j = -0.5 + 0.3 j), the ego
+    0.6-1.2 m behind the first one.  Candidates 0..2 are the reference's three regions (left of both, between, right of both;
+    planning/overtake_traj_planner.py:162-246); candidates 3.. re-evaluate those regions with the lateral excursion of the
+    reference curve scaled (7 values) and the safety margin varied (3 values) -- the same QP structure (documented extension).
+    Returns the arrays planning.pack_candidates takes: x0 (6,), s_ref, ey_ref (C,N+1), xlb, xub (C,N+1,2)."""
+    rng = np.random.default_rng(seed)
+    veh_l, veh_w, width = 0.4, 0.2, 1.0
+    j = np.arange(2)
+    tt = time + 0.1 * np.arange(N + 1)
+    riv_s = (1.2 + 0.02 * j)[:, None] * tt[None, :] + (10.5 + 1.5 * j)[:, None]
+    riv_e = (-0.5 + 0.3 * j)[:, None] * np.ones(N + 1)[None, :]
+    vx = 1.5
+    x0 = np.array([vx, 0.0, 0.0, 0.0, riv_s[0, 0] - rng.uniform(0.6, 1.2), rng.uniform(-0.1, 0.1)])
+    edges = np.array([-(width - 0.5 * veh_w), riv_e[0, 0], riv_e[1, 0], width - 0.5 * veh_w])
+    scales = np.linspace(0.7, 1.3, 7)
+    margins = np.array([0.15, 0.10, 0.20])
+    s_ref = np.zeros((C, N + 1)); ey_ref = np.zeros((C, N + 1))
+    xlb = np.full((C, N + 1, 2), -np.inf); xub = np.full((C, N + 1, 2), np.inf)
+    half = width - 0.5 * veh_w
+    s_pred = x0[4] + 0.1 * np.arange(N + 1) * x0[0]
+    for c in range(C):
+        region = c % 3
+        k = 0 if c < 3 else (c - 3) // 3
+        scale, margin = (1.0, 0.15) if c < 3 else (scales[k % 7], margins[(k // 7) % 3])
+        tgt = 0.5 * (edges[region] + edges[region + 1])
+        u = np.linspace(0.0, 1.0, N + 1)
+        s_ref[c] = s_pred
+        ey_ref[c] = x0[5] + scale * (tgt - x0[5]) * (3 * u ** 2 - 2 * u ** 3)
+        xub[c, 1:, 0] = 5.0                                        # vx_{k+1} <= 5 (:276)
+        xlb[c, :N, 1], xub[c, :N, 1] = -half, half                 # |ey_k| <= width - veh_width / 2 (:277-278)
+        for side in (region - 1, region):                          # rival on the left / right of the region (:286-324)
+            if 0 <= side < 2:
+                near = (s_pred[:N] >= riv_s[side, :N] - veh_l - margin) & (s_pred[:N] <= riv_s[side, :N] + veh_l + margin)
+                xlb[c, :N, 1] = np.where(near, np.maximum(xlb[c, :N, 1], riv_e[side, :N] + veh_w + margin), xlb[c, :N, 1])
+    return dict(x0=x0, s_ref=s_ref, ey_ref=ey_ref, xlb=xlb, xub=xub, rivals=np.stack([riv_s, riv_e], axis=1))

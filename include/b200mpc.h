@@ -36,7 +36,7 @@ extern "C" {
 
 #define B200MPC_VERSION 100
 #define B200MPC_NMAX 64   /* max horizon */
-#define B200MPC_MMAX 4    /* max rivals per instance */
+#define B200MPC_MMAX 8    /* max rivals per instance (one warp lane per column of the stage Hessian: 8 + 2M + 1 <= 32) */
 
 typedef struct b200mpc_handle b200mpc_handle;
 
@@ -53,7 +53,10 @@ enum b200mpc_solve_status {
     B200MPC_SOLVED = 0,        /* E_0 <= tol (or acceptable_tol for acceptable_iter iterations) */
     B200MPC_MAX_ITER = 1,      /* iterate returned (reference: opti.debug.value, control.py:602) */
     B200MPC_LINESEARCH = 2,    /* filter line search failed after the slack resets */
-    B200MPC_INERTIA = 3        /* inertia correction exhausted */
+    B200MPC_INERTIA = 3,       /* inertia correction exhausted */
+    B200MPC_INFEASIBLE_X0 = 4  /* x_0 violates its own stage-0 bound rows (control.py:582-586, :228-232 impose v_min <= vx_0 <= v_max,
+                                  |ey_0| <= width on the fixed x_0): the reference's NLP is infeasible and IPOPT fails; the
+                                  iterate returned is the solution without those rows */
 };
 
 /* Problem data shared by every instance of a batch: the *Param objects of the reference
@@ -79,6 +82,12 @@ typedef struct {
 #define B200MPC_FLAG_STAGE_BOUNDS 1 /* record carries per-stage bounds on (vx_i, ey_i): (N+1) x {lb_vx, lb_ey, ub_vx, ub_ey};
                                        +-1e300 or +-inf = no bound (:276-324); vmin/vmax/width are then ignored */
 #define B200MPC_FLAG_EY_RATE 2      /* record carries wd[0..N-1]: cost += wd[i]*(ey_{i+1}-ey_i)^2 (:325-327) */
+#define B200MPC_FLAG_RIVAL_SIZE 4   /* record carries (L_j, W_j), j < M: l_agent+l_obs, w_agent+w_obs of every rival, which the
+                                       reference reads per rival (control.py:530-535, :316-319); L, W of the params are then ignored */
+
+/* start point of the interior-point iteration */
+#define B200MPC_START_ROLLOUT 0     /* x_i = A^i x_0 (u = 0 roll-out), dynamically feasible; the default */
+#define B200MPC_START_ZERO 1        /* x_1..x_N = 0: what CasADi's Opti hands IPOPT (no opti.set_initial in control.py:476-607) */
 
 /* Interior-point options (IPOPT option names where they exist). */
 typedef struct {
@@ -91,6 +100,9 @@ typedef struct {
     double bound_push;      /* 1e-2 */
     double bound_frac;      /* 1e-2 */
     double max_grad;        /* nlp_scaling_max_gradient, 100 */
+    int32_t start;          /* B200MPC_START_ROLLOUT (default) or B200MPC_START_ZERO */
+    int32_t max_reset;      /* elastic slack resets per solve when the filter line search fails (our stand-in for IPOPT's
+                               restoration phase), 5 */
 } b200mpc_ipm_options;
 
 /* 32-byte per-instance record: what the planner's argmin / the multi-GPU all-gather moves. */
@@ -104,7 +116,8 @@ typedef struct {
 int b200mpc_version(void);
 void b200mpc_default_ipm_options(b200mpc_ipm_options *opt);
 
-/* device < 0: current CUDA device.  max_batch bounds the staging buffers of the host-pointer API. */
+/* device < 0: current CUDA device.  max_batch (>= 1) is a capacity HINT for the staging buffers of the host-pointer API:
+ * they are allocated on first use and grown on demand, so a larger batch is never an error. */
 int b200mpc_create(int device, int max_batch, b200mpc_handle **out);
 /* The same with the handle's stream created at the device's highest priority when high_priority != 0: for short kernels
  * that must not queue behind the pending blocks of other handles' batches (the planner's exchange / argmin step). */
@@ -118,7 +131,7 @@ uint64_t b200mpc_launch_count(const b200mpc_handle *h);
 
 /* doubles per instance of the packed input record for (N, M, xt_per_stage) and flags == 0:
  *   [x0 6][lap_off M][pad to even][xtarget 6 or 6(N+1)][obs j=0..M-1: s_0..s_N, ey_0..ey_N][pad to even]
- * with flags the record continues with [bounds 4(N+1)] and/or [wd N][pad to even]
+ * with flags the record continues with [bounds 4(N+1)] and/or [wd N][pad to even] and/or [L_0 W_0 .. L_{M-1} W_{M-1}]
  * (b200mpc_cbf_record_doubles_ex gives the total).
  * lap_off[j] = (num_cycle_ego - num_cycle_obs)*lap_length (control.py:538-540); obs rows are rows 4,5
  * of get_trajectory_nsteps' (6,N+1) prediction (control.py:509-511). */

@@ -28,13 +28,15 @@ class CbfProblem:
 
     def __init__(self, x0, xt, obs, A, B, Q, R, N, alpha=0.8, margin=0.2, degree=6,
                  umax=(0.5, 1.0), vmin=0.0, vmax=10.0, width=1.0, L=0.4, W=0.2,
-                 lap_off=None, slack_w=1e4):
+                 lap_off=None, slack_w=1e4, sizes=None):
         self.N, self.M = N, obs.shape[0]
         M = self.M
         self.x0, self.xt, self.obs = np.asarray(x0, float), xt, obs  # obs (M,2,N+1): s, ey
         self.A, self.B, self.Q, self.R = A, B, Q, R
         self.alpha, self.margin, self.deg = alpha, margin, degree
-        self.L, self.W = L, W
+        # per-rival (l_agent+l_obs, w_agent+w_obs) (control.py:530-535); one pair for all when not given
+        self.Lj = np.full(self.M, float(L)) if sizes is None else np.asarray(sizes, float).reshape(self.M, 2)[:, 0]
+        self.Wj = np.full(self.M, float(W)) if sizes is None else np.asarray(sizes, float).reshape(self.M, 2)[:, 1]
         # (num_cycle_ego-num_cycle_obs)*lap_length, applied to h but not h_next (:539-542)
         self.lap_off = np.zeros(M) if lap_off is None else np.asarray(lap_off, float)
         self.slack_w = slack_w
@@ -74,12 +76,14 @@ class CbfProblem:
         return self.x0 if i == 0 else w[self.ix(i)]
 
     def start(self):
-        """u = 0 roll-out from x0, sigma = 0 (solver start point)."""
+        """start_mode "rollout": u = 0 roll-out from x0, sigma = 0 (DESIGN.md: solver start point);
+        "zero": w = 0, what Opti hands IPOPT (the reference never calls opti.set_initial in control.py:476-607)."""
         w = np.zeros(self.n)
+        if self.start_mode == "zero":
+            return w
         x = self.x0
         for i in range(1, self.N + 1):
-            if self.start_mode == "rollout":
-                x = self.A @ x
+            x = self.A @ x
             w[self.ix(i)] = x
         return w
 
@@ -112,7 +116,7 @@ class CbfProblem:
         ds = x[4] - self.obs[j, 0, i] - off
         de = x[5] - self.obs[j, 1, i]
         p = self.deg
-        return ds ** p / self.L ** p + de ** p / self.W ** p - 1 - self.margin - w[self.isg(j, i)], ds, de
+        return ds ** p / self.Lj[j] ** p + de ** p / self.Wj[j] ** p - 1 - self.margin - w[self.isg(j, i)], ds, de
 
     def g(self, w):
         out = np.zeros(self.m)
@@ -135,11 +139,11 @@ class CbfProblem:
                 _, ds, de = self._h(w, j, i, self.lap_off[j])
                 _, dsn, den = self._h(w, j, i + 1, 0.0)
                 if i > 0:
-                    J[r, self.ix(i).start + 4] = -a * p * ds ** (p - 1) / self.L ** p
-                    J[r, self.ix(i).start + 5] = -a * p * de ** (p - 1) / self.W ** p
+                    J[r, self.ix(i).start + 4] = -a * p * ds ** (p - 1) / self.Lj[j] ** p
+                    J[r, self.ix(i).start + 5] = -a * p * de ** (p - 1) / self.Wj[j] ** p
                 J[r, self.isg(j, i)] = a
-                J[r, self.ix(i + 1).start + 4] = p * dsn ** (p - 1) / self.L ** p
-                J[r, self.ix(i + 1).start + 5] = p * den ** (p - 1) / self.W ** p
+                J[r, self.ix(i + 1).start + 4] = p * dsn ** (p - 1) / self.Lj[j] ** p
+                J[r, self.ix(i + 1).start + 5] = p * den ** (p - 1) / self.Wj[j] ** p
                 J[r, self.isg(j, i + 1)] = -1.0
                 r += 1
         return J
@@ -161,11 +165,11 @@ class CbfProblem:
                 _, dsn, den = self._h(w, j, i + 1, 0.0)
                 if i > 0:
                     k = self.ix(i).start
-                    H[k + 4, k + 4] += y[r] * a * c2 * ds ** (p - 2) / self.L ** p
-                    H[k + 5, k + 5] += y[r] * a * c2 * de ** (p - 2) / self.W ** p
+                    H[k + 4, k + 4] += y[r] * a * c2 * ds ** (p - 2) / self.Lj[j] ** p
+                    H[k + 5, k + 5] += y[r] * a * c2 * de ** (p - 2) / self.Wj[j] ** p
                 k = self.ix(i + 1).start
-                H[k + 4, k + 4] -= y[r] * c2 * dsn ** (p - 2) / self.L ** p
-                H[k + 5, k + 5] -= y[r] * c2 * den ** (p - 2) / self.W ** p
+                H[k + 4, k + 4] -= y[r] * c2 * dsn ** (p - 2) / self.Lj[j] ** p
+                H[k + 5, k + 5] -= y[r] * c2 * den ** (p - 2) / self.Wj[j] ** p
                 r += 1
         return H
 
@@ -174,7 +178,7 @@ OPTS = dict(tol=1e-8, max_iter=200, mu_init=0.1, kappa_eps=10.0, kappa_mu=0.2, t
             tau_min=0.99, gamma_theta=1e-5, gamma_phi=1e-8, delta_sw=1.0, s_theta=1.1, s_phi=2.3,
             eta_phi=1e-8, gamma_alpha=0.05, s_max=100.0, bound_push=1e-2, bound_frac=1e-2,
             kappa_sigma=1e10, acceptable_tol=1e-6, acceptable_iter=15, max_grad=100.0,
-            rho=1e3, elastic=True)
+            rho=1e3, elastic=True, max_reset=5)
 
 
 def ipm_solve(P, verbose=False, **kw):
@@ -251,7 +255,7 @@ def ipm_solve(P, verbose=False, **kw):
     theta_max = 1e4 * max(1.0, th0)
     theta_min = 1e-4 * max(1.0, th0)
     filt = []
-    it, status, n_acc = 0, 1, 0
+    it, status, n_acc, n_reset = 0, 1, 0, 0
     hist = []
     while True:
         E0, dual, prim, comp = errors(w, s, t, lam, y, z, v, zL, zU, 0.0)
@@ -364,10 +368,20 @@ def ipm_solve(P, verbose=False, **kw):
             a *= 0.5
             nls += 1
         if not accepted:
-            status = 2
-            if verbose:
-                print("line search failed (restoration needed)", th, ph, gphi, a_max)
-            break
+            # IPOPT would enter its restoration phase.  The rows are elastic: remove their residual exactly by enlarging
+            # the slacks (t' = max(t, s-g), s' = g+t'), restart the filter (ocp_oracle.c does the same)
+            if not el or n_reset >= o["max_reset"]:
+                status = 2
+                if verbose:
+                    print("line search failed (restoration needed)", th, ph, gphi, a_max)
+                break
+            n_reset += 1
+            gcur = gs(w)
+            t = np.maximum(t, s - gcur)
+            s = gcur + t
+            filt = []
+            it += 1
+            continue
         if not ftype:
             filt.append(((1 - o["gamma_theta"]) * th, ph - o["gamma_phi"] * th))
         w, s, t = wt, st, tt

@@ -110,8 +110,9 @@ static void eval_c(const ctx_t *c, const double *w, double *r) {
  * hes (optional): 4 second derivatives [ss_i, ee_i, ss_{i+1}, ee_{i+1}] (scaled). */
 static void eval_rows(const ctx_t *c, const double *w, double *g, double *jac, double *hes) {
     const orc_problem *p = c->p;
-    double iL6 = 1.0 / pow6(p->L), iW6 = 1.0 / pow6(p->W), a = 1.0 - p->alpha;
-    for (int j = 0; j < c->M; j++)
+    double a = 1.0 - p->alpha;
+    for (int j = 0; j < c->M; j++) {
+        double iL6 = 1.0 / pow6(p->per_rival_size ? p->Lj[j] : p->L), iW6 = 1.0 / pow6(p->per_rival_size ? p->Wj[j] : p->W);
         for (int i = 0; i < c->N; i++) {
             int r = j * c->N + i;
             double ds = XK(c, w, i, 4) - p->obs_s[j][i] - p->lap_off[j];
@@ -139,6 +140,7 @@ static void eval_rows(const ctx_t *c, const double *w, double *g, double *jac, d
                 q[3] = sc * (30.0 * pow4(den) * iW6);
             }
         }
+    }
 }
 
 /* columns of w touched by row r, in the order of the jac entries; -1: x_0 (not a variable) */
@@ -283,6 +285,8 @@ void orc_default_options(orc_options *o) {
     o->acceptable_tol = 1e-6;
     o->acceptable_iter = 15;
     o->max_grad = 100.0;
+    o->start = 0;
+    o->max_reset = 5;
 }
 
 int orc_solve(const orc_problem *p, const orc_options *o, orc_result *res) {
@@ -337,8 +341,8 @@ int orc_solve(const orc_problem *p, const orc_options *o, orc_result *res) {
     for (int i = 0; i < N; i++)
         for (int a = 0; a < 2; a++) { lb[IU(c, i) + a] = -p->umax[a]; ub[IU(c, i) + a] = p->umax[a]; }
     for (int k = 0; k < ns; k++) lb[nx + nu + k] = 0.0;
-    /* ---- start: u = 0 roll-out, sigma = 0, pushed into the bounds */
-    {
+    /* ---- start: u = 0 roll-out (start = 0) or w = 0 (start = 1: buf is calloc'ed), sigma = 0, pushed into the bounds */
+    if (o->start == 0) {
         double x[6];
         memcpy(x, p->x0, sizeof(x));
         for (int i = 1; i <= N; i++) {
@@ -645,7 +649,7 @@ int orc_solve(const orc_problem *p, const orc_options *o, orc_result *res) {
             /* IPOPT would enter its restoration phase here.  The rows are elastic, so their
              * residual can be removed exactly by enlarging the slacks: t' = max(t, s-g), s' = g+t'
              * (both only grow); then restart the filter.  At most max_reset times per solve. */
-            if (n_reset >= 5) { status = 2; break; }
+            if (n_reset >= o->max_reset) { status = 2; break; }
             n_reset++;
             for (int r = 0; r < m; r++) {
                 double tn = dmax(t[r], s[r] - g[r]);
@@ -698,6 +702,15 @@ done:
     memcpy(res->sigma, w + nx + nu, sizeof(double) * ns);
     res->cost = eval_f(c, w);
     res->kkt_err = E0;
+    /* control.py:582-586 (and :228-232) impose the bound rows on stage 0 as well, where x_0 is fixed by :497: an x_0
+     * outside them (beyond IPOPT's constr_viol_tol 1e-4) makes the reference's NLP infeasible.  The solve above is that
+     * of the problem without the stage-0 rows; it is returned with status 4. */
+    {
+        double l0 = p->per_stage_bounds ? p->xlb[0] : p->vmin, u0 = p->per_stage_bounds ? p->xub[0] : p->vmax;
+        double l1 = p->per_stage_bounds ? p->xlb[1] : -p->width, u1 = p->per_stage_bounds ? p->xub[1] : p->width;
+        const double ctol = 1e-4;
+        if (p->x0[0] < l0 - ctol || p->x0[0] > u0 + ctol || p->x0[5] < l1 - ctol || p->x0[5] > u1 + ctol) status = 4;
+    }
     res->status = status;
     res->iters = iter;
     res->n_refactor = n_refac;

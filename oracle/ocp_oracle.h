@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 #define ORC_NMAX 64 /* max horizon */
-#define ORC_MMAX 4  /* max rivals inside the +-2*vx window */
+#define ORC_MMAX 8  /* max rivals inside the +-2*vx window */
 
 typedef struct {
     int N;              /* horizon (num_horizon) */
@@ -49,6 +49,8 @@ typedef struct {
     double xlb[(ORC_NMAX + 1) * 2];     /* per stage i: lower bound on (vx_i, ey_i), -HUGE_VAL = none (:276-324) */
     double xub[(ORC_NMAX + 1) * 2];     /* per stage i: upper bound on (vx_i, ey_i), +HUGE_VAL = none */
     double wd[ORC_NMAX];                /* cost += wd[i]*(ey_{i+1}-ey_i)^2, i=0..N-1 (:325-327: 30 for i=1..N-2) */
+    int per_rival_size;                 /* 1: use Lj/Wj instead of L/W (control.py:530-535 reads the size of every rival) */
+    double Lj[ORC_MMAX], Wj[ORC_MMAX];
 } orc_problem;
 
 typedef struct {
@@ -61,6 +63,9 @@ typedef struct {
     double acceptable_tol; /* 1e-6 */
     int acceptable_iter;   /* 15 */
     double max_grad;       /* nlp_scaling_max_gradient = 100 */
+    int start;             /* 0: u = 0 roll-out of x_0 (DESIGN.md deviation 1); 1: w = 0, what Opti/IPOPT start from
+                              (no opti.set_initial in control.py:476-607), pushed into the bounds */
+    int max_reset;         /* elastic slack resets when the line search fails (stand-in for IPOPT's restoration phase), 5 */
 } orc_options;
 
 typedef struct {
@@ -70,7 +75,8 @@ typedef struct {
     double cost;        /* unscaled objective, as the reference's `cost` expression */
     double kkt_err;     /* final scaled optimality error E_0 */
     double elastic_max; /* max_r t_r (0 => CBF rows hold exactly) */
-    int status;         /* 0 converged, 1 max_iter, 2 line search failed, 3 inertia failed */
+    int status;         /* 0 converged, 1 max_iter, 2 line search failed, 3 inertia failed, 4 x_0 violates its own stage-0
+                           bound rows (control.py:582-586 impose them on the fixed x_0: IPOPT reports infeasibility) */
     int iters;
     int n_refactor;     /* inertia-correction refactorisations */
     int n_backtrack;    /* line-search halvings */

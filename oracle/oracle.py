@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-NMAX, MMAX = 64, 4
+NMAX, MMAX = 64, 8
 
 
 class Problem(C.Structure):
@@ -30,6 +30,7 @@ class Problem(C.Structure):
         ("per_stage_bounds", C.c_int),
         ("xlb", C.c_double * ((NMAX + 1) * 2)), ("xub", C.c_double * ((NMAX + 1) * 2)),
         ("wd", C.c_double * NMAX),
+        ("per_rival_size", C.c_int), ("Lj", C.c_double * MMAX), ("Wj", C.c_double * MMAX),
     ]
 
 
@@ -37,7 +38,7 @@ class Options(C.Structure):
     _fields_ = [
         ("tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double), ("rho", C.c_double),
         ("bound_push", C.c_double), ("bound_frac", C.c_double), ("acceptable_tol", C.c_double),
-        ("acceptable_iter", C.c_int), ("max_grad", C.c_double),
+        ("acceptable_iter", C.c_int), ("max_grad", C.c_double), ("start", C.c_int), ("max_reset", C.c_int),
     ]
 
 
@@ -123,7 +124,7 @@ def _fill(dst, src):
     C.memmove(dst, a.ctypes.data, a.nbytes)
 
 
-def solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=1, xlb=None, xub=None, wd=None, **opt):
+def solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=1, xlb=None, xub=None, wd=None, sizes=None, **opt):
     """x0 (B,6); xt (B,N+1,6) or (6,); obs (B,M,2,N+1) [s, ey]; lap_off (B,M); prm: dict of
     model/limits (A,B,Q,R,N,umax,vmin,vmax,width,alpha,margin,L,W,slack_w).  Returns dict of arrays."""
     x0 = np.atleast_2d(np.asarray(x0, float))
@@ -153,6 +154,11 @@ def solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=1, xlb=None, xub=None, w
             _fill(p.xub, np.asarray(xub, float).reshape(Bn, N + 1, 2)[b])
         if wd is not None:
             _fill(p.wd, np.asarray(wd, float).reshape(Bn, N)[b])
+        if sizes is not None and M > 0:
+            sz = np.broadcast_to(np.asarray(sizes, float), (Bn, M, 2))[b]
+            p.per_rival_size = 1
+            for j in range(M):
+                p.Lj[j], p.Wj[j] = sz[j, 0], sz[j, 1]
     o = default_options(**opt)
     R = (Result * Bn)()
     lib().orc_solve_batch(P, Bn, C.byref(o), R, nthreads)

@@ -28,6 +28,7 @@ static KParams make_kp(const b200mpc_cbf_params *p, const b200mpc_ipm_options *o
     kp.obs_off = kp.hdr + (p->xt_per_stage ? 6 * (p->N + 1) : 6);
     kp.bnd_off = cbf_base_doubles(p->N, p->M, p->xt_per_stage);
     kp.wd_off = kp.bnd_off + ((p->flags & B200MPC_FLAG_STAGE_BOUNDS) ? 4 * (p->N + 1) : 0);
+    kp.sz_off = kp.wd_off + ((p->flags & B200MPC_FLAG_EY_RATE) ? ((p->N + 1) & ~1) : 0);
     double L2 = p->L * p->L, W2 = p->W * p->W;
     kp.iL6 = 1.0 / (L2 * L2 * L2);
     kp.iW6 = 1.0 / (W2 * W2 * W2);
@@ -46,6 +47,10 @@ extern "C" int emu_cbf_solve(const b200mpc_cbf_params *prm, const b200mpc_ipm_op
     KParams kp = make_kp(prm, opt, B);
     if (prm->flags == (B200MPC_FLAG_STAGE_BOUNDS | B200MPC_FLAG_EY_RATE) && prm->M == 0) {
         run<0, 3, 0>(kp, B, in, rec, aux, xpred, upred, sigma);
+        return 0;
+    }
+    if (prm->flags == B200MPC_FLAG_RIVAL_SIZE && prm->M == 2) {
+        run<2, 4, 0>(kp, B, in, rec, aux, xpred, upred, sigma);
         return 0;
     }
     if (prm->flags != 0) return -1;

@@ -33,11 +33,13 @@ def test_struct_layouts_and_record_sizes():
     _capi, L = _lib_or_skip()
     from car_racing_b200 import batch
     assert C.sizeof(_capi.CbfParams) == 16 + 8 * (36 + 12 + 36 + 4 + 2 + 8)
-    assert C.sizeof(_capi.IpmOptions) == 8 + 4 + 4 + 8 * 6
+    assert C.sizeof(_capi.IpmOptions) == 8 + 4 + 4 + 8 * 6 + 4 + 4
     for N in (1, 10, 20, 50, 64):
-        for M in range(5):
+        for M in range(_capi.MMAX + 1):
             for ps in (0, 1):
                 assert L.b200mpc_cbf_record_doubles(N, M, ps) == batch.cbf_record_doubles(N, M, ps)
+                for fl in (3, 4):
+                    assert L.b200mpc_cbf_record_doubles_ex(N, M, ps, fl) == batch.cbf_record_doubles(N, M, ps, fl)
         assert L.b200mpc_ilqr_record_doubles(N) == batch.ilqr_record_doubles(N)
     assert C.sizeof(_capi.PlantParams) == 16 + 12 * 8
     assert _capi.make_plant_params(9, 25.4).n_sub == 100
@@ -47,9 +49,9 @@ def test_struct_layouts_and_record_sizes():
         assert L.b200mpc_lmpc_record_doubles(N, K) == batch.lmpc_record_doubles(N, K)
     assert L.b200mpc_lmpc_record_doubles(17, 44) < 0 and L.b200mpc_lmpc_record_doubles(12, 65) < 0
     assert batch.cbf_record_doubles(20, 3, 0) * 8 == 1136      # algorithmic input bytes
-    assert L.b200mpc_cbf_record_doubles(65, 0, 0) < 0 and L.b200mpc_cbf_record_doubles(20, 5, 0) < 0
+    assert L.b200mpc_cbf_record_doubles(65, 0, 0) < 0 and L.b200mpc_cbf_record_doubles(20, _capi.MMAX + 1, 0) < 0
     o = _capi.default_options()
-    assert o.tol == 1e-8 and o.max_iter == 200 and o.rho == 1e3
+    assert o.tol == 1e-8 and o.max_iter == 200 and o.rho == 1e3 and o.start == _capi.START_ROLLOUT and o.max_reset == 5
 
 
 def test_no_device_is_a_loud_error():
@@ -62,7 +64,7 @@ def test_no_device_is_a_loud_error():
 
 
 def test_pack_cbf_layout():
-    from car_racing_b200 import batch
+    from car_racing_b200 import _capi, batch
     N, M, B = 4, 2, 3
     rng = np.random.default_rng(0)
     x0 = rng.normal(size=(B, 6)); obs = rng.normal(size=(B, M, 2, N + 1)); lo = rng.normal(size=(B, M))
@@ -77,7 +79,15 @@ def test_pack_cbf_layout():
     rec, m, ps = batch.pack_cbf(x0, xt, np.zeros((B, 0, 2, N + 1)), None, N)
     assert m == 0 and rec.shape[1] == 12
     with pytest.raises(ValueError):
-        batch.pack_cbf(x0, xt, np.zeros((B, 5, 2, N + 1)), None, N)
+        batch.pack_cbf(x0, xt, np.zeros((B, _capi.MMAX + 1, 2, N + 1)), None, N)
+    # per-rival sizes: appended block, flag RIVAL_SIZE; only wd given: the planner blocks travel together
+    sz = np.array([[0.5, 0.2], [0.4, 0.3]])
+    rec, m, ps = batch.pack_cbf(x0, xt, obs, lo, N, sizes=sz)
+    assert rec.shape[1] == batch.cbf_record_doubles(N, M, 0, _capi.FLAG_RIVAL_SIZE) and (rec[:, -4:] == sz.ravel()).all()
+    rec, m, ps = batch.pack_cbf(x0, xt, np.zeros((B, 0, 2, N + 1)), None, N, wd=np.ones((B, N)))
+    assert batch.cbf_flags(0, wd=1) == 3 and rec.shape[1] == batch.cbf_record_doubles(N, 0, 0, 3)
+    with pytest.raises(ValueError):
+        batch.pack_cbf(x0, xt, obs, lo, N, xlb=np.zeros((B, N + 1, 2)))
 
 
 def test_handle_pickles_without_native_state():

@@ -311,7 +311,7 @@ def test_capi_argument_validation(crb):
     p.N = 65
     assert call(p) == -1 and b"out of range" in L.b200mpc_last_error(h.ptr)
     p = _capi.make_cbf_params(prm, 3, False)
-    p.M = 5
+    p.M = _capi.MMAX + 1
     assert call(p) == -1
     p = _capi.make_cbf_params(prm, 3, False)
     assert call(p, B=0) == -1 and call(p, inp=None) == -1 and call(p, out=None) == -1
@@ -321,6 +321,10 @@ def test_capi_argument_validation(crb):
     assert call(p) == -1 and b"flags" in L.b200mpc_last_error(h.ptr)
     bad = _capi.default_options()
     bad.max_iter = 0
+    assert call(_capi.make_cbf_params(prm, 3, False), opt=bad) == -1
+    bad = _capi.default_options(start=2)
+    assert call(_capi.make_cbf_params(prm, 3, False), opt=bad) == -1
+    bad = _capi.default_options(max_reset=-1)
     assert call(_capi.make_cbf_params(prm, 3, False), opt=bad) == -1
     ip = _capi.make_ilqr_params(dict(A=prm["A"], B=prm["B"], Q=prm["Q"], R=prm["R"], N=70, max_iter=10, L=0.4, W=0.2))
     assert L.b200mpc_ilqr_solve(h.ptr, C.byref(ip), 1, rec_in.ctypes.data_as(C.c_void_p), rec_out.ctypes.data_as(C.c_void_p), None, None) == -1

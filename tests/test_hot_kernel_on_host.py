@@ -31,14 +31,17 @@ def _options():
     o = _capi.IpmOptions()       # b200mpc_default_ipm_options (car_racing_b200/csrc/capi.cu), set here because the library
     o.tol, o.max_iter, o.acceptable_iter, o.acceptable_tol = 1e-8, 200, 15, 1e-6     # itself is not loaded on the CPU tier
     o.mu_init, o.rho, o.bound_push, o.bound_frac, o.max_grad = 0.1, 1e3, 1e-2, 1e-2, 100.0
+    o.start, o.max_reset = _capi.START_ROLLOUT, 5
     return o
 
 
-def _solve(L, x0, xt, obs, lap_off, prm, specialised=1, xlb=None, xub=None, wd=None):
+def _solve(L, x0, xt, obs, lap_off, prm, specialised=1, xlb=None, xub=None, wd=None, sizes=None, **opt):
     N = int(prm["N"])
-    records, M, per_stage = batch.pack_cbf(x0, xt, obs, lap_off, N, xlb=xlb, xub=xub, wd=wd)
-    flags = (_capi.FLAG_STAGE_BOUNDS if xlb is not None else 0) | (_capi.FLAG_EY_RATE if wd is not None else 0)
+    records, M, per_stage = batch.pack_cbf(x0, xt, obs, lap_off, N, xlb=xlb, xub=xub, wd=wd, sizes=sizes)
+    flags = batch.cbf_flags(M, xlb, xub, wd, sizes)
     p, o = _capi.make_cbf_params(prm, M, per_stage, flags), _options()
+    for k, v in opt.items():
+        setattr(o, k, v)
     B = records.shape[0]
     rec = np.zeros(B, dtype=_capi.RECORD_DTYPE)
     aux, x, u = np.zeros((B, 4)), np.zeros((B, N + 1, 6)), np.zeros((B, N, 2))
@@ -96,3 +99,29 @@ def test_other_instantiations_on_host(oracle):
     pprm = planning.planner_params(p.racing_game_param.matrix_A, p.racing_game_param.matrix_B, N)
     ref = oracle.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, pprm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"])
     _agree(_solve(L, kw["x0"], kw["xt"], kw["obs"], None, pprm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"]), ref)
+
+
+def test_zero_start_rival_sizes_and_x0_rows_on_host(oracle):
+    """Round-2 options of the hot kernel against the oracle: B200MPC_START_ZERO (w = 0, what Opti/IPOPT start from), per-rival
+    (L, W) in the record (flag RIVAL_SIZE, <2,4,0>), and status 4 when x_0 violates the bound rows the reference imposes on
+    stage 0 (control.py:582-586)."""
+    L = _lib()
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(3, N=12, M=2, seed=4)
+    prm = scenarios.default_cbf_params(N=12)
+    # zero start: a bounded number of iterations; the iterates must be the oracle's (same status, iteration count, point)
+    kw = dict(start=_capi.START_ZERO, max_iter=60, max_reset=50)
+    g, r = _solve(L, x0, xt, obs, lap_off, prm, **kw), oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, **kw)
+    assert (g["status"] == r["status"]).all() and (g["iters"] == r["iters"]).all()
+    assert np.abs(g["x"] - r["x"]).max() < 1e-6 and np.abs(g["u"] - r["u"]).max() < 1e-6
+    # per-rival sizes: a long, narrow rival and a short, wide one
+    sizes = np.array([[0.55, 0.18], [0.35, 0.27]])
+    g = _solve(L, x0, xt, obs, lap_off, prm, sizes=sizes)
+    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, sizes=sizes)
+    _agree(g, r)
+    same = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    assert np.abs(r["u"] - same["u"]).max() > 1e-6              # the sizes are really used
+    # x_0 outside |ey| <= width: the reference's NLP is infeasible
+    x0b = x0.copy()
+    x0b[0, 5] = prm["width"] + 0.05
+    g, r = _solve(L, x0b, xt, obs, lap_off, prm), oracle.solve_cbf_batch(x0b, xt, obs, lap_off, prm)
+    assert g["status"][0] == 4 and r["status"][0] == 4 and (g["status"][1:] == r["status"][1:]).all()

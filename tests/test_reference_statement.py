@@ -41,7 +41,8 @@ def capture_cbf(monkeypatch):
         seen.update(x0=np.array(x0, float).reshape(6), xt=np.array(xt, float), obs=np.array(obs, float)[0],
                     lap_off=None if lap_off is None else np.array(lap_off, float).reshape(-1), prm=dict(prm), extra=opt)
         N = prm["N"]
-        return dict(u=np.zeros((1, N, 2)), x=np.zeros((1, N + 1, 6)), status=np.array([0]), u0=np.zeros((1, 2)), cost=np.zeros(1))
+        return dict(u=np.zeros((1, N, 2)), x=np.zeros((1, N + 1, 6)), status=np.array([0]), u0=np.zeros((1, 2)), cost=np.zeros(1),
+                    iters=np.array([0]), elastic_max=np.zeros(1), kkt_err=np.zeros(1))
     monkeypatch.setattr(control.batch, "solve_cbf_batch", fake)
     return seen
 
