@@ -1,22 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- MPC-CBF solves/sec (N=20, 6-state, 3 rivals), BASELINE.json's metric.
+"""bench.py -- BASELINE.json's metric: MPC-CBF solves/sec (N=20, 6-state, 3 rivals); the other BASELINE configs on request.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5] [--batch B]
 
-A "step" is one pass of the hot path over one batch of B=1024 synthetic config-2 scenarios
-(car_racing_b200/scenarios.py, seed 1).  With N>1 (torchrun, one rank per
-GPU) every rank solves its own 1024-scenario shard (weak scaling) and the step ends with one NCCL
-all-gather of the 32-byte records + the argmin kernel.
+A "step" is one pass of the hot path over one batch of synthetic scenarios of the chosen BASELINE.json config
+(car_racing_b200/scenarios.py, seed 1 + rank):
+    --config 2 (default)  MPC-CBF N=20, 3 static rivals, l_shape, 1024 scenarios per GPU          (configs[1], the metric's config)
+    --config 3            overtake planner: 64 candidate QPs x 2 moving rivals, goggle, per GPU  (configs[2])
+    --config 4            LMPC N=12, 44 safe-set points, ellipse, 512 scenarios per GPU           (configs[3]: 4096 over 8 GPUs)
+    --config 5            iLQR N=50, 1024 scenarios per GPU                                      (configs[4]: 8192 over 8 GPUs)
+With N>1 (torchrun, one rank per GPU) every rank solves its own shard (weak scaling) and the step ends with the exchange
+of the 32-byte records: the solver kernels' epilogue stores them into every rank's gathered buffer over NVLink
+(b200mpc_comm_*, csrc/exchange.cuh), then one argmin kernel per rank.  If the peers' windows cannot be mapped (no CUDA IPC),
+the exchange falls back to one NCCL all-gather per step and the line says so (`config.exchange`).
 
-`value`    : whole-job solves/s with the packed inputs already resident in HBM (kernel only).
-`e2e`      : the same metric through the host-pointer C-ABI call (pinned host buffers; H2D of the
-             records, kernel, D2H of the 32-byte result records inside the timed region).
-`roofline` : algorithmic HBM bytes / kernel time against the measured copy bandwidth -- stated
-             honestly: this kernel is FP64-latency / shared-memory bound, not HBM bound.
-`--impl reference` times the CPU implementation of the path (the oracle port: CasADi/IPOPT is not
-installable here) on the host cores.
+`value`    : whole-job solves/s with the packed inputs already resident in HBM (kernels only), exchange included.
+`e2e`      : the same metric through the host-pointer C-ABI call (pinned host buffers; H2D of the records, kernel, D2H of
+             the 32-byte result records inside the timed region; N>1: the exchange and the D2H of its argmin as well).
+`roofline` : algorithmic HBM bytes / kernel time against the measured copy bandwidth -- stated honestly: these kernels
+             are FP64-latency bound, not HBM bound; `roofline.fp64` puts the counted FP64 work beside it.
+`--impl reference` times the CPU implementation of the path on the host cores: CasADi/IPOPT is probed for, but it is not
+installable here, so the arm times the oracle port (oracle/*.c) and says so.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -30,16 +37,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OUT = sys.stdout
-METRIC = "MPC-CBF solves/sec (N=20, 6-state, 3 obs)"
-ALG_BYTES_PER_SOLVE = 1136 + 536      # 1136 B in (one packed record) + 536 B out
-N_H, M_OBS = 20, 3
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
-    return 6650.0, "fallback"
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
+    return 6650.0, 1965.0, "fallback"
 
 
 class ClockSampler:
@@ -75,61 +80,210 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def workload(B, seed):
-    from car_racing_b200 import batch, scenarios
-    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=N_H, M=M_OBS, seed=seed)
-    prm = scenarios.default_cbf_params(N=N_H)
-    rec, M, ps = batch.pack_cbf(x0, xt, obs, lap_off, N_H)
-    return (x0, xt, obs, lap_off), prm, rec
+# ------------------------------------------------------------------------------------------------ workloads
+class Work:
+    """One BASELINE config: host records of this rank's shard, the three ways to run it (device pointers, host pointers,
+    CPU oracle) and its algorithmic bytes per solve."""
+    key = metric = kernel = None
+    default_batch = 1024
+
+    def config(self, B, world, D, exchange):
+        """The `config` object of the JSON line -- the same for both arms (--impl ours / reference)."""
+        return {"workload": self.workload % B, "baseline_config": self.key, "global_batch": B * world,
+                "parallelism": "dp%d: independent scenario shards, one exchange of the 32-byte records + argmin per step" % world,
+                "exchange": exchange, "batches_in_flight": D,
+                "pipelining": ("steps are issued round-robin on %d streams (one handle each): the stragglers of one batch overlap "
+                               "the next batches; timed first start event -> last end event, flushes included" % D)
+                if D > 1 else "none: one batch at a time",
+                "l2": "256 MiB buffer written before every timed step, on the step's stream (inputs are << L2)",
+                "solver": self.solver}
 
 
-def cpu_port_rate(B_sample, nthreads, seed=1):
-    """The CPU restatement (oracle/ocp_oracle.c) on `nthreads` host threads; returns (solves/s, seconds, passes)."""
+class Work2(Work):
+    key, default_batch, kernel = 2, 1024, "ocp_ipm_kernel<3,0,20>"
+    metric = "MPC-CBF solves/sec (N=20, 6-state, 3 obs)"
+    workload = "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 per GPU (BASELINE config 2)"
+    solver = "FP64 barrier-SQP (IPOPT conventions), Riccati KKT, tol 1e-8"
+    alg_out = 536
+
+    def __init__(self, B, seed):
+        from car_racing_b200 import _capi, batch, scenarios
+        self.raw = scenarios.mpccbf_scenarios(B, N=20, M=3, seed=seed)
+        self.prm = scenarios.default_cbf_params(N=20)
+        self.rec, M, ps = batch.pack_cbf(*self.raw, 20)
+        self.p, self.o = _capi.make_cbf_params(self.prm, M, ps), _capi.default_options()
+        self.alg_bytes = self.rec.shape[1] * 8 + self.alg_out
+
+    def device(self, L, h, B, d_in, d_rec):
+        import ctypes as C
+        return L.b200mpc_cbf_solve_device(h.ptr, C.byref(self.p), C.byref(self.o), B, d_in, d_rec, None, None, None, None)
+
+    def host(self, L, h, B, p_in, p_out, blocking=False):
+        import ctypes as C
+        fn = L.b200mpc_cbf_solve if blocking else L.b200mpc_cbf_solve_async
+        return fn(h.ptr, C.byref(self.p), C.byref(self.o), B, p_in, p_out, None, None, None, None)
+
+    def cpu(self, orc, n, nthreads):
+        x0, xt, obs, lo = self.raw
+        return orc.solve_cbf_batch(x0[:n], xt, obs[:n], lo[:n], self.prm, nthreads=nthreads)
+
+
+class Work3(Work2):
+    key, default_batch, kernel = 3, 64, "ocp_ipm_kernel<0,3,0>"
+    metric = "overtake-planner candidate solves/sec (N=10, 64 candidates, 2 rivals)"
+    workload = "overtake planner: %d lane/side/gap candidate QPs x 2 moving rivals, goggle, N=10, per GPU (BASELINE config 3)"
+    solver = "FP64 barrier method (IPOPT conventions) on the candidate QP, Riccati KKT, tol 1e-8"
+
+    def __init__(self, B, seed):
+        from car_racing_b200 import _capi, batch, planning, scenarios
+        sc = scenarios.planner_scenarios(C=B, N=10, seed=seed)
+        self.kw, _ = planning.pack_candidates(sc["x0"], sc["s_ref"], sc["ey_ref"], sc["xlb"], sc["xub"], 10)
+        self.prm = planning.planner_params(scenarios.LTI_A, scenarios.LTI_B, 10)
+        kw = self.kw
+        self.rec, M, ps = batch.pack_cbf(kw["x0"], kw["xt"], kw["obs"], None, 10, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"])
+        self.p = _capi.make_cbf_params(self.prm, 0, True, _capi.FLAG_STAGE_BOUNDS | _capi.FLAG_EY_RATE)
+        self.o = _capi.default_options()
+        self.alg_bytes = self.rec.shape[1] * 8 + 6 * 11 * 8 + 16        # in: the packed record; out: trajectory 6 x 11 + costs
+
+    def cpu(self, orc, n, nthreads):
+        kw = self.kw
+        return orc.solve_cbf_batch(kw["x0"][:n], kw["xt"][:n], kw["obs"][:n], None, self.prm, xlb=kw["xlb"][:n], xub=kw["xub"][:n],
+                                   wd=kw["wd"][:n], nthreads=nthreads)
+
+
+class Work4(Work):
+    key, default_batch, kernel = 4, 512, "lmpc_kernel"
+    metric = "LMPC solves/sec (N=12, 44 safe-set points)"
+    workload = "LMPC N=12, learned safe-set terminal constraint (44 points), ellipse, batch=%d scenarios per GPU (BASELINE config 4: 4096 over 8 GPUs)"
+    solver = "FP64 barrier method (IPOPT conventions), condensed KKT, tol 1e-8"
+
+    def __init__(self, B, seed):
+        from car_racing_b200 import _capi, batch, scenarios
+        self.raw = scenarios.lmpc_scenarios(B, seed=seed)
+        self.prm = scenarios.default_lmpc_params()
+        self.rec, K = batch.pack_lmpc(*self.raw, int(self.prm["N"]))
+        self.p, self.o = _capi.make_lmpc_params(self.prm, K), _capi.default_options()
+        self.alg_bytes = self.rec.shape[1] * 8 + (13 * 6 + 12 * 2) * 8
+
+    def device(self, L, h, B, d_in, d_rec):
+        import ctypes as C
+        return L.b200mpc_lmpc_solve_device(h.ptr, C.byref(self.p), C.byref(self.o), B, d_in, d_rec, None, None, None, None)
+
+    def host(self, L, h, B, p_in, p_out, blocking=False):
+        import ctypes as C
+        fn = L.b200mpc_lmpc_solve if blocking else L.b200mpc_lmpc_solve_async
+        return fn(h.ptr, C.byref(self.p), C.byref(self.o), B, p_in, p_out, None, None, None, None)
+
+    def cpu(self, orc, n, nthreads):
+        return orc.solve_lmpc_batch(*[a[:n] for a in self.raw], self.prm, nthreads=nthreads)
+
+
+class Work5(Work):
+    key, default_batch, kernel = 5, 1024, "ilqr_kernel"
+    metric = "iLQR solves/sec (N=50, 1 rival)"
+    workload = "iLQR N=50, LTI bicycle model + 1 rival, batch=%d random (x0, obstacle) scenarios per GPU (BASELINE config 5: 8192 over 8 GPUs)"
+    solver = "FP64 iLQR as control.ilqr (max_iter 150, regularised backward pass)"
+
+    def __init__(self, B, seed):
+        from car_racing_b200 import _capi, batch, scenarios
+        self.raw = scenarios.ilqr_scenarios(B, N=50, seed=seed)
+        p = scenarios.default_cbf_params()
+        self.prm = dict(A=p["A"], B=p["B"], Q=p["Q"], R=p["R"], N=50, max_iter=150, L=0.4, W=0.2)
+        self.rec = batch.pack_ilqr(*self.raw, 50)
+        self.p = _capi.make_ilqr_params(self.prm)
+        self.alg_bytes = self.rec.shape[1] * 8 + 32
+
+    def device(self, L, h, B, d_in, d_rec):
+        import ctypes as C
+        return L.b200mpc_ilqr_solve_device(h.ptr, C.byref(self.p), B, d_in, d_rec, None, None)
+
+    def host(self, L, h, B, p_in, p_out, blocking=False):
+        import ctypes as C
+        fn = L.b200mpc_ilqr_solve if blocking else L.b200mpc_ilqr_solve_async
+        return fn(h.ptr, C.byref(self.p), B, p_in, p_out, None, None)
+
+    def cpu(self, orc, n, nthreads):
+        x0, xt, obs, lo = self.raw
+        return orc.solve_ilqr_batch(x0[:n], xt, obs[:n], lo[:n], self.prm, nthreads=nthreads)
+
+
+WORKS = {2: Work2, 3: Work3, 4: Work4, 5: Work5}
+
+
+def reference_solver_probe():
+    """is the reference's own solver (CasADi + IPOPT) or an install of the reference present on this box?"""
+    probe = {"casadi": False, "reference_install": os.path.isdir(os.path.join(ROOT, "baseline", "_ref")),
+             "reference_checkout": os.path.isdir("/root/reference")}
+    try:
+        import casadi  # noqa: F401
+        probe["casadi"] = True
+    except Exception:
+        pass
+    return probe
+
+
+def cpu_port_rate(work, n, nthreads, budget_s=10.0, max_passes=16):
+    """The CPU restatement (oracle/) on `nthreads` host threads over the first n instances of the same workload; whole
+    passes until ~budget_s of wall time.  Returns (solves/s, seconds, passes)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
-    from car_racing_b200 import scenarios
-    (x0, xt, obs, lap_off), prm, _ = workload(B_sample, seed)
     orc.lib()
     t = time.perf_counter()
     passes = 0
-    while True:       # bounded sample: whole passes over the batch until ~10 s of wall time (at most 16 passes)
-        orc.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=nthreads)
+    while True:
+        work.cpu(orc, n, nthreads)
         passes += 1
         dt = time.perf_counter() - t
-        if dt >= 10.0 or passes >= 16:
+        if dt >= budget_s or passes >= max_passes:
             break
-    return B_sample * passes / dt, dt, passes
+    return n * passes / dt, dt, passes
+
+
+def cpu_baseline_obj(work, v, cores, sample, probe):
+    return {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample,
+            "build": "oracle/Makefile: gcc -O3 -march=x86-64-v3 -ffp-contract=off, pthreads",
+            "reference_solver_probe": probe,
+            "note": ("CasADi/IPOPT is not importable here and the reference has no compiled sources: the CPU arm is the oracle port "
+                     "of the same problem and interior-point method" if work.key != 5 else
+                     "C port of control.ilqr (pinned to the reference's own outputs, tests/golden/ilqr_golden.npz); the reference's "
+                     "numpy control.ilqr itself needs the /root/reference checkout, which does not travel to the GPU box "
+                     "(measured in the build container: p50 20 ms per solve on one core, SURVEY.md 8(d))")}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path for this metric.  CasADi/IPOPT cannot be installed
-    here, so the arm times the oracle port on all host threads.  Rank 0 only."""
+    """--impl reference: the reference's CPU path for this metric on all host threads (rank 0 only)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     B = args.batch
+    work = WORKS[args.config](B, 1)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
-    from car_racing_b200 import scenarios
-    (x0, xt, obs, lap_off), prm, _ = workload(B, 1)
     orc.lib()
+    probe = reference_solver_probe()
     for _ in range(args.warmup):
-        orc.solve_cbf_batch(x0[:64], xt, obs[:64], lap_off[:64], prm, nthreads=cores)
+        work.cpu(orc, min(64, B), cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=cores)
+        work.cpu(orc, B, cores)
     dt = time.perf_counter() - t0
     val = B * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": work.metric, "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 per GPU (BASELINE config 2)" % B,
-                       "note": "CasADi/IPOPT not installable offline; CPU port of the same NLP + interior point (oracle/ocp_oracle.c)"},
-            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
-                             "sample": "%d instances per step, %d pthreads" % (B, cores)},
+            "config": work.config(B, max(world, args.gpus), max(1, args.inflight), exchange_name(max(world, args.gpus), None)),
+            "cpu_baseline": cpu_baseline_obj(work, val, cores, "%d instances per step, %d pthreads" % (B, cores), probe),
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=OUT, flush=True)
+
+
+def exchange_name(world, px):
+    if world <= 1:
+        return "none (one GPU)"
+    if px is None or px == "p2p":
+        return "p2p: records stored into every rank's window from the solver epilogue (b200mpc_comm_*), 1 argmin kernel per rank"
+    return "nccl: all_gather_into_tensor of the records + argmin kernel (peer windows could not be mapped: %s)" % px
 
 
 def _claim_stdout():
@@ -141,20 +295,40 @@ def _claim_stdout():
     return real
 
 
+def fp64_roofline(work, solves_per_s, sm_mhz):
+    """Counted FP64 work of the kernel (ncu: smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on, tools/fp64_counts.py)
+    against 148 SMs x 64 FMA lanes x 2 flop x clock.  The counts are per kernel build: the file records the library's hash."""
+    p = os.path.join(ROOT, "profiles", "fp64_counts.json")
+    if not os.path.exists(p):
+        return None
+    doc = json.load(open(p))
+    ent = doc.get("kernels", {}).get(work.kernel)
+    if not ent:
+        return None
+    lib = os.path.join(ROOT, "car_racing_b200", "libb200mpc.so")
+    sha = hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16]
+    peak = 148 * 64 * 2 * (sm_mhz or 1965.0) * 1e6 / 1e12
+    ach = ent["flops_per_solve"] * solves_per_s / 1e12
+    return {"flops_per_solve": ent["flops_per_solve"], "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_def": "148 SM x 64 FP64 FMA/clk x 2 x %.0f MHz" % (sm_mhz or 1965.0),
+            "source": "profiles/fp64_counts.json (%s)" % ent.get("report", "?"), "counts_from_this_build": doc.get("lib_sha16") == sha}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="instances per GPU per step")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKS), help="BASELINE.json config (2 = the metric's)")
+    ap.add_argument("--batch", type=int, default=None, help="instances per GPU per step (default: the config's)")
     ap.add_argument("--inflight", type=int, default=6,
                     help="batches in flight (streams driven round-robin); 1 = strictly one batch at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange-priority", default="normal", choices=["high", "normal"],
-                    help="N>1: stream priority of the exchange step (NCCL all-gather + argmin); measured on 2 B200: high is "
-                         "slower (profiles/r03e_exchange_priority.json)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: force the NCCL all-gather form of the exchange")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = WORKS[args.config].default_batch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -168,7 +342,6 @@ def main():
     import ctypes as C
     import torch
     import torch.distributed as dist
-    import car_racing_b200 as crb
     from car_racing_b200 import _capi, sharding
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
@@ -176,60 +349,63 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        # The exchange is 32 KB per rank and step, but its kernels share the SMs with up to D in-flight solver grids (7 resident
-        # CTAs per SM).  Tried: exchange on high-priority streams (NCCL's and the argmin handle's) so that the block scheduler
-        # places its CTAs first -- measured SLOWER on 2 B200 (696-703 k against 733-750 k solves/s, r03e), so normal is the default.
-        pg_opts = None
-        if args.exchange_priority == "high":
-            pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
+        dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     D = max(1, args.inflight)
-    _, prm, rec_host = workload(B, seed=1 + rank)            # each rank: its own shard of scenarios
+    work = WORKS[args.config](B, seed=1 + rank)                 # each rank: its own shard of scenarios
+    rec_host = np.ascontiguousarray(work.rec)
     hs = [_capi.Handle(device=local_rank, max_batch=B) for _ in range(D)]   # one stream + staging buffers per slot
     L = _capi.lib()
-    p = _capi.make_cbf_params(prm, M_OBS, False)
-    o = _capi.default_options()
     exts = [torch.cuda.ExternalStream(h.stream, device=dev) for h in hs]
     d_in = torch.from_numpy(rec_host).to(dev)
     d_rec = [torch.zeros((B, 4), dtype=torch.float64, device=dev) for _ in range(D)]
     d_all = [torch.zeros((world * B, 4), dtype=torch.float64, device=dev) for _ in range(D)]
-    d_arg = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(D)]
+    d_arg = [torch.full((1,), -7, dtype=torch.int32, device=dev) for _ in range(D)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     torch.cuda.synchronize()
 
-    # N>1: the exchange step (all-gather of the 32-byte records + argmin) runs on its own stream.  NCCL completes collectives
-    # in issue order, so an all-gather enqueued on a solver stream would hold that stream until every EARLIER batch's
-    # stragglers have finished on every rank; here the solver stream only records an event and moves on to its next batch
-    # (result buffers are double-buffered per slot).
-    hc = _capi.Handle(device=local_rank, max_batch=B, high_priority=args.exchange_priority == "high") if world > 1 else None
+    # ---- N>1: the exchange.  p2p: the library's window (the solver epilogue stores the records into every rank's gathered
+    #      buffer); its argmin kernel runs on the exchange handle's stream and waits on the device for the arrivals.
+    hc = _capi.Handle(device=local_rank, max_batch=B) if world > 1 else None
     ext_c = torch.cuda.ExternalStream(hc.stream, device=dev) if world > 1 else None
-    d_rec2 = [[d_rec[k], torch.zeros_like(d_rec[k])] for k in range(D)]
-    ag_done = [[None, None] for _ in range(D)]
-    n_issued = [0] * D
+    px, px_why = None, "p2p"
+    if world > 1 and args.exchange == "p2p":
+        try:
+            px = sharding.PeerExchange(hc, rank, world, max_batch=B, slots=D)
+        except Exception as e:                       # CUDA IPC / peer access unavailable on this box
+            px, px_why = None, str(e).replace("\n", " ")[:160]
+        ok = torch.tensor([1 if px is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if px is not None:
+                px.close()
+            px = None
+    elif world > 1:
+        px_why = "--exchange nccl"
+    ag_done = [None] * D
 
     def step_device(k):
-        """One step = one batch of B instances: L2 flush, the solve kernel on slot k's stream; (N>1) all-gather of the
-        32-byte records + argmin on the exchange stream."""
+        """One step = one batch of B instances: L2 flush, the solve kernel on slot k's stream; (N>1) the exchange."""
         h = hs[k]
-        b = n_issued[k] & 1
-        n_issued[k] += 1
         with torch.cuda.stream(exts[k]):
             flush.zero_()
-            if ag_done[k][b] is not None:
-                exts[k].wait_event(ag_done[k][b])          # the exchange that last read this result buffer
-            rc = L.b200mpc_cbf_solve_device(h.ptr, C.byref(p), C.byref(o), B, d_in.data_ptr(), d_rec2[k][b].data_ptr(), None, None, None, None)
-            h.check(rc, "b200mpc_cbf_solve_device")
-            if world > 1:
+            if px is not None:
+                px.publish_next(h, k)
+            elif world > 1 and ag_done[k] is not None:
+                exts[k].wait_event(ag_done[k])            # the all-gather that last read this result buffer
+            h.check(work.device(L, h, B, d_in.data_ptr(), d_rec[k].data_ptr()), "solve_device")
+            if world > 1 and px is None:
                 ev = torch.cuda.Event()
                 ev.record(exts[k])
-        if world > 1:
+        if px is not None:
+            px.argmin(hc, k, d_arg[k].data_ptr(), d_all[k].data_ptr())
+        elif world > 1:
             with torch.cuda.stream(ext_c):
                 ext_c.wait_event(ev)
-                dist.all_gather_into_tensor(d_all[k], d_rec2[k][b])
+                dist.all_gather_into_tensor(d_all[k], d_rec[k])
                 hc.check(L.b200mpc_argmin_cost_device(hc.ptr, d_all[k].data_ptr(), world * B, 0, d_arg[k].data_ptr()), "argmin")
-                ag_done[k][b] = torch.cuda.Event()
-                ag_done[k][b].record(ext_c)
+                ag_done[k] = torch.cuda.Event()
+                ag_done[k].record(ext_c)
 
     def barrier():
         torch.cuda.synchronize()
@@ -247,24 +423,22 @@ def main():
     sampler.start()
 
     # ---- (a) one batch at a time: per-step CUDA events on the launching stream (the kernel's launch duration for the
-    #      roofline, and the latency of one 1024-instance batch)
+    #      roofline, and the latency of one batch); no exchange here
     evs = []
     for _ in range(args.steps):
         with torch.cuda.stream(exts[0]):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(exts[0])
-            rc = L.b200mpc_cbf_solve_device(hs[0].ptr, C.byref(p), C.byref(o), B, d_in.data_ptr(), d_rec[0].data_ptr(), None, None, None, None)
-            hs[0].check(rc, "b200mpc_cbf_solve_device")
+            hs[0].check(work.device(L, hs[0], B, d_in.data_ptr(), d_rec[0].data_ptr()), "solve_device")
             e1.record(exts[0])
             evs.append((e0, e1))
     barrier()
-    ms_serial = [a.elapsed_time(b) for a, b in evs]
-    kernel_ms = float(np.mean(ms_serial))
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
 
     # ---- (b) the timed region of the contract: exactly K steps, D batches in flight (slot = step mod D, each slot its
     #      own stream), L2 flush before every step, bracketed by barrier + synchronize; device time = first start event
-    #      to the last end event over all streams
+    #      to the last end event over all streams (exchange stream included)
     launches0 = launches()
     barrier()
     wall0 = time.perf_counter()
@@ -287,10 +461,30 @@ def main():
     status = sharding.tensor_to_records(d_rec[0])["status"]
     conv = float((status == 0).mean())
 
+    # ---- the exchange delivered what a host-side gather + argmin gives: every slot's gathered buffer holds this rank's
+    #      records at its shard, all ranks hold the same buffer, and the device argmin equals numpy's first-min
+    exchange_ok = None
+    if world > 1:
+        exchange_ok = True
+        for k in range(min(D, args.steps)):
+            allr = sharding.tensor_to_records(d_all[k])
+            mine = sharding.tensor_to_records(d_rec[k])
+            same_shard = bool((allr[rank * B:(rank + 1) * B].tobytes() == mine.tobytes()))
+            arg_ok = int(d_arg[k].item()) == sharding.argmin_first(allr)
+            digest = torch.tensor([float(np.frombuffer(hashlib.sha256(allr.tobytes()).digest()[:6], dtype=np.uint16).sum())],
+                                  dtype=torch.float64, device=dev)
+            lo, hi = digest.clone(), digest.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            exchange_ok = exchange_ok and same_shard and arg_ok and float(lo.item()) == float(hi.item())
+
     # ---- (c) end to end through the host-pointer C-ABI, the same D slots: every step copies its records from pinned
-    #      host memory (H2D), solves, copies the 32-byte result records back (D2H) and the host reads them
+    #      host memory (H2D), solves, copies the 32-byte result records back (D2H) and the host reads them; N>1: the step
+    #      also publishes into the exchange window, and the argmin over the gathered records is copied back and read
     pin_in = [torch.from_numpy(rec_host).pin_memory() for _ in range(D)]
     pin_out = [torch.zeros((B, 4), dtype=torch.float64).pin_memory() for _ in range(D)]
+    pin_arg = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(D)]
+    arg_ev = [None] * D
 
     def e2e_run(nsteps):
         acc = 0.0
@@ -299,14 +493,26 @@ def main():
             if i >= D:
                 hs[k].synchronize()
                 acc += float(pin_out[k][0, 0])                # the step's result is read on the host
+                if arg_ev[k] is not None:
+                    arg_ev[k].synchronize()
+                    acc += float(pin_arg[k][0])
             with torch.cuda.stream(exts[k]):
                 flush.zero_()
-            fn = L.b200mpc_cbf_solve_async if D > 1 else L.b200mpc_cbf_solve
-            rc = fn(hs[k].ptr, C.byref(p), C.byref(o), B, pin_in[k].data_ptr(), pin_out[k].data_ptr(), None, None, None, None)
-            hs[k].check(rc, "b200mpc_cbf_solve(_async)")
+            if px is not None:
+                px.publish_next(hs[k], k)
+            hs[k].check(work.host(L, hs[k], B, pin_in[k].data_ptr(), pin_out[k].data_ptr(), blocking=(D == 1)), "solve(host)")
+            if px is not None:
+                px.argmin(hc, k, d_arg[k].data_ptr(), None)
+                with torch.cuda.stream(ext_c):
+                    pin_arg[k].copy_(d_arg[k], non_blocking=True)
+                    arg_ev[k] = torch.cuda.Event()
+                    arg_ev[k].record(ext_c)
         for k in range(D):
             hs[k].synchronize()
             acc += float(pin_out[k][0, 0])
+            if arg_ev[k] is not None:
+                arg_ev[k].synchronize()
+                acc += float(pin_arg[k][0])
         return acc
 
     e2e_run(max(args.warmup, D))
@@ -320,12 +526,12 @@ def main():
     lat, lat_b = [], []
     for k in range(220):      # 20 warm-ups, 200 timed single-instance calls
         t0 = time.perf_counter()
-        L.b200mpc_cbf_solve(hs[0].ptr, C.byref(p), C.byref(o), 1, pin_in[0].data_ptr(), pin_out[0].data_ptr(), None, None, None, None)
+        work.host(L, hs[0], 1, pin_in[0].data_ptr(), pin_out[0].data_ptr(), blocking=True)
         if k >= 20:
             lat.append(1e3 * (time.perf_counter() - t0))
     for k in range(8):
         t0 = time.perf_counter()
-        L.b200mpc_cbf_solve(hs[0].ptr, C.byref(p), C.byref(o), B, pin_in[0].data_ptr(), pin_out[0].data_ptr(), None, None, None, None)
+        work.host(L, hs[0], B, pin_in[0].data_ptr(), pin_out[0].data_ptr(), blocking=True)
         if k >= 2:
             lat_b.append(1e3 * (time.perf_counter() - t0))
     clocks = sampler.stop()
@@ -336,66 +542,63 @@ def main():
         tt = torch.tensor([t_dev, t_e2e, wall], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev, t_e2e, wall = [float(v) for v in tt.tolist()]
-        cv = torch.tensor([conv], dtype=torch.float64, device=dev)
+        cv = torch.tensor([conv, 1.0 if exchange_ok else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(cv, op=dist.ReduceOp.MIN)
-        conv = float(cv.item())
+        conv, exchange_ok = float(cv[0].item()), bool(cv[1].item() > 0.5)
     total = B * world * args.steps
     value = total / t_dev
-    hbm_peak, peak_src = peaks()
-    achieved = ALG_BYTES_PER_SOLVE * B / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    hbm_peak, sm_max, peak_src = peaks()
+    achieved = work.alg_bytes * B / (kernel_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        t = json.load(open(tp))
+        ent = t.get("kernels", {}).get(work.kernel) or (t if work.key == 2 and "dram_bytes_per_launch" in t else None)
+        if ent:
+            traffic, traffic_src = ent.get("dram_bytes_per_launch"), "profiles/dram_traffic.json (ncu --set full, one B=%s launch)" % ent.get("batch", "1024")
+    cfg = work.config(B, world, D, exchange_name(world, "p2p" if px is not None else px_why))
     line = {
-        "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": work.metric, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 per GPU (BASELINE config 2)" % B,
-                   "global_batch": B * world, "parallelism": "dp%d (independent scenario shards + 1 all-gather of 32-B records and argmin per step, on an exchange stream%s)" % (world, ", high priority" if world > 1 and args.exchange_priority == "high" else ""),
-                   "l2": "256 MiB buffer written before every timed step, on the step's stream (inputs are 1.1 MB << L2)",
-                   "batches_in_flight": D,
-                   "pipelining": ("steps are issued round-robin on %d streams (one handle each): the stragglers of one 1024-instance "
-                                  "batch overlap the next batches; timed first start event -> last end event, flushes included" % D)
-                   if D > 1 else "none: one batch at a time",
-                   "solver": "FP64 barrier-SQP (IPOPT conventions), Riccati KKT, tol 1e-8", "converged_frac": conv},
+        "dtype": "f64", "data": "synthetic", "config": cfg, "converged_frac": conv,
         "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(rec_host.nbytes),
-                "d2h_bytes_per_step": int(B * 32), "ms_per_step": 1e3 * t_e2e / args.steps,
-                "batches_in_flight": D, "p50_latency_ms_batch1": float(np.median(lat)), "p10_p90_latency_ms_batch1": [float(np.percentile(lat, 10)), float(np.percentile(lat, 90))],
+                "d2h_bytes_per_step": int(B * 32 + (4 if px is not None else 0)), "ms_per_step": 1e3 * t_e2e / args.steps,
+                "batches_in_flight": D, "p50_latency_ms_batch1": float(np.median(lat)),
+                "p10_p90_latency_ms_batch1": [float(np.percentile(lat, 10)), float(np.percentile(lat, 90))],
                 "p50_latency_ms_one_batch": float(np.median(lat_b)),
-                "note": ("per rank: host records -> H2D -> solve -> D2H -> host read; the cross-rank exchange step (all-gather + argmin) is part of "
-                         "`value` only") if world > 1 else "host records -> H2D -> solve -> D2H -> host read"},
+                "note": ("per rank: host records -> H2D -> solve (its epilogue stores the records into every rank's window) -> D2H -> host "
+                         "read; + the argmin over the gathered records -> D2H -> host read" if px is not None else
+                         "host records -> H2D -> solve -> D2H -> host read" +
+                         ("; the NCCL form of the exchange is part of `value` only" if world > 1 else ""))},
         "one_batch_at_a_time": {"value": B * world / (kernel_ms * 1e-3), "unit": "solves/s", "ms_per_step": kernel_ms,
-                                "note": "the same kernel, steps serialised on one stream (per-step CUDA events); its launch duration is the roofline's"},
+                                "note": "the same kernel, steps serialised on one stream (per-step CUDA events), no exchange; its launch duration is the roofline's"},
         "gpu_launches": int(launches_dev),
         "gpu_launches_incl_e2e": int(launches_total),
         "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "note": "algorithmic bytes = 1672 B/solve x %d; the kernel is FP64-latency/shared-memory bound, see profiles/ and DESIGN.md" % B},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": work.kernel,
+                     "note": "algorithmic bytes = %d B/solve x %d solves per launch / mean launch duration (one batch at a time); the kernel "
+                             "is FP64-latency bound, see roofline.fp64, profiles/ and DESIGN.md" % (work.alg_bytes, B)},
     }
-    # what actually bounds the kernel (ncu, crowded launch; measured once per kernel version, not live): see DESIGN.md section 5
-    sp = os.path.join(ROOT, "profiles", "r01x_ncu_crowded_b8192_summary.json")
-    if os.path.exists(sp):
-        m = json.load(open(sp))["metrics"]
-        g = lambda k: float(m[k]["value"]) if k in m else None
-        line["roofline"]["ncu_crowded_launch"] = {
-            "source": "profiles/r01x_ncu_crowded_b8192_summary.json",
-            "issue_slots_busy_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-            "fp64_pipe_busy_pct": g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
-            "dram_pct_of_peak": g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
-            "icache_hit_pct": g("sm__icc_request_hit_rate.pct"),
-            "bound": "dependent-issue latency (stall_wait 45 %), after the instruction-fetch bound was removed"}
+    if exchange_ok is not None:
+        line["exchange_verified"] = exchange_ok
+    f64 = fp64_roofline(work, value / world, clocks.get("sm_mhz") or sm_max)
+    if f64:
+        line["roofline"]["fp64"] = f64
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, dt, passes = cpu_port_rate(min(B, 1024), cores)
-        line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
-                                "sample": "the same %d scenarios, %d passes, %d pthreads (%.1f s)" % (min(B, 1024), passes, cores, dt)}
+        n = min(B, 1024)
+        v, dt, passes = cpu_port_rate(work, n, cores)
+        line["cpu_baseline"] = cpu_baseline_obj(work, v, cores, "the same %d scenarios, %d passes, %d pthreads (%.1f s)" % (n, passes, cores, dt),
+                                                reference_solver_probe())
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line), file=OUT, flush=True)
+    if px is not None:
+        barrier()
+        px.close()
     if world > 1:
         dist.destroy_process_group()
 

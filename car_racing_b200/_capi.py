@@ -108,7 +108,10 @@ EXPORTS = [
     "b200mpc_cbf_solve_async", "b200mpc_synchronize", "b200mpc_host_alloc", "b200mpc_host_free", "b200mpc_planner_select_device", "b200mpc_plan_and_track", "b200mpc_ilqr_solve_async", "b200mpc_lmpc_solve_async",
     "b200mpc_planner_prepare_device", "b200mpc_planner_prepare", "b200mpc_plan_and_track_prepared",
     "b200mpc_rival_rollout", "b200mpc_rival_rollout_device", "b200mpc_curv_to_glob", "b200mpc_curv_to_glob_device",
+    "b200mpc_comm_create", "b200mpc_comm_export", "b200mpc_comm_connect", "b200mpc_comm_destroy", "b200mpc_comm_publish_next",
+    "b200mpc_comm_argmin",
 ]
+COMM_HANDLE_BYTES, COMM_MAX_WORLD = 64, 16
 
 _lib = None
 
@@ -177,6 +180,13 @@ def lib():
     sysid_args = [vp, C.POINTER(SysidParams), ip, dp, dp, dp, dp, ip, ip, dp, dp]
     L.b200mpc_lmpc_sysid.argtypes = sysid_args
     L.b200mpc_lmpc_sysid_device.argtypes = sysid_args
+    L.b200mpc_comm_create.argtypes = [vp, ip, ip, ip, ip, C.POINTER(vp)]
+    L.b200mpc_comm_export.argtypes = [vp, dp]
+    L.b200mpc_comm_connect.argtypes = [vp, dp]
+    L.b200mpc_comm_destroy.argtypes = [vp]
+    L.b200mpc_comm_destroy.restype = None
+    L.b200mpc_comm_publish_next.argtypes = [vp, vp, ip]
+    L.b200mpc_comm_argmin.argtypes = [vp, vp, ip, ip, dp, dp]
     plant_args = [vp, C.POINTER(PlantParams), ip, dp, ip, ip, dp, dp, ip, dp, dp, dp]
     L.b200mpc_plant_step.argtypes = plant_args
     L.b200mpc_plant_step_device.argtypes = plant_args

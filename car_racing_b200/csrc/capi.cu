@@ -8,6 +8,7 @@
 #include <string>
 
 #include "../../include/b200mpc.h"
+#include "exchange.cuh"
 #include "frenet.cuh"
 #include "ilqr.cuh"
 #include "lmpc.cuh"
@@ -37,6 +38,24 @@ struct b200mpc_handle {
     size_t c_in = 0, c_rec = 0, c_aux = 0, c_x = 0, c_u = 0, c_sig = 0, c_laps = 0, c_seg = 0, c_idx = 0, c_stat = 0, c_chain = 0;
     uint64_t launches = 0;
     std::string err;
+    // one-shot: the next solver launch also publishes its records into this slot of the exchange window
+    b200mpc_comm *xchg_comm = nullptr;
+    int xchg_slot = 0;
+};
+
+// exchange window of one rank (csrc/exchange.cuh)
+struct b200mpc_comm {
+    int device = 0, rank = 0, world = 1, max_batch = 0, slots = 0;
+    void *window = nullptr;                      // own window: rec | cnt | ack
+    size_t window_bytes = 0;
+    void *peer_base[XCHG_MAX_WORLD] = {};        // every rank's window in this process' address space
+    bool peer_opened[XCHG_MAX_WORLD] = {};
+    XchgTable *d_table = nullptr;
+    bool connected = false;
+    struct Use { int B; unsigned long long cum; };
+    static constexpr int RING = 8;
+    unsigned long long published[64] = {}, consumed[64] = {}, cum[64] = {};
+    Use ring[64][RING];
 };
 
 static thread_local std::string g_create_err;
@@ -151,6 +170,23 @@ int b200mpc_lmpc_record_doubles(int N, int K) {
 
 }  // extern "C"
 
+// The one-shot exchange request of b200mpc_comm_publish_next: consumed by the next solver launch on the handle.
+static int take_xchg(b200mpc_handle *h, int B, XchgArgs *xa) {
+    *xa = XchgArgs{nullptr, 0, 0, 0};
+    b200mpc_comm *c = h->xchg_comm;
+    if (!c) return B200MPC_OK;
+    h->xchg_comm = nullptr;
+    if (B > c->max_batch) return fail(h, B200MPC_ERR_ARG, "exchange: B exceeds the max_batch of the communicator");
+    const int s = h->xchg_slot;
+    if (c->published[s] - c->consumed[s] >= (unsigned long long)b200mpc_comm::RING)
+        return fail(h, B200MPC_ERR_ARG, "exchange: too many unconsumed uses of one slot (call b200mpc_comm_argmin)");
+    c->published[s]++;
+    c->cum[s] += (unsigned long long)B;
+    c->ring[s][c->published[s] % b200mpc_comm::RING] = {B, c->cum[s]};
+    *xa = XchgArgs{c->d_table, s, B, c->published[s]};
+    return B200MPC_OK;
+}
+
 static int check_cbf(b200mpc_handle *h, const b200mpc_cbf_params *p, const b200mpc_ipm_options *o, int B, const void *in,
                      const void *rec) {
     if (!h) return B200MPC_ERR_ARG;
@@ -200,7 +236,9 @@ int b200mpc_cbf_solve_device(b200mpc_handle *h, const b200mpc_cbf_params *prm, c
     } else if (FL != 0 && FL != B200MPC_FLAG_RIVAL_SIZE)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: flags must be 0, STAGE_BOUNDS|EY_RATE (M = 0) or RIVAL_SIZE");
     if (FL == 0 && prm->N == 20 && M == 3 && !prm->xt_per_stage) NT = 20;
-    CbfLaunch l{h->stream, h->device, h->max_smem_optin, h->smem_pad, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma};
+    XchgArgs xa;
+    if ((rc = take_xchg(h, B, &xa))) return rc;
+    CbfLaunch l{h->stream, h->device, h->max_smem_optin, h->smem_pad, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma, xa};
     int e = (FL == B200MPC_FLAG_RIVAL_SIZE) ? (M <= 4 ? launch_cbf_set3(l, kp, M, FL, NT) : launch_cbf_set4(l, kp, M, FL, NT))
             : (M == 0 || NT) ? launch_cbf_set0(l, kp, M, FL, NT)
             : (M <= 4)       ? launch_cbf_set1(l, kp, M, FL, NT)
@@ -284,7 +322,9 @@ int b200mpc_ilqr_solve_device(b200mpc_handle *h, const b200mpc_ilqr_params *prm,
     IlqrPlan pl(prm->N, kp.in_stride);
     size_t smem = pl.bytes();
     CK(h, cudaFuncSetAttribute(ilqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ilqr_kernel<<<B, 32, smem, h->stream>>>(kp, d_in, d_rec, d_xpred, d_upred);
+    XchgArgs xa;
+    if ((rc = take_xchg(h, B, &xa))) return rc;
+    ilqr_kernel<<<B, 32, smem, h->stream>>>(kp, d_in, d_rec, d_xpred, d_upred, xa);
     CK(h, cudaGetLastError());
     h->launches++;
     return B200MPC_OK;
@@ -347,7 +387,9 @@ int b200mpc_lmpc_solve_device(b200mpc_handle *h, const b200mpc_lmpc_params *prm,
     if ((int)smem > h->max_smem_optin)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_lmpc_solve: N, K too large for one CTA's shared memory");
     CK(h, cudaFuncSetAttribute(lmpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lmpc_kernel<<<B, LMPC_NT, smem, h->stream>>>(kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_lambda);
+    XchgArgs xa;
+    if ((rc = take_xchg(h, B, &xa))) return rc;
+    lmpc_kernel<<<B, LMPC_NT, smem, h->stream>>>(kp, d_in, d_rec, d_aux, d_xpred, d_upred, d_lambda, xa);
     CK(h, cudaGetLastError());
     h->launches++;
     return B200MPC_OK;
@@ -881,6 +923,126 @@ int b200mpc_argmin_cost_device(b200mpc_handle *h, const b200mpc_record *d_rec, i
     if (!d_rec || !d_out || B < 1) return fail(h, B200MPC_ERR_ARG, "b200mpc_argmin_cost_device: bad arguments");
     CK(h, cudaSetDevice(h->device));
     argmin_cost_kernel<<<1, 256, 0, h->stream>>>(d_rec, B, max_status, d_out);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return B200MPC_OK;
+}
+
+
+// ---- exchange window (include/b200mpc.h, csrc/exchange.cuh)
+#ifdef B200MPC_HOST_EMULATION   // tests/host_emulation: "device" memory is host memory of this process, the handle is the pointer
+static int ipc_export(void *base, void *out64) { memset(out64, 0, 64); memcpy(out64, &base, sizeof(base)); return 0; }
+static int ipc_open(const void *in64, void **base) { memcpy(base, in64, sizeof(*base)); return 0; }
+static void ipc_close(void *) {}
+#else
+static_assert(sizeof(cudaIpcMemHandle_t) <= B200MPC_COMM_HANDLE_BYTES, "IPC handle size");
+static int ipc_export(void *base, void *out64) {
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, base);
+    if (e != cudaSuccess) return (int)e;
+    memset(out64, 0, 64);
+    memcpy(out64, &hd, sizeof(hd));
+    return 0;
+}
+static int ipc_open(const void *in64, void **base) {
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, in64, sizeof(hd));
+    return (int)cudaIpcOpenMemHandle(base, hd, cudaIpcMemLazyEnablePeerAccess);
+}
+static void ipc_close(void *base) { cudaIpcCloseMemHandle(base); }
+#endif
+
+static size_t comm_rec_bytes(const b200mpc_comm *c) { return (size_t)c->slots * c->world * c->max_batch * sizeof(b200mpc_record); }
+static size_t comm_ctr_bytes(const b200mpc_comm *c) { return (size_t)c->slots * c->world * sizeof(unsigned long long); }
+
+int b200mpc_comm_create(b200mpc_handle *h, int rank, int world, int max_batch, int slots, b200mpc_comm **out) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!out || world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world || max_batch < 1 || slots < 1 || slots > 64)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_comm_create: bad arguments");
+    *out = nullptr;
+    CK(h, cudaSetDevice(h->device));
+    b200mpc_comm *c = new (std::nothrow) b200mpc_comm();
+    if (!c) return fail(h, B200MPC_ERR_NOMEM, "out of host memory");
+    c->device = h->device; c->rank = rank; c->world = world; c->max_batch = max_batch; c->slots = slots;
+    c->window_bytes = comm_rec_bytes(c) + 2 * comm_ctr_bytes(c);
+    cudaError_t e = cudaMalloc(&c->window, c->window_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->window, 0, c->window_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_table, sizeof(XchgTable));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        std::string m = cudaGetErrorString(e);
+        b200mpc_comm_destroy(c);
+        return fail(h, B200MPC_ERR_NOMEM, "b200mpc_comm_create: " + m);
+    }
+    c->peer_base[rank] = c->window;
+    *out = c;
+    return B200MPC_OK;
+}
+
+int b200mpc_comm_export(b200mpc_comm *c, void *handle_out) {
+    if (!c || !handle_out) return B200MPC_ERR_ARG;
+    cudaSetDevice(c->device);
+    return ipc_export(c->window, handle_out) == 0 ? B200MPC_OK : B200MPC_ERR_CUDA;
+}
+
+int b200mpc_comm_connect(b200mpc_comm *c, const void *handles) {
+    if (!c || (!handles && c->world > 1)) return B200MPC_ERR_ARG;
+    if (cudaSetDevice(c->device) != cudaSuccess) return B200MPC_ERR_CUDA;
+    for (int p = 0; p < c->world; p++) {
+        if (p == c->rank || c->peer_opened[p]) continue;
+        void *base = nullptr;
+        if (ipc_open((const char *)handles + (size_t)p * B200MPC_COMM_HANDLE_BYTES, &base) != 0 || !base) {
+            g_create_err = "b200mpc_comm_connect: cannot map the window of rank " + std::to_string(p) +
+                           " (CUDA IPC / peer access unavailable: " + cudaGetErrorString(cudaGetLastError()) + ")";
+            return B200MPC_ERR_CUDA;
+        }
+        c->peer_base[p] = base;
+        c->peer_opened[p] = true;
+    }
+    XchgTable t;
+    memset(&t, 0, sizeof(t));
+    t.rank = c->rank; t.world = c->world; t.max_batch = c->max_batch; t.slots = c->slots;
+    for (int p = 0; p < c->world; p++) {
+        char *b = (char *)c->peer_base[p];
+        t.rec[p] = (b200mpc_record *)b;
+        t.cnt[p] = (unsigned long long *)(b + comm_rec_bytes(c));
+        t.ack[p] = (unsigned long long *)(b + comm_rec_bytes(c) + comm_ctr_bytes(c));
+    }
+    if (cudaMemcpy(c->d_table, &t, sizeof(t), cudaMemcpyHostToDevice) != cudaSuccess) return B200MPC_ERR_CUDA;
+    c->connected = true;
+    return B200MPC_OK;
+}
+
+void b200mpc_comm_destroy(b200mpc_comm *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < c->world; p++)
+        if (c->peer_opened[p]) ipc_close(c->peer_base[p]);
+    if (c->d_table) cudaFree(c->d_table);
+    if (c->window) cudaFree(c->window);
+    delete c;
+}
+
+int b200mpc_comm_publish_next(b200mpc_handle *h, b200mpc_comm *c, int slot) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!c || !c->connected || slot < 0 || slot >= c->slots || c->device != h->device)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_comm_publish_next: communicator not connected, slot out of range or wrong device");
+    h->xchg_comm = c;
+    h->xchg_slot = slot;
+    return B200MPC_OK;
+}
+
+int b200mpc_comm_argmin(b200mpc_handle *h, b200mpc_comm *c, int slot, int max_status, int32_t *d_out, b200mpc_record *d_all) {
+    if (!h) return B200MPC_ERR_ARG;
+    if (!c || !c->connected || slot < 0 || slot >= c->slots || c->device != h->device)
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_comm_argmin: communicator not connected, slot out of range or wrong device");
+    if (c->consumed[slot] >= c->published[slot])
+        return fail(h, B200MPC_ERR_ARG, "b200mpc_comm_argmin: nothing published into this slot");
+    CK(h, cudaSetDevice(h->device));
+    const unsigned long long use = ++c->consumed[slot];
+    const b200mpc_comm::Use u = c->ring[slot][use % b200mpc_comm::RING];
+    xchg_argmin_kernel<<<1, 256, 0, h->stream>>>(c->d_table, slot, u.B, u.cum, use, max_status, d_out, d_all);
     CK(h, cudaGetLastError());
     h->launches++;
     return B200MPC_OK;

@@ -91,7 +91,7 @@ __device__ __forceinline__ void xchg_publish(const XchgArgs &xa, int lane, int i
 // first-min argmin over the world * B gathered records (rank-major = instance order of the global batch; lowest index
 // wins ties, overtake_traj_planner.py:244), optionally copies them out, then acknowledges the use to every peer.
 // want[q] = cumulative arrival count expected from rank q (host-side bookkeeping: sum of B over the uses of the slot).
-__global__ void xchg_argmin_kernel(const XchgTable *__restrict__ tab, int slot, int B, unsigned long long want, unsigned long long use,
+static __global__ void xchg_argmin_kernel(const XchgTable *__restrict__ tab, int slot, int B, unsigned long long want, unsigned long long use,
                                    int max_status, int32_t *__restrict__ out, b200mpc_record *__restrict__ copy_out) {
     __shared__ double sc[32];
     __shared__ int si[32];

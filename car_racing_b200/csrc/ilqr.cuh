@@ -41,7 +41,7 @@ struct IlqrPlan {
 
 __global__ void __launch_bounds__(32) ilqr_kernel(const __grid_constant__ IlqrKParams kp, const double *__restrict__ in,
                                                   b200mpc_record *__restrict__ rec, double *__restrict__ xpred,
-                                                  double *__restrict__ upred) {
+                                                  double *__restrict__ upred, const XchgArgs xa = XchgArgs{nullptr, 0, 0, 0}) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x, inst = blockIdx.x;
     const int N = kp.p.N;
@@ -267,14 +267,15 @@ __global__ void __launch_bounds__(32) ilqr_kernel(const __grid_constant__ IlqrKP
             if (lamb > max_lamb) { it++; break; }
         }
     }
-    if (lane == 0) {
+    {
         b200mpc_record rc;
         rc.cost = cost;
         rc.u0[0] = U[0];
         rc.u0[1] = U[1];
         rc.status = conv ? 0 : 1;
         rc.iters = it;
-        rec[inst] = rc;
+        if (lane == 0) rec[inst] = rc;
+        xchg_publish(xa, lane, inst, rc);
     }
     if (xpred != nullptr)
         for (int e = lane; e < 6 * (N + 1); e += 32) xpred[(size_t)inst * 6 * (N + 1) + e] = X[e];

@@ -51,7 +51,7 @@ constexpr int LMPC_NT = 128;   // threads per instance
 __global__ void __launch_bounds__(LMPC_NT) lmpc_kernel(const __grid_constant__ LmpcKParams kp, const double *__restrict__ in,
                                                   b200mpc_record *__restrict__ rec, double *__restrict__ aux,
                                                   double *__restrict__ xpred, double *__restrict__ upred,
-                                                  double *__restrict__ lambda_out) {
+                                                  double *__restrict__ lambda_out, const XchgArgs xa = XchgArgs{nullptr, 0, 0, 0}) {
     extern __shared__ __align__(16) double sm[];
     constexpr int NT = LMPC_NT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, inst = blockIdx.x;
@@ -563,14 +563,15 @@ __global__ void __launch_bounds__(LMPC_NT) lmpc_kernel(const __grid_constant__ L
         iter++;
     }
     double cost = objective(W, 0.0, false);
-    if (tid == 0) {
+    if (tid < 32) {     // warp 0 (convergent here): result record, and its copy into every rank's gathered buffer
         b200mpc_record rc;
         rc.cost = cost;
         rc.u0[0] = W[OU];
         rc.u0[1] = W[OU + 1];
         rc.status = status;
         rc.iters = iter;
-        rec[inst] = rc;
+        if (tid == 0) rec[inst] = rc;
+        xchg_publish(xa, tid, inst, rc);
     }
     if (aux != nullptr && tid < 4) aux[(size_t)inst * 4 + tid] = (tid == 0) ? E0 : (tid == 3 ? (double)n_back : 0.0);
     if (xpred != nullptr)

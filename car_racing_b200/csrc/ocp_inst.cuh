@@ -19,7 +19,7 @@ static int launch_cbf_one(const CbfLaunch &l, const KParams &kp) {
         if (e != cudaSuccess) return (int)e;
         granted[d] = (int)smem;
     }
-    ocp_ipm_kernel<M, FL, NT><<<kp.B, 32, smem, l.stream>>>(kp, l.in, l.rec, l.aux, l.x, l.u, l.sig);
+    ocp_ipm_kernel<M, FL, NT><<<kp.B, 32, smem, l.stream>>>(kp, l.in, l.rec, l.aux, l.x, l.u, l.sig, l.xa);
     return (int)cudaGetLastError();
 }
 

@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/b200mpc.h"
+#include "exchange.cuh"
 
 namespace b200mpc {
 
@@ -1147,7 +1148,7 @@ template <int M, int FL, int NT>
 __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KParams kp, const double *__restrict__ in,
                                                      b200mpc_record *__restrict__ rec, double *__restrict__ aux,
                                                      double *__restrict__ xpred, double *__restrict__ upred,
-                                                     double *__restrict__ sigma) {
+                                                     double *__restrict__ sigma, const XchgArgs xa = XchgArgs{nullptr, 0, 0, 0}) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x;
     const int inst = blockIdx.x;
@@ -1722,14 +1723,15 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     double tm = 0.0;
     for (int r = lane; r < R; r += 32) tm = fmax(tm, q.T[r]);
     tm = warp_max_nn(tm);
-    if (lane == 0) {
+    {
         b200mpc_record rc;
         rc.cost = cost;
         rc.u0[0] = q.W[OU];
         rc.u0[1] = q.W[OU + 1];
         rc.status = status;
         rc.iters = iter;
-        rec[inst] = rc;
+        if (lane == 0) rec[inst] = rc;
+        xchg_publish(xa, lane, inst, rc);   // sharded batch: lane p stores the record into rank p's gathered buffer (exchange.cuh)
     }
     if (aux != nullptr && lane < 4) {
         double v = (lane == 0) ? E0 : (lane == 1) ? tm : (lane == 2) ? (double)n_refac : (double)n_back;

@@ -18,6 +18,7 @@ struct CbfLaunch {
     const double *in;
     b200mpc_record *rec;
     double *aux, *x, *u, *sig;
+    XchgArgs xa;           // tab == nullptr: no exchange (exchange.cuh)
 };
 
 enum { CBF_LAUNCH_NOT_HERE = -1000, CBF_LAUNCH_SMEM = -1001 };

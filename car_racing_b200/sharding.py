@@ -1,13 +1,77 @@
-"""Multi-GPU plumbing: one process per GPU, contiguous block partition of the instance batch, one
-all-gather of the 32-byte per-instance records (torch.distributed: NCCL over NVLink on GPUs, gloo in
-the CPU tests), then the same first-min argmin on every rank
+"""Multi-GPU plumbing: one process per GPU, contiguous block partition of the instance batch, one exchange of the
+32-byte per-instance records, then the same first-min argmin on every rank
 (overtake_traj_planner.py:244: `direction_flag = cost_selection.index(min(cost_selection))`).
-The solve itself needs no collective: instances are independent."""
+The solve itself needs no collective: instances are independent.
+
+Two forms of the exchange:
+  * PeerExchange -- the product path on GPUs: the library's own window (b200mpc_comm_*, csrc/exchange.cuh); the solver
+    kernels' epilogue stores each record into every rank's gathered buffer over NVLink, no collective kernel.
+    torch.distributed is only used once, to hand the 64-byte window handles around.
+  * all_gather_records -- torch.distributed.all_gather_into_tensor (NCCL on GPUs, gloo in the CPU tests) for callers
+    that hold their records in torch tensors."""
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _capi
 from ._capi import RECORD_DTYPE
+
+
+class PeerExchange:
+    """The exchange window of this rank (include/b200mpc.h: b200mpc_comm_*).
+
+        px = PeerExchange(handle, rank, world, max_batch=B, slots=D)      # collective: every rank, same arguments
+        px.publish_next(handle_k, slot)                                   # the next solve on handle_k publishes into `slot`
+        L.b200mpc_cbf_solve_device(handle_k.ptr, ...)                     #   (every rank solves the same B in that step)
+        px.argmin(handle_c, slot, d_arg_ptr, d_all_ptr)                   # on handle_c's stream: wait, argmin, copy, release
+
+    `allgather` hands the 64-byte handles around: a callable bytes -> list of `world` bytes objects; default
+    torch.distributed.all_gather_object on the default group."""
+
+    def __init__(self, handle, rank, world, max_batch, slots, allgather=None):
+        self.rank, self.world, self.max_batch, self.slots = int(rank), int(world), int(max_batch), int(slots)
+        L = _capi.lib()
+        c = C.c_void_p()
+        handle.check(L.b200mpc_comm_create(handle.ptr, self.rank, self.world, self.max_batch, self.slots, C.byref(c)),
+                     "b200mpc_comm_create")
+        self._c = c
+        mine = (C.c_char * _capi.COMM_HANDLE_BYTES)()
+        if L.b200mpc_comm_export(self._c, mine) != 0:
+            raise _capi.B200MPCError("b200mpc_comm_export failed")
+        if allgather is None:
+            def allgather(b):
+                out = [None] * self.world
+                dist.all_gather_object(out, b)
+                return out
+        blobs = allgather(bytes(mine.raw)) if self.world > 1 else [bytes(mine.raw)]
+        if len(blobs) != self.world or any(len(b) != _capi.COMM_HANDLE_BYTES for b in blobs):
+            raise ValueError("allgather must return `world` handles of %d bytes" % _capi.COMM_HANDLE_BYTES)
+        rc = L.b200mpc_comm_connect(self._c, b"".join(blobs))
+        if rc != 0:
+            msg = L.b200mpc_last_error(None).decode()
+            self.close()
+            raise _capi.B200MPCError("b200mpc_comm_connect failed (%d): %s" % (rc, msg))
+
+    def publish_next(self, handle, slot):
+        handle.check(_capi.lib().b200mpc_comm_publish_next(handle.ptr, self._c, int(slot)), "b200mpc_comm_publish_next")
+
+    def argmin(self, handle, slot, d_out, d_all=None, max_status=0):
+        """d_out: device pointer of one int32; d_all: optional device pointer of world * B records."""
+        handle.check(_capi.lib().b200mpc_comm_argmin(handle.ptr, self._c, int(slot), int(max_status), d_out, d_all),
+                     "b200mpc_comm_argmin")
+
+    def close(self):
+        c, self._c = getattr(self, "_c", None), None
+        if c:
+            _capi.lib().b200mpc_comm_destroy(c)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def shard_range(B, rank, world):

@@ -395,6 +395,33 @@ int b200mpc_plan_and_track_prepared(b200mpc_handle *h, const b200mpc_cbf_params 
  * lowest index wins ties (list.index(min(...)), overtake_traj_planner.py:244); *d_out = -1 if none. */
 int b200mpc_argmin_cost_device(b200mpc_handle *h, const b200mpc_record *d_rec, int B, int max_status, int32_t *d_out);
 
+/* ---- Exchange step of a batch sharded over G GPUs, one process per GPU.
+ * Replaces the join of the reference's fan-out -- one forked process per candidate, results gathered through a
+ * Manager().dict(), then `cost_selection.index(min(cost_selection))` (planning/overtake_traj_planner.py:177-204, :244) -- for a
+ * candidate / scenario batch whose shards live on different GPUs.  It is not a collective call after the solve: each rank
+ * owns a window in its HBM that the peers map over NVLink (CUDA IPC), and the solver kernels' epilogue stores every
+ * 32-byte result record straight into all ranks' gathered buffers as the instance finishes (csrc/exchange.cuh).
+ *
+ *   b200mpc_comm_create   on every rank: allocates the window (slots x world x max_batch records + counters)
+ *   b200mpc_comm_export   64-byte handle of the own window; the caller hands all ranks' handles to every rank (any
+ *                         transport: torch.distributed, MPI, a file)
+ *   b200mpc_comm_connect  maps the peers' windows
+ *   b200mpc_comm_publish_next(h, c, slot)   the NEXT b200mpc_{cbf,ilqr,lmpc}_solve* call on handle h also publishes its B
+ *                         records (every rank must solve the same B in that step) into slot `slot` of every rank
+ *   b200mpc_comm_argmin   on handle h's stream: waits until all world x B records of the slot's oldest unconsumed use
+ *                         have arrived, writes the first-min argmin over them (global instance order = rank-major) to d_out
+ *                         and, if d_all != NULL, a copy of the gathered records; then releases the slot to the peers.
+ * Uses of one slot must be issued in the same order on every rank; `slots` steps can be in flight. */
+typedef struct b200mpc_comm b200mpc_comm;
+#define B200MPC_COMM_HANDLE_BYTES 64
+#define B200MPC_COMM_MAX_WORLD 16
+int b200mpc_comm_create(b200mpc_handle *h, int rank, int world, int max_batch, int slots, b200mpc_comm **out);
+int b200mpc_comm_export(b200mpc_comm *c, void *handle_out);
+int b200mpc_comm_connect(b200mpc_comm *c, const void *handles /* world x B200MPC_COMM_HANDLE_BYTES, rank-major */);
+void b200mpc_comm_destroy(b200mpc_comm *c);
+int b200mpc_comm_publish_next(b200mpc_handle *h, b200mpc_comm *c, int slot);
+int b200mpc_comm_argmin(b200mpc_handle *h, b200mpc_comm *c, int slot, int max_status, int32_t *d_out, b200mpc_record *d_all);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,16 @@ TOL_U, TOL_C = 1e-4, 1e-5
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _compare(g, r, min_match=0.97):
+def _log(info):
+    """Append the measured rates to gpurun_out/parity_rates.jsonl (GPU box runs): the gates below are set from them."""
+    import json
+    d = os.path.join(os.path.dirname(GOLD.rstrip("/")), "..", "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_rates.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=os.environ.get("PYTEST_CURRENT_TEST", "?"), **info)) + "\n")
+
+
+def _compare(g, r, min_match=0.99):
     both = (g["status"] == 0) & (r["status"] == 0)
     du = np.abs(g["u0"] - r["u0"]).max(axis=1)
     dc = np.abs(g["cost"] - r["cost"])
@@ -22,7 +31,9 @@ def _compare(g, r, min_match=0.97):
                 gpu_fail=int((g["status"] != 0).sum()), cpu_fail=int((r["status"] != 0).sum()),
                 worst_du=float(du[both].max()) if both.any() else 0.0, worst_dc=float(dc[both].max()) if both.any() else 0.0,
                 iters_equal=float((g["iters"] == r["iters"]).mean()))
+    info["match_frac"], info["gate"] = float(match.mean()), min_match
     print(info)
+    _log(info)
     assert match.mean() >= min_match, info
     return match, info
 
@@ -41,15 +52,91 @@ def test_mpccbf_config2_parity(crb, oracle):
     assert g["kkt_err"][g["status"] == 0].max() <= 1e-6
 
 
-@pytest.mark.parametrize("N,M", [(10, 0), (20, 0), (10, 1), (12, 2), (20, 4), (5, 3), (1, 1), (32, 3)])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_mpccbf_full_batch_parity(crb, oracle, seed):
+    """The BASELINE batch itself: 1024 config-2 instances per seed (round 1 had this only as a report under profiles/).
+    Gate: same status, and where both converge |du| < 1e-4 and |dcost| < 1e-5, on >= 99.5 % of the instances.  The few
+    outside are NOT other optima: they stop one iteration apart at a different final mu and the objective carries the
+    barrier residual of the 63 slack variables (1e4 * sigma, sigma ~ mu/z), which is the size of the cost tolerance."""
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(1024, N=20, M=3, seed=seed)
+    prm = scenarios.default_cbf_params(N=20)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
+    match, info = _compare(g, r, min_match=0.995)
+    assert (g["status"] == r["status"]).mean() >= 0.999
+    both = (g["status"] == 0) & (r["status"] == 0)
+    out = both & ~match
+    assert (np.abs(g["cost"] - r["cost"])[out] < 1e-3).all(), "an instance converged to a different optimum"
+    assert np.abs(g["u0"] - r["u0"])[both].max() < 5e-3
+    assert np.abs(g["x"][match & both] - r["x"][match & both]).max() < 1e-4
+    assert np.abs(g["sigma"][match & both] - r["sigma"][match & both]).max() < 1e-6
+
+
+def test_kkt_certificate_on_every_converged_instance(crb):
+    """Solver-independent certificate (tests/kkt_check.py: feasibility, NNLS multiplier recovery on the active set,
+    stationarity, complementarity) on ALL converged, non-elastic instances of one BASELINE batch."""
+    from kkt_check import certificate
+    B = 1024
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=20, M=3, seed=1)
+    prm = scenarios.default_cbf_params(N=20)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    n = n_pass = 0
+    worst = dict(dyn=0.0, row_viol=0.0, stat=0.0, comp=0.0)
+    for b in range(B):
+        if g["status"][b] != 0 or g["elastic_max"][b] > 1e-7:
+            continue
+        c = certificate(x0[b], xt, obs[b], lap_off[b], prm, g["x"][b], g["u"][b], g["sigma"][b])
+        n += 1
+        ok = c["dyn"] < 1e-8 and c["row_viol"] < 1e-6 and c["stat"] < 1e-4 and c["comp"] < 1e-4
+        n_pass += ok
+        for k in worst:
+            worst[k] = max(worst[k], float(c[k]))
+    info = dict(certified=n, passed=int(n_pass), pass_rate=n_pass / max(n, 1), worst=worst,
+                converged=int((g["status"] == 0).sum()), elastic=int(((g["status"] == 0) & (g["elastic_max"] > 1e-7)).sum()))
+    print(info)
+    _log(info)
+    assert n >= 0.98 * B and worst["dyn"] < 1e-8 and worst["row_viol"] < 1e-6
+    # the NNLS recovery is itself approximate at active-set changes (|stat| up to ~3e-4 on a handful of instances)
+    assert n_pass >= 0.99 * n and worst["stat"] < 1e-2
+
+
+@pytest.mark.parametrize("N,M", [(10, 0), (20, 0), (10, 1), (12, 2), (20, 4), (5, 3), (1, 1), (32, 3), (15, 6), (10, 8)])
 def test_cbf_shapes_parity(crb, oracle, N, M):
-    """mpc_lti (M=0) and other horizon / rival-count combinations, incl. N=1 and M=MMAX."""
-    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(48, N=N, M=max(M, 1), seed=10 + N + M)
+    """mpc_lti (M=0) and other horizon / rival-count combinations, incl. N=1 and M=MMAX (8)."""
+    B = 192
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=N, M=max(M, 1), seed=10 + N + M)
     obs, lap_off = obs[:, :M], lap_off[:, :M]
     prm = scenarios.default_cbf_params(N=N, width=0.8 if M == 0 else 1.0)
     g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
     r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
-    _compare(g, r, min_match=0.95)
+    _compare(g, r, min_match=0.99)
+
+
+def test_per_rival_sizes_zero_start_and_x0_rows(crb, oracle):
+    """Round-2 options through the C-ABI on the GPU: per-rival (L, W) in the record (flag RIVAL_SIZE), the zero start of
+    Opti/IPOPT (B200MPC_START_ZERO, bounded iteration count: same iterates as the oracle), status 4 for an x_0 outside the
+    stage-0 rows."""
+    B, N, M = 96, 20, 3
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=N, M=M, seed=31)
+    prm = scenarios.default_cbf_params(N=N)
+    rng = np.random.default_rng(5)
+    sizes = np.stack([rng.uniform(0.35, 0.5, (B, M)), rng.uniform(0.18, 0.26, (B, M))], axis=2)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm, sizes=sizes)
+    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, sizes=sizes, nthreads=os.cpu_count() or 1)
+    _compare(g, r, min_match=0.97)
+    kw = dict(start=1, max_iter=40, max_reset=50)
+    g = crb.solve_cbf_batch(x0[:32], xt, obs[:32], lap_off[:32], prm, **kw)
+    r = oracle.solve_cbf_batch(x0[:32], xt, obs[:32], lap_off[:32], prm, nthreads=os.cpu_count() or 1, **kw)
+    same = (g["status"] == r["status"]) & (g["iters"] == r["iters"])
+    info = dict(zero_start_same_path=float(same.mean()), x_diff=float(np.abs(g["x"] - r["x"])[same].max()))
+    print(info)
+    _log(info)
+    assert same.mean() >= 0.9 and info["x_diff"] < 1e-5
+    x0b = x0[:8].copy()
+    x0b[0, 5], x0b[1, 0] = 1.2, -0.3
+    g = crb.solve_cbf_batch(x0b, xt, obs[:8], lap_off[:8], prm)
+    r = oracle.solve_cbf_batch(x0b, xt, obs[:8], lap_off[:8], prm)
+    assert (g["status"][:2] == 4).all() and (g["status"] == r["status"]).all()
 
 
 def test_mpc_lti_anchor_on_gpu(crb):
@@ -255,14 +342,14 @@ def test_planner_drop_in_on_gpu(crb, oracle):
 
 
 def test_max_sizes_and_odd_batches(crb, oracle):
-    """Maximum horizon / rival count of the C-ABI (N=64, M=4) and batch sizes that are not a multiple of anything."""
-    N, M = 64, 4
-    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(9, N=N, M=M, seed=21)
-    obs[:, :, 0, :] += 3.0                                  # keep the long horizon feasible: rivals further ahead
-    prm = scenarios.default_cbf_params(N=N)
-    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
-    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
-    _compare(g, r, min_match=0.85)
+    """Maximum horizon / rival count of the C-ABI (N=64, M=4 and M=8) and batch sizes that are not a multiple of anything."""
+    for (N, M, B, gate) in ((64, 4, 64, 0.95), (64, 8, 24, 0.9)):
+        x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=N, M=M, seed=21)
+        obs[:, :, 0, :] += 3.0                                  # keep the long horizon feasible: rivals further ahead
+        prm = scenarios.default_cbf_params(N=N)
+        g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+        r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
+        _compare(g, r, min_match=gate)
     for B in (1, 3, 33):
         x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=20, M=3, seed=30 + B)
         prm = scenarios.default_cbf_params(N=20)

@@ -160,3 +160,78 @@ def test_gpu_tests_also_pass_on_the_host_library(emu, oracle, module, name):
     fn = getattr(importlib.import_module(module), name)
     args = {"crb": crb, "oracle": oracle}
     fn(**{k: args[k] for k in inspect.signature(fn).parameters})
+
+
+def test_exchange_window_protocol_two_ranks_in_one_process(emu):
+    """b200mpc_comm_* (csrc/exchange.cuh) on the host library: two "ranks" (two handles, two windows whose handles are
+    exchanged by hand) publish their shards from the solver kernel's epilogue into BOTH gathered buffers; each rank's argmin
+    kernel then sees all records in rank-major order.  Three uses of one slot exercise the arrival counters and the
+    acknowledgements; the MPC-CBF, iLQR and LMPC kernels all carry the epilogue."""
+    import ctypes as C
+    from car_racing_b200 import sharding
+    L = _capi.lib()
+    B, world = 3, 2
+    hs = [_capi.Handle(), _capi.Handle()]
+    # windows of both ranks inside this one process: create and export both, then connect both (the product does the
+    # hand-over of the 64-byte handles with torch.distributed, one process per GPU)
+    px = [sharding.PeerExchange.__new__(sharding.PeerExchange) for _ in range(world)]
+    blobs = []
+    for r in range(world):
+        c = C.c_void_p()
+        hs[r].check(L.b200mpc_comm_create(hs[r].ptr, r, world, 4, 2, C.byref(c)), "comm_create")
+        px[r]._c, px[r].rank, px[r].world = c, r, world
+        buf = (C.c_char * _capi.COMM_HANDLE_BYTES)()
+        assert L.b200mpc_comm_export(c, buf) == 0
+        blobs.append(bytes(buf.raw))
+    assert L.b200mpc_comm_publish_next(hs[0].ptr, px[0]._c, 0) == -1          # not connected yet
+    for r in range(world):
+        assert L.b200mpc_comm_connect(px[r]._c, b"".join(blobs)) == 0
+    prm = scenarios.default_cbf_params(N=10)
+    o = _capi.default_options()
+    shards = [scenarios.mpccbf_scenarios(B, N=10, M=1, seed=40 + r) for r in range(world)]
+    p = _capi.make_cbf_params(prm, 1, False)
+    P = batch._ptr
+    for use in range(3):
+        recs = []
+        for r in range(world):
+            x0, xt, obs, lo = shards[r]
+            x0 = x0 + 0.01 * use
+            rin, M, ps = batch.pack_cbf(x0, xt, obs, lo, 10)
+            rec = np.zeros(B, dtype=_capi.RECORD_DTYPE)
+            px[r].publish_next(hs[r], 1)
+            hs[r].check(L.b200mpc_cbf_solve(hs[r].ptr, C.byref(p), C.byref(o), B, P(rin), P(rec), None, None, None, None), "solve")
+            recs.append(rec)
+        want = np.concatenate(recs)
+        for r in range(world):
+            arg = np.zeros(1, dtype=np.int32)
+            allr = np.zeros(world * B, dtype=_capi.RECORD_DTYPE)
+            px[r].argmin(hs[r], 1, P(arg), P(allr))
+            assert (allr["cost"] == want["cost"]).all() and (allr["u0"] == want["u0"]).all() and (allr["iters"] == want["iters"]).all()
+            assert arg[0] == sharding.argmin_first(want)
+    # a solve without publish_next leaves the window alone; argmin without a publication is an error
+    rec = np.zeros(B, dtype=_capi.RECORD_DTYPE)
+    hs[0].check(L.b200mpc_cbf_solve(hs[0].ptr, C.byref(p), C.byref(o), B, P(rin), P(rec), None, None, None, None), "solve")
+    assert L.b200mpc_comm_argmin(hs[0].ptr, px[0]._c, 1, 0, P(np.zeros(1, dtype=np.int32)), None) == -1
+    # the other two solver kernels publish as well
+    x0, xt, obs, lo = scenarios.ilqr_scenarios(2, N=12, seed=2)
+    iprm = dict(A=prm["A"], B=prm["B"], Q=prm["Q"], R=prm["R"], N=12, max_iter=20, L=0.4, W=0.2)
+    outs = []
+    for r in range(world):
+        px[r].publish_next(hs[r], 0)
+        outs.append(crb.solve_ilqr_batch(x0 + 0.02 * r, xt, obs, lo, iprm, want=(), handle=hs[r])["record"])
+    allr = np.zeros(4, dtype=_capi.RECORD_DTYPE)
+    arg = np.zeros(1, dtype=np.int32)
+    px[1].argmin(hs[1], 0, P(arg), P(allr))
+    px[0].argmin(hs[0], 0, P(arg), None)
+    assert (allr["cost"] == np.concatenate(outs)["cost"]).all()
+    sc = scenarios.lmpc_scenarios(2, seed=5)
+    lprm = scenarios.default_lmpc_params()
+    outs = []
+    for r in range(world):
+        px[r].publish_next(hs[r], 0)
+        outs.append(crb.solve_lmpc_batch(*sc, lprm, want=(), handle=hs[r])["record"])
+    px[0].argmin(hs[0], 0, P(arg), P(allr))
+    px[1].argmin(hs[1], 0, P(arg), None)
+    assert (allr["cost"] == np.concatenate(outs)["cost"]).all() and arg[0] == sharding.argmin_first(np.concatenate(outs))
+    for x in px:
+        x.close()

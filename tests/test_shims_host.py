@@ -25,9 +25,15 @@ def _capture(monkeypatch):
     seen = {}
 
     def fake(x0, xt, obs, lap_off, prm, want=("aux", "x", "u", "sigma"), handle=None, **opt):
-        seen.update(x0=np.array(x0), xt=np.array(xt), obs=np.array(obs), lap_off=lap_off, prm=prm)
+        seen.update(x0=np.array(x0), xt=np.array(xt), obs=np.array(obs), lap_off=lap_off, prm=prm, opt=opt)
+        seen.setdefault("calls", []).append(dict(opt))
         N = prm["N"]
-        return dict(u=np.zeros((1, N, 2)) + 0.25, x=np.zeros((1, N + 1, 6)), status=np.array([0]), u0=np.zeros((1, 2)))
+        k = len(seen["calls"]) - 1
+        st = seen.get("statuses", [0])
+        el = seen.get("elastic", [0.0])
+        return dict(u=np.zeros((1, N, 2)) + 0.25, x=np.zeros((1, N + 1, 6)), status=np.array([st[min(k, len(st) - 1)]]),
+                    u0=np.zeros((1, 2)), iters=np.array([7]), cost=np.zeros(1), kkt_err=np.zeros(1),
+                    elastic_max=np.array([el[min(k, len(el) - 1)]]))
     monkeypatch.setattr(control.batch, "solve_cbf_batch", fake)
     return seen
 
@@ -52,15 +58,65 @@ def test_mpccbf_filter_and_lap_offset(monkeypatch):
     assert seen["xt"].shape == (6,)
 
 
-def test_mpccbf_rejects_mixed_rival_sizes(monkeypatch):
-    _capture(monkeypatch)
-    vehicles = {"ego": Rival(0, 0, 0), "a": Rival(4.0, 0, 0.1), "b": Rival(4.5, 0, -0.3, length=0.6)}
+def _mpccbf_args(vehicles, N=5):
     param = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.eye(6), matrix_R=np.eye(2),
-                                  num_horizon=5, alpha=0.8)
+                                  num_horizon=N, alpha=0.8)
     sysp = types.SimpleNamespace(delta_max=0.5, a_max=1.0, v_max=10, v_min=0)
-    with pytest.raises(NotImplementedError):
-        control.mpccbf(np.array([1.2, 0, 0, 0, 3.0, 0.0]), np.zeros(6), param, vehicles, "ego", 19.2296, 0.0, 0.1, False,
-                       types.SimpleNamespace(width=1.0), sysp)
+    return (np.array([1.2, 0, 0, 0, 3.0, 0.0]), np.zeros(6), param, vehicles, "ego", 19.2296, 0.0, 0.1, False,
+            types.SimpleNamespace(width=1.0), sysp)
+
+
+def test_mpccbf_mixed_rival_sizes_go_into_the_record(monkeypatch):
+    """control.py:530-535 reads every rival's own length / width: different rivals -> the per-rival block of the record."""
+    seen = _capture(monkeypatch)
+    vehicles = {"ego": Rival(0, 0, 0), "a": Rival(4.0, 0, 0.1), "b": Rival(4.5, 0, -0.3, length=0.6, width=0.3)}
+    control.mpccbf(*_mpccbf_args(vehicles))
+    assert np.allclose(seen["opt"]["sizes"], [[0.4, 0.2], [0.5, 0.25]])
+    vehicles["b"] = Rival(4.5, 0, -0.3)
+    control.mpccbf(*_mpccbf_args(vehicles))
+    assert seen["opt"]["sizes"] is None and seen["prm"]["L"] == 0.4 and seen["prm"]["W"] == 0.2
+
+
+def test_mpccbf_keeps_the_nearest_rivals_beyond_the_kernel_limit(monkeypatch):
+    from car_racing_b200 import _capi
+    seen = _capture(monkeypatch)
+    vehicles = {"ego": Rival(0, 0, 0)}
+    gaps = np.linspace(-2.0, 2.2, _capi.MMAX + 3)             # all inside the +-2.4 m window
+    for k, g in enumerate(gaps):
+        vehicles["car%d" % k] = Rival(3.0 + g, 0.0, 0.1 * k - 0.5)
+    with pytest.warns(UserWarning, match="nearest"):
+        control.mpccbf(*_mpccbf_args(vehicles))
+    assert seen["obs"].shape[1] == _capi.MMAX
+    kept_gap = np.abs(seen["obs"][0, :, 0, 0] - 3.0)
+    assert kept_gap.max() <= np.sort(np.abs(gaps))[_capi.MMAX - 1] + 1e-12
+    assert (np.diff(seen["obs"][0, :, 0, 0]) > 0).all()       # the reference's rival order is kept
+
+
+def test_single_instance_retries(monkeypatch):
+    """MAX_ITER at the batch default of 200 iterations -> IPOPT's limit; an elastic solution -> a stiffer penalty; the shim
+    never raises, mpc_lti does (control.py:242)."""
+    seen = _capture(monkeypatch)
+    vehicles = {"ego": Rival(0, 0, 0), "a": Rival(4.0, 0, 0.1)}
+    seen["statuses"], seen["elastic"] = [1, 0], [0.0, 0.0]
+    control.mpccbf(*_mpccbf_args(vehicles))
+    assert len(seen["calls"]) == 2 and seen["calls"][1]["max_iter"] == 3000 and control.last_solve["status"] == 0
+    seen.pop("calls")
+    seen["statuses"], seen["elastic"] = [0, 0], [0.3, 0.0]
+    control.mpccbf(*_mpccbf_args(vehicles))
+    assert len(seen["calls"]) == 2 and seen["calls"][1]["rho"] == 1e5 and control.last_solve["elastic_max"] == 0.0
+    seen.pop("calls")
+    seen["statuses"], seen["elastic"] = [0, 1], [0.3, 0.0]
+    with pytest.warns(UserWarning, match="elastically"):
+        control.mpccbf(*_mpccbf_args(vehicles))
+    assert control.last_solve["elastic_max"] == 0.3 and control.last_solve["retries"][0][0].startswith("rho")
+    seen.pop("calls")
+    seen["statuses"], seen["elastic"] = [4], [0.0]
+    a = _mpccbf_args(vehicles)
+    control.mpccbf(*a)                                        # infeasible x0: reported, the iterate is used (control.py:600-603)
+    assert control.last_solve["status"] == 4
+    lti = types.SimpleNamespace(matrix_A=scenarios.LTI_A, matrix_B=scenarios.LTI_B, matrix_Q=np.eye(6), matrix_R=np.eye(2), num_horizon=5)
+    with pytest.raises(RuntimeError, match="stage-0"):
+        control.mpc_lti(a[0], a[1], lti, a[10], types.SimpleNamespace(width=1.0))
 
 
 def test_mpc_multi_agents_targets(monkeypatch):

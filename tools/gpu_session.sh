@@ -1,0 +1,40 @@
+#!/bin/bash
+# GPU-box session: everything measured in one gpurun call (box acquisition dominates the cost of a call).
+#   gpurun --timeout 2400 -- tools/gpu_session.sh <tag> [steps...]      steps default: all
+tag=${1:-s}; shift
+steps=${@:-pytest smoke bench configs reference clocks ncu counts start launches}
+mkdir -p gpurun_out
+run() { echo "== $1"; shift; "$@"; echo "   exit $?"; }
+for s in $steps; do
+case $s in
+  pytest)   rm -f gpurun_out/parity_rates.jsonl
+            timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/${tag}_pytest.log; tail -5 gpurun_out/${tag}_pytest.log
+            [ -f gpurun_out/parity_rates.jsonl ] && mv gpurun_out/parity_rates.jsonl gpurun_out/${tag}_parity_rates.jsonl ;;
+  smoke)    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -6 gpurun_out/${tag}_smoke.log ;;
+  bench)    timeout 400 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 600 gpurun_out/${tag}_bench.json ;;
+  configs)  for c in 3 4 5; do timeout 400 python bench.py --config $c > gpurun_out/${tag}_bench_c$c.json 2> gpurun_out/${tag}_bench_c$c.err; python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${tag}_bench_c$c.json"))
+    print("config $c:", round(d["value"]), "solves/s  e2e", round(d["e2e"]["value"]), " serial", round(d["one_batch_at_a_time"]["value"]), " p50 B=1 %.3f ms" % d["e2e"]["p50_latency_ms_batch1"], " conv", d["converged_frac"], " cpu", d.get("cpu_baseline", {}).get("value"))
+except Exception as e:
+    print("config $c failed:", e)
+PY
+            done ;;
+  reference) timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>&1; tail -c 300 gpurun_out/${tag}_bench_reference.json ;;
+  clocks)   timeout 300 python tools/phase_clocks.py scratch/variants/libb200mpc_clocks.so --out gpurun_out/${tag}_phase_clocks.json | cut -c1-400 ;;
+  ncu)      timeout 600 ncu --set full --import-source on --clock-control none -k regex:ocp_ipm -s 1 -c 1 -f -o gpurun_out/${tag}_crowded python tools/one_launch.py --B 8192 2>&1 | tail -3
+            ls -la gpurun_out/${tag}_crowded.ncu-rep ;;
+  counts)   M="smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"
+            timeout 300 ncu --metrics $M --clock-control none -k regex:ocp_ipm -s 1 -c 1 --csv --log-file gpurun_out/${tag}_cnt_cbf.csv python tools/one_launch.py --B 1024 > /dev/null 2>&1
+            timeout 300 ncu --metrics $M --clock-control none -k regex:ocp_ipm -s 1 -c 1 --csv --log-file gpurun_out/${tag}_cnt_planner.csv python tools/one_launch.py --B 64 --kind planner > /dev/null 2>&1
+            timeout 300 ncu --metrics $M --clock-control none -k regex:lmpc_kernel -s 1 -c 1 --csv --log-file gpurun_out/${tag}_cnt_lmpc.csv python tools/one_launch.py --B 512 --kind lmpc > /dev/null 2>&1
+            timeout 300 ncu --metrics $M --clock-control none -k regex:ilqr_kernel -s 1 -c 1 --csv --log-file gpurun_out/${tag}_cnt_ilqr.csv python tools/one_launch.py --B 1024 --kind ilqr > /dev/null 2>&1
+            python tools/fp64_counts.py gpurun_out/${tag}_cnt_cbf.csv:1024 gpurun_out/${tag}_cnt_planner.csv:64 gpurun_out/${tag}_cnt_lmpc.csv:512 gpurun_out/${tag}_cnt_ilqr.csv:1024 > gpurun_out/${tag}_fp64_counts.json; head -c 900 gpurun_out/${tag}_fp64_counts.json ;;
+  start)    timeout 900 python tools/start_report.py --out gpurun_out/${tag}_start_report.json | tail -1 ;;
+  launches) timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; wc -l gpurun_out/${tag}_launches.csv ;;
+  variants) tools/variants.sh run ;;
+  *) echo "unknown step $s" ;;
+esac
+done
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu,power.draw --format=csv,noheader

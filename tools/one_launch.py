@@ -19,7 +19,7 @@ from car_racing_b200 import scenarios              # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=8192)
 ap.add_argument("--reps", type=int, default=1)
-ap.add_argument("--kind", default="cbf", choices=["cbf", "lmpc", "ilqr"])
+ap.add_argument("--kind", default="cbf", choices=["cbf", "lmpc", "ilqr", "planner"])
 a = ap.parse_args()
 if a.kind == "lmpc":     # BASELINE config 4: N=12, 44 safe-set points (ncu: -k regex:lmpc_kernel)
     sc = scenarios.lmpc_scenarios(min(a.B, 512), seed=3)
@@ -32,6 +32,12 @@ elif a.kind == "ilqr":   # BASELINE config 5: N=50 (ncu: -k regex:ilqr_kernel)
     iprm = dict(A=p["A"], B=p["B"], Q=p["Q"], R=p["R"], N=50, max_iter=150, L=0.4, W=0.2)
     x0, xt, obs, lo = scenarios.ilqr_scenarios(a.B, N=50, seed=1)
     fn = lambda: crb.solve_ilqr_batch(x0, xt, obs, lo, iprm, want=())
+elif a.kind == "planner":   # BASELINE config 3: 64 candidate QPs per planner call (ncu: -k regex:ocp_ipm)
+    from car_racing_b200 import planning
+    sc = scenarios.planner_scenarios(C=a.B, N=10, seed=1)
+    kw, _ = planning.pack_candidates(sc["x0"], sc["s_ref"], sc["ey_ref"], sc["xlb"], sc["xub"], 10)
+    pprm = planning.planner_params(scenarios.LTI_A, scenarios.LTI_B, 10)
+    fn = lambda: crb.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, pprm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"], want=())
 if a.kind != "cbf":
     g = fn()
     for _ in range(a.reps):

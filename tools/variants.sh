@@ -21,13 +21,18 @@ case "$1" in
   build)
     shift
     mkdir -p $VDIR
-    $NVCC $FLAGS -o $VDIR/libb200mpc_base.so car_racing_b200/csrc/capi.cu
+    build_one() {   # name, defs: all translation units in parallel (__graft_entry__.compile_lib)
+      python -c "
+import sys, __graft_entry__ as g
+g.compile_lib(out='$VDIR/libb200mpc_$1.so', extra_flags=sys.argv[1].split(), verbose=False)" "$2"
+      n=$(cuobjdump -sass -fun '_ZN7b200mpc14ocp_ipm_kernelILi3ELi0ELi20EEEvNS_7KParamsEPKdP14b200mpc_recordPdS6_S6_S6_NS_8XchgArgsE' $VDIR/libb200mpc_$1.so 2>/dev/null | grep -cE "^\s+/\*[0-9a-f]{4,5}\*/" || true)
+      echo "[variants] $1: ocp_ipm_kernel<3,0,20> = $n SASS instructions"
+    }
+    [ "$NO_BASE" = "1" ] || build_one base ""
     for spec in "$@"; do
       name=${spec%%:*}; defs=${spec#*:}
       echo "[variants] $name: $defs"
-      $NVCC $FLAGS $defs -o $VDIR/libb200mpc_$name.so car_racing_b200/csrc/capi.cu
-      n=$(cuobjdump -sass -fun '_ZN7b200mpc14ocp_ipm_kernelILi3ELi0ELi20EEEvNS_7KParamsEPKdP14b200mpc_recordPdS6_S6_S6_' $VDIR/libb200mpc_$name.so 2>/dev/null | grep -cE "^\s+/\*[0-9a-f]{4,5}\*/" || true)
-      echo "[variants] $name: ocp_ipm_kernel<3,0,20> = $n SASS instructions"
+      build_one "$name" "$defs"
     done
     ;;
   run)
