@@ -9,8 +9,16 @@
 // Linear algebra: NOT a Riccati sweep.  Near the optimum only ~3 of the 44 lambdas leave their bound, so any stage-wise
 // elimination of the terminal hull constraint meets a 7x7 Schur complement with condition number > 1e15 (measured in the
 // oracle's first draft).  Instead the states are condensed through the LTV model once per solve (dx = G du + dx_p, G in
-// shared memory) and the reduced KKT system in (du, dlambda, nu) -- 75x75 at N=12, K=44 -- is solved by a CTA-level LU
-// with partial pivoting (16 rows x 8 column lanes per pass).  Dynamics multipliers follow from the costate recursion.
+// shared memory) and each iteration solves a reduced KKT system by a CTA-level LU with partial pivoting (16 rows x 8 column
+// lanes per pass).  Round 2: the system is no longer (du, dlambda, nu) with all K lambdas (75x75 at N=12, K=44) but
+// (du, dlambda_F, nu) with only the NF = min(7, K) lambdas of largest lambda_k/z_k -- a vertex of the hull constraint has at
+// most 7 positive weights (6 state rows + the simplex row) -- kept explicit: 38x38.  The other lambdas sit at their bound,
+// their diagonal block z_k/lambda_k is large and well scaled, and they are eliminated exactly:
+// dlambda_k = d_k (rhs_k - e_k' nu), d_k = lambda_k/z_k, which adds -sum_B d_k e_k e_k' (small, PSD) to the nu block.  The
+// ill-conditioning that broke the 7x7 form came from the few HUGE d_k of the free lambdas; those are exactly the ones that
+// stay in the pivoted system.  Half the elimination steps (each costs 2 block barriers), 1/8 of the flops, and the matrix
+// shrinks from 45.6 KB to 11.9 KB of shared memory (2 -> 4 CTAs per SM).  Dynamics multipliers follow from the costate
+// recursion.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,11 +36,13 @@ struct LmpcKParams {
 __host__ __device__ inline int lmpc_record_doubles(int N, int K) { return (8 + 54 * N + 7 * K + 1) & ~1; }
 
 struct LmpcPlan {
-    int N, K, NX, NU, NW, NR, ND, ME;
-    int oIN, oW, oD, oZL, oZU, oGF, oRHS, oSIG, oDP, oKD, oLAM, oLAMN, oCEQ, oG, oRQ, oKK, oPIV, oRED, oXS, total;
+    int N, K, NX, NU, NW, NR, ND, ME, NF;
+    int oIN, oW, oD, oZL, oZU, oGF, oRHS, oSIG, oDP, oKD, oLAM, oLAMN, oCEQ, oG, oRQ, oKK, oPIV, oRED, oXS, oFI, total;
     __host__ __device__ LmpcPlan(int N_, int K_, int in_stride) {
         N = N_; K = K_;
-        NX = 6 * (N + 1); NU = 2 * N; NW = NX + NU + K; NR = NU + K; ND = NR + 7; ME = 6 * N + 7;
+        NX = 6 * (N + 1); NU = 2 * N; NW = NX + NU + K; ME = 6 * N + 7;
+        NF = K < 7 ? K : 7;          // lambdas kept explicit in the pivoted system
+        NR = NU + NF; ND = NR + 7;   // reduced KKT: (du, dlambda_F, nu)
         int o = 2;
         auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
         oIN = take(in_stride);
@@ -40,7 +50,7 @@ struct LmpcPlan {
         oDP = take(NX); oKD = take(NX);
         oLAM = take(ME); oLAMN = take(ME); oCEQ = take(ME);
         oG = take(6 * N * NU); oRQ = take(NU * NU);
-        oKK = take(ND * (ND + 1)); oPIV = take(ND + 2); oRED = take(16); oXS = take(ND);
+        oKK = take(ND * (ND + 1)); oPIV = take(ND + 2); oRED = take(16); oXS = take(ND); oFI = take(8 + K);
         total = o;
     }
     __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(double); }
@@ -57,10 +67,11 @@ __global__ void __launch_bounds__(LMPC_NT) lmpc_kernel(const __grid_constant__ L
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, inst = blockIdx.x;
     const int N = kp.p.N, K = kp.p.K;
     const LmpcPlan pl(N, K, kp.in_stride);
-    const int NX = pl.NX, NU = pl.NU, NW = pl.NW, NR = pl.NR, ND = pl.ND, ME = pl.ME, OU = NX, OL = NX + NU, LD = ND + 1;
+    const int NX = pl.NX, NU = pl.NU, NW = pl.NW, NR = pl.NR, ND = pl.ND, ME = pl.ME, NF = pl.NF, OU = NX, OL = NX + NU, LD = ND + 1;
     double *IN = sm + pl.oIN, *W = sm + pl.oW, *D = sm + pl.oD, *ZL = sm + pl.oZL, *ZU = sm + pl.oZU, *GF = sm + pl.oGF;
     double *RHS = sm + pl.oRHS, *SIG = sm + pl.oSIG, *DP = sm + pl.oDP, *KD = sm + pl.oKD, *LAM = sm + pl.oLAM, *LAMN = sm + pl.oLAMN;
     double *CEQ = sm + pl.oCEQ, *G = sm + pl.oG, *RQ = sm + pl.oRQ, *KK = sm + pl.oKK, *PIV = sm + pl.oPIV, *RED = sm + pl.oRED, *XS = sm + pl.oXS;
+    int *FI = reinterpret_cast<int *>(sm + pl.oFI);     // FI[0..NF-1]: the explicit lambdas; FI[16 + k]: slot of lambda k in F or -1
     int red_phase = 0;
     // block reductions: one barrier each (two alternating scratch rows)
     auto bred = [&](double v, int op) -> double {
@@ -358,7 +369,28 @@ __global__ void __launch_bounds__(LMPC_NT) lmpc_kernel(const __grid_constant__ L
             KD[e] = s;
         }
         __syncthreads();
-        // ---- reduced KKT matrix  [Rh E'; E 0 | rhs]
+        // ---- the NF lambdas that stay explicit: largest d_k = lambda_k/z_k = smallest SIG (ties -> lower index); warp 0,
+        //      NF rounds of warp-argmin over at most 2 candidates per lane
+        if (wid == 0) {
+            double c0 = (lane < K) ? SIG[OL + lane] : 1e300 * 1e300, c1 = (lane + 32 < K) ? SIG[OL + lane + 32] : 1e300 * 1e300;
+            for (int k = lane; k < K; k += 32) FI[16 + k] = -1;
+            __syncwarp();
+            for (int f = 0; f < NF; f++) {
+                double best = (c0 <= c1) ? c0 : c1;
+                int bi = (c0 <= c1) ? lane : lane + 32;
+                for (int off = 16; off > 0; off >>= 1) {
+                    double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == (bi & 31)) {
+                    if (bi < 32) c0 = 1e300 * 1e300; else c1 = 1e300 * 1e300;
+                    FI[f] = bi;
+                    FI[16 + bi] = f;
+                }
+            }
+        }
+        // ---- reduced KKT matrix  [Rh 0 Eu'; 0 Sig_F E_F'; Eu E_F -S_B | rhs]
         for (int e = tid; e < ND * LD; e += NT) KK[e] = 0.0;
         __syncthreads();
         for (int e = tid; e < NU * NU; e += NT) {   // Rh_uu = RQ + G' diag(sig_x) G + K_uu
@@ -374,15 +406,31 @@ __global__ void __launch_bounds__(LMPC_NT) lmpc_kernel(const __grid_constant__ L
             else if (ia == ib + 1 || ib == ia + 1) s -= df * d2;
             KK[a * LD + b] = s;
         }
-        for (int k = tid; k < K; k += NT) {
-            KK[(NU + k) * LD + NU + k] = SIG[OL + k];
+        // explicit lambdas F (written by warp 0 before the barrier above): diagonal z/lambda, their columns e_k = (-SS[:,k]; 1)
+        for (int f = tid; f < NF; f += NT) {
+            const int k = FI[f];
+            KK[(NU + f) * LD + NU + f] = SIG[OL + k];
             for (int a = 0; a < 6; a++) {
-                KK[(NU + k) * LD + NR + a] = -SS[a * K + k];
-                KK[(NR + a) * LD + NU + k] = -SS[a * K + k];
+                KK[(NU + f) * LD + NR + a] = -SS[a * K + k];
+                KK[(NR + a) * LD + NU + f] = -SS[a * K + k];
             }
-            KK[(NU + k) * LD + NR + 6] = 1.0;
-            KK[(NR + 6) * LD + NU + k] = 1.0;
-            KK[(NU + k) * LD + ND] = RHS[OL + k];
+            KK[(NU + f) * LD + NR + 6] = 1.0;
+            KK[(NR + 6) * LD + NU + f] = 1.0;
+            KK[(NU + f) * LD + ND] = RHS[OL + k];
+        }
+        // eliminated lambdas B: -S_B = -sum_B d_k e_k e_k' into the nu block, -sum_B d_k e_k rhs_k into its right-hand side
+        for (int e = tid; e < 7 * 8; e += NT) {
+            const int a = e >> 3, b = e & 7;     // b == 7: the right-hand side column
+            double acc = 0.0;
+            for (int k = 0; k < K; k++) {
+                if (FI[16 + k] >= 0) continue;
+                const double dk = rcp(SIG[OL + k]);
+                const double ea = (a < 6) ? -SS[a * K + k] : 1.0;
+                const double eb = (b < 6) ? -SS[b * K + k] : ((b == 6) ? 1.0 : RHS[OL + k]);
+                acc += dk * ea * eb;
+            }
+            if (b < 7) KK[(NR + a) * LD + NR + b] = -acc;
+            else XS[a] = acc;                    // picked up below when the nu right-hand side is written
         }
         for (int e = tid; e < 6 * NU; e += NT) {
             int a = e / NU, c = e - a * NU;
@@ -395,8 +443,9 @@ __global__ void __launch_bounds__(LMPC_NT) lmpc_kernel(const __grid_constant__ L
             for (int r = 0; r < 6 * N; r++) s += G[r * NU + c] * (RHS[6 + r] - KD[6 + r]);
             KK[c * LD + ND] = s;
         }
-        if (tid < 6) KK[(NR + tid) * LD + ND] = -(CEQ[6 * N + tid] + DP[6 * N + tid]);
-        if (tid == 6) KK[(NR + 6) * LD + ND] = -CEQ[6 * N + 6];
+        __syncthreads();     // XS from the B loop
+        if (tid < 6) KK[(NR + tid) * LD + ND] = -(CEQ[6 * N + tid] + DP[6 * N + tid]) - XS[tid];
+        if (tid == 6) KK[(NR + 6) * LD + ND] = -CEQ[6 * N + 6] - XS[6];
         __syncthreads();
         // ---- LU with partial pivoting on the augmented matrix (ND x ND+1), then column-oriented back substitution
         bool singular = false;
@@ -446,7 +495,18 @@ __global__ void __launch_bounds__(LMPC_NT) lmpc_kernel(const __grid_constant__ L
         for (int e = tid; e < ND; e += NT) KK[e * LD + ND] = XS[e];
         __syncthreads();
         // ---- direction: du, dlambda from the solve; dx = G du + dp; nu+ ; costate recursion for the dynamics multipliers
-        for (int e = tid; e < NR; e += NT) D[OU + e] = KK[e * LD + ND];
+        for (int e = tid; e < NU; e += NT) D[OU + e] = KK[e * LD + ND];
+        for (int k = tid; k < K; k += NT) {   // dlambda: explicit ones from the solve, the eliminated ones d_k (rhs_k - e_k' nu)
+            const int f = FI[16 + k];
+            double v;
+            if (f >= 0) v = KK[(NU + f) * LD + ND];
+            else {
+                double t = RHS[OL + k] - KK[(NR + 6) * LD + ND];
+                for (int a = 0; a < 6; a++) t += SS[a * K + k] * KK[(NR + a) * LD + ND];
+                v = t * rcp(SIG[OL + k]);
+            }
+            D[OL + k] = v;
+        }
         for (int e = tid; e < 7; e += NT) LAMN[6 * N + e] = KK[(NR + e) * LD + ND];
         __syncthreads();
         for (int e = 6 + tid; e < NX; e += NT) {

@@ -1,4 +1,4 @@
-// b200mpc: the instantiation sets of ocp_ipm_kernel (see ocp_launch.cuh).  Compiled with -DOCP_INST_SET=k (one set per
+// b200mpc: the instantiation sets of ocp_ipm_kernel (see ocp_launch.cuh).  Compiled with OCP_INST_SET = k defined (one set per
 // translation unit, CUDA build) or -DOCP_INST_EMU (tests/host_emulation: a reduced list inside capi's translation unit).
 #pragma once
 #include "ocp_launch.cuh"

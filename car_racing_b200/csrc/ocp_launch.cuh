@@ -1,6 +1,6 @@
 // b200mpc: launch interface of ocp_ipm_kernel's template instantiations.
 //
-// The instantiations are compiled in several translation units (ocp_inst.cu with -DOCP_INST_SET=k, built in parallel by
+// The instantiations are compiled in several translation units (generated wrappers "#define OCP_INST_SET k + #include ocp_inst.cuh", built in parallel by
 // __graft_entry__.build()) because each one is ~8 k SASS instructions; capi.cu only sees this header.
 //   set 0: <3,0,20> (BASELINE north star), <0,0,0> (mpc_lti), <0,3,0> (planner candidate QP)
 //   set 1: <1..4,0,0>      set 2: <5..8,0,0>

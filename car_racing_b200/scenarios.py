@@ -133,10 +133,43 @@ def select_points(ss_xcurv, Qfun, it, x0, num_ss_points, shift=0):
     return xcurv[lo:lo + n, :].T, Qfun[lo:lo + n, it]
 
 
-def lmpc_scenarios(B, N=12, num_ss_points=44, num_ss_iter=2, seed=1, ltv_noise=5e-4):
+def lmpc_feasible(x0, A, Bm, C, SS, umax=(0.5, 1.0), vmax=10.0, width=1.0):
+    """Does control.lmpc's QP (control.py:640-701) have a feasible point for this instance?  Phase-1 LP in (u, lambda):
+    LTV roll-out, input box, vx / ey rows for 0 < i < N, x_N = SS lambda on the simplex."""
+    from scipy.optimize import linprog
+    N, K = A.shape[0], SS.shape[1]
+    G = np.zeros((N + 1, 6, 2 * N))
+    g0 = np.zeros((N + 1, 6))
+    g0[0] = x0
+    for i in range(N):
+        G[i + 1] = A[i] @ G[i]
+        G[i + 1][:, 2 * i:2 * i + 2] += Bm[i]
+        g0[i + 1] = A[i] @ g0[i] + C[i]
+    nv = 2 * N + K
+    Aeq = np.zeros((7, nv))
+    beq = np.zeros(7)
+    Aeq[:6, :2 * N], Aeq[:6, 2 * N:], beq[:6] = G[N], -SS, -g0[N]
+    Aeq[6, 2 * N:], beq[6] = 1.0, 1.0
+    rows, rhs = [], []
+    for i in range(1, N):
+        for sign, comp, lim in ((1.0, 0, vmax), (1.0, 5, width), (-1.0, 5, width)):
+            r = np.zeros(nv)
+            r[:2 * N] = sign * G[i][comp]
+            rows.append(r)
+            rhs.append(lim - sign * g0[i][comp])
+    res = linprog(np.zeros(nv), A_ub=np.array(rows), b_ub=np.array(rhs), A_eq=Aeq, b_eq=beq,
+                  bounds=[(-umax[0], umax[0]), (-umax[1], umax[1])] * N + [(0, None)] * K, method="highs")
+    return res.status == 0
+
+
+def lmpc_scenarios(B, N=12, num_ss_points=44, num_ss_iter=2, seed=1, ltv_noise=5e-4, feasible_only=True):
     """Config 4: B sampled (x0, u_old); safe set = 22 consecutive points from each of two stored
     laps (control.py:625-638) that pass close to x0; LTV model = the identified LTI model plus a small per-stage
     perturbation (not on the s column: it would be multiplied by the absolute arc length) and an affine term.
+    feasible_only: a drawn instance whose QP has no feasible point (the terminal equality x_N = SS lambda pins all six
+    states to a thin sheet; with the perturbed model ~13 % of the draws cannot reach it inside the input box) is drawn again --
+    every instance returned has a solution, so a non-converged one is a solver defect (round 1 counted those draws as
+    solver failures).  feasible_only=False keeps them (the edge-case test wants them).
     Returns x0 (B,6), u_old (B,2), A (B,N,6,6), Bm (B,N,6,2), C (B,N,6), SS (B,6,K), Qfun (B,K)."""
     rng = np.random.default_rng(seed)
     K = num_ss_points
@@ -144,7 +177,8 @@ def lmpc_scenarios(B, N=12, num_ss_points=44, num_ss_iter=2, seed=1, ltv_noise=5
     x0 = np.zeros((B, 6)); u_old = np.zeros((B, 2))
     A = np.zeros((B, N, 6, 6)); Bm = np.zeros((B, N, 6, 2)); C = np.zeros((B, N, 6))
     SS = np.zeros((B, 6, K)); Qf = np.zeros((B, K))
-    for b in range(B):
+    b = tries = 0
+    while b < B:
         warm, _ = _pid_lap(rng.uniform(1.1, 1.4), 40, rng, s0=rng.uniform(0.0, 15.0))
         xb = warm[-1]
         starts, cols, qs = [], [], []
@@ -169,6 +203,10 @@ def lmpc_scenarios(B, N=12, num_ss_points=44, num_ss_iter=2, seed=1, ltv_noise=5
         C[b] = ltv_noise * rng.normal(size=(N, 6))
         SS[b] = np.concatenate(cols, axis=1)
         Qf[b] = np.concatenate(qs)
+        tries += 1
+        if feasible_only and tries < 25 and not lmpc_feasible(x0[b], A[b], Bm[b], C[b], SS[b]):
+            continue                     # (after 25 draws the instance is kept as it is: e.g. K = 1 is never feasible)
+        b, tries = b + 1, 0
     return x0, u_old, A, Bm, C, SS, Qf
 
 

@@ -34,6 +34,27 @@ PY
   start)    timeout 900 python tools/start_report.py --out gpurun_out/${tag}_start_report.json | tail -1 ;;
   launches) timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; wc -l gpurun_out/${tag}_launches.csv ;;
   variants) tools/variants.sh run ;;
+  multi)    # N GPUs of this box (gpurun --gpus N): the contract's launch line, configs 2, 4, 5; both forms of the exchange for config 2
+            NG=$(nvidia-smi -L | wc -l)
+            for c in 2 4 5; do
+              timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --config $c > gpurun_out/${tag}_bench_${NG}gpu_c$c.json 2> gpurun_out/${tag}_bench_${NG}gpu_c$c.err
+              python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${tag}_bench_${NG}gpu_c$c.json"))
+    print("N=$NG config $c:", round(d["value"]), "solves/s  ms/step %.3f" % d["ms_per_step"], " e2e", round(d["e2e"]["value"]), " exchange:", d["config"]["exchange"][:40], " verified:", d.get("exchange_verified"))
+except Exception as e:
+    print("N=$NG config $c failed:", e)
+PY
+            done
+            timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --exchange nccl > gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.json 2> gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.err
+            python -c "
+import json
+d = json.load(open('gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.json')); print('N=$NG config 2 nccl exchange:', round(d['value']), 'solves/s  e2e', round(d['e2e']['value']))" ;;
+  single)   timeout 400 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_1gpu.json 2> gpurun_out/${tag}_bench_1gpu.err
+            python -c "
+import json
+d = json.load(open('gpurun_out/${tag}_bench_1gpu.json')); print('N=1 config 2:', round(d['value']), 'solves/s  e2e', round(d['e2e']['value']))" ;;
   *) echo "unknown step $s" ;;
 esac
 done

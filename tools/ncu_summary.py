@@ -43,9 +43,13 @@ doc["warp_instructions_per_instance"] = round(sum(int(r[ix["Instructions Execute
 doc["stall_samples_pct"] = {s: round(100.0 * v / alls, 2) for s, v in sorted(tot.items(), key=lambda x: -x[1]) if v}
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, capture_output=True)
-    cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(dis) if ".section" in l and ".text." in l and KERNEL in l][0]
+    dis, start = [], []
+    for cub in sorted(f for f in os.listdir(td) if f.endswith(".cubin")):     # one cubin per translation unit
+        dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout.split("\n")
+        start = [i for i, l in enumerate(dis) if ".section" in l and ".text." in l and KERNEL in l]
+        if start:
+            break
+start = start[0]
 end = next(i for i in range(start + 1, len(dis)) if dis[i].startswith("\t.section"))
 ins, pending, outer = [], [], None
 for l in dis[start:end]:
@@ -59,7 +63,7 @@ for l in dis[start:end]:
             pending = []
         ins.append(outer)
 if len(ins) == len(data):
-    srcl = open(os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", "ocp_ipm.cuh")).read().split("\n")
+    srcl = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "car_racing_b200", "csrc", "ocp_ipm.cuh")).read().split("\n")
     agg = collections.defaultdict(lambda: [0, 0, 0, 0])
     for o, r in zip(ins, data):
         a = agg[o]
