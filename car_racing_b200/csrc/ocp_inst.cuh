@@ -7,7 +7,7 @@ namespace b200mpc {
 
 template <int M, int FL, int NT>
 static int launch_cbf_one(const CbfLaunch &l, const KParams &kp) {
-    SmemPlan<M> pl(kp.p.N, kp.in_stride);
+    SmemPlan<M> pl(kp.p.N, kp.in_stride, FL);
     size_t smem = pl.bytes() + l.smem_pad;
     if ((int)smem > l.max_smem_optin) return CBF_LAUNCH_SMEM;
     // the opt-in shared-memory size is a per-device function attribute: set it once per (instantiation, device), and again

@@ -48,6 +48,7 @@ struct KParams {
     int32_t wd_off;     // offset of the ey-rate weights (flag EY_RATE)
     int32_t sz_off;     // offset of the per-rival (L_j, W_j) block (flag RIVAL_SIZE)
     double iL6, iW6;    // 1/L^6, 1/W^6
+    double Q2[36];      // Q + Q' (the objective's Hessian block and gradient matrix), formed once on the host
 };
 
 __host__ __device__ inline int cbf_hdr_doubles(int M) { return (6 + M + 1) & ~1; }
@@ -68,10 +69,12 @@ template <int M>
 struct SmemPlan {
     static constexpr int NXA = 6 + M, NUA = 2 + M, NZ = NXA + NUA;
     static constexpr int NXAP = (NXA + 1) & ~1, NUAP = (NUA + 1) & ~1, NC = 8 + M;
+    // row of the feedback law in KFB: NXA gains, then the feed-forward term, padded to an even length
+    static constexpr int NKP = (NXA + 2) & ~1;
     int N, R, NB, NW, OU, OS;
-    int oIN, oW, oD, oHD, oZL, oZU, oS, oT, oY, oZ, oV, oDG, oG, oSIGE, oYHAT, oJD, oJA, oLAM, oCRES, oKFB, oKFF, oPT, oQV,
-        oGUU, oGVU, oYF, oYG, oS0, oJDC, oGX, oAB, total;
-    __host__ __device__ SmemPlan(int N_, int in_stride) {
+    int oIN, oW, oD, oHD, oZL, oZU, oS, oT, oY, oZ, oV, oDG, oG, oSIGE, oYHAT, oJD, oJA, oLAM, oCRES, oKFB, oPT, oQV,
+        oGUU, oGVU, oYF, oYG, oS0, oJDC, oAB, total;
+    __host__ __device__ SmemPlan(int N_, int in_stride, int flags) {
         N = N_;
         R = M * N;
         NB = 4 * N + M * (N + 1);
@@ -87,12 +90,11 @@ struct SmemPlan {
         oDG = take(R); oG = take(R); oSIGE = take(R); oYHAT = take(R); oJD = take(R);
         oJA = take(4 * R);
         oLAM = take(6 * N + 6); oCRES = take(6 * N + 6);
-        oKFB = take(N * NUA * NXAP); oKFF = take(N * NUAP);
+        oKFB = take(N * NUA * NKP);
         oPT = take((NC + 1) * NXAP); oQV = take(NXAP);
         oGUU = take(NUA * NUAP); oGVU = take(NUAP); oYF = take(NXA * NUAP); oYG = take(NUAP);
         oS0 = take((M > 0 ? M : 1) * (M + 2));
-        oJDC = take(N + 2);
-        oGX = take(6 * (N + 1));
+        oJDC = take((flags & B200MPC_FLAG_EY_RATE) ? N + 2 : 0);   // ey-rate differences of the direction (planner QP only)
         oAB = take(48);   // rows of [A | B] for the Riccati sweep (16-byte loads instead of constant-bank loads)
         total = o;
     }
@@ -251,6 +253,7 @@ template <int M, int FL, int NT>
 struct Ipm {
     static constexpr int NXA = 6 + M, NUA = 2 + M, NZ = NXA + NUA;
     static constexpr int NXAP = (NXA + 1) & ~1, NUAP = (NUA + 1) & ~1, NC = 8 + M, MM = (M > 0 ? M : 1);
+    static constexpr int NKP = SmemPlan<M>::NKP;
     const KParams &kp;
     const int lane;
     static constexpr bool kStaticN = NT > 0;
@@ -258,8 +261,8 @@ struct Ipm {
     // that overshoots any horizon lets the compiler drop the loop (back edge, loop-carried moves)
     static constexpr int KSTEP = (NT > 0 && NT < 32) ? (1 << 20) : 32;
     const int N, R, NB, NW, OU, OS;
-    double *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM, *CRES, *KFB, *KFF, *PT,
-        *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC, *GX, *ABs;
+    double *IN, *W, *D, *HD, *ZL, *ZU, *S, *T, *Y, *Z, *V, *DG, *GR, *SIGE, *YHAT, *JD, *JA, *LAM, *CRES, *KFB, *PT,
+        *QVs, *GUU, *GVU, *YF, *YG, *S0, *JDC, *ABs;
     const double *xt, *obs, *lapoff, *bnd, *wdp, *szp;
     // per-stage bounds / ey-rate cost present (planner QP): compile-time so that the MPC-CBF path pays nothing
     static constexpr bool psb = (FL & B200MPC_FLAG_STAGE_BOUNDS) != 0, hwd = (FL & B200MPC_FLAG_EY_RATE) != 0;
@@ -283,11 +286,10 @@ struct Ipm {
         IN = sm + pl.oIN; W = sm + pl.oW; D = sm + pl.oD; HD = sm + pl.oHD; ZL = sm + pl.oZL; ZU = sm + pl.oZU;
         S = sm + pl.oS; T = sm + pl.oT; Y = sm + pl.oY; Z = sm + pl.oZ; V = sm + pl.oV;
         DG = sm + pl.oDG; GR = sm + pl.oG; SIGE = sm + pl.oSIGE; YHAT = sm + pl.oYHAT; JD = sm + pl.oJD;
-        JA = sm + pl.oJA; LAM = sm + pl.oLAM; CRES = sm + pl.oCRES; KFB = sm + pl.oKFB; KFF = sm + pl.oKFF;
+        JA = sm + pl.oJA; LAM = sm + pl.oLAM; CRES = sm + pl.oCRES; KFB = sm + pl.oKFB;
         PT = sm + pl.oPT; QVs = sm + pl.oQV; GUU = sm + pl.oGUU; GVU = sm + pl.oGVU; YF = sm + pl.oYF; YG = sm + pl.oYG;
         S0 = sm + pl.oS0;
         JDC = sm + pl.oJDC;
-        GX = sm + pl.oGX;
         ABs = sm + pl.oAB;
         bnd = IN + kp.bnd_off;
         wdp = IN + kp.wd_off;
@@ -478,28 +480,27 @@ struct Ipm {
     __device__ __forceinline__ double input_cost(const double (&u)[2]) const {
         return u[0] * (kp.p.R[0] * u[0] + kp.p.R[1] * u[1]) + u[1] * (kp.p.R[2] * u[0] + kp.p.R[3] * u[1]);
     }
-    // scaled gradient of the objective wrt x_i -> dst[0..5] (shared memory); returns max |.|
-    __device__ __forceinline__ double grad_x_store(int i, const double (&x)[6], double *dst) const {
+    // Component a of the scaled objective gradient wrt x_i; d = x_i - xt_i.  Called from rolled loops with a warp-uniform
+    // runtime a (register-indexed constant-bank loads of Q + Q').  The gradient is recomputed where it is needed (error,
+    // assembly, costate residual: 36 FMAs per stage each) instead of being cached in shared memory -- those 126 doubles,
+    // with the feed-forward terms folded into KFB's padding, are what lets an 8th CTA fit an SM.
+    __device__ __forceinline__ double grad_x_comp(int i, int a, const double (&d)[6], double ey) const {
+        const double *q2 = kp.Q2 + 6 * a;
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) acc += q2[b] * d[b];
+        acc *= df;
+        if (hwd && a == 5) {   // d/d ey_i of  wd_{i-1}(ey_i-ey_{i-1})^2 + wd_i(ey_{i+1}-ey_i)^2
+            double tt = wdp[i - 1] * (ey - W[6 * (i - 1) + 5]);
+            if (i < N) tt -= wdp[i] * (W[6 * (i + 1) + 5] - ey);
+            acc += 2.0 * df * tt;
+        }
+        return acc;
+    }
+    __device__ __forceinline__ void diff_target(int i, const double (&x)[6], double (&d)[6]) const {
         const double *t = xtp(i);
-        double d[6];
 #pragma unroll
         for (int a = 0; a < 6; a++) d[a] = x[a] - t[a];
-        double gm = 0.0;
-#pragma unroll 1
-        for (int a = 0; a < 6; a++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int b = 0; b < 6; b++) acc += (kp.p.Q[6 * a + b] + kp.p.Q[6 * b + a]) * d[b];
-            acc *= df;
-            if (hwd && a == 5) {   // d/d ey_i of  wd_{i-1}(ey_i-ey_{i-1})^2 + wd_i(ey_{i+1}-ey_i)^2
-                double tt = wdp[i - 1] * (x[5] - W[6 * (i - 1) + 5]);
-                if (i < N) tt -= wdp[i] * (W[6 * (i + 1) + 5] - x[5]);
-                acc += 2.0 * df * tt;
-            }
-            dst[a] = acc;
-            gm = fmax(gm, fabs(acc));
-        }
-        return gm;
     }
 
     // ---- Newton steps of the row slacks / multipliers from JD (all at the current iterate)
@@ -618,7 +619,6 @@ struct Ipm {
             load_x<false>(k + 1, 0.0, xn);
             load_u<false>(k, 0.0, u);
             dyn_res<false, true>(k, 0.0, x, u);
-            grad_x_store(k + 1, xn, GX + 6 * (k + 1));   // objective gradient of x_{k+1}, shared by the later phases
 #pragma unroll 1
             for (int j = 0; j < M; j++) {
                 int r = j * N + k;
@@ -662,9 +662,12 @@ struct Ipm {
                 }
                 double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
                 zsum += zl.x + zl.y + zu.x + zu.y;
+                double xk[6], dk[6];
+                load_x<false>(k, 0.0, xk);
+                diff_target(k, xk, dk);
 #pragma unroll 1
                 for (int a = 0; a < 6; a++) {
-                    double s = GX[6 * k + a] + LAM[6 * (k - 1) + a];
+                    double s = grad_x_comp(k, a, dk, xk[5]) + LAM[6 * (k - 1) + a];
 #pragma unroll
                     for (int b = 0; b < 6; b++) s -= kp.p.A[6 * b + a] * lamn[b];
                     if (a == 0) s += -zl.x + zu.x;
@@ -768,9 +771,9 @@ struct Ipm {
     __device__ void assemble() {
         for (int k = lane; k <= N; k += KSTEP) {
             if (k >= 1) {
-                double x[6], g[6], hd[6];
+                double x[6], dk[6], hd[6], gb0, gb5;
                 load_x<false>(k, 0.0, x);
-                ld6(GX + 6 * k, g);
+                diff_target(k, x, dk);
 #pragma unroll
                 for (int a = 0; a < 6; a++) hd[a] = 0.0;
                 double2 zl = ld2(ZL + bsx(k)), zu = ld2(ZU + bsx(k));
@@ -778,13 +781,21 @@ struct Ipm {
                     double lb = xlb(k, 0), ub = xub(k, 0);
                     double il = has(lb) ? rcp(x[0] - lb) : 0.0, iu = has(ub) ? rcp(ub - x[0]) : 0.0;
                     hd[0] = zl.x * il + zu.x * iu;
-                    g[0] += -mu * il + mu * iu;
+                    gb0 = -mu * il + mu * iu;
                     lb = xlb(k, 1);
                     ub = xub(k, 1);
                     il = has(lb) ? rcp(x[5] - lb) : 0.0;
                     iu = has(ub) ? rcp(ub - x[5]) : 0.0;
                     hd[5] = zl.y * il + zu.y * iu;
-                    g[5] += -mu * il + mu * iu;
+                    gb5 = -mu * il + mu * iu;
+                }
+                // base gradient of the barrier problem -> D (overwritten by the forward pass)
+#pragma unroll 1
+                for (int a = 0; a < 6; a++) {
+                    double gv = grad_x_comp(k, a, dk, x[5]);
+                    if (a == 0) gv += gb0;
+                    if (a == 5) gv += gb5;
+                    D[6 * k + a] = gv;
                 }
 #pragma unroll 1
                 for (int j = 0; j < M; j++) {  // Hessian of -y_r g_r: diagonal on (s, ey) (control.py:544-557, degree 6)
@@ -800,7 +811,6 @@ struct Ipm {
                     hd[5] -= yd * p4(x[5] - obs_e(j, k)) * iW6(j);
                 }
                 st6(HD + 6 * k, hd);
-                st6(D + 6 * k, g);  // base gradient of the barrier problem; D is overwritten by the forward pass
             }
 #pragma unroll 1
             for (int j = 0; j < M; j++) {
@@ -1015,19 +1025,18 @@ struct Ipm {
                 if (!ok) return false;   // checked after the solves so that they overlap the factorisation's latency
                 if (lane < NXA) {
 #pragma unroll
-                    for (int m = 0; m < NUA; m++) KFB[(k * NUA + m) * NXAP + lane] = -kv[m];
+                    for (int m = 0; m < NUA; m++) KFB[(k * NUA + m) * NKP + lane] = -kv[m];
                     double yp[NUAP];
 #pragma unroll
                     for (int m = 0; m < NUA; m++) yp[m] = yv[m];
                     if (NUAP > NUA) yp[NUAP - 1] = 0.0;
                     stv<NUAP>(YF + lane * NUAP, yp);
                 } else if (gcol) {
-                    double yp[NUAP], kq[NUAP];
+                    double yp[NUAP];
 #pragma unroll
-                    for (int m = 0; m < NUA; m++) { yp[m] = yv[m]; kq[m] = -kv[m]; }
-                    if (NUAP > NUA) { yp[NUAP - 1] = 0.0; kq[NUAP - 1] = 0.0; }
+                    for (int m = 0; m < NUA; m++) { yp[m] = yv[m]; KFB[(k * NUA + m) * NKP + NXA] = -kv[m]; }   // feed-forward term
+                    if (NUAP > NUA) yp[NUAP - 1] = 0.0;
                     stv<NUAP>(YG, yp);
-                    stv<NUAP>(KFF + k * NUAP, kq);
                 }
             }
             __syncwarp();
@@ -1120,9 +1129,9 @@ struct Ipm {
         const int mrow = (lane < NUA) ? lane : 0;
         const int arow_i = (lane < 6) ? lane : 0;
         for (int k = 0; k < N; k++) {
-            double kr[NXAP];
-            ldv<NXAP>(KFB + (k * NUA + mrow) * NXAP, kr);
-            double s = KFF[k * NUAP + mrow];
+            double kr[NKP];
+            ldv<NKP>(KFB + (k * NUA + mrow) * NKP, kr);
+            double s = kr[NXA];
             double t = -CRES[6 * k + arow_i];
 #pragma unroll
             for (int c = 0; c < NXA; c++) s += kr[c] * dx[c];
@@ -1152,7 +1161,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x;
     const int inst = blockIdx.x;
-    const SmemPlan<M> pl(NT ? NT : kp.p.N, NT ? cbf_record_doubles(NT, M, 0, FL) : kp.in_stride);
+    const SmemPlan<M> pl(NT ? NT : kp.p.N, NT ? cbf_record_doubles(NT, M, 0, FL) : kp.in_stride, FL);
     Ipm<M, FL, NT> S_(kp, pl, sm, lane);
     Ipm<M, FL, NT> &q = S_;
     using IP = Ipm<M, FL, NT>;
@@ -1260,9 +1269,11 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         double gm = (M > 0) ? kp.p.slack_w : 0.0;
         for (int k = lane; k <= N; k += KSTEP) {
             if (k >= 1) {
-                double x[6];
+                double x[6], dk[6];
                 q.template load_x<false>(k, 0.0, x);
-                gm = fmax(gm, q.grad_x_store(k, x, q.GX + 6 * k));   // df == 1 here
+                q.diff_target(k, x, dk);
+#pragma unroll 1
+                for (int a = 0; a < 6; a++) gm = fmax(gm, fabs(q.grad_x_comp(k, a, dk, x[5])));   // df == 1 here
             }
             if (k < N) {
                 double u[2];
@@ -1398,7 +1409,7 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
                 q.JD[r] = ja[0] * dxk[4] + ja[1] * dxk[5] + q.DG[r] * q.a1 * q.D[q.isg(j, k)] + ja[2] * dxn[4] + ja[3] * dxn[5] -
                           q.DG[r] * q.D[q.isg(j, k + 1)];
             }
-            q.JDC[k] = dxn[5] - dxk[5];
+            if (q.hwd) q.JDC[k] = dxn[5] - dxk[5];
         }
         __syncwarp();
         double a_max = 1.0, a_z = 1.0, gphi = 0.0, th = 0.0;
@@ -1431,11 +1442,12 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
 #pragma unroll
                     for (int a = 0; a < 6; a++) gphi += gbx[a] * d[a];
                 } else {   // long horizons: recompute the base gradient from the iterate
-                    double g[6];
-                    ld6(q.GX + 6 * k, g);
-                    q.barrier_grad_x(k, x, g);
-#pragma unroll
-                    for (int a = 0; a < 6; a++) gphi += g[a] * d[a];
+                    double dk[6], gb[6] = {0, 0, 0, 0, 0, 0};
+                    q.diff_target(k, x, dk);
+                    q.barrier_grad_x(k, x, gb);
+                    gphi += gb[0] * d[0] + gb[5] * d[5];
+#pragma unroll 1
+                    for (int a = 0; a < 6; a++) gphi += q.grad_x_comp(k, a, dk, x[5]) * q.D[6 * k + a];
                 }
             }
 #pragma unroll 1
@@ -1565,11 +1577,11 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
         //      K d + Jc' lam+ = rhs  =>  lam+_i = (rhs - K d)_{x_i} + A' lam+_{i+1}
         // (a) residuals res_i = (rhs - K d)_{x_i} for all stages in parallel -> CRES (dead until the next eval)
         for (int i = lane + 1; i <= N; i += KSTEP) {
-            double x[6], d[6], g[6];
+            double x[6], d[6], dk[6], g[6] = {0, 0, 0, 0, 0, 0};
             q.template load_x<false>(i, 0.0, x);
             ld6(q.D + 6 * i, d);
-            ld6(q.GX + 6 * i, g);
-            q.barrier_grad_x(i, x, g);
+            q.diff_target(i, x, dk);
+            q.barrier_grad_x(i, x, g);        // barrier terms of vx_i, ey_i only (g[0], g[5])
             double r4 = 0.0, r5 = 0.0;
 #pragma unroll 1
             for (int j = 0; j < M; j++) {
@@ -1593,8 +1605,8 @@ __global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KPa
             for (int a2 = 0; a2 < 6; a2++) {
                 double kd = (q.HD[6 * i + a2] + dw_try) * q.D[6 * i + a2];
 #pragma unroll
-                for (int b = 0; b < 6; b++) kd += q.df * (kp.p.Q[6 * a2 + b] + kp.p.Q[6 * b + a2]) * d[b];
-                double gg = (a2 == 0) ? g0 : ((a2 == 5) ? g5 : q.GX[6 * i + a2]);
+                for (int b = 0; b < 6; b++) kd += q.df * kp.Q2[6 * a2 + b] * d[b];
+                double gg = q.grad_x_comp(i, a2, dk, x[5]) + ((a2 == 0) ? g0 : ((a2 == 5) ? g5 : 0.0));
                 double res = -gg - kd;
                 if (a2 == 4) res += r4;
                 if (a2 == 5) res += r5;

@@ -32,6 +32,8 @@ static KParams make_kp(const b200mpc_cbf_params *p, const b200mpc_ipm_options *o
     double L2 = p->L * p->L, W2 = p->W * p->W;
     kp.iL6 = 1.0 / (L2 * L2 * L2);
     kp.iW6 = 1.0 / (W2 * W2 * W2);
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) kp.Q2[6 * a + b] = p->Q[6 * a + b] + p->Q[6 * b + a];
     return kp;
 }
 
