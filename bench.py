@@ -35,6 +35,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# every stream its own hardware queue (D solver streams + the exchange stream + torch's + NCCL's): with the default of 8
+# connections streams alias, and the exchange window's waiting kernels would block unrelated streams behind them
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 OUT = sys.stdout
 

@@ -184,6 +184,11 @@ static int take_xchg(b200mpc_handle *h, int B, XchgArgs *xa) {
     c->cum[s] += (unsigned long long)B;
     c->ring[s][c->published[s] % b200mpc_comm::RING] = {B, c->cum[s]};
     *xa = XchgArgs{c->d_table, s, B, c->published[s]};
+    if (c->world > 1 && c->published[s] > 1) {   // gate: every rank has consumed the previous use of this slot
+        xchg_wait_ack_kernel<<<1, 32, 0, h->stream>>>(c->d_table, s, c->published[s]);
+        CK(h, cudaGetLastError());
+        h->launches++;
+    }
     return B200MPC_OK;
 }
 
@@ -1044,7 +1049,7 @@ int b200mpc_comm_argmin(b200mpc_handle *h, b200mpc_comm *c, int slot, int max_st
     CK(h, cudaSetDevice(h->device));
     const unsigned long long use = ++c->consumed[slot];
     const b200mpc_comm::Use u = c->ring[slot][use % b200mpc_comm::RING];
-    xchg_argmin_kernel<<<1, 256, 0, h->stream>>>(c->d_table, slot, u.B, u.cum, use, max_status, d_out, d_all);
+    xchg_argmin_kernel<<<1, 32, 0, h->stream>>>(c->d_table, slot, u.B, u.cum, use, max_status, d_out, d_all);
     CK(h, cudaGetLastError());
     h->launches++;
     return B200MPC_OK;

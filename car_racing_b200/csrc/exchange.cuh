@@ -13,12 +13,16 @@
 //   cnt[S][world]  (u64)        records of rank r that have arrived for slot s, cumulative over the uses of the slot
 //   ack[S][world]  (u64)        uses of slot s that rank r has consumed (its argmin kernel has read its own copy)
 // Protocol for use number n = 1, 2, ... of slot s with B records per rank:
-//   producer warp (rank q, any peer p):  wait own.ack[s][p] >= n - 1   (p has consumed the previous use: flow control)
-//                                        peer[p].rec[s][q * B + i] = record;  fence.sys;  peer[p].cnt[s][q] += 1 (sys atomic)
-//   consumer (xchg_argmin_kernel, rank p): wait own.cnt[s][q] >= cumulative count for all q;  argmin (+ optional copy-out);
-//                                        fence.sys;  peer[q].ack[s][p] = n  for all q
-// Dead-lock freedom: a producer of use n only waits for consumers of use n - 1, which only wait for producers of use
-// n - 1; the uses of one slot are issued in stream order on every rank.
+//   gate (xchg_wait_ack_kernel, one warp, on the solver's stream BEFORE the solver grid of use n):
+//                                        wait own.ack[s][p] >= n - 1 for all p  (every rank has consumed the previous use of the
+//                                        slot: flow control, a fast rank cannot lap a slow one)
+//   producer warp (rank q, any peer p):  peer[p].rec[s][q * B + i] = record;  peer[p].cnt[s][q] += 1 (release, system scope)
+//   consumer (xchg_argmin_kernel, one warp, rank p): wait own.cnt[s][q] >= cumulative count for all q;  argmin (+ copy-out);
+//                                        peer[q].ack[s][p] = n (release)  for all q
+// Dead-lock freedom: the gate of use n only waits for consumers of use n - 1, which only wait for producers of use n - 1;
+// the uses of one slot are issued in stream order on every rank.  Solver CTAs never spin (a spinning CTA would hold its SM
+// slot), and the two spinning kernels are ONE warp each with < 40 registers, which fits beside a full complement of solver
+// CTAs on an SM (8 x 7936 + 1280 registers <= 65536, 4.7 KB of shared memory to spare): they can always be placed.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -49,6 +53,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ void add_release_sys(unsigned long long *p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ void xchg_backoff() {}
+__device__ __forceinline__ unsigned long long xchg_now_ns() { return 0ull; }
 #else
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
@@ -62,7 +67,15 @@ __device__ __forceinline__ void add_release_sys(unsigned long long *p, unsigned 
     asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void xchg_backoff() { __nanosleep(200); }
+__device__ __forceinline__ unsigned long long xchg_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 #endif
+// A peer that never arrives (a crashed rank, streams aliased onto one hardware queue -- see b200mpc_comm_create) must not
+// hang the GPU: every spin gives up after this long; the consumer then reports -2 instead of an index.
+constexpr unsigned long long XCHG_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 
 // Epilogue of a solver warp: the lanes of one warp call this convergently; `rc` is the instance's record (valid in every
 // lane).  Lane p < world stores it into rank p's gathered buffer and signals its arrival there.
@@ -70,9 +83,6 @@ __device__ __forceinline__ void xchg_publish(const XchgArgs &xa, int lane, int i
     if (xa.tab == nullptr) return;
     const XchgTable &t = *xa.tab;
     for (int p = lane; p < t.world; p += 32) {
-        // flow control: rank p must have consumed the previous use of this slot (its ack lands in OUR window)
-        const unsigned long long *ack = t.ack[t.rank] + (size_t)xa.slot * t.world + p;
-        while (ld_acquire_sys(ack) + 1 < xa.use) xchg_backoff();
         b200mpc_record *dst = t.rec[p] + ((size_t)xa.slot * t.world + t.rank) * t.max_batch + inst;
 #ifdef B200MPC_HOST_EMULATION
         *dst = rc;
@@ -87,21 +97,37 @@ __device__ __forceinline__ void xchg_publish(const XchgArgs &xa, int lane, int i
     }
 }
 
-// Consumer: one CTA.  Waits until every rank's `B` records of this use have arrived in this rank's window, takes the
+// Consumer: one warp.  Waits until every rank's `B` records of this use have arrived in this rank's window, takes the
 // first-min argmin over the world * B gathered records (rank-major = instance order of the global batch; lowest index
 // wins ties, overtake_traj_planner.py:244), optionally copies them out, then acknowledges the use to every peer.
 // want[q] = cumulative arrival count expected from rank q (host-side bookkeeping: sum of B over the uses of the slot).
-static __global__ void xchg_argmin_kernel(const XchgTable *__restrict__ tab, int slot, int B, unsigned long long want, unsigned long long use,
+// Gate of a use: one warp on the solver's stream ahead of the solver grid.
+static __global__ void __launch_bounds__(32) xchg_wait_ack_kernel(const XchgTable *__restrict__ tab, int slot, unsigned long long use) {
+    const XchgTable &t = *tab;
+    for (int p = threadIdx.x; p < t.world; p += 32) {
+        const unsigned long long *ack = t.ack[t.rank] + (size_t)slot * t.world + p;   // rank p's acks land in OUR window
+        const unsigned long long t0 = xchg_now_ns();
+        while (ld_acquire_sys(ack) + 1 < use) {
+            xchg_backoff();
+            if (xchg_now_ns() - t0 > XCHG_TIMEOUT_NS) break;
+        }
+    }
+}
+
+static __global__ void __launch_bounds__(32) xchg_argmin_kernel(const XchgTable *__restrict__ tab, int slot, int B, unsigned long long want, unsigned long long use,
                                    int max_status, int32_t *__restrict__ out, b200mpc_record *__restrict__ copy_out) {
-    __shared__ double sc[32];
-    __shared__ int si[32];
     const XchgTable &t = *tab;
     const int world = t.world;
-    if ((int)threadIdx.x < world) {
-        const unsigned long long *c = t.cnt[t.rank] + (size_t)slot * world + threadIdx.x;
-        while (ld_acquire_sys(c) < want) xchg_backoff();
+    bool late = false;
+    for (int q = threadIdx.x; q < world; q += 32) {
+        const unsigned long long *c = t.cnt[t.rank] + (size_t)slot * world + q;
+        const unsigned long long t0 = xchg_now_ns();
+        while (ld_acquire_sys(c) < want) {
+            xchg_backoff();
+            if (xchg_now_ns() - t0 > XCHG_TIMEOUT_NS) { late = true; break; }
+        }
     }
-    __syncthreads();
+    late = __any_sync(0xffffffffu, late);
     const b200mpc_record *base = t.rec[t.rank] + (size_t)slot * world * t.max_batch;
     double best = 1e300 * 1e300;
     int bi = 0x7fffffff;
@@ -116,15 +142,9 @@ static __global__ void xchg_argmin_kernel(const XchgTable *__restrict__ tab, int
         int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if ((threadIdx.x & 31) == 0) { sc[w] = best; si[w] = bi; }
-    __syncthreads();      // also: every thread has finished reading the slot
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < nw; k++)
-            if (sc[k] < best || (sc[k] == best && si[k] < bi)) { best = sc[k]; bi = si[k]; }
-        if (out != nullptr) *out = (bi == 0x7fffffff) ? -1 : bi;
-    }
-    if ((int)threadIdx.x < world) st_release_sys(t.ack[threadIdx.x] + (size_t)slot * world + t.rank, use);
+    __syncwarp();      // every lane has finished reading the slot (and its copy-out stores are issued)
+    if (threadIdx.x == 0 && out != nullptr) *out = late ? -2 : ((bi == 0x7fffffff) ? -1 : bi);   // -2: a rank's records never arrived
+    for (int q = threadIdx.x; q < world; q += 32) st_release_sys(t.ack[q] + (size_t)slot * world + t.rank, use);
 }
 
 }  // namespace b200mpc

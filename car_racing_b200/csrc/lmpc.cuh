@@ -57,8 +57,11 @@ struct LmpcPlan {
 };
 
 constexpr int LMPC_NT = 128;   // threads per instance
+#ifndef LMPC_MIN_CTAS
+#define LMPC_MIN_CTAS 4        // 50.5 KB of shared memory per CTA at N=12, K=44 -> 4 CTAs fit an SM; cap the registers at 128 to match
+#endif
 
-__global__ void __launch_bounds__(LMPC_NT) lmpc_kernel(const __grid_constant__ LmpcKParams kp, const double *__restrict__ in,
+__global__ void __launch_bounds__(LMPC_NT, LMPC_MIN_CTAS) lmpc_kernel(const __grid_constant__ LmpcKParams kp, const double *__restrict__ in,
                                                   b200mpc_record *__restrict__ rec, double *__restrict__ aux,
                                                   double *__restrict__ xpred, double *__restrict__ upred,
                                                   double *__restrict__ lambda_out, const XchgArgs xa = XchgArgs{nullptr, 0, 0, 0}) {

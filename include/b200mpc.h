@@ -411,7 +411,11 @@ int b200mpc_argmin_cost_device(b200mpc_handle *h, const b200mpc_record *d_rec, i
  *   b200mpc_comm_argmin   on handle h's stream: waits until all world x B records of the slot's oldest unconsumed use
  *                         have arrived, writes the first-min argmin over them (global instance order = rank-major) to d_out
  *                         and, if d_all != NULL, a copy of the gathered records; then releases the slot to the peers.
- * Uses of one slot must be issued in the same order on every rank; `slots` steps can be in flight. */
+ * Uses of one slot must be issued in the same order on every rank; `slots` steps can be in flight.  The two waiting
+ * kernels (the gate ahead of a solve that reuses a slot, and the argmin) spin on the device: give every stream its own
+ * hardware queue (CUDA_DEVICE_MAX_CONNECTIONS >= number of streams in use, set before CUDA initialises; the default of 8
+ * aliases streams, and a spinning kernel then blocks an unrelated stream behind it).  A wait gives up after 20 s; the argmin
+ * then writes -2. */
 typedef struct b200mpc_comm b200mpc_comm;
 #define B200MPC_COMM_HANDLE_BYTES 64
 #define B200MPC_COMM_MAX_WORLD 16

@@ -20,7 +20,7 @@
 #else
 #define __shared__ static
 #endif
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 struct EmuIdx { int x; };
 /* one host thread per CUDA thread of a block (emu_launch below); single-threaded callers leave the defaults */
 static thread_local EmuIdx threadIdx = {0}, blockIdx = {0};

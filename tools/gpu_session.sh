@@ -34,10 +34,39 @@ PY
   start)    timeout 900 python tools/start_report.py --out gpurun_out/${tag}_start_report.json | tail -1 ;;
   launches) timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; wc -l gpurun_out/${tag}_launches.csv ;;
   variants) tools/variants.sh run ;;
+  varbench) # every library under scratch/variants swapped in: short bench of configs 2 and 4
+            cp car_racing_b200/libb200mpc.so /tmp/libb200mpc_original.so
+            for so in scratch/variants/libb200mpc_*.so; do
+              name=$(basename $so .so); name=${name#libb200mpc_}
+              cp $so car_racing_b200/libb200mpc.so
+              for c in 2 4; do
+                timeout 300 python bench.py --config $c --no-cpu-baseline --steps 24 > gpurun_out/${tag}_var_${name}_c$c.json 2>/dev/null
+                python -c "
+import json
+try:
+    d = json.load(open('gpurun_out/${tag}_var_${name}_c$c.json')); print('variant $name config $c:', round(d['value']), 'solves/s  serial', round(d['one_batch_at_a_time']['value']), ' p50 B=1 %.3f ms' % d['e2e']['p50_latency_ms_batch1'])
+except Exception as e:
+    print('variant $name config $c failed', e)"
+              done
+            done
+            cp /tmp/libb200mpc_original.so car_racing_b200/libb200mpc.so ;;
+  inflight) for D in 4 8 10; do timeout 300 python bench.py --no-cpu-baseline --inflight $D --steps 48 > gpurun_out/${tag}_bench_D$D.json 2>/dev/null
+              python -c "
+import json
+d = json.load(open('gpurun_out/${tag}_bench_D$D.json')); print('D=$D:', round(d['value']), 'solves/s  e2e', round(d['e2e']['value']))"; done ;;
+  latency)  timeout 600 python tools/shim_latency.py --out gpurun_out/${tag}_shim_latency.json > /dev/null 2> gpurun_out/${tag}_shim_latency.err
+            python -c "
+import json
+d = json.load(open('gpurun_out/${tag}_shim_latency.json'))
+print('mpccbf', d['mpccbf_test']['latency'], d['mpccbf_test']['statuses'], d['mpccbf_test']['ego_passed_rivals'])
+print('mpc_lti', d['mpc_lti_tracking']['latency']['p50_ms'], 'ilqr', d['ilqr_test']['latency']['p50_ms'], 'lmpc step', d['lmpc_step']['both']['p50_ms'], 'overtake', d['overtaking_step']['fused']['p50_ms'], d['overtaking_step']['two_calls']['p50_ms'])" ;;
+  ncusum)   timeout 600 ncu --set full --import-source on --clock-control none -k regex:ocp_ipm -s 1 -c 1 -f -o gpurun_out/${tag}_crowded python tools/one_launch.py --B 8192 2>&1 | tail -1
+            timeout 600 ncu --set full --import-source on --clock-control none -k regex:lmpc_kernel -s 1 -c 1 -f -o gpurun_out/${tag}_lmpc4096 python tools/one_launch.py --B 4096 --kind lmpc 2>&1 | tail -1
+            ls -la gpurun_out/${tag}_*.ncu-rep ;;
   multi)    # N GPUs of this box (gpurun --gpus N): the contract's launch line, configs 2, 4, 5; both forms of the exchange for config 2
             NG=$(nvidia-smi -L | wc -l)
             for c in 2 4 5; do
-              timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --config $c > gpurun_out/${tag}_bench_${NG}gpu_c$c.json 2> gpurun_out/${tag}_bench_${NG}gpu_c$c.err
+              timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --config $c --no-cpu-baseline > gpurun_out/${tag}_bench_${NG}gpu_c$c.json 2> gpurun_out/${tag}_bench_${NG}gpu_c$c.err
               python - <<PY
 import json
 try:
@@ -47,7 +76,7 @@ except Exception as e:
     print("N=$NG config $c failed:", e)
 PY
             done
-            timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --exchange nccl > gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.json 2> gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.err
+            timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --exchange nccl --no-cpu-baseline > gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.json 2> gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.err
             python -c "
 import json
 d = json.load(open('gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.json')); print('N=$NG config 2 nccl exchange:', round(d['value']), 'solves/s  e2e', round(d['e2e']['value']))" ;;
