@@ -2,7 +2,7 @@
 headline metrics, warp-stall sampling totals, and samples attributed to the kernel-body source line that
 (transitively) inlined each SASS instruction (nvdisasm -gi on the cubin of the same build).
 
-    python tools/ncu_summary.py gpurun_out/x.ncu-rep car_racing_b200/libb200mpc.so B > profiles/x_summary.json
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep build/obj_libb200mpc.so/ocp_inst0.o B [kernel-name-fragment source.cuh] > profiles/x_summary.json
 """
 import collections
 import csv
@@ -15,7 +15,8 @@ import sys
 import tempfile
 
 rep, so, B = sys.argv[1], sys.argv[2], int(sys.argv[3])
-KERNEL = "ocp_ipm_kernelILi3ELi0ELi20"
+KERNEL = sys.argv[4] if len(sys.argv) > 4 else "ocp_ipm_kernelILi3ELi0ELi20"     # mangled-name fragment of the captured kernel
+SRC = sys.argv[5] if len(sys.argv) > 5 else "ocp_ipm.cuh"                          # the source file its body lives in
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -63,7 +64,7 @@ for l in dis[start:end]:
             pending = []
         ins.append(outer)
 if len(ins) == len(data):
-    srcl = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "car_racing_b200", "csrc", "ocp_ipm.cuh")).read().split("\n")
+    srcl = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "car_racing_b200", "csrc", SRC)).read().split("\n")
     agg = collections.defaultdict(lambda: [0, 0, 0, 0])
     for o, r in zip(ins, data):
         a = agg[o]
