@@ -131,7 +131,9 @@ static __global__ void __launch_bounds__(32) xchg_argmin_kernel(const XchgTable 
     const b200mpc_record *base = t.rec[t.rank] + (size_t)slot * world * t.max_batch;
     double best = 1e300 * 1e300;
     int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < world * B; i += blockDim.x) {
+    // one warp reads world * B records: 4 independent 32-byte loads in flight per lane (the loop is latency bound)
+#pragma unroll 4
+    for (int i = threadIdx.x; i < world * B; i += 32) {
         const int q = i / B, k = i - q * B;
         const b200mpc_record r = base[(size_t)q * t.max_batch + k];
         if (copy_out != nullptr) copy_out[i] = r;

@@ -37,7 +37,7 @@ __host__ __device__ inline int lmpc_record_doubles(int N, int K) { return (8 + 5
 
 struct LmpcPlan {
     int N, K, NX, NU, NW, NR, ND, ME, NF;
-    int oIN, oW, oD, oZL, oZU, oGF, oRHS, oSIG, oDP, oKD, oLAM, oLAMN, oCEQ, oG, oRQ, oKK, oPIV, oRED, oXS, oFI, total;
+    int oIN, oW, oD, oZL, oZU, oGF, oRHS, oSIG, oDP, oKD, oLAM, oLAMN, oCEQ, oG, oRQ, oKK, oPIV, oRED, oXS, oFI, oDK, total;
     __host__ __device__ LmpcPlan(int N_, int K_, int in_stride) {
         N = N_; K = K_;
         NX = 6 * (N + 1); NU = 2 * N; NW = NX + NU + K; ME = 6 * N + 7;
@@ -50,7 +50,7 @@ struct LmpcPlan {
         oDP = take(NX); oKD = take(NX);
         oLAM = take(ME); oLAMN = take(ME); oCEQ = take(ME);
         oG = take(6 * N * NU); oRQ = take(NU * NU);
-        oKK = take(ND * (ND + 1)); oPIV = take(ND + 2); oRED = take(16); oXS = take(ND); oFI = take(8 + K);
+        oKK = take(ND * (ND + 1)); oPIV = take(ND + 2); oRED = take(16); oXS = take(ND); oFI = take(8 + K); oDK = take(K);
         total = o;
     }
     __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(double); }
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(LMPC_NT, LMPC_MIN_CTAS) lmpc_kernel(const __gr
     double *IN = sm + pl.oIN, *W = sm + pl.oW, *D = sm + pl.oD, *ZL = sm + pl.oZL, *ZU = sm + pl.oZU, *GF = sm + pl.oGF;
     double *RHS = sm + pl.oRHS, *SIG = sm + pl.oSIG, *DP = sm + pl.oDP, *KD = sm + pl.oKD, *LAM = sm + pl.oLAM, *LAMN = sm + pl.oLAMN;
     double *CEQ = sm + pl.oCEQ, *G = sm + pl.oG, *RQ = sm + pl.oRQ, *KK = sm + pl.oKK, *PIV = sm + pl.oPIV, *RED = sm + pl.oRED, *XS = sm + pl.oXS;
+    double *DK = sm + pl.oDK;
     int *FI = reinterpret_cast<int *>(sm + pl.oFI);     // FI[0..NF-1]: the explicit lambdas; FI[16 + k]: slot of lambda k in F or -1
     int red_phase = 0;
     // block reductions: one barrier each (two alternating scratch rows)
@@ -258,9 +259,10 @@ __global__ void __launch_bounds__(LMPC_NT, LMPC_MIN_CTAS) lmpc_kernel(const __gr
         }
         return bsum(la.value());
     };
-    // optimality error (same scaling as the oracle); needs GF, CEQ current
-    auto kkt_error = [&](double m) -> double {
-        double dual = 0.0, prim = 0.0, comp = 0.0, zsum = 0.0, ysum = 0.0;
+    // optimality error (same scaling as the oracle) for barrier parameter 0 (-> e0) and m (-> em) in ONE pass: dual and
+    // primal residuals do not depend on it (one set of block reductions instead of two); needs GF, CEQ current
+    auto kkt_error2 = [&](double m, double &e0, double &em) {
+        double dual = 0.0, prim = 0.0, comp = 0.0, compm = 0.0, zsum = 0.0, ysum = 0.0;
         for (int e = 6 + tid; e < NW; e += NT) {
             double rw = df * GF[e] - ZL[e] + ZU[e];
             if (e < NX) {
@@ -277,16 +279,17 @@ __global__ void __launch_bounds__(LMPC_NT, LMPC_MIN_CTAS) lmpc_kernel(const __gr
                 for (int a = 0; a < 6; a++) rw -= SS[a * K + k] * LAM[6 * N + a];
             }
             dual = fmax(dual, fabs(rw));
-            if (has_l(e)) { comp = fmax(comp, fabs((W[e] - lbv(e)) * ZL[e] - m)); zsum += ZL[e]; }
-            if (has_u(e)) { comp = fmax(comp, fabs((ubv(e) - W[e]) * ZU[e] - m)); zsum += ZU[e]; }
+            if (has_l(e)) { double v = (W[e] - lbv(e)) * ZL[e]; comp = fmax(comp, fabs(v)); compm = fmax(compm, fabs(v - m)); zsum += ZL[e]; }
+            if (has_u(e)) { double v = (ubv(e) - W[e]) * ZU[e]; comp = fmax(comp, fabs(v)); compm = fmax(compm, fabs(v - m)); zsum += ZU[e]; }
         }
         for (int e = tid; e < ME; e += NT) { prim = fmax(prim, fabs(CEQ[e])); ysum += fabs(LAM[e]); }
-        dual = bmax(dual); prim = bmax(prim); comp = bmax(comp); zsum = bsum(zsum); ysum = bsum(ysum);
+        dual = bmax(dual); prim = bmax(prim); comp = bmax(comp); compm = bmax(compm); zsum = bsum(zsum); ysum = bsum(ysum);
         const double s_max = 100.0;
         int nmul = ME + nbc;
         double sd = fmax(s_max, (ysum + zsum) / (double)(nmul > 0 ? nmul : 1)) / s_max;
         double sc = fmax(s_max, zsum / (double)(nbc > 0 ? nbc : 1)) / s_max;
-        return fmax(dual / sd, fmax(prim, comp / sc));
+        e0 = fmax(dual / sd, fmax(prim, comp / sc));
+        em = fmax(dual / sd, fmax(prim, compm / sc));
     };
 
     // ---- scaling
@@ -325,7 +328,8 @@ __global__ void __launch_bounds__(LMPC_NT, LMPC_MIN_CTAS) lmpc_kernel(const __gr
         gradient();
         residual(0.0, false, CEQ);
         __syncthreads();
-        E0 = kkt_error(0.0);
+        double em;
+        kkt_error2(mu, E0, em);
         if (E0 <= o.tol) { status = B200MPC_SOLVED; break; }
         if (E0 <= o.acceptable_tol) {
             if (++n_acc >= o.acceptable_iter) { status = B200MPC_SOLVED; break; }
@@ -333,11 +337,12 @@ __global__ void __launch_bounds__(LMPC_NT, LMPC_MIN_CTAS) lmpc_kernel(const __gr
             n_acc = 0;
         if (iter >= o.max_iter) { status = B200MPC_MAX_ITER; break; }
         for (;;) {
-            double em = kkt_error(mu);
             if (em <= kappa_eps * mu && mu > o.tol / 11.0) {
                 mu = fmax(o.tol / 11.0, fmin(kappa_mu * mu, mu * sqrt(mu)));
                 nfilt = 0;
                 fpos = 0;
+                double e0_;
+                kkt_error2(mu, e0_, em);
             } else
                 break;
         }
@@ -395,13 +400,15 @@ __global__ void __launch_bounds__(LMPC_NT, LMPC_MIN_CTAS) lmpc_kernel(const __gr
         }
         // ---- reduced KKT matrix  [Rh 0 Eu'; 0 Sig_F E_F'; Eu E_F -S_B | rhs]
         for (int e = tid; e < ND * LD; e += NT) KK[e] = 0.0;
+        for (int k = tid; k < K; k += NT) DK[k] = rcp(SIG[OL + k]);     // d_k = lambda_k / z_k, once per iteration
         __syncthreads();
         for (int e = tid; e < NU * NU; e += NT) {   // Rh_uu = RQ + G' diag(sig_x) G + K_uu
             int a = e / NU, b = e - a * NU;
             double s = RQ[e];
-            for (int r = 0; r < 6 * N; r++) {
-                double sg = SIG[6 + r];
-                if (sg != 0.0) s += G[r * NU + a] * sg * G[r * NU + b];
+            // G' diag(sig_x) G: sig_x is nonzero only on the bounded states, vx_i and ey_i of the stages 0 < i < N (has_l / has_u)
+            for (int i = 1; i < N; i++) {
+                const int r0 = 6 * (i - 1), r5 = r0 + 5;
+                s += G[r0 * NU + a] * SIG[6 + r0] * G[r0 * NU + b] + G[r5 * NU + a] * SIG[6 + r5] * G[r5 * NU + b];
             }
             int ia = a >> 1, ib = b >> 1, ca = a & 1, cb = b & 1;
             double r2 = R[2 * ca + cb] + R[2 * cb + ca], d2 = dR[2 * ca + cb] + dR[2 * cb + ca];
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(LMPC_NT, LMPC_MIN_CTAS) lmpc_kernel(const __gr
             double acc = 0.0;
             for (int k = 0; k < K; k++) {
                 if (FI[16 + k] >= 0) continue;
-                const double dk = rcp(SIG[OL + k]);
+                const double dk = DK[k];
                 const double ea = (a < 6) ? -SS[a * K + k] : 1.0;
                 const double eb = (b < 6) ? -SS[b * K + k] : ((b == 6) ? 1.0 : RHS[OL + k]);
                 acc += dk * ea * eb;
@@ -506,7 +513,7 @@ __global__ void __launch_bounds__(LMPC_NT, LMPC_MIN_CTAS) lmpc_kernel(const __gr
             else {
                 double t = RHS[OL + k] - KK[(NR + 6) * LD + ND];
                 for (int a = 0; a < 6; a++) t += SS[a * K + k] * KK[(NR + a) * LD + ND];
-                v = t * rcp(SIG[OL + k]);
+                v = t * DK[k];
             }
             D[OL + k] = v;
         }
