@@ -89,6 +89,10 @@ class Work:
     CPU oracle) and its algorithmic bytes per solve."""
     key = metric = kernel = None
     default_batch = 1024
+    # A batch ends with its own stragglers (heavy-tailed iteration counts), so one stream turns a batch around in the time of
+    # its slowest instance; D streams overlap D batches until the SMs are full.  MPC-CBF / LMPC fill the SMs at D = 6; an iLQR
+    # solve is so short (mean 5 iterations, the slowest instance of a shard 25-45) that the SMs are full only at D = 16.
+    default_inflight = 6
 
     def config(self, B, world, D, exchange):
         """The `config` object of the JSON line -- the same for both arms (--impl ours / reference)."""
@@ -182,7 +186,7 @@ class Work4(Work):
 
 
 class Work5(Work):
-    key, default_batch, kernel = 5, 1024, "ilqr_kernel"
+    key, default_batch, kernel, default_inflight = 5, 1024, "ilqr_kernel", 16
     metric = "iLQR solves/sec (N=50, 1 rival)"
     workload = "iLQR N=50, LTI bicycle model + 1 rival, batch=%d random (x0, obstacle) scenarios per GPU (BASELINE config 5: 8192 over 8 GPUs)"
     solver = "FP64 iLQR as control.ilqr (max_iter 150, regularised backward pass)"
@@ -325,13 +329,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(WORKS), help="BASELINE.json config (2 = the metric's)")
     ap.add_argument("--batch", type=int, default=None, help="instances per GPU per step (default: the config's)")
-    ap.add_argument("--inflight", type=int, default=6,
-                    help="batches in flight (streams driven round-robin); 1 = strictly one batch at a time")
+    ap.add_argument("--inflight", type=int, default=None,
+                    help="batches in flight (streams driven round-robin); 1 = strictly one batch at a time; default: the config's "
+                         "(6; 16 for the iLQR config, whose short solves are bound by each batch's own stragglers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: force the NCCL all-gather form of the exchange")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = WORKS[args.config].default_batch
+    if args.inflight is None:
+        args.inflight = WORKS[args.config].default_inflight
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
