@@ -80,6 +80,14 @@ PY
             python -c "
 import json
 d = json.load(open('gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.json')); print('N=$NG config 2 nccl exchange:', round(d['value']), 'solves/s  e2e', round(d['e2e']['value']))" ;;
+  multiD)   # config 2 on all GPUs of the box with more batches in flight (slack for the slowest shard)
+            NG=$(nvidia-smi -L | wc -l)
+            for D in 8 10; do
+              timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $NG --inflight $D --no-cpu-baseline > gpurun_out/${tag}_bench_${NG}gpu_c2_D$D.json 2> gpurun_out/${tag}_bench_${NG}gpu_c2_D$D.err
+              python -c "
+import json
+d = json.load(open('gpurun_out/${tag}_bench_${NG}gpu_c2_D$D.json')); print('N=$NG config 2 D=$D:', round(d['value']), 'solves/s  ms/step %.3f' % d['ms_per_step'], ' e2e', round(d['e2e']['value']), d.get('exchange_verified'))"
+            done ;;
   single)   timeout 400 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_1gpu.json 2> gpurun_out/${tag}_bench_1gpu.err
             python -c "
 import json
