@@ -517,7 +517,7 @@ def main():
                 px.publish_next(hs[k], k)
             hs[k].check(work.host(L, hs[k], B, pin_in[k].data_ptr(), pin_out[k].data_ptr(), blocking=(D == 1)), "solve(host)")
             if px is not None:
-                px.argmin(hcs[k], k, d_arg[k].data_ptr(), None)
+                px.argmin(hcs[k], k, d_arg[k].data_ptr(), d_all[k].data_ptr())     # the same exchange work as the `value` leg
                 with torch.cuda.stream(ext_cs[k]):
                     pin_arg[k].copy_(d_arg[k], non_blocking=True)
                     arg_ev[k] = torch.cuda.Event()
