@@ -94,7 +94,7 @@ class Work:
     # solve is so short (mean 5 iterations, the slowest instance of a shard 25-45) that the SMs are full only at D = 16.
     default_inflight = 6
 
-    def config(self, B, world, D, exchange):
+    def config(self, B, world, D, exchange, l2="rotate"):
         """The `config` object of the JSON line -- the same for both arms (--impl ours / reference)."""
         return {"workload": self.workload % B, "baseline_config": self.key, "global_batch": B * world,
                 "parallelism": "dp%d: independent scenario shards, one exchange of the 32-byte records + argmin per step" % world,
@@ -102,7 +102,7 @@ class Work:
                 "pipelining": ("steps are issued round-robin on %d streams (one handle each): the stragglers of one batch overlap "
                                "the next batches; timed first start event -> last end event, flushes included" % D)
                 if D > 1 else "none: one batch at a time",
-                "l2": "256 MiB buffer written before every timed step, on the step's stream (inputs are << L2)",
+                "l2": L2_TEXT[l2],
                 "solver": self.solver}
 
 
@@ -215,6 +215,12 @@ class Work5(Work):
 
 
 WORKS = {2: Work2, 3: Work3, 4: Work4, 5: Work5}
+L2_BYTES = 126 * 1024 * 1024
+L2_TEXT = {
+    "rotate": ("inputs larger than L2: every step reads its records from the next of R device copies (R x record bytes > 1.15 x the 126 MB "
+               "L2, round-robin over the whole run), so a copy is touched again only after more than an L2's worth of other inputs; the "
+               "end-to-end leg (fresh H2D every step) writes a 256 MiB buffer before every step instead"),
+    "flush": "256 MiB buffer written before every timed step, on the step's stream (inputs are << L2)"}
 
 
 def reference_solver_probe():
@@ -278,7 +284,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": work.metric, "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": work.config(B, max(world, args.gpus), max(1, args.inflight), exchange_name(max(world, args.gpus), None)),
+            "config": work.config(B, max(world, args.gpus), max(1, args.inflight), exchange_name(max(world, args.gpus), None), args.l2),
             "cpu_baseline": cpu_baseline_obj(work, val, cores, "%d instances per step, %d pthreads" % (B, cores), probe),
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -334,6 +340,9 @@ def main():
                          "(6; 16 for the iLQR config, whose short solves are bound by each batch's own stragglers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: force the NCCL all-gather form of the exchange")
+    ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
+                    help="how the timed steps are kept from re-reading their inputs out of L2: rotate through device copies of the "
+                         "records that together exceed L2 (default), or write a 256 MiB buffer before every step")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = WORKS[args.config].default_batch
@@ -368,6 +377,15 @@ def main():
     L = _capi.lib()
     exts = [torch.cuda.ExternalStream(h.stream, device=dev) for h in hs]
     d_in = torch.from_numpy(rec_host).to(dev)
+    # --l2 rotate: R copies of this rank's records (different addresses, same contents), together > 1.15 x L2; step i reads copy i mod R
+    R_COPIES = max(2, -(-int(1.15 * L2_BYTES) // rec_host.nbytes)) if args.l2 == "rotate" else 1
+    d_ins = [d_in] + [d_in.clone() for _ in range(R_COPIES - 1)]
+    n_steps_issued = [0]
+
+    def next_input():
+        p = d_ins[n_steps_issued[0] % R_COPIES].data_ptr()
+        n_steps_issued[0] += 1
+        return p
     d_rec = [torch.zeros((B, 4), dtype=torch.float64, device=dev) for _ in range(D)]
     d_all = [torch.zeros((world * B, 4), dtype=torch.float64, device=dev) for _ in range(D)]
     d_arg = [torch.full((1,), -7, dtype=torch.int32, device=dev) for _ in range(D)]
@@ -403,12 +421,13 @@ def main():
         """One step = one batch of B instances: L2 flush, the solve kernel on slot k's stream; (N>1) the exchange."""
         h = hs[k]
         with torch.cuda.stream(exts[k]):
-            flush.zero_()
+            if args.l2 == "flush":
+                flush.zero_()
             if px is not None:
                 px.publish_next(h, k)
             elif world > 1 and ag_done[k] is not None:
                 exts[k].wait_event(ag_done[k])            # the all-gather that last read this result buffer
-            h.check(work.device(L, h, B, d_in.data_ptr(), d_rec[k].data_ptr()), "solve_device")
+            h.check(work.device(L, h, B, next_input(), d_rec[k].data_ptr()), "solve_device")
             if world > 1 and px is None:
                 ev = torch.cuda.Event()
                 ev.record(exts[k])
@@ -442,10 +461,11 @@ def main():
     evs = []
     for _ in range(args.steps):
         with torch.cuda.stream(exts[0]):
-            flush.zero_()
+            if args.l2 == "flush":
+                flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(exts[0])
-            hs[0].check(work.device(L, hs[0], B, d_in.data_ptr(), d_rec[0].data_ptr()), "solve_device")
+            hs[0].check(work.device(L, hs[0], B, next_input(), d_rec[0].data_ptr()), "solve_device")
             e1.record(exts[0])
             evs.append((e0, e1))
     barrier()
@@ -571,11 +591,11 @@ def main():
         ent = t.get("kernels", {}).get(work.kernel) or (t if work.key == 2 and "dram_bytes_per_launch" in t else None)
         if ent:
             traffic, traffic_src = ent.get("dram_bytes_per_launch"), "profiles/dram_traffic.json (ncu --set full, one B=%s launch)" % ent.get("batch", "1024")
-    cfg = work.config(B, world, D, exchange_name(world, "p2p" if px is not None else px_why))
+    cfg = work.config(B, world, D, exchange_name(world, "p2p" if px is not None else px_why), args.l2)
     line = {
         "metric": work.metric, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": cfg, "converged_frac": conv,
+        "dtype": "f64", "data": "synthetic", "config": cfg, "converged_frac": conv, "input_copies_rotated": R_COPIES,
         "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(rec_host.nbytes),
                 "d2h_bytes_per_step": int(B * 32 + (4 if px is not None else 0)), "ms_per_step": 1e3 * t_e2e / args.steps,
                 "batches_in_flight": D, "p50_latency_ms_batch1": float(np.median(lat)),
