@@ -318,13 +318,16 @@ def fp64_roofline(work, solves_per_s, sm_mhz):
     ent = doc.get("kernels", {}).get(work.kernel)
     if not ent:
         return None
-    lib = os.path.join(ROOT, "car_racing_b200", "libb200mpc.so")
-    sha = hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16]
+    h = hashlib.sha256()            # identity of the kernels: the CUDA sources + the header (tools/fp64_counts.py: source_sha16)
+    csrc = os.path.join(ROOT, "car_racing_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + ["../../include/b200mpc.h"]:
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    sha = h.hexdigest()[:16]
     peak = 148 * 64 * 2 * (sm_mhz or 1965.0) * 1e6 / 1e12
     ach = ent["flops_per_solve"] * solves_per_s / 1e12
     return {"flops_per_solve": ent["flops_per_solve"], "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "peak_def": "148 SM x 64 FP64 FMA/clk x 2 x %.0f MHz" % (sm_mhz or 1965.0),
-            "source": "profiles/fp64_counts.json (%s)" % ent.get("report", "?"), "counts_from_this_build": doc.get("lib_sha16") == sha}
+            "source": "profiles/fp64_counts.json (%s)" % ent.get("report", "?"), "counts_from_these_sources": doc.get("src_sha16") == sha}
 
 
 def main():

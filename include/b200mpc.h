@@ -15,6 +15,11 @@
  *   b200mpc_plant_step    <- DynamicBicycleModel.forward_dynamics (utils/base.py:897-942, system/vehicle_dynamics.py:4-49)
  *   b200mpc_argmin_cost   <- the argmin of OvertakeTrajPlanner.solve_optimization_problem
  *                            (car_racing/planning/overtake_traj_planner.py:244)
+ *   b200mpc_comm_*        <- the join of that planner's fan-out (overtake_traj_planner.py:177-204: one forked process per
+ *                            candidate, costs gathered through a Manager().dict()) for a batch sharded over several GPUs:
+ *                            records exchanged through peer-mapped windows from the solver kernels' epilogue + argmin
+ *   b200mpc_planner_*, b200mpc_plan_and_track*, b200mpc_rival_rollout, b200mpc_curv_to_glob: the callers either side of the
+ *                            solves (SURVEY 8(f) "next" rows), see the comments at the declarations
  *
  * Conventions: plain pointers + sizes, IEEE double, C-contiguous, caller-owned buffers.
  * `*_solve` take HOST pointers (pageable or pinned) and perform H2D + kernel + D2H on the

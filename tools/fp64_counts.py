@@ -18,7 +18,17 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAMES = {"ocp_ipm_kernel<3, 0, 20>": "ocp_ipm_kernel<3,0,20>", "ocp_ipm_kernel<0, 3, 0>": "ocp_ipm_kernel<0,3,0>",
          "lmpc_kernel": "lmpc_kernel", "ilqr_kernel": "ilqr_kernel"}
-doc = {"lib_sha16": hashlib.sha256(open(os.path.join(ROOT, "car_racing_b200", "libb200mpc.so"), "rb").read()).hexdigest()[:16],
+def source_sha16():
+    """Identity of the kernels the counts belong to: hash of the CUDA sources and the C-ABI header (the built library's own
+    hash is not reproducible: two nvcc runs on the same sources give different files)."""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "car_racing_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + ["../../include/b200mpc.h"]:
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+doc = {"src_sha16": source_sha16(),
        "definition": "flops = 2*dfma + dmul + dadd (smsp__sass_thread_inst_executed_op_*_pred_on.sum) / batch of the launch",
        "kernels": {}}
 traffic = {"kernels": {}}

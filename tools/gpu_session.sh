@@ -34,6 +34,11 @@ PY
   start)    timeout 900 python tools/start_report.py --out gpurun_out/${tag}_start_report.json | tail -1 ;;
   launches) timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; wc -l gpurun_out/${tag}_launches.csv ;;
   variants) tools/variants.sh run ;;
+  sweep)    timeout 600 python tools/config_sweep.py --no-cpu --out gpurun_out/${tag}_config_sweep.json > /dev/null 2> gpurun_out/${tag}_config_sweep.err; python -c "
+import json
+d = json.load(open('gpurun_out/${tag}_config_sweep.json'))
+print('batch sweep:', [(e['B'], round(e['solves_per_s'])) for e in d['config2_batch_sweep']])
+print('overtaking step:', d.get('overtaking_step'))" ;;
   varbench) # every library under scratch/variants swapped in: short bench of configs 2 and 4
             cp car_racing_b200/libb200mpc.so /tmp/libb200mpc_original.so
             for so in scratch/variants/libb200mpc_*.so; do
