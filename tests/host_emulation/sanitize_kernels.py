@@ -65,7 +65,39 @@ def main():
         (_, flag, _, _), _ = planning.plan_and_track(p, x, prm, p.track, sysp, time=None)
         return "3 candidates + selection + tracking solve, region %d, tracking status %d" % (flag, p.tracking_status)
 
-    for name, fn in (("ocp_ipm_kernel<3,0,20>", cbf), ("ilqr_kernel", ilqr), ("lmpc_kernel", lmpc), ("sysid_kernel", sysid),
+    def exchange():
+        import ctypes as C
+        L = _capi.lib()
+        hs = [_capi.Handle(), _capi.Handle()]
+        cs, blobs = [], []
+        for r in range(2):
+            c = C.c_void_p()
+            hs[r].check(L.b200mpc_comm_create(hs[r].ptr, r, 2, 4, 2, C.byref(c)), "comm_create")
+            buf = (C.c_char * _capi.COMM_HANDLE_BYTES)()
+            L.b200mpc_comm_export(c, buf)
+            cs.append(c)
+            blobs.append(bytes(buf.raw))
+        for r in range(2):
+            assert L.b200mpc_comm_connect(cs[r], b"".join(blobs)) == 0
+        prm = scenarios.default_cbf_params(N=10)
+        p, o = _capi.make_cbf_params(prm, 1, False), _capi.default_options()
+        args = []
+        for use in range(2):
+            for r in range(2):
+                x0, xt, obs, lo = scenarios.mpccbf_scenarios(2, N=10, M=1, seed=40 + r)
+                rin, M, ps = batch.pack_cbf(x0, xt, obs, lo, 10)
+                rec = np.zeros(2, dtype=_capi.RECORD_DTYPE)
+                L.b200mpc_comm_publish_next(hs[r].ptr, cs[r], 0)
+                hs[r].check(L.b200mpc_cbf_solve(hs[r].ptr, C.byref(p), C.byref(o), 2, batch._ptr(rin), batch._ptr(rec), None, None, None, None), "solve")
+            for r in range(2):
+                arg, allr = np.zeros(1, dtype=np.int32), np.zeros(4, dtype=_capi.RECORD_DTYPE)
+                hs[r].check(L.b200mpc_comm_argmin(hs[r].ptr, cs[r], 0, 0, batch._ptr(arg), batch._ptr(allr)), "argmin")
+                args.append(int(arg[0]))
+        for c in cs:
+            L.b200mpc_comm_destroy(c)
+        return "2 ranks x 2 instances x 2 uses of one slot, argmin %s" % args
+
+    for name, fn in (("ocp_ipm_kernel<3,0,20>", cbf), ("exchange window: publish epilogue + xchg_wait_ack_kernel + xchg_argmin_kernel", exchange), ("ilqr_kernel", ilqr), ("lmpc_kernel", lmpc), ("sysid_kernel", sysid),
                      ("ocp_ipm_kernel<0,3,0> + planner_select_kernel + ocp_ipm_kernel<M,0,0>", planner)):
         report(name, fn)
     print("summary: done")

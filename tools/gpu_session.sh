@@ -34,6 +34,15 @@ PY
   start)    timeout 900 python tools/start_report.py --out gpurun_out/${tag}_start_report.json | tail -1 ;;
   launches) timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; wc -l gpurun_out/${tag}_launches.csv ;;
   variants) tools/variants.sh run ;;
+  sanitize) # compute-sanitizer on small launches of the four solver kernels: memcheck (global / shared out-of-bounds), racecheck
+            # (shared-memory hazards between warps / lanes), synccheck (barrier misuse)
+            for tool in memcheck racecheck synccheck; do
+              for k in "cbf 48" "planner 16" "lmpc 8" "ilqr 32"; do
+                set -- $k
+                timeout 600 compute-sanitizer --tool $tool --print-limit 5 python tools/one_launch.py --kind $1 --B $2 --reps 1 > gpurun_out/${tag}_sanitizer_${tool}_$1.log 2>&1
+                echo "$tool $1 B=$2: $(grep -E "ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/${tag}_sanitizer_${tool}_$1.log | tail -1)"
+              done
+            done ;;
   sweep)    timeout 600 python tools/config_sweep.py --no-cpu --out gpurun_out/${tag}_config_sweep.json > /dev/null 2> gpurun_out/${tag}_config_sweep.err; python -c "
 import json
 d = json.load(open('gpurun_out/${tag}_config_sweep.json'))
