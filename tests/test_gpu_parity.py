@@ -135,7 +135,7 @@ def test_per_rival_sizes_zero_start_and_x0_rows(crb, oracle):
     sizes = np.stack([rng.uniform(0.35, 0.5, (B, M)), rng.uniform(0.18, 0.26, (B, M))], axis=2)
     g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm, sizes=sizes)
     r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, sizes=sizes, nthreads=os.cpu_count() or 1)
-    _compare(g, r, min_match=0.97)
+    _compare(g, r, min_match=0.98)      # measured 96 of 96
     kw = dict(start=1, max_iter=40, max_reset=50)
     g = crb.solve_cbf_batch(x0[:32], xt, obs[:32], lap_off[:32], prm, **kw)
     r = oracle.solve_cbf_batch(x0[:32], xt, obs[:32], lap_off[:32], prm, nthreads=os.cpu_count() or 1, **kw)
@@ -143,7 +143,7 @@ def test_per_rival_sizes_zero_start_and_x0_rows(crb, oracle):
     info = dict(zero_start_same_path=float(same.mean()), x_diff=float(np.abs(g["x"] - r["x"])[same].max()))
     print(info)
     _log(info)
-    assert same.mean() >= 0.9 and info["x_diff"] < 1e-5
+    assert same.mean() >= 0.95 and info["x_diff"] < 1e-5      # measured 32 of 32, x_diff 0
     x0b = x0[:8].copy()
     x0b[0, 5], x0b[1, 0] = 1.2, -0.3
     g = crb.solve_cbf_batch(x0b, xt, obs[:8], lap_off[:8], prm)
@@ -176,7 +176,7 @@ def test_moving_rivals_lap_offsets_per_stage_targets(crb, oracle):
     prm = scenarios.default_cbf_params(N=N, alpha=0.6, margin=0.15, Q=np.diag([10.0, 0, 0, 5.0, 0, 50.0]))
     g = crb.solve_cbf_batch(x0, xts, obs, lap_off, prm)
     r = oracle.solve_cbf_batch(x0, xts, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
-    _compare(g, r, min_match=0.95)
+    _compare(g, r, min_match=0.98)      # measured 64 of 64
 
 
 def test_full_size_properties(crb):
@@ -331,7 +331,7 @@ def test_planner_candidate_qp_parity(crb, oracle):
     g = crb.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, prm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"])
     r = oracle.solve_cbf_batch(kw["x0"], kw["xt"], kw["obs"], None, prm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"],
                                nthreads=os.cpu_count() or 1)
-    match, info = _compare(g, r, min_match=0.97)
+    match, info = _compare(g, r, min_match=0.98)     # measured 57 of 57 (37 solved, 20 infeasible regions stop the same way)
     ok = (g["status"] == 0) & (r["status"] == 0)
     # the rest are dynamically infeasible regions (a rival row demands a 0.4 m lateral jump within one step): both
     # solvers stop the same way and the drop-in then takes the reference's heuristic trajectory (:365-374)
@@ -355,7 +355,8 @@ def test_planner_drop_in_on_gpu(crb, oracle):
 
 def test_max_sizes_and_odd_batches(crb, oracle):
     """Maximum horizon / rival count of the C-ABI (N=64, M=4 and M=8) and batch sizes that are not a multiple of anything."""
-    for (N, M, B, gate) in ((64, 4, 64, 0.95), (64, 8, 24, 0.9)):
+    for (N, M, B, gate) in ((64, 4, 64, 0.95), (64, 8, 24, 0.95)):      # measured 62 of 64 (|dcost| 5e-5 on the two: 3.4x the
+        # horizon, 3.4x the barrier residual in the cost) and 24 of 24
         x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=N, M=M, seed=21)
         obs[:, :, 0, :] += 3.0                                  # keep the long horizon feasible: rivals further ahead
         prm = scenarios.default_cbf_params(N=N)
@@ -367,7 +368,7 @@ def test_max_sizes_and_odd_batches(crb, oracle):
         prm = scenarios.default_cbf_params(N=20)
         g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
         r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm)
-        _compare(g, r, min_match=0.95)
+        _compare(g, r, min_match=0.96)      # measured 1 of 1, 3 of 3, 33 of 33
         assert g["x"].shape == (B, 21, 6) and g["sigma"].shape == (B, 3, 21)
 
 
@@ -386,7 +387,8 @@ def test_blocked_lane_elastic_rows(crb, oracle):
     same_status = g["status"] == r["status"]
     both = (g["status"] == 0) & (r["status"] == 0)
     print("status gpu", g["status"], "cpu", r["status"], "elastic gpu", g["elastic_max"].round(4))
-    assert same_status.mean() >= 0.8
+    _log(dict(blocked_lane_same_status=float(same_status.mean()), both_converged=int(both.sum())))
+    assert same_status.mean() >= 0.8      # 16 instances on the edge of feasibility: a rounding-level difference flips max_iter / converged
     if both.any():
         assert np.abs(g["elastic_max"][both] - r["elastic_max"][both]).max() < 1e-4
         assert np.abs(g["cost"][both] - r["cost"][both]).max() < 1e-3 * np.abs(r["cost"][both]).max()
@@ -463,7 +465,7 @@ def test_lmpc_shapes_parity(crb, oracle, N, K):
     prm = scenarios.default_lmpc_params(N=N, Q=np.diag([0.5, 0, 0, 0.1, 0, 2.0]))
     g = crb.solve_lmpc_batch(*sc, prm)
     r = oracle.solve_lmpc_batch(*sc, prm, nthreads=os.cpu_count() or 1)
-    _, info = _compare(g, r, min_match=0.95)
+    _, info = _compare(g, r, min_match=0.95)     # 24 instances: measured 24 of 24 on all shapes
     if K > 1:   # K = 1 pins x_N to one stored state: infeasible, both sides must stop the same way
         assert info["both_converged"] >= 0.9 * 24
 
