@@ -388,7 +388,7 @@ def test_blocked_lane_elastic_rows(crb, oracle):
     both = (g["status"] == 0) & (r["status"] == 0)
     print("status gpu", g["status"], "cpu", r["status"], "elastic gpu", g["elastic_max"].round(4))
     _log(dict(blocked_lane_same_status=float(same_status.mean()), both_converged=int(both.sum())))
-    assert same_status.mean() >= 0.8      # 16 instances on the edge of feasibility: a rounding-level difference flips max_iter / converged
+    assert same_status.mean() >= 0.9      # measured 16 of 16; 16 instances on the edge of feasibility: a rounding-level difference flips max_iter / converged
     if both.any():
         assert np.abs(g["elastic_max"][both] - r["elastic_max"][both]).max() < 1e-4
         assert np.abs(g["cost"][both] - r["cost"][both]).max() < 1e-3 * np.abs(r["cost"][both]).max()
