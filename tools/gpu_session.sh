@@ -22,7 +22,7 @@ except Exception as e:
 PY
             done ;;
   reference) timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>&1; tail -c 300 gpurun_out/${tag}_bench_reference.json ;;
-  clocks)   timeout 300 python tools/phase_clocks.py scratch/variants/libb200mpc_clocks.so --out gpurun_out/${tag}_phase_clocks.json | cut -c1-400 ;;
+  clocks)   timeout 300 python tools/phase_clocks.py variants_build/libb200mpc_clocks.so --out gpurun_out/${tag}_phase_clocks.json | cut -c1-400 ;;
   ncu)      timeout 600 ncu --set full --import-source on --clock-control none -k regex:ocp_ipm -s 1 -c 1 -f -o gpurun_out/${tag}_crowded python tools/one_launch.py --B 8192 2>&1 | tail -3
             ls -la gpurun_out/${tag}_crowded.ncu-rep ;;
   counts)   M="smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"
@@ -50,7 +50,7 @@ print('batch sweep:', [(e['B'], round(e['solves_per_s'])) for e in d['config2_ba
 print('overtaking step:', d.get('overtaking_step'))" ;;
   varbench) # every library under scratch/variants swapped in: short bench of configs 2 and 4
             cp car_racing_b200/libb200mpc.so /tmp/libb200mpc_original.so
-            for so in scratch/variants/libb200mpc_*.so; do
+            for so in variants_build/libb200mpc_*.so; do
               name=$(basename $so .so); name=${name#libb200mpc_}
               cp $so car_racing_b200/libb200mpc.so
               for c in 2 4; do

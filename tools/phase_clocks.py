@@ -2,7 +2,7 @@
 the SM is crowded?  Needs a library built with -DB200MPC_PHASE_CLOCKS (tools/variants.sh build clocks:"-DB200MPC_PHASE_CLOCKS"):
 that build writes the counters over the first 13 doubles of each instance's x_pred slot.
 
-    python tools/phase_clocks.py scratch/variants/libb200mpc_clocks.so [--out gpurun_out/phase_clocks.json]
+    python tools/phase_clocks.py variants_build/libb200mpc_clocks.so [--out gpurun_out/phase_clocks.json]
 
 The same 148 scenarios are tiled 1x, 4x, 7x (B = 148, 592, 1036: one wave each, every copy does identical work), so the
 ratio of a phase's cycles between the runs is the slowdown caused by sharing the SM, not by a different instance mix."""

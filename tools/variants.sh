@@ -2,7 +2,7 @@
 # A/B harness for kernel experiments under a tight GPU budget: variants are compiled HERE (nvcc cross-compiles without a
 # GPU, free) and travel with the gpurun snapshot; ONE gpurun call then times all of them back to back.
 #
-#   tools/variants.sh build  name1:"-DFOO"  name2:"-DBAR=2 -DBAZ"     # here: scratch/variants/libb200mpc_<name>.so (+ "base")
+#   tools/variants.sh build  name1:"-DFOO"  name2:"-DBAR=2 -DBAZ"     # here: variants_build/libb200mpc_<name>.so (+ "base")
 #   gpurun -- tools/variants.sh run                                    # on the box: per variant parity subset + timings
 #
 # `run` swaps each variant into car_racing_b200/libb200mpc.so (the product loads only that path), runs
@@ -13,7 +13,7 @@
 # tests/test_library_on_host.py   (logic on the host-compiled library), and compare `cuobjdump -sass` instruction counts.
 set -e
 cd "$(dirname "$0")/.."
-VDIR=scratch/variants
+VDIR=variants_build   # git-ignored, NOT gpurun-ignored: the variant libraries travel with the snapshot
 LIB=car_racing_b200/libb200mpc.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC"
