@@ -343,6 +343,9 @@ def main():
                          "(6; 16 for the iLQR config, whose short solves are bound by each batch's own stragglers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: force the NCCL all-gather form of the exchange")
+    ap.add_argument("--same-shards", action="store_true",
+                    help="diagnostic: every rank solves the SAME scenarios (seed 1) instead of its own shard (seed 1 + rank) -- "
+                         "separates the cost of the exchange from the unequal work of random shards")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="how the timed steps are kept from re-reading their inputs out of L2: rotate through device copies of the "
                          "records that together exceed L2 (default), or write a 256 MiB buffer before every step")
@@ -374,7 +377,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     D = max(1, args.inflight)
-    work = WORKS[args.config](B, seed=1 + rank)                 # each rank: its own shard of scenarios
+    work = WORKS[args.config](B, seed=1 if args.same_shards else 1 + rank)      # each rank: its own shard of scenarios
     rec_host = np.ascontiguousarray(work.rec)
     hs = [_capi.Handle(device=local_rank, max_batch=B) for _ in range(D)]   # one stream + staging buffers per slot
     L = _capi.lib()
@@ -598,7 +601,8 @@ def main():
     line = {
         "metric": work.metric, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": cfg, "converged_frac": conv, "input_copies_rotated": R_COPIES,
+        "dtype": "f64", "data": "synthetic" + (" (diagnostic: the same shard on every rank)" if args.same_shards else ""),
+        "config": cfg, "converged_frac": conv, "input_copies_rotated": R_COPIES,
         "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(rec_host.nbytes),
                 "d2h_bytes_per_step": int(B * 32 + (4 if px is not None else 0)), "ms_per_step": 1e3 * t_e2e / args.steps,
                 "batches_in_flight": D, "p50_latency_ms_batch1": float(np.median(lat)),

@@ -102,6 +102,14 @@ d = json.load(open('gpurun_out/${tag}_bench_${NG}gpu_c2_nccl.json')); print('N=$
 import json
 d = json.load(open('gpurun_out/${tag}_bench_${NG}gpu_c2_D$D.json')); print('N=$NG config 2 D=$D:', round(d['value']), 'solves/s  ms/step %.3f' % d['ms_per_step'], ' e2e', round(d['e2e']['value']), d.get('exchange_verified'))"
             done ;;
+  sameshards) NG=$(nvidia-smi -L | wc -l)
+            timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $NG --same-shards --no-cpu-baseline > gpurun_out/${tag}_bench_${NG}gpu_c2_sameshards.json 2> gpurun_out/${tag}_bench_${NG}gpu_c2_sameshards.err
+            timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus $NG --no-cpu-baseline > gpurun_out/${tag}_bench_${NG}gpu_c2.json 2> gpurun_out/${tag}_bench_${NG}gpu_c2.err
+            timeout 150 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_1gpu_c2.json 2>/dev/null
+            python -c "
+import json
+a = json.load(open('gpurun_out/${tag}_bench_${NG}gpu_c2_sameshards.json')); b = json.load(open('gpurun_out/${tag}_bench_${NG}gpu_c2.json')); c = json.load(open('gpurun_out/${tag}_bench_1gpu_c2.json'))
+print('N=$NG same shards:', round(a['value']), ' own shards:', round(b['value']), ' 1 GPU same box:', round(c['value']), ' efficiency %.3f / %.3f' % (a['value'] / ($NG * c['value']), b['value'] / ($NG * c['value'])))" ;;
   single)   timeout 400 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_1gpu.json 2> gpurun_out/${tag}_bench_1gpu.err
             python -c "
 import json
