@@ -143,10 +143,15 @@ __device__ __forceinline__ double rcp(double x) {
 #else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #endif
+#ifdef B200MPC_ORDER3   // one third-order step r (1 + e + e^2): 1e-6 -> 1e-18, dependent chain of 3 instead of 4
+    double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
+#else
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
+#endif
 }
 __device__ __forceinline__ double rsq(double x) {
     double y;
@@ -155,9 +160,14 @@ __device__ __forceinline__ double rsq(double x) {
 #else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #endif
+#ifdef B200MPC_ORDER3   // one third-order step y (1 + e/2 + 3 e^2/8), e = 1 - x y^2: dependent chain of 4 instead of 6
+    double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
+#else
     double h = 0.5 * x;
     y = y * fma(-h * y, y, 1.5);   // seed 1e-6 -> 1.3e-12 -> 4e-16 (measured over 60 binades, profiles/r01k_rsq_accuracy.txt)
     return y * fma(-h * y, y, 1.5);
+#endif
 }
 __device__ __forceinline__ double p4(double a) { double b = a * a; return b * b; }
 __device__ __forceinline__ double p5(double a) { double b = a * a; return b * b * a; }
@@ -892,6 +902,207 @@ struct Ipm {
             }
             __syncwarp();
             BCLK(0)
+#ifdef B200MPC_ROWFOLD
+            // (2) column l of G = base + T'(P T)[:, l] + sum_j SIGE_j ct_j ct_j[l].  The row vectors are ct_j = T'c_j with
+            //     c_j = (ja0, ja1) on (s, ey) of x_k and (ja2, ja3) on (s, ey) of x_{k+1}, so the whole sum over the rivals
+            //     folds into four scalars S0..S3 = sum_j ja._j w_j (w_j = SIGE_j ct_j[l]): S2, S3 join (P T)[4:6, l] BEFORE
+            //     the product with [A B]', S0, S1 land on rows s, ey.  The input rows (G_uu feeds the Cholesky) and the
+            //     gradient come before the barrier, the six state rows after it: they are needed only in (4) and issue
+            //     in the shadow of the factorisation's dependent chain (one basic block with (3)).
+            double g[NZ], gv, dsg, cv4, cv5, S0 = 0.0, S1 = 0.0;
+            {
+                double colv[NXAP], qvs[NXAP];
+                ldv<NXAP>(PT + cmap * NXAP, colv);
+                ldv<NXAP>(QVs, qvs);
+                int idx = idx_base + k * idx_step;
+                bool live = k >= kmin;
+                dsg = live ? HD[idx] + dw : 0.0;
+                gv = live ? D[idx] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) gv += tcol[q] * qvs[q];
+#pragma unroll
+                for (int j = 0; j < M; j++) gv += psel[j] * qvs[6 + j];
+                double S2 = 0.0, S3 = 0.0;
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    int r = j * N + k;
+                    double ja[4];
+                    ldv<4>(JA + 4 * r, ja);
+                    double dgr = DG[r], sg = SIGE[r], yh = YHAT[r];
+                    double own = tcol[4] * ja[2] + tcol[5] * ja[3];
+                    own += e4 * ja[0] + e5 * ja[1];
+                    own += crow[j] * dgr;
+                    double w = sg * own;
+                    S0 += ja[0] * w;
+                    S1 += ja[1] * w;
+                    S2 += ja[2] * w;
+                    S3 += ja[3] * w;
+                    g[6 + j] = (((6 + j) == lane) ? dsg : 0.0) + (dgr * a1) * w;
+                    g[NXA + 2 + j] = (colv[6 + j] + (((NXA + 2 + j) == lane) ? dsg : 0.0)) - dgr * w;
+                    gv -= yh * own;
+                }
+                if (hwd) {   // curvature of wd_k (ey_{k+1}-ey_k)^2: a pure "cost row" J = e5'(dx_{k+1}-dx_k), weight 2 df wd_k
+                    double w = (2.0 * df * wdp[k]) * (tcol[5] - ((lane == 5) ? 1.0 : 0.0));
+                    S3 += w;
+                    S1 -= w;
+                }
+                gv -= S2 * c6[4] + S3 * c6[5];
+                cv4 = colv[4] + S2;
+                cv5 = colv[5] + S3;
+                colv[4] = cv4;
+                colv[5] = cv5;
+#pragma unroll
+                for (int c = 0; c < 2; c++) g[NXA + c] = rrcol[c] + (((NXA + c) == lane) ? dsg : 0.0);
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    double ab[2];
+                    ldv<2>(ABs + 8 * q + 6, ab);
+#pragma unroll
+                    for (int c = 0; c < 2; c++) g[NXA + c] += ab[c] * colv[q];
+                }
+                if (lane >= NXA && lane < NZ) {
+                    double gu[NUAP];
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) gu[m] = g[NXA + m];
+                    if (NUAP > NUA) gu[NUAP - 1] = 0.0;
+                    stv<NUAP>(GUU + (lane - NXA) * NUAP, gu);
+                    GVU[lane - NXA] = gv;
+                }
+            }
+            __syncwarp();
+            BCLK(1)
+            {   // state rows of the column (PT is rewritten only after the next barrier)
+                double c4[4];
+                ldv<4>(PT + cmap * NXAP, c4);
+                const double colv[6] = {c4[0], c4[1], c4[2], c4[3], cv4, cv5};
+#pragma unroll
+                for (int a = 0; a < 6; a++) g[a] = qqcol[a] + ((a == lane) ? dsg : 0.0);
+                g[4] += S0;
+                g[5] += S1;
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    double ab[6];
+                    ld6(ABs + 8 * q, ab);
+#pragma unroll
+                    for (int a = 0; a < 6; a++) g[a] += ab[a] * colv[q];
+                }
+            }
+#elif defined(B200MPC_GX_LATE)
+            // (2) column l of G, split: the input rows (G_uu feeds the Cholesky) and the gradient before the barrier, the
+            //     state rows after it -- they are needed only in (4), so they issue in the shadow of the factorisation's
+            //     dependent chain (one basic block with (3))
+            double g[NZ], gv, wj[MM], dsg;
+            {
+                double colv[NXAP], qvs[NXAP];
+                ldv<NXAP>(PT + cmap * NXAP, colv);
+                ldv<NXAP>(QVs, qvs);
+#pragma unroll
+                for (int c = 0; c < 2; c++) g[NXA + c] = rrcol[c];
+                double ab4[2], ab5[2];
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    double ab[2];
+                    ldv<2>(ABs + 8 * q + 6, ab);
+#pragma unroll
+                    for (int c = 0; c < 2; c++) g[NXA + c] += ab[c] * colv[q];
+                    if (q == 4) { ab4[0] = ab[0]; ab4[1] = ab[1]; }
+                    if (q == 5) { ab5[0] = ab[0]; ab5[1] = ab[1]; }
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) g[NXA + 2 + j] = colv[6 + j];
+                int idx = idx_base + k * idx_step;
+                bool live = k >= kmin;
+                dsg = live ? HD[idx] + dw : 0.0;
+                gv = live ? D[idx] : 0.0;
+#pragma unroll
+                for (int a = NXA; a < NZ; a++) g[a] += (a == lane) ? dsg : 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) gv += tcol[q] * qvs[q];
+#pragma unroll
+                for (int j = 0; j < M; j++) gv += psel[j] * qvs[6 + j];
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    int r = j * N + k;
+                    double ja[4];
+                    ldv<4>(JA + 4 * r, ja);
+                    double dgr = DG[r], sg = SIGE[r], yh = YHAT[r];
+                    double own = tcol[4] * ja[2] + tcol[5] * ja[3];
+                    own += e4 * ja[0] + e5 * ja[1];
+                    own += crow[j] * dgr;
+                    double w = sg * own;
+                    wj[j] = w;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) g[NXA + c] += (ab4[c] * ja[2] + ab5[c] * ja[3]) * w;
+                    g[NXA + 2 + j] -= dgr * w;
+                    double er = -(ja[2] * c6[4] + ja[3] * c6[5]);
+                    gv += (sg * er - yh) * own;
+                }
+                if (hwd) {
+                    double sg = 2.0 * df * wdp[k];
+                    double own = tcol[5] - ((lane == 5) ? 1.0 : 0.0);
+                    double w = sg * own;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) g[NXA + c] += ab5[c] * w;
+                    gv += (sg * (-c6[5])) * own;
+                }
+                if (lane >= NXA && lane < NZ) {
+                    double gu[NUAP];
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) gu[m] = g[NXA + m];
+                    if (NUAP > NUA) gu[NUAP - 1] = 0.0;
+                    stv<NUAP>(GUU + (lane - NXA) * NUAP, gu);
+                    GVU[lane - NXA] = gv;
+                }
+            }
+            __syncwarp();
+            BCLK(1)
+            {   // state rows of the column (PT is rewritten only after the next barrier)
+                double colv[6];
+                ld6(PT + cmap * NXAP, colv);
+#pragma unroll
+                for (int a = 0; a < 6; a++) g[a] = qqcol[a];
+#pragma unroll
+                for (int j = 0; j < M; j++) g[6 + j] = 0.0;
+                double ab4[6], ab5[6];
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    double ab[6];
+                    ld6(ABs + 8 * q, ab);
+#pragma unroll
+                    for (int a = 0; a < 6; a++) g[a] += ab[a] * colv[q];
+                    if (q == 4) {
+#pragma unroll
+                        for (int c = 0; c < 6; c++) ab4[c] = ab[c];
+                    }
+                    if (q == 5) {
+#pragma unroll
+                        for (int c = 0; c < 6; c++) ab5[c] = ab[c];
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < NXA; a++) g[a] += (a == lane) ? dsg : 0.0;
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    int r = j * N + k;
+                    double ja[4];
+                    ldv<4>(JA + 4 * r, ja);
+                    double dgr = DG[r], w = wj[j];
+#pragma unroll
+                    for (int a = 0; a < 6; a++) {
+                        double ct = ab4[a] * ja[2] + ab5[a] * ja[3];
+                        if (a == 4) ct += ja[0];
+                        if (a == 5) ct += ja[1];
+                        g[a] += ct * w;
+                    }
+                    g[6 + j] += (dgr * a1) * w;
+                }
+                if (hwd) {
+                    double w = 2.0 * df * wdp[k] * (tcol[5] - ((lane == 5) ? 1.0 : 0.0));
+#pragma unroll
+                    for (int a = 0; a < 6; a++) g[a] += (ab5[a] - ((a == 5) ? 1.0 : 0.0)) * w;
+                }
+            }
+#else
             // (2) column l of G = base + T'PT + sum_j SIGE_j ct_j ct_j', own gradient component
             double g[NZ], gv;
             {
@@ -979,6 +1190,96 @@ struct Ipm {
             }
             __syncwarp();
             BCLK(1)
+#endif
+#ifdef B200MPC_LDL
+            // (3) root-free factorisation G_uu = L D L' (L unit lower) redundantly in every lane, column solves.  Against
+            //     the Cholesky form: a reciprocal instead of a reciprocal square root per pivot, and the substitutions carry
+            //     no scaling on their dependent chains (one FMA per step): s = L^-1 b forward, k = L^-T (D^-1 s) backward.
+            //     YF / YG keep the unscaled s; (4) subtracts s_a' D^-1 s_own.
+            double Lt[NUA][NUA], rd[NUA], sv[NUA], tv[NUA];
+            {
+                double Vr[NUA][NUA];   // unscaled entries v_iq = l_iq d_q
+#pragma unroll
+                for (int a = 0; a < NUA; a++) {
+                    double row[NUAP];
+                    ldv<NUAP>(GUU + a * NUAP, row);
+#pragma unroll
+                    for (int b = 0; b <= a; b++) Vr[a][b] = row[b];
+                }
+#pragma unroll
+                for (int j = 0; j < NUA; j++) {
+                    double d = Vr[j][j];
+#pragma unroll
+                    for (int q = 0; q < j; q++) d -= Lt[j][q] * Vr[j][q];
+                    if (!(d > 0.0)) ok = false;
+                    double r = rcp(d);
+                    rd[j] = r;
+#pragma unroll
+                    for (int i = j + 1; i < NUA; i++) {
+                        double v = Vr[i][j];
+#pragma unroll
+                        for (int q = 0; q < j; q++) v -= Lt[i][q] * Vr[j][q];
+                        Vr[i][j] = v;
+                        Lt[i][j] = v * r;
+                    }
+                }
+                double gvu[NUAP], kv[NUA];
+                ldv<NUAP>(GVU, gvu);
+                const bool gcol = (lane == NZ);  // this lane solves the gradient column
+#pragma unroll
+                for (int a = 0; a < NUA; a++) {
+                    double v = gcol ? gvu[a] : g[NXA + a];
+#pragma unroll
+                    for (int q = 0; q < a; q++) v -= Lt[a][q] * sv[q];
+                    sv[a] = v;
+                }
+#pragma unroll
+                for (int a = 0; a < NUA; a++) tv[a] = sv[a] * rd[a];
+#pragma unroll
+                for (int a = NUA - 1; a >= 0; a--) {
+                    double v = tv[a];
+#pragma unroll
+                    for (int q = a + 1; q < NUA; q++) v -= Lt[q][a] * kv[q];
+                    kv[a] = v;
+                }
+                if (!ok) return false;   // checked after the solves so that they overlap the factorisation's latency
+                if (lane < NXA) {
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) KFB[(k * NUA + m) * NKP + lane] = -kv[m];
+                    double yp[NUAP];
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) yp[m] = sv[m];
+                    if (NUAP > NUA) yp[NUAP - 1] = 0.0;
+                    stv<NUAP>(YF + lane * NUAP, yp);
+                } else if (gcol) {
+                    double yp[NUAP];
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) { yp[m] = sv[m]; KFB[(k * NUA + m) * NKP + NXA] = -kv[m]; }   // feed-forward term
+                    if (NUAP > NUA) yp[NUAP - 1] = 0.0;
+                    stv<NUAP>(YG, yp);
+                }
+            }
+            __syncwarp();
+            BCLK(2)
+            // (4) row b of P = G_xx - S' D^-1 S, p = g_x - S' D^-1 s_g (state lanes keep them in registers)
+            {
+                double yg[NUAP];
+                ldv<NUAP>(YG, yg);
+                double pn = gv;
+#pragma unroll
+                for (int m = 0; m < NUA; m++) pn -= tv[m] * yg[m];
+                pv = pn;
+#pragma unroll
+                for (int a = 0; a < NXA; a++) {
+                    double ya[NUAP];
+                    ldv<NUAP>(YF + a * NUAP, ya);
+                    double sa = g[a];
+#pragma unroll
+                    for (int m = 0; m < NUA; m++) sa -= ya[m] * tv[m];
+                    Pr[a] = sa;
+                }
+            }
+#else
             // (3) Cholesky of G_uu redundantly in every lane (rsqrt: no division); column solves
             double Lm[NUA][NUA], rinv[NUA], yv[NUA];
             {
@@ -1059,6 +1360,7 @@ struct Ipm {
                     Pr[a] = s;
                 }
             }
+#endif
             BCLK(3)
         }
         // stage 0: x_0 is fixed (control.py:497), sigma_{.,0} is free: d sigma_0 = -P_ss^-1 p_s  -> QVs[6+j]
@@ -1128,15 +1430,50 @@ struct Ipm {
         if (M > 0 && lane < M) D[isg(lane, 0)] = QVs[6 + lane];
         const int mrow = (lane < NUA) ? lane : 0;
         const int arow_i = (lane < 6) ? lane : 0;
+#ifdef B200MPC_FWD_PF   // the next stage's gain row and residual are fetched while this stage's chain runs
+        double krn[NKP], tcn;
+        ldv<NKP>(KFB + mrow * NKP, krn);
+        tcn = CRES[arow_i];
+#endif
         for (int k = 0; k < N; k++) {
             double kr[NKP];
+#ifdef B200MPC_FWD_PF
+#pragma unroll
+            for (int c = 0; c < NKP; c++) kr[c] = krn[c];
+            const double tck = tcn;
+            {
+                const int kn = (k + 1 < N) ? k + 1 : k;
+                ldv<NKP>(KFB + (kn * NUA + mrow) * NKP, krn);
+                tcn = CRES[6 * kn + arow_i];
+            }
+#else
             ldv<NKP>(KFB + (k * NUA + mrow) * NKP, kr);
+            const double tck = CRES[6 * k + arow_i];
+#endif
+#ifdef B200MPC_FWD_TREE   // three / two partial sums instead of one chain of NXA / 6 dependent FMAs
+            double s = kr[NXA], s1 = 0.0, s2 = 0.0;
+            double t = -tck, t1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < NXA; c += 3) {
+                s += kr[c] * dx[c];
+                if (c + 1 < NXA) s1 += kr[c + 1] * dx[c + 1];
+                if (c + 2 < NXA) s2 += kr[c + 2] * dx[c + 2];
+            }
+            s += s1 + s2;
+#pragma unroll
+            for (int b = 0; b < 6; b += 2) {
+                t += arow[b] * dx[b];
+                t1 += arow[b + 1] * dx[b + 1];
+            }
+            t += t1;
+#else
             double s = kr[NXA];
-            double t = -CRES[6 * k + arow_i];
+            double t = -tck;
 #pragma unroll
             for (int c = 0; c < NXA; c++) s += kr[c] * dx[c];
 #pragma unroll
             for (int b = 0; b < 6; b++) t += arow[b] * dx[b];
+#endif
             double du[NUA];
 #pragma unroll
             for (int m = 0; m < NUA; m++) du[m] = __shfl_sync(0xffffffffu, s, m);
@@ -1153,8 +1490,17 @@ struct Ipm {
 };
 
 // ---------------------------------------------------------------- kernel
+// 248 registers, not 255: the register file is granted per warp in units of 256, so 8 resident solver warps take 8 x 7936 and
+// leave room for the one-warp exchange kernels (csrc/exchange.cuh) on a full SM; above 248 they would take all 65536.
+#ifdef B200MPC_HOST_EMULATION
+#define OCP_KERNEL_BOUNDS
+#elif defined(B200MPC_MAXNREG)
+#define OCP_KERNEL_BOUNDS __maxnreg__(B200MPC_MAXNREG)
+#else
+#define OCP_KERNEL_BOUNDS __launch_bounds__(32)
+#endif
 template <int M, int FL, int NT>
-__global__ void __launch_bounds__(32) ocp_ipm_kernel(const __grid_constant__ KParams kp, const double *__restrict__ in,
+__global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams kp, const double *__restrict__ in,
                                                      b200mpc_record *__restrict__ rec, double *__restrict__ aux,
                                                      double *__restrict__ xpred, double *__restrict__ upred,
                                                      double *__restrict__ sigma, const XchgArgs xa = XchgArgs{nullptr, 0, 0, 0}) {

@@ -6,7 +6,7 @@
 #   gpurun -- tools/variants.sh run                                    # on the box: per variant parity subset + timings
 #
 # `run` swaps each variant into car_racing_b200/libb200mpc.so (the product loads only that path), runs
-#   - the config-2 parity tests (-m gpu -k "config2 or shapes or anchor or blocked"),
+#   - the config-2 parity tests (-m gpu -k "config2 or shapes or anchor or blocked"; VARIANT_TESTS overrides the selection),
 #   - a crowded launch (B=8192), a lone instance (B=1), and a short bench without the CPU leg,
 # prints one table row per variant, writes gpurun_out/variants.txt and restores the original library.
 # Before building a variant, check it on the host first: B200MPC_EMU_CXXFLAGS="<same -D flags>" python -m pytest
@@ -43,7 +43,7 @@ g.compile_lib(out='$VDIR/libb200mpc_$1.so', extra_flags=sys.argv[1].split(), ver
     for so in $VDIR/libb200mpc_*.so; do
       name=$(basename $so .so); name=${name#libb200mpc_}
       cp $so $LIB
-      par=$(timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "config2 or shapes or anchor or blocked" 2>&1 | tail -1)
+      par=$(timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "${VARIANT_TESTS:-config2 or shapes or anchor or blocked}" 2>&1 | tail -1)
       crowded=$(timeout 120 python tools/one_launch.py --B 8192 --reps 3 2>&1 | tail -1)
       lone=$(timeout 60 python tools/one_launch.py --B 1 --reps 3 2>&1 | tail -1)
       timeout 200 python bench.py --no-cpu-baseline --steps 24 > gpurun_out/variant_${name}_bench.json 2>/dev/null || true
