@@ -133,41 +133,33 @@ __device__ __forceinline__ double warp_min_nn(double v) {
     unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
     return __hiloint2double((int)mh, (int)ml);
 }
-// branch-free FP64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) + two Newton
-// steps (quadratic: 20 -> 40 -> 80 bits).  The compiler's IEEE division carries a slow-path call per site (~20 instructions, 2 branches); the
-// solver's operands are positive, finite and far from the denormal range, and 1-ulp differences are irrelevant here.
+// branch-free FP64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, relative error < 1e-6 measured
+// over 60 binades, profiles/r01k_rsq_accuracy.txt) + ONE third-order step: r (1 + e + e^2) with e = 1 - x r, and
+// y (1 + e/2 + 3 e^2/8) with e = 1 - x y^2 -- error e^3 ~ 1e-18, and a dependent chain of 3 / 4 instructions where two
+// Newton steps have 4 / 6 (+4.7 % solves/s, profiles/r06_variants_1.txt).
+// The compiler's IEEE division carries a slow-path call per site (~20 instructions, 2 branches); the solver's operands
+// are positive, finite and far from the denormal range, and 1-ulp differences are irrelevant here.
+// tests/host_emulation (the kernel source compiled by g++) has no hardware seed: it takes the exact value off by 9e-7,
+// so that the correction step is what the host tests check.
 __device__ __forceinline__ double rcp(double x) {
     double r;
-#ifdef B200MPC_HOST_EMULATION   // tests/host_emulation: the kernel source compiled by g++; the seed is exact there
-    r = 1.0 / x;
+#ifdef B200MPC_HOST_EMULATION
+    r = (1.0 / x) * (1.0 + 9e-7);
 #else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #endif
-#ifdef B200MPC_ORDER3   // one third-order step r (1 + e + e^2): 1e-6 -> 1e-18, dependent chain of 3 instead of 4
     double e = fma(-x, r, 1.0);
     return fma(r, fma(e, e, e), r);
-#else
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-#endif
 }
 __device__ __forceinline__ double rsq(double x) {
     double y;
 #ifdef B200MPC_HOST_EMULATION
-    y = 1.0 / sqrt(x);
+    y = (1.0 / sqrt(x)) * (1.0 - 9e-7);
 #else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #endif
-#ifdef B200MPC_ORDER3   // one third-order step y (1 + e/2 + 3 e^2/8), e = 1 - x y^2: dependent chain of 4 instead of 6
     double e = fma(-(x * y), y, 1.0);
     return fma(y * e, fma(e, 0.375, 0.5), y);
-#else
-    double h = 0.5 * x;
-    y = y * fma(-h * y, y, 1.5);   // seed 1e-6 -> 1.3e-12 -> 4e-16 (measured over 60 binades, profiles/r01k_rsq_accuracy.txt)
-    return y * fma(-h * y, y, 1.5);
-#endif
 }
 __device__ __forceinline__ double p4(double a) { double b = a * a; return b * b; }
 __device__ __forceinline__ double p5(double a) { double b = a * a; return b * b * a; }
@@ -902,7 +894,6 @@ struct Ipm {
             }
             __syncwarp();
             BCLK(0)
-#ifdef B200MPC_ROWFOLD
             // (2) column l of G = base + T'(P T)[:, l] + sum_j SIGE_j ct_j ct_j[l].  The row vectors are ct_j = T'c_j with
             //     c_j = (ja0, ja1) on (s, ey) of x_k and (ja2, ja3) on (s, ey) of x_{k+1}, so the whole sum over the rivals
             //     folds into four scalars S0..S3 = sum_j ja._j w_j (w_j = SIGE_j ct_j[l]): S2, S3 join (P T)[4:6, l] BEFORE
@@ -987,211 +978,6 @@ struct Ipm {
                     for (int a = 0; a < 6; a++) g[a] += ab[a] * colv[q];
                 }
             }
-#elif defined(B200MPC_GX_LATE)
-            // (2) column l of G, split: the input rows (G_uu feeds the Cholesky) and the gradient before the barrier, the
-            //     state rows after it -- they are needed only in (4), so they issue in the shadow of the factorisation's
-            //     dependent chain (one basic block with (3))
-            double g[NZ], gv, wj[MM], dsg;
-            {
-                double colv[NXAP], qvs[NXAP];
-                ldv<NXAP>(PT + cmap * NXAP, colv);
-                ldv<NXAP>(QVs, qvs);
-#pragma unroll
-                for (int c = 0; c < 2; c++) g[NXA + c] = rrcol[c];
-                double ab4[2], ab5[2];
-#pragma unroll
-                for (int q = 0; q < 6; q++) {
-                    double ab[2];
-                    ldv<2>(ABs + 8 * q + 6, ab);
-#pragma unroll
-                    for (int c = 0; c < 2; c++) g[NXA + c] += ab[c] * colv[q];
-                    if (q == 4) { ab4[0] = ab[0]; ab4[1] = ab[1]; }
-                    if (q == 5) { ab5[0] = ab[0]; ab5[1] = ab[1]; }
-                }
-#pragma unroll
-                for (int j = 0; j < M; j++) g[NXA + 2 + j] = colv[6 + j];
-                int idx = idx_base + k * idx_step;
-                bool live = k >= kmin;
-                dsg = live ? HD[idx] + dw : 0.0;
-                gv = live ? D[idx] : 0.0;
-#pragma unroll
-                for (int a = NXA; a < NZ; a++) g[a] += (a == lane) ? dsg : 0.0;
-#pragma unroll
-                for (int q = 0; q < 6; q++) gv += tcol[q] * qvs[q];
-#pragma unroll
-                for (int j = 0; j < M; j++) gv += psel[j] * qvs[6 + j];
-#pragma unroll
-                for (int j = 0; j < M; j++) {
-                    int r = j * N + k;
-                    double ja[4];
-                    ldv<4>(JA + 4 * r, ja);
-                    double dgr = DG[r], sg = SIGE[r], yh = YHAT[r];
-                    double own = tcol[4] * ja[2] + tcol[5] * ja[3];
-                    own += e4 * ja[0] + e5 * ja[1];
-                    own += crow[j] * dgr;
-                    double w = sg * own;
-                    wj[j] = w;
-#pragma unroll
-                    for (int c = 0; c < 2; c++) g[NXA + c] += (ab4[c] * ja[2] + ab5[c] * ja[3]) * w;
-                    g[NXA + 2 + j] -= dgr * w;
-                    double er = -(ja[2] * c6[4] + ja[3] * c6[5]);
-                    gv += (sg * er - yh) * own;
-                }
-                if (hwd) {
-                    double sg = 2.0 * df * wdp[k];
-                    double own = tcol[5] - ((lane == 5) ? 1.0 : 0.0);
-                    double w = sg * own;
-#pragma unroll
-                    for (int c = 0; c < 2; c++) g[NXA + c] += ab5[c] * w;
-                    gv += (sg * (-c6[5])) * own;
-                }
-                if (lane >= NXA && lane < NZ) {
-                    double gu[NUAP];
-#pragma unroll
-                    for (int m = 0; m < NUA; m++) gu[m] = g[NXA + m];
-                    if (NUAP > NUA) gu[NUAP - 1] = 0.0;
-                    stv<NUAP>(GUU + (lane - NXA) * NUAP, gu);
-                    GVU[lane - NXA] = gv;
-                }
-            }
-            __syncwarp();
-            BCLK(1)
-            {   // state rows of the column (PT is rewritten only after the next barrier)
-                double colv[6];
-                ld6(PT + cmap * NXAP, colv);
-#pragma unroll
-                for (int a = 0; a < 6; a++) g[a] = qqcol[a];
-#pragma unroll
-                for (int j = 0; j < M; j++) g[6 + j] = 0.0;
-                double ab4[6], ab5[6];
-#pragma unroll
-                for (int q = 0; q < 6; q++) {
-                    double ab[6];
-                    ld6(ABs + 8 * q, ab);
-#pragma unroll
-                    for (int a = 0; a < 6; a++) g[a] += ab[a] * colv[q];
-                    if (q == 4) {
-#pragma unroll
-                        for (int c = 0; c < 6; c++) ab4[c] = ab[c];
-                    }
-                    if (q == 5) {
-#pragma unroll
-                        for (int c = 0; c < 6; c++) ab5[c] = ab[c];
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < NXA; a++) g[a] += (a == lane) ? dsg : 0.0;
-#pragma unroll
-                for (int j = 0; j < M; j++) {
-                    int r = j * N + k;
-                    double ja[4];
-                    ldv<4>(JA + 4 * r, ja);
-                    double dgr = DG[r], w = wj[j];
-#pragma unroll
-                    for (int a = 0; a < 6; a++) {
-                        double ct = ab4[a] * ja[2] + ab5[a] * ja[3];
-                        if (a == 4) ct += ja[0];
-                        if (a == 5) ct += ja[1];
-                        g[a] += ct * w;
-                    }
-                    g[6 + j] += (dgr * a1) * w;
-                }
-                if (hwd) {
-                    double w = 2.0 * df * wdp[k] * (tcol[5] - ((lane == 5) ? 1.0 : 0.0));
-#pragma unroll
-                    for (int a = 0; a < 6; a++) g[a] += (ab5[a] - ((a == 5) ? 1.0 : 0.0)) * w;
-                }
-            }
-#else
-            // (2) column l of G = base + T'PT + sum_j SIGE_j ct_j ct_j', own gradient component
-            double g[NZ], gv;
-            {
-                double colv[NXAP], qvs[NXAP];
-                ldv<NXAP>(PT + cmap * NXAP, colv);
-                ldv<NXAP>(QVs, qvs);
-#pragma unroll
-                for (int a = 0; a < 6; a++) g[a] = qqcol[a];
-#pragma unroll
-                for (int j = 0; j < M; j++) g[6 + j] = 0.0;
-#pragma unroll
-                for (int c = 0; c < 2; c++) g[NXA + c] = rrcol[c];
-                double ab4[8], ab5[8];
-#pragma unroll
-                for (int q = 0; q < 6; q++) {
-                    double ab[8];
-                    ldv<8>(ABs + 8 * q, ab);
-#pragma unroll
-                    for (int a = 0; a < 6; a++) g[a] += ab[a] * colv[q];
-#pragma unroll
-                    for (int c = 0; c < 2; c++) g[NXA + c] += ab[6 + c] * colv[q];
-                    if (q == 4) {
-#pragma unroll
-                        for (int c = 0; c < 8; c++) ab4[c] = ab[c];
-                    }
-                    if (q == 5) {
-#pragma unroll
-                        for (int c = 0; c < 8; c++) ab5[c] = ab[c];
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < M; j++) g[NXA + 2 + j] = colv[6 + j];
-                int idx = idx_base + k * idx_step;
-                bool live = k >= kmin;
-                double dsg = live ? HD[idx] + dw : 0.0;
-                gv = live ? D[idx] : 0.0;
-#pragma unroll
-                for (int a = 0; a < NZ; a++) g[a] += (a == lane) ? dsg : 0.0;
-#pragma unroll
-                for (int q = 0; q < 6; q++) gv += tcol[q] * qvs[q];
-#pragma unroll
-                for (int j = 0; j < M; j++) gv += psel[j] * qvs[6 + j];
-#pragma unroll
-                for (int j = 0; j < M; j++) {
-                    int r = j * N + k;
-                    double ja[4];
-                    ldv<4>(JA + 4 * r, ja);
-                    double dgr = DG[r], sg = SIGE[r], yh = YHAT[r];
-                    double own = tcol[4] * ja[2] + tcol[5] * ja[3];
-                    own += e4 * ja[0] + e5 * ja[1];
-                    own += crow[j] * dgr;
-                    double w = sg * own;
-#pragma unroll
-                    for (int a = 0; a < 6; a++) {
-                        double ct = ab4[a] * ja[2] + ab5[a] * ja[3];
-                        if (a == 4) ct += ja[0];
-                        if (a == 5) ct += ja[1];
-                        g[a] += ct * w;
-                    }
-                    g[6 + j] += (dgr * a1) * w;
-#pragma unroll
-                    for (int c = 0; c < 2; c++) g[NXA + c] += (ab4[6 + c] * ja[2] + ab5[6 + c] * ja[3]) * w;
-                    g[NXA + 2 + j] -= dgr * w;
-                    double er = -(ja[2] * c6[4] + ja[3] * c6[5]);
-                    gv += (sg * er - yh) * own;
-                }
-                if (hwd) {   // curvature of wd_k (ey_{k+1}-ey_k)^2: a pure "cost row" J = e5'(dx_{k+1}-dx_k), weight 2 df wd_k
-                    double sg = 2.0 * df * wdp[k];
-                    double own = tcol[5] - ((lane == 5) ? 1.0 : 0.0);
-                    double w = sg * own;
-#pragma unroll
-                    for (int a = 0; a < 6; a++) g[a] += (ab5[a] - ((a == 5) ? 1.0 : 0.0)) * w;
-#pragma unroll
-                    for (int c = 0; c < 2; c++) g[NXA + c] += ab5[6 + c] * w;
-                    gv += (sg * (-c6[5])) * own;
-                }
-                if (lane >= NXA && lane < NZ) {
-                    double gu[NUAP];
-#pragma unroll
-                    for (int m = 0; m < NUA; m++) gu[m] = g[NXA + m];
-                    if (NUAP > NUA) gu[NUAP - 1] = 0.0;
-                    stv<NUAP>(GUU + (lane - NXA) * NUAP, gu);
-                    GVU[lane - NXA] = gv;
-                }
-            }
-            __syncwarp();
-            BCLK(1)
-#endif
-#ifdef B200MPC_LDL
             // (3) root-free factorisation G_uu = L D L' (L unit lower) redundantly in every lane, column solves.  Against
             //     the Cholesky form: a reciprocal instead of a reciprocal square root per pivot, and the substitutions carry
             //     no scaling on their dependent chains (one FMA per step): s = L^-1 b forward, k = L^-T (D^-1 s) backward.
@@ -1279,88 +1065,6 @@ struct Ipm {
                     Pr[a] = sa;
                 }
             }
-#else
-            // (3) Cholesky of G_uu redundantly in every lane (rsqrt: no division); column solves
-            double Lm[NUA][NUA], rinv[NUA], yv[NUA];
-            {
-#pragma unroll
-                for (int a = 0; a < NUA; a++) {
-                    double row[NUAP];
-                    ldv<NUAP>(GUU + a * NUAP, row);
-#pragma unroll
-                    for (int b = 0; b <= a; b++) Lm[a][b] = row[b];
-                }
-#pragma unroll
-                for (int j = 0; j < NUA; j++) {
-                    double d = Lm[j][j];
-#pragma unroll
-                    for (int q = 0; q < j; q++) d -= Lm[j][q] * Lm[j][q];
-                    if (!(d > 0.0)) ok = false;
-                    double ri = rsq(d);
-                    rinv[j] = ri;
-#pragma unroll
-                    for (int i = j + 1; i < NUA; i++) {
-                        double s = Lm[i][j];
-#pragma unroll
-                        for (int q = 0; q < j; q++) s -= Lm[i][q] * Lm[j][q];
-                        Lm[i][j] = s * ri;
-                    }
-                }
-                double gvu[NUAP], kv[NUA];
-                ldv<NUAP>(GVU, gvu);
-                const bool gcol = (lane == NZ);  // this lane solves the gradient column
-#pragma unroll
-                for (int a = 0; a < NUA; a++) {
-                    double s = gcol ? gvu[a] : g[NXA + a];
-#pragma unroll
-                    for (int q = 0; q < a; q++) s -= Lm[a][q] * yv[q];
-                    yv[a] = s * rinv[a];
-                }
-#pragma unroll
-                for (int a = NUA - 1; a >= 0; a--) {
-                    double s = yv[a];
-#pragma unroll
-                    for (int q = a + 1; q < NUA; q++) s -= Lm[q][a] * kv[q];
-                    kv[a] = s * rinv[a];
-                }
-                if (!ok) return false;   // checked after the solves so that they overlap the factorisation's latency
-                if (lane < NXA) {
-#pragma unroll
-                    for (int m = 0; m < NUA; m++) KFB[(k * NUA + m) * NKP + lane] = -kv[m];
-                    double yp[NUAP];
-#pragma unroll
-                    for (int m = 0; m < NUA; m++) yp[m] = yv[m];
-                    if (NUAP > NUA) yp[NUAP - 1] = 0.0;
-                    stv<NUAP>(YF + lane * NUAP, yp);
-                } else if (gcol) {
-                    double yp[NUAP];
-#pragma unroll
-                    for (int m = 0; m < NUA; m++) { yp[m] = yv[m]; KFB[(k * NUA + m) * NKP + NXA] = -kv[m]; }   // feed-forward term
-                    if (NUAP > NUA) yp[NUAP - 1] = 0.0;
-                    stv<NUAP>(YG, yp);
-                }
-            }
-            __syncwarp();
-            BCLK(2)
-            // (4) row b of P = G_xx - Y'Y, p = g_x - Y' y_g (state lanes keep them in registers)
-            {
-                double yg[NUAP];
-                ldv<NUAP>(YG, yg);
-                double pn = gv;
-#pragma unroll
-                for (int m = 0; m < NUA; m++) pn -= yv[m] * yg[m];
-                pv = pn;
-#pragma unroll
-                for (int a = 0; a < NXA; a++) {
-                    double ya[NUAP];
-                    ldv<NUAP>(YF + a * NUAP, ya);
-                    double s = g[a];
-#pragma unroll
-                    for (int m = 0; m < NUA; m++) s -= ya[m] * yv[m];
-                    Pr[a] = s;
-                }
-            }
-#endif
             BCLK(3)
         }
         // stage 0: x_0 is fixed (control.py:497), sigma_{.,0} is free: d sigma_0 = -P_ss^-1 p_s  -> QVs[6+j]
@@ -1430,29 +1134,12 @@ struct Ipm {
         if (M > 0 && lane < M) D[isg(lane, 0)] = QVs[6 + lane];
         const int mrow = (lane < NUA) ? lane : 0;
         const int arow_i = (lane < 6) ? lane : 0;
-#ifdef B200MPC_FWD_PF   // the next stage's gain row and residual are fetched while this stage's chain runs
-        double krn[NKP], tcn;
-        ldv<NKP>(KFB + mrow * NKP, krn);
-        tcn = CRES[arow_i];
-#endif
         for (int k = 0; k < N; k++) {
             double kr[NKP];
-#ifdef B200MPC_FWD_PF
-#pragma unroll
-            for (int c = 0; c < NKP; c++) kr[c] = krn[c];
-            const double tck = tcn;
-            {
-                const int kn = (k + 1 < N) ? k + 1 : k;
-                ldv<NKP>(KFB + (kn * NUA + mrow) * NKP, krn);
-                tcn = CRES[6 * kn + arow_i];
-            }
-#else
             ldv<NKP>(KFB + (k * NUA + mrow) * NKP, kr);
-            const double tck = CRES[6 * k + arow_i];
-#endif
-#ifdef B200MPC_FWD_TREE   // three / two partial sums instead of one chain of NXA / 6 dependent FMAs
+            // three / two partial sums instead of one chain of NXA / 6 dependent FMAs (the sweep is a dependent chain)
             double s = kr[NXA], s1 = 0.0, s2 = 0.0;
-            double t = -tck, t1 = 0.0;
+            double t = -CRES[6 * k + arow_i], t1 = 0.0;
 #pragma unroll
             for (int c = 0; c < NXA; c += 3) {
                 s += kr[c] * dx[c];
@@ -1466,14 +1153,6 @@ struct Ipm {
                 t1 += arow[b + 1] * dx[b + 1];
             }
             t += t1;
-#else
-            double s = kr[NXA];
-            double t = -tck;
-#pragma unroll
-            for (int c = 0; c < NXA; c++) s += kr[c] * dx[c];
-#pragma unroll
-            for (int b = 0; b < 6; b++) t += arow[b] * dx[b];
-#endif
             double du[NUA];
 #pragma unroll
             for (int m = 0; m < NUA; m++) du[m] = __shfl_sync(0xffffffffu, s, m);
