@@ -101,6 +101,21 @@ struct SmemPlan {
     __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(double); }
 };
 
+// The once-per-iteration phases keep their loops over the six state rows (OCP_ROLL_A) and over the rivals (OCP_ROLL_J) rolled
+// for code size (instruction cache); the unroll factors are build switches so that the trade against the
+// dependent-chain latency of a rolled iteration can be measured (tools/variants.sh; profiles/r06_variants_3.txt: x2 / x3 of the
+// row loops +0.7 % / -0.2 %, x3 of the rival loops -12 % on a full SM)
+#ifndef B200MPC_UNROLL_A
+#define B200MPC_UNROLL_A 1
+#endif
+#ifndef B200MPC_UNROLL_J
+#define B200MPC_UNROLL_J 1
+#endif
+#define OCP_STR2_(x) #x
+#define OCP_STR_(x) OCP_STR2_(x)
+#define OCP_ROLL_A _Pragma(OCP_STR_(unroll B200MPC_UNROLL_A))
+#define OCP_ROLL_J _Pragma(OCP_STR_(unroll B200MPC_UNROLL_J))
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -258,6 +273,14 @@ struct Ipm {
     static constexpr int NKP = SmemPlan<M>::NKP;
     const KParams &kp;
     const int lane;
+    // role lane of the backward sweep: when the sweep's NZ + 1 lanes fit a half-warp (M <= 3), lanes 16..31 mirror lanes 0..15
+    // (same column, same arithmetic: free in SIMT) and take the second half of the columns of [A B] in step (1)
+#if !defined(B200MPC_NO_MIRROR)
+    static constexpr bool kMirror = (NZ + 1 <= 16);
+#else
+    static constexpr bool kMirror = false;
+#endif
+    const int rl;
     static constexpr bool kStaticN = NT > 0;
     // stage loops: with a compile-time horizon below 32 every stage has its own lane and the loop runs once -- a step
     // that overshoots any horizon lets the compiler drop the loop (back edge, loop-carried moves)
@@ -283,7 +306,7 @@ struct Ipm {
     double arow[6], brow[2];   // row `lane` of A and B (lanes < 6), for the forward sweep
 
     __device__ Ipm(const KParams &kp_, const SmemPlan<M> &pl, double *sm, int lane_)
-        : kp(kp_), lane(lane_), N(NT ? NT : pl.N), R(M * (NT ? NT : pl.N)), NB(NT ? 4 * NT + M * (NT + 1) : pl.NB),
+        : kp(kp_), lane(lane_), rl(kMirror ? (lane_ & 15) : lane_), N(NT ? NT : pl.N), R(M * (NT ? NT : pl.N)), NB(NT ? 4 * NT + M * (NT + 1) : pl.NB),
           NW(NT ? 8 * NT + 6 + M * (NT + 1) : pl.NW), OU(NT ? 6 * (NT + 1) : pl.OU), OS(NT ? 8 * NT + 6 : pl.OS) {
         IN = sm + pl.oIN; W = sm + pl.oW; D = sm + pl.oD; HD = sm + pl.oHD; ZL = sm + pl.oZL; ZU = sm + pl.oZU;
         S = sm + pl.oS; T = sm + pl.oT; Y = sm + pl.oY; Z = sm + pl.oZ; V = sm + pl.oV;
@@ -304,7 +327,7 @@ struct Ipm {
         rho = kp.o.rho;
         df = 1.0;
         mu = kp.o.mu_init;
-        const int l = lane;
+        const int l = rl;
         isx = l < 6;
         iss = l >= 6 && l < NXA;
         isu = l >= NXA && l < NXA + 2;
@@ -353,14 +376,14 @@ struct Ipm {
         for (int q = 0; q < 6; q++) {
             double v = 0.0;
 #pragma unroll
-            for (int c = 0; c < 6; c++) v = (lane == c) ? Q2(q, c) : v;
+            for (int c = 0; c < 6; c++) v = (rl == c) ? Q2(q, c) : v;
             qqcol[q] = df * v;
         }
 #pragma unroll
         for (int q = 0; q < 2; q++) {
             double v = 0.0;
 #pragma unroll
-            for (int c = 0; c < 2; c++) v = (lane == NXA + c) ? R2(q, c) : v;
+            for (int c = 0; c < 2; c++) v = (rl == NXA + c) ? R2(q, c) : v;
             rrcol[q] = df * v;
         }
     }
@@ -446,7 +469,7 @@ struct Ipm {
     template <bool useD, bool store>
     __device__ __forceinline__ double dyn_res(int k, double al, const double (&x)[6], const double (&u)[2]) const {
         double acc = 0.0;
-#pragma unroll 1
+OCP_ROLL_A
         for (int a = 0; a < 6; a++) {
             double s = W[6 * (k + 1) + a];
             if (useD) s += al * D[6 * (k + 1) + a];
@@ -466,7 +489,7 @@ struct Ipm {
 #pragma unroll
         for (int a = 0; a < 6; a++) d[a] = x[a] - t[a];
         double f = 0.0;
-#pragma unroll 1
+OCP_ROLL_A
         for (int a = 0; a < 6; a++) {
             const double *Qr = kp.p.Q + 6 * a;
             double acc = 0.0, da = 0.0;
@@ -550,7 +573,7 @@ struct Ipm {
                 if (hwd) f += wdp[k] * (xn[5] - x[5]) * (xn[5] - x[5]);   // overtake_traj_planner.py:325-327
             }
             // one rolled loop over the rivals (the kernel is instruction-fetch bound: code size counts)
-#pragma unroll 1
+OCP_ROLL_J
             for (int j = 0; j < M; j++) {
                 double sv = W[isg(j, k)];
                 if (useD) sv += al * D[isg(j, k)];
@@ -621,7 +644,7 @@ struct Ipm {
             load_x<false>(k + 1, 0.0, xn);
             load_u<false>(k, 0.0, u);
             dyn_res<false, true>(k, 0.0, x, u);
-#pragma unroll 1
+OCP_ROLL_J
             for (int j = 0; j < M; j++) {
                 int r = j * N + k;
                 RowV v = row_vals(j, k, x, xn, W[isg(j, k)], W[isg(j, k + 1)]);
@@ -651,7 +674,7 @@ struct Ipm {
             }
             if (k >= 1) {
                 double jy4 = 0.0, jy5 = 0.0;
-#pragma unroll 1
+OCP_ROLL_J
                 for (int j = 0; j < M; j++) {  // J'y on (s, ey)
                     if (k < N) {
                         int r = j * N + k;
@@ -667,7 +690,7 @@ struct Ipm {
                 double xk[6], dk[6];
                 load_x<false>(k, 0.0, xk);
                 diff_target(k, xk, dk);
-#pragma unroll 1
+OCP_ROLL_A
                 for (int a = 0; a < 6; a++) {
                     double s = grad_x_comp(k, a, dk, xk[5]) + LAM[6 * (k - 1) + a];
 #pragma unroll
@@ -678,7 +701,7 @@ struct Ipm {
                     dual = fmax(dual, fabs(s));
                 }
             }
-#pragma unroll 1
+OCP_ROLL_J
             for (int j = 0; j < M; j++) {  // sigma_{j,k}
                 double zl = ZL[bss(j, k)];
                 double rw = df * kp.p.slack_w - zl;
@@ -707,7 +730,7 @@ struct Ipm {
                     prim = fmax(prim, fabs(c6[a]));
                     ysum += fabs(lamn[a]);
                 }
-#pragma unroll 1
+OCP_ROLL_J
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     dual = fmax(dual, fabs(Y[r] - Z[r]));
@@ -739,7 +762,7 @@ struct Ipm {
                 if (has(xlb(k, 1))) acc((ey - xlb(k, 1)) * zl.y);
                 if (has(xub(k, 1))) acc((xub(k, 1) - ey) * zu.y);
             }
-#pragma unroll 1
+OCP_ROLL_J
             for (int j = 0; j < M; j++) acc(W[isg(j, k)] * ZL[bss(j, k)]);
             if (k < N) {
                 double u[2];
@@ -749,7 +772,7 @@ struct Ipm {
                 acc((kp.p.umax[0] - u[0]) * zu.x);
                 acc((u[1] + kp.p.umax[1]) * zl.y);
                 acc((kp.p.umax[1] - u[1]) * zu.y);
-#pragma unroll 1
+OCP_ROLL_J
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     acc(S[r] * Z[r]);
@@ -792,14 +815,14 @@ struct Ipm {
                     gb5 = -mu * il + mu * iu;
                 }
                 // base gradient of the barrier problem -> D (overwritten by the forward pass)
-#pragma unroll 1
+OCP_ROLL_A
                 for (int a = 0; a < 6; a++) {
                     double gv = grad_x_comp(k, a, dk, x[5]);
                     if (a == 0) gv += gb0;
                     if (a == 5) gv += gb5;
                     D[6 * k + a] = gv;
                 }
-#pragma unroll 1
+OCP_ROLL_J
                 for (int j = 0; j < M; j++) {  // Hessian of -y_r g_r: diagonal on (s, ey) (control.py:544-557, degree 6)
                     if (k < N) {
                         int r = j * N + k;
@@ -814,7 +837,7 @@ struct Ipm {
                 }
                 st6(HD + 6 * k, hd);
             }
-#pragma unroll 1
+OCP_ROLL_J
             for (int j = 0; j < M; j++) {
                 double is = rcp(W[isg(j, k)]);
                 HD[isg(j, k)] = ZL[bss(j, k)] * is;
@@ -829,7 +852,7 @@ struct Ipm {
                 st2(HD + OU + 2 * k, zl.x * il0 + zu.x * iu0, zl.y * il1 + zu.y * iu1);
                 st2(D + OU + 2 * k, df * (R2(0, 0) * u[0] + R2(0, 1) * u[1]) - mu * il0 + mu * iu0,
                     df * (R2(1, 0) * u[0] + R2(1, 1) * u[1]) - mu * il1 + mu * iu1);
-#pragma unroll 1
+OCP_ROLL_J
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     double s = S[r], tt = T[r];
@@ -860,11 +883,11 @@ struct Ipm {
 #endif
         double Pr[NXA], pv;
         {   // terminal value function: stage-N state block
-            int idx = isx ? 6 * N + lane : (iss ? isg(jrole, N) : 0);
+            int idx = isx ? 6 * N + rl : (iss ? isg(jrole, N) : 0);
             double dN = (isx || iss) ? HD[idx] + dw : 0.0;
             pv = (isx || iss) ? D[idx] : 0.0;
 #pragma unroll
-            for (int b = 0; b < NXA; b++) Pr[b] = ((b < 6) ? qqcol[b < 6 ? b : 0] : 0.0) + ((b == lane) ? dN : 0.0);
+            for (int b = 0; b < NXA; b++) Pr[b] = ((b < 6) ? qqcol[b < 6 ? b : 0] : 0.0) + ((b == rl) ? dN : 0.0);
         }
         bool ok = true;
         for (int k = N - 1; k >= 0; k--) {
@@ -872,24 +895,26 @@ struct Ipm {
             double c6[6];
             ld6(CRES + 6 * k, c6);
             {
-                double ptx[8];
+                constexpr int NCOL = kMirror ? 4 : 8;   // columns of [A B] per lane
+                const int c0 = kMirror ? (lane >> 4) * NCOL : 0;
+                double ptx[NCOL];
 #pragma unroll
-                for (int c = 0; c < 8; c++) ptx[c] = 0.0;
+                for (int c = 0; c < NCOL; c++) ptx[c] = 0.0;
                 double qv = pv;
 #pragma unroll
                 for (int b = 0; b < 6; b++) {
-                    double ab[8];
-                    ldv<8>(ABs + 8 * b, ab);
+                    double ab[NCOL];
+                    ldv<NCOL>(ABs + 8 * b + c0, ab);
 #pragma unroll
-                    for (int c = 0; c < 8; c++) ptx[c] += Pr[b] * ab[c];
+                    for (int c = 0; c < NCOL; c++) ptx[c] += Pr[b] * ab[c];
                     qv -= Pr[b] * c6[b];
                 }
-                if (lane < NXA) {
+                if (rl < NXA) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) PT[c * NXAP + lane] = ptx[c];
+                    for (int c = 0; c < NCOL; c++) PT[(c0 + c) * NXAP + rl] = ptx[c];
 #pragma unroll
-                    for (int j = 0; j < M; j++) PT[(8 + j) * NXAP + lane] = Pr[6 + j];
-                    QVs[lane] = qv;
+                    for (int j = 0; j < M; j++) PT[(8 + j) * NXAP + rl] = Pr[6 + j];
+                    QVs[rl] = qv;
                 }
             }
             __syncwarp();
@@ -928,12 +953,12 @@ struct Ipm {
                     S1 += ja[1] * w;
                     S2 += ja[2] * w;
                     S3 += ja[3] * w;
-                    g[6 + j] = (((6 + j) == lane) ? dsg : 0.0) + (dgr * a1) * w;
-                    g[NXA + 2 + j] = (colv[6 + j] + (((NXA + 2 + j) == lane) ? dsg : 0.0)) - dgr * w;
+                    g[6 + j] = (((6 + j) == rl) ? dsg : 0.0) + (dgr * a1) * w;
+                    g[NXA + 2 + j] = (colv[6 + j] + (((NXA + 2 + j) == rl) ? dsg : 0.0)) - dgr * w;
                     gv -= yh * own;
                 }
                 if (hwd) {   // curvature of wd_k (ey_{k+1}-ey_k)^2: a pure "cost row" J = e5'(dx_{k+1}-dx_k), weight 2 df wd_k
-                    double w = (2.0 * df * wdp[k]) * (tcol[5] - ((lane == 5) ? 1.0 : 0.0));
+                    double w = (2.0 * df * wdp[k]) * (tcol[5] - ((rl == 5) ? 1.0 : 0.0));
                     S3 += w;
                     S1 -= w;
                 }
@@ -943,7 +968,7 @@ struct Ipm {
                 colv[4] = cv4;
                 colv[5] = cv5;
 #pragma unroll
-                for (int c = 0; c < 2; c++) g[NXA + c] = rrcol[c] + (((NXA + c) == lane) ? dsg : 0.0);
+                for (int c = 0; c < 2; c++) g[NXA + c] = rrcol[c] + (((NXA + c) == rl) ? dsg : 0.0);
 #pragma unroll
                 for (int q = 0; q < 6; q++) {
                     double ab[2];
@@ -967,7 +992,7 @@ struct Ipm {
                 ldv<4>(PT + cmap * NXAP, c4);
                 const double colv[6] = {c4[0], c4[1], c4[2], c4[3], cv4, cv5};
 #pragma unroll
-                for (int a = 0; a < 6; a++) g[a] = qqcol[a] + ((a == lane) ? dsg : 0.0);
+                for (int a = 0; a < 6; a++) g[a] = qqcol[a] + ((a == rl) ? dsg : 0.0);
                 g[4] += S0;
                 g[5] += S1;
 #pragma unroll
@@ -1011,7 +1036,7 @@ struct Ipm {
                 }
                 double gvu[NUAP], kv[NUA];
                 ldv<NUAP>(GVU, gvu);
-                const bool gcol = (lane == NZ);  // this lane solves the gradient column
+                const bool gcol = (rl == NZ);  // this lane solves the gradient column
 #pragma unroll
                 for (int a = 0; a < NUA; a++) {
                     double v = gcol ? gvu[a] : g[NXA + a];
@@ -1037,7 +1062,7 @@ struct Ipm {
                     for (int m = 0; m < NUA; m++) yp[m] = sv[m];
                     if (NUAP > NUA) yp[NUAP - 1] = 0.0;
                     stv<NUAP>(YF + lane * NUAP, yp);
-                } else if (gcol) {
+                } else if (lane == NZ) {
                     double yp[NUAP];
 #pragma unroll
                     for (int m = 0; m < NUA; m++) { yp[m] = sv[m]; KFB[(k * NUA + m) * NKP + NXA] = -kv[m]; }   // feed-forward term
@@ -1171,12 +1196,13 @@ struct Ipm {
 // ---------------------------------------------------------------- kernel
 // 248 registers, not 255: the register file is granted per warp in units of 256, so 8 resident solver warps take 8 x 7936 and
 // leave room for the one-warp exchange kernels (csrc/exchange.cuh) on a full SM; above 248 they would take all 65536.
+// __maxnreg__ and __launch_bounds__ exclude each other; measured the same speed either way (profiles/r06_variants_3.txt).
 #ifdef B200MPC_HOST_EMULATION
 #define OCP_KERNEL_BOUNDS
-#elif defined(B200MPC_MAXNREG)
-#define OCP_KERNEL_BOUNDS __maxnreg__(B200MPC_MAXNREG)
-#else
+#elif defined(B200MPC_LAUNCH_BOUNDS)
 #define OCP_KERNEL_BOUNDS __launch_bounds__(32)
+#else
+#define OCP_KERNEL_BOUNDS __maxnreg__(248)
 #endif
 template <int M, int FL, int NT>
 __global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams kp, const double *__restrict__ in,
@@ -1297,7 +1323,7 @@ __global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams
                 double x[6], dk[6];
                 q.template load_x<false>(k, 0.0, x);
                 q.diff_target(k, x, dk);
-#pragma unroll 1
+OCP_ROLL_A
                 for (int a = 0; a < 6; a++) gm = fmax(gm, fabs(q.grad_x_comp(k, a, dk, x[5])));   // df == 1 here
             }
             if (k < N) {
@@ -1426,7 +1452,7 @@ __global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams
             double dxk[6], dxn[6];
             ld6(q.D + 6 * k, dxk);
             ld6(q.D + 6 * (k + 1), dxn);
-#pragma unroll 1
+OCP_ROLL_J
             for (int j = 0; j < M; j++) {
                 int r = j * N + k;
                 double ja[4];
@@ -1471,11 +1497,11 @@ __global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams
                     q.diff_target(k, x, dk);
                     q.barrier_grad_x(k, x, gb);
                     gphi += gb[0] * d[0] + gb[5] * d[5];
-#pragma unroll 1
+OCP_ROLL_A
                     for (int a = 0; a < 6; a++) gphi += q.grad_x_comp(k, a, dk, x[5]) * q.D[6 * k + a];
                 }
             }
-#pragma unroll 1
+OCP_ROLL_J
             for (int j = 0; j < M; j++) {
                 double w = q.W[q.isg(j, k)], dd = q.D[q.isg(j, k)], zlc = q.ZL[q.bss(j, k)];
                 double dzl = (mu - zlc * dd) * rcp(w) - zlc;
@@ -1505,7 +1531,7 @@ __global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams
                 ld6(q.CRES + 6 * k, c6);
 #pragma unroll
                 for (int a = 0; a < 6; a++) th += fabs(c6[a]);
-#pragma unroll 1
+OCP_ROLL_J
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     double ds, dt, dy, dz, dv;
@@ -1608,7 +1634,7 @@ __global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams
             q.diff_target(i, x, dk);
             q.barrier_grad_x(i, x, g);        // barrier terms of vx_i, ey_i only (g[0], g[5])
             double r4 = 0.0, r5 = 0.0;
-#pragma unroll 1
+OCP_ROLL_J
             for (int j = 0; j < M; j++) {
                 if (i < N) {
                     int r = j * N + i;
@@ -1626,7 +1652,7 @@ __global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams
                 if (i < N) r5 += 2.0 * q.df * q.wdp[i] * q.JDC[i];
             }
             const double g0 = g[0], g5 = g[5];
-#pragma unroll 1
+OCP_ROLL_A
             for (int a2 = 0; a2 < 6; a2++) {
                 double kd = (q.HD[6 * i + a2] + dw_try) * q.D[6 * i + a2];
 #pragma unroll
@@ -1692,7 +1718,7 @@ __global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams
                 for (int a2 = 0; a2 < 6; a2++) x[a2] += a * d[a2];
                 st6(q.W + 6 * k, x);
             }
-#pragma unroll 1
+OCP_ROLL_J
             for (int j = 0; j < M; j++) {
                 double w = q.W[q.isg(j, k)], dd = q.D[q.isg(j, k)], zlc = q.ZL[q.bss(j, k)];
                 zlc += a_z * ((mu - zlc * dd) * rcp(w) - zlc);
@@ -1720,7 +1746,7 @@ __global__ void OCP_KERNEL_BOUNDS ocp_ipm_kernel(const __grid_constant__ KParams
                 st2(q.ZL + q.bsu(k), zln[0], zln[1]);
                 st2(q.ZU + q.bsu(k), zun[0], zun[1]);
                 st2(q.W + OU + 2 * k, un[0], un[1]);
-#pragma unroll 1
+OCP_ROLL_J
                 for (int j = 0; j < M; j++) {
                     int r = j * N + k;
                     double ds, dt, dy, dz, dv;
