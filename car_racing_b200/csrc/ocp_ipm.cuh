@@ -104,9 +104,9 @@ struct SmemPlan {
 // The once-per-iteration phases keep their loops over the six state rows (OCP_ROLL_A) and over the rivals (OCP_ROLL_J) rolled
 // for code size (instruction cache); the unroll factors are build switches so that the trade against the
 // dependent-chain latency of a rolled iteration can be measured (tools/variants.sh; profiles/r06_variants_3.txt: x2 / x3 of the
-// row loops +0.7 % / -0.2 %, x3 of the rival loops -12 % on a full SM)
+// row loops +0.7 % / -0.2 %, x3 of the rival loops -12 % on a full SM; r06_variants_4.txt: x2 of the row loops +2 %, the default)
 #ifndef B200MPC_UNROLL_A
-#define B200MPC_UNROLL_A 1
+#define B200MPC_UNROLL_A 2
 #endif
 #ifndef B200MPC_UNROLL_J
 #define B200MPC_UNROLL_J 1
@@ -912,9 +912,11 @@ OCP_ROLL_J
                 if (rl < NXA) {
 #pragma unroll
                     for (int c = 0; c < NCOL; c++) PT[(c0 + c) * NXAP + rl] = ptx[c];
+                }
+                if (lane < NXA) {   // the mirror half would store the same values to the same addresses
 #pragma unroll
-                    for (int j = 0; j < M; j++) PT[(8 + j) * NXAP + rl] = Pr[6 + j];
-                    QVs[rl] = qv;
+                    for (int j = 0; j < M; j++) PT[(8 + j) * NXAP + lane] = Pr[6 + j];
+                    QVs[lane] = qv;
                 }
             }
             __syncwarp();
@@ -1159,6 +1161,9 @@ OCP_ROLL_J
         if (M > 0 && lane < M) D[isg(lane, 0)] = QVs[6 + lane];
         const int mrow = (lane < NUA) ? lane : 0;
         const int arow_i = (lane < 6) ? lane : 0;
+        // slot of this lane's input component in D: u_k at OU + 2k + lane, sigma_{j,k+1} at isg(j, k + 1) -- base + k * step, no branch
+        const int dst_base = (lane < 2) ? OU + lane : isg((lane < NUA) ? lane - 2 : 0, 1);
+        const int dst_step = (lane < 2) ? 2 : 1;
         for (int k = 0; k < N; k++) {
             double kr[NKP];
             ldv<NKP>(KFB + (k * NUA + mrow) * NKP, kr);
@@ -1182,7 +1187,7 @@ OCP_ROLL_J
 #pragma unroll
             for (int m = 0; m < NUA; m++) du[m] = __shfl_sync(0xffffffffu, s, m);
             t += brow[0] * du[0] + brow[1] * du[1];
-            if (lane < NUA) D[(lane < 2) ? OU + 2 * k + lane : isg(lane - 2, k + 1)] = s;
+            if (lane < NUA) D[dst_base + k * dst_step] = s;
             if (lane < 6) D[6 * (k + 1) + lane] = t;
 #pragma unroll
             for (int a = 0; a < 6; a++) dx[a] = __shfl_sync(0xffffffffu, t, a);
