@@ -219,8 +219,15 @@ static KParams make_kp(const b200mpc_cbf_params *p, const b200mpc_ipm_options *o
     double L2 = p->L * p->L, W2 = p->W * p->W;
     kp.iL6 = 1.0 / (L2 * L2 * L2);
     kp.iW6 = 1.0 / (W2 * W2 * W2);
+    kp.q_diag = 1;
     for (int a = 0; a < 6; a++)
-        for (int b = 0; b < 6; b++) kp.Q2[6 * a + b] = p->Q[6 * a + b] + p->Q[6 * b + a];
+        for (int b = 0; b < 6; b++) {
+            kp.Q2[6 * a + b] = p->Q[6 * a + b] + p->Q[6 * b + a];
+            if (a != b && p->Q[6 * a + b] != 0.0) kp.q_diag = 0;
+        }
+#ifdef B200MPC_NO_QDIAG   // A/B switch (tools/variants.sh): always the general path
+    kp.q_diag = 0;
+#endif
     return kp;
 }
 

@@ -47,6 +47,8 @@ struct KParams {
     int32_t bnd_off;    // offset of the per-stage bound block (flag STAGE_BOUNDS)
     int32_t wd_off;     // offset of the ey-rate weights (flag EY_RATE)
     int32_t sz_off;     // offset of the per-rival (L_j, W_j) block (flag RIVAL_SIZE)
+    int32_t q_diag;     // Q is diagonal (every configuration of the reference: base.py:231,277,384): the O(N) phases take one
+                        // product per state row instead of six -- same bits, the skipped terms are exact zeros
     double iL6, iW6;    // 1/L^6, 1/W^6
     double Q2[36];      // Q + Q' (the objective's Hessian block and gradient matrix), formed once on the host
 };
@@ -489,6 +491,11 @@ OCP_ROLL_A
 #pragma unroll
         for (int a = 0; a < 6; a++) d[a] = x[a] - t[a];
         double f = 0.0;
+        if (kp.q_diag) {   // warp-uniform
+#pragma unroll
+            for (int a = 0; a < 6; a++) f += d[a] * (kp.p.Q[7 * a] * d[a]);
+            return f;
+        }
 OCP_ROLL_A
         for (int a = 0; a < 6; a++) {
             const double *Qr = kp.p.Q + 6 * a;
@@ -512,8 +519,12 @@ OCP_ROLL_A
     __device__ __forceinline__ double grad_x_comp(int i, int a, const double (&d)[6], double ey) const {
         const double *q2 = kp.Q2 + 6 * a;
         double acc = 0.0;
+        if (kp.q_diag) {   // warp-uniform; d_a re-formed from shared memory (a is a runtime index in the callers' rolled loops)
+            acc = q2[a] * (W[6 * i + a] - xtp(i)[a]);
+        } else {
 #pragma unroll
-        for (int b = 0; b < 6; b++) acc += q2[b] * d[b];
+            for (int b = 0; b < 6; b++) acc += q2[b] * d[b];
+        }
         acc *= df;
         if (hwd && a == 5) {   // d/d ey_i of  wd_{i-1}(ey_i-ey_{i-1})^2 + wd_i(ey_{i+1}-ey_i)^2
             double tt = wdp[i - 1] * (ey - W[6 * (i - 1) + 5]);
@@ -1660,8 +1671,11 @@ OCP_ROLL_J
 OCP_ROLL_A
             for (int a2 = 0; a2 < 6; a2++) {
                 double kd = (q.HD[6 * i + a2] + dw_try) * q.D[6 * i + a2];
+                if (kp.q_diag) kd += q.df * kp.Q2[7 * a2] * q.D[6 * i + a2];
+                else {
 #pragma unroll
-                for (int b = 0; b < 6; b++) kd += q.df * kp.Q2[6 * a2 + b] * d[b];
+                    for (int b = 0; b < 6; b++) kd += q.df * kp.Q2[6 * a2 + b] * d[b];
+                }
                 double gg = q.grad_x_comp(i, a2, dk, x[5]) + ((a2 == 0) ? g0 : ((a2 == 5) ? g5 : 0.0));
                 double res = -gg - kd;
                 if (a2 == 4) res += r4;

@@ -139,6 +139,22 @@ def test_cbf_shapes_parity(crb, oracle, N, M):
     _compare(g, r, min_match=0.97, max_other=2)
 
 
+def test_full_weight_matrix(crb, oracle):
+    """A Q with off-diagonal entries takes the kernel's general path (the reference's diagonal Q takes one product per row,
+    KParams::q_diag): parity with the oracle on both."""
+    B, N, M = 96, 20, 3
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(B, N=N, M=M, seed=41)
+    prm = scenarios.default_cbf_params(N=N)
+    Q = np.array(prm["Q"], float)
+    Q[0, 3] = Q[3, 0] = 1.5
+    Q[3, 5] = Q[5, 3] = -2.0
+    Q[1, 1] = 0.5
+    prm = dict(prm, Q=Q)
+    g = crb.solve_cbf_batch(x0, xt, obs, lap_off, prm)
+    r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm, nthreads=os.cpu_count() or 1)
+    _compare(g, r, min_match=0.96, max_other=1)
+
+
 def test_per_rival_sizes_zero_start_and_x0_rows(crb, oracle):
     """Round-2 options through the C-ABI on the GPU: per-rival (L, W) in the record (flag RIVAL_SIZE), the zero start of
     Opti/IPOPT (B200MPC_START_ZERO, bounded iteration count: same iterates as the oracle), status 4 for an x_0 outside the

@@ -101,6 +101,26 @@ def test_other_instantiations_on_host(oracle):
     _agree(_solve(L, kw["x0"], kw["xt"], kw["obs"], None, pprm, xlb=kw["xlb"], xub=kw["xub"], wd=kw["wd"]), ref)
 
 
+def test_full_weight_matrix_on_host(oracle):
+    """The reference's Q is diagonal in every configuration and the kernel takes a one-product-per-row path for it
+    (KParams::q_diag, set by the host from Q); a Q with off-diagonal entries must take the general path and agree with the
+    oracle as well, and a diagonal Q must give the same bits on both paths."""
+    L = _lib()
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(3, N=12, M=2, seed=6)
+    prm = scenarios.default_cbf_params(N=12)
+    Q = np.array(prm["Q"], float)
+    Q[0, 3] = Q[3, 0] = 1.5
+    Q[3, 5] = Q[5, 3] = -2.0
+    Q[1, 1] = 0.5
+    prm_full = dict(prm, Q=Q)
+    _agree(_solve(L, x0, xt, obs, lap_off, prm_full), oracle.solve_cbf_batch(x0, xt, obs, lap_off, prm_full))
+    tiny = np.array(prm["Q"], float)
+    tiny[0, 1] = 1e-300            # numerically nothing, but not zero: the general path
+    a = _solve(L, x0, xt, obs, lap_off, prm)
+    b = _solve(L, x0, xt, obs, lap_off, dict(prm, Q=tiny))
+    assert np.array_equal(a["iters"], b["iters"]) and np.abs(a["u0"] - b["u0"]).max() < 1e-12 and np.abs(a["x"] - b["x"]).max() < 1e-10
+
+
 def test_zero_start_rival_sizes_and_x0_rows_on_host(oracle):
     """Round-2 options of the hot kernel against the oracle: B200MPC_START_ZERO (w = 0, what Opti/IPOPT start from), per-rival
     (L, W) in the record (flag RIVAL_SIZE, <2,4,0>), and status 4 when x_0 violates the bound rows the reference imposes on
