@@ -107,7 +107,7 @@ class Work:
 
 
 class Work2(Work):
-    key, default_batch, kernel = 2, 1024, "ocp_ipm_kernel<3,0,20>"
+    key, default_batch, kernel = 2, 1024, "ocp_ipm_kernel<3,QDIAG,20>"
     metric = "MPC-CBF solves/sec (N=20, 6-state, 3 obs)"
     workload = "MPC-CBF N=20, 3 static rivals, l_shape, batch=%d random x0 per GPU (BASELINE config 2)"
     solver = "FP64 barrier-SQP (IPOPT conventions), Riccati KKT, tol 1e-8"

@@ -250,6 +250,7 @@ int b200mpc_cbf_solve_device(b200mpc_handle *h, const b200mpc_cbf_params *prm, c
     } else if (FL != 0 && FL != B200MPC_FLAG_RIVAL_SIZE)
         return fail(h, B200MPC_ERR_ARG, "b200mpc_cbf_solve: flags must be 0, STAGE_BOUNDS|EY_RATE (M = 0) or RIVAL_SIZE");
     if (FL == 0 && prm->N == 20 && M == 3 && !prm->xt_per_stage) NT = 20;
+    if (NT == 20 && kp.q_diag) FL = OCP_FL_QDIAG;   // the north star with the reference's diagonal Q: no general path in the kernel
     XchgArgs xa;
     if ((rc = take_xchg(h, B, &xa))) return rc;
     CbfLaunch l{h->stream, h->device, h->max_smem_optin, h->smem_pad, d_in, d_rec, d_aux, d_xpred, d_upred, d_sigma, xa};

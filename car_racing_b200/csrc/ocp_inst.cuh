@@ -30,7 +30,7 @@ static int launch_cbf_one(const CbfLaunch &l, const KParams &kp) {
 // host emulation: every code path once (runtime horizon, compile-time horizon, planner blocks, per-rival sizes, M > 4),
 // not every rival count -- g++ needs ~20 s per instantiation
 int launch_cbf_set0(const CbfLaunch &l, const KParams &kp, int M, int FL, int NT) {
-    OCP_CASE(3, 0, 20) OCP_CASE(0, 0, 0) OCP_CASE(0, 3, 0)
+    OCP_CASE(3, OCP_FL_QDIAG, 20) OCP_CASE(3, 0, 20) OCP_CASE(0, 0, 0) OCP_CASE(0, 3, 0)
     return CBF_LAUNCH_NOT_HERE;
 }
 int launch_cbf_set1(const CbfLaunch &l, const KParams &kp, int M, int FL, int NT) {
@@ -49,7 +49,7 @@ int launch_cbf_set4(const CbfLaunch &, const KParams &, int, int, int) { return 
 #else
 #if OCP_INST_SET == 0
 int launch_cbf_set0(const CbfLaunch &l, const KParams &kp, int M, int FL, int NT) {
-    OCP_CASE(3, 0, 20) OCP_CASE(0, 0, 0) OCP_CASE(0, 3, 0)
+    OCP_CASE(3, OCP_FL_QDIAG, 20) OCP_CASE(3, 0, 20) OCP_CASE(0, 0, 0) OCP_CASE(0, 3, 0)
     return CBF_LAUNCH_NOT_HERE;
 }
 #elif OCP_INST_SET == 1

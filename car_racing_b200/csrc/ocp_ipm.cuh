@@ -37,6 +37,8 @@
 
 namespace b200mpc {
 
+enum { OCP_FL_QDIAG = 8 };   // internal template flag (not a b200mpc_cbf_params flag): Q is diagonal, known at compile time
+
 struct KParams {
     b200mpc_cbf_params p;
     b200mpc_ipm_options o;
@@ -296,6 +298,11 @@ struct Ipm {
     // per-rival sizes (control.py:530-535 reads length / width of every rival): the record carries (L_j, W_j), the kernel
     // turns them into 1/L_j^6, 1/W_j^6 in place once after staging; without the flag they are kernel-parameter constants
     static constexpr bool prs = (FL & B200MPC_FLAG_RIVAL_SIZE) != 0;
+    // diagonal Q: instantiations with the internal bit OCP_FL_QDIAG know it at compile time and carry no general path at all
+    // (the north star: its hot loop body must stay small, the second path cost 5 points of instruction-fetch stalls); the
+    // others ask the kernel parameter
+    static constexpr bool kQD = (FL & OCP_FL_QDIAG) != 0;
+    __device__ __forceinline__ bool qdiag() const { return kQD || kp.q_diag != 0; }
     int nb_count;        // number of bound + row multipliers (for the error scaling)
     double df, mu, rho, a1;  // a1 = 1 - alpha
     // lane = column role of the Riccati sweep (set once)
@@ -491,7 +498,7 @@ OCP_ROLL_A
 #pragma unroll
         for (int a = 0; a < 6; a++) d[a] = x[a] - t[a];
         double f = 0.0;
-        if (kp.q_diag) {   // warp-uniform
+        if (qdiag()) {   // warp-uniform
 #pragma unroll
             for (int a = 0; a < 6; a++) f += d[a] * (kp.p.Q[7 * a] * d[a]);
             return f;
@@ -519,7 +526,7 @@ OCP_ROLL_A
     __device__ __forceinline__ double grad_x_comp(int i, int a, const double (&d)[6], double ey) const {
         const double *q2 = kp.Q2 + 6 * a;
         double acc = 0.0;
-        if (kp.q_diag) {   // warp-uniform; d_a re-formed from shared memory (a is a runtime index in the callers' rolled loops)
+        if (qdiag()) {   // warp-uniform; d_a re-formed from shared memory (a is a runtime index in the callers' rolled loops)
             acc = q2[a] * (W[6 * i + a] - xtp(i)[a]);
         } else {
 #pragma unroll
@@ -1671,7 +1678,7 @@ OCP_ROLL_J
 OCP_ROLL_A
             for (int a2 = 0; a2 < 6; a2++) {
                 double kd = (q.HD[6 * i + a2] + dw_try) * q.D[6 * i + a2];
-                if (kp.q_diag) kd += q.df * kp.Q2[7 * a2] * q.D[6 * i + a2];
+                if (q.qdiag()) kd += q.df * kp.Q2[7 * a2] * q.D[6 * i + a2];
                 else {
 #pragma unroll
                     for (int b = 0; b < 6; b++) kd += q.df * kp.Q2[6 * a2 + b] * d[b];

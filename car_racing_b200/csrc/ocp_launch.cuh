@@ -2,7 +2,8 @@
 //
 // The instantiations are compiled in several translation units (generated wrappers "#define OCP_INST_SET k + #include ocp_inst.cuh", built in parallel by
 // __graft_entry__.build()) because each one is ~8 k SASS instructions; capi.cu only sees this header.
-//   set 0: <3,0,20> (BASELINE north star), <0,0,0> (mpc_lti), <0,3,0> (planner candidate QP)
+//   set 0: <3,QDIAG,20> (BASELINE north star: diagonal Q at compile time), <3,0,20> (the same shape, any Q), <0,0,0> (mpc_lti),
+//          <0,3,0> (planner candidate QP)
 //   set 1: <1..4,0,0>      set 2: <5..8,0,0>
 //   set 3: <1..4,4,0>      set 4: <5..8,4,0>     (flag RIVAL_SIZE: per-rival (L, W) in the record)
 #pragma once

@@ -32,8 +32,12 @@ static KParams make_kp(const b200mpc_cbf_params *p, const b200mpc_ipm_options *o
     double L2 = p->L * p->L, W2 = p->W * p->W;
     kp.iL6 = 1.0 / (L2 * L2 * L2);
     kp.iW6 = 1.0 / (W2 * W2 * W2);
+    kp.q_diag = 1;
     for (int a = 0; a < 6; a++)
-        for (int b = 0; b < 6; b++) kp.Q2[6 * a + b] = p->Q[6 * a + b] + p->Q[6 * b + a];
+        for (int b = 0; b < 6; b++) {
+            kp.Q2[6 * a + b] = p->Q[6 * a + b] + p->Q[6 * b + a];
+            if (a != b && p->Q[6 * a + b] != 0.0) kp.q_diag = 0;
+        }
     return kp;
 }
 
@@ -57,7 +61,8 @@ extern "C" int emu_cbf_solve(const b200mpc_cbf_params *prm, const b200mpc_ipm_op
     }
     if (prm->flags != 0) return -1;
     if (specialised && prm->N == 20 && prm->M == 3 && !prm->xt_per_stage) {
-        run<3, 0, 20>(kp, B, in, rec, aux, xpred, upred, sigma);
+        if (kp.q_diag) run<3, OCP_FL_QDIAG, 20>(kp, B, in, rec, aux, xpred, upred, sigma);   // as capi.cu dispatches
+        else run<3, 0, 20>(kp, B, in, rec, aux, xpred, upred, sigma);
         return 0;
     }
     switch (prm->M) {

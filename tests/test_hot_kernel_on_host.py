@@ -119,6 +119,14 @@ def test_full_weight_matrix_on_host(oracle):
     a = _solve(L, x0, xt, obs, lap_off, prm)
     b = _solve(L, x0, xt, obs, lap_off, dict(prm, Q=tiny))
     assert np.array_equal(a["iters"], b["iters"]) and np.abs(a["u0"] - b["u0"]).max() < 1e-12 and np.abs(a["x"] - b["x"]).max() < 1e-10
+    # the north-star shape: <3, QDIAG, 20> (diagonal Q known at compile time) against <3, 0, 20> on its general path
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(2, N=20, M=3, seed=0)
+    prm = scenarios.default_cbf_params(N=20)
+    tiny = np.array(prm["Q"], float)
+    tiny[0, 1] = 1e-300
+    a = _solve(L, x0, xt, obs, lap_off, prm)
+    b = _solve(L, x0, xt, obs, lap_off, dict(prm, Q=tiny))
+    assert np.array_equal(a["iters"], b["iters"]) and np.abs(a["u0"] - b["u0"]).max() < 1e-12 and np.abs(a["x"] - b["x"]).max() < 1e-10
 
 
 def test_zero_start_rival_sizes_and_x0_rows_on_host(oracle):

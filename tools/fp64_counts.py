@@ -16,7 +16,7 @@ import re
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = {"ocp_ipm_kernel<3, 0, 20>": "ocp_ipm_kernel<3,0,20>", "ocp_ipm_kernel<0, 3, 0>": "ocp_ipm_kernel<0,3,0>",
+NAMES = {"ocp_ipm_kernel<3, 8, 20>": "ocp_ipm_kernel<3,QDIAG,20>", "ocp_ipm_kernel<3, 0, 20>": "ocp_ipm_kernel<3,0,20>", "ocp_ipm_kernel<0, 3, 0>": "ocp_ipm_kernel<0,3,0>",
          "lmpc_kernel": "lmpc_kernel", "ilqr_kernel": "ilqr_kernel"}
 def source_sha16():
     """Identity of the kernels the counts belong to: hash of the CUDA sources and the C-ABI header (the built library's own

@@ -15,7 +15,7 @@ import sys
 import tempfile
 
 rep, so, B = sys.argv[1], sys.argv[2], int(sys.argv[3])
-KERNEL = sys.argv[4] if len(sys.argv) > 4 else "ocp_ipm_kernelILi3ELi0ELi20"     # mangled-name fragment of the captured kernel
+KERNEL = sys.argv[4] if len(sys.argv) > 4 else "ocp_ipm_kernelILi3ELi8ELi20"     # mangled-name fragment of the captured kernel
 SRC = sys.argv[5] if len(sys.argv) > 5 else "ocp_ipm.cuh"                          # the source file its body lives in
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))

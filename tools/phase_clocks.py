@@ -1,4 +1,4 @@
-"""Per-phase cycle counters of ocp_ipm_kernel<3,0,20> at 1, 4 and 7 resident warps per SM -- which phases slow down when
+"""Per-phase cycle counters of ocp_ipm_kernel<3,QDIAG,20> at 1, 4 and 7 resident warps per SM -- which phases slow down when
 the SM is crowded?  Needs a library built with -DB200MPC_PHASE_CLOCKS (tools/variants.sh build clocks:"-DB200MPC_PHASE_CLOCKS"):
 that build writes the counters over the first 13 doubles of each instance's x_pred slot.
 

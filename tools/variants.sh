@@ -25,8 +25,8 @@ case "$1" in
       python -c "
 import sys, __graft_entry__ as g
 g.compile_lib(out='$VDIR/libb200mpc_$1.so', extra_flags=sys.argv[1].split(), verbose=False)" "$2"
-      n=$(cuobjdump -sass -fun '_ZN7b200mpc14ocp_ipm_kernelILi3ELi0ELi20EEEvNS_7KParamsEPKdP14b200mpc_recordPdS6_S6_S6_NS_8XchgArgsE' $VDIR/libb200mpc_$1.so 2>/dev/null | grep -cE "^\s+/\*[0-9a-f]{4,5}\*/" || true)
-      echo "[variants] $1: ocp_ipm_kernel<3,0,20> = $n SASS instructions"
+      n=$(cuobjdump -sass -fun '_ZN7b200mpc14ocp_ipm_kernelILi3ELi8ELi20EEEvNS_7KParamsEPKdP14b200mpc_recordPdS6_S6_S6_NS_8XchgArgsE' $VDIR/libb200mpc_$1.so 2>/dev/null | grep -cE "^\s+/\*[0-9a-f]{4,5}\*/" || true)
+      echo "[variants] $1: ocp_ipm_kernel<3,QDIAG,20> = $n SASS instructions"
     }
     [ "$NO_BASE" = "1" ] || build_one base ""
     for spec in "$@"; do
