@@ -18,7 +18,7 @@ the exchange falls back to one NCCL all-gather per step and the line says so (`c
 `e2e`      : the same metric through the host-pointer C-ABI call (pinned host buffers; H2D of the records, kernel, D2H of
              the 32-byte result records inside the timed region; N>1: the exchange and the D2H of its argmin as well).
 `roofline` : algorithmic HBM bytes / kernel time against the measured copy bandwidth -- stated honestly: these kernels
-             are FP64-latency bound, not HBM bound; `roofline.fp64` puts the counted FP64 work beside it.
+             are bound by FP64 issue and instruction delivery, not by HBM; `roofline.fp64` puts the counted FP64 work beside it.
 `--impl reference` times the CPU implementation of the path on the host cores: CasADi/IPOPT is probed for, but it is not
 installable here, so the arm times the oracle port (oracle/*.c) and says so.
 """
@@ -621,7 +621,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": work.kernel,
                      "note": "algorithmic bytes = %d B/solve x %d solves per launch / mean launch duration (one batch at a time); the kernel "
-                             "is FP64-latency bound, see roofline.fp64, profiles/ and DESIGN.md" % (work.alg_bytes, B)},
+                             "is bound by FP64 issue and instruction delivery, not by HBM: see roofline.fp64, profiles/ and DESIGN.md section 5" % (work.alg_bytes, B)},
     }
     if exchange_ok is not None:
         line["exchange_verified"] = exchange_ok
