@@ -1073,7 +1073,12 @@ OCP_ROLL_J
                     for (int q = a + 1; q < NUA; q++) v -= Lt[q][a] * kv[q];
                     kv[a] = v;
                 }
-                if (!ok) return false;   // checked after the solves so that they overlap the factorisation's latency
+                if (!ok) {   // checked after the solves so that they overlap the factorisation's latency
+                    // the state rows above read PT after the last barrier, and the retry's first stage rewrites it: order them
+                    // (found by ThreadSanitizer on the host emulation; the warp is converged here in practice, not by contract)
+                    __syncwarp();
+                    return false;
+                }
                 if (lane < NXA) {
 #pragma unroll
                     for (int m = 0; m < NUA; m++) KFB[(k * NUA + m) * NKP + lane] = -kv[m];
@@ -1114,7 +1119,7 @@ OCP_ROLL_J
         }
         // stage 0: x_0 is fixed (control.py:497), sigma_{.,0} is free: d sigma_0 = -P_ss^-1 p_s  -> QVs[6+j]
         if (M > 0) {
-            if (iss) {
+            if (iss && lane == rl) {   // not the mirror half: it would store the same values to the same addresses
 #pragma unroll
                 for (int j = 0; j < M; j++) S0[jrole * (M + 2) + j] = Pr[6 + j];
                 S0[jrole * (M + 2) + M] = pv;

@@ -97,7 +97,7 @@ def main():
             L.b200mpc_comm_destroy(c)
         return "2 ranks x 2 instances x 2 uses of one slot, argmin %s" % args
 
-    for name, fn in (("ocp_ipm_kernel<3,0,20>", cbf), ("exchange window: publish epilogue + xchg_wait_ack_kernel + xchg_argmin_kernel", exchange), ("ilqr_kernel", ilqr), ("lmpc_kernel", lmpc), ("sysid_kernel", sysid),
+    for name, fn in (("ocp_ipm_kernel<3,QDIAG,20>", cbf), ("exchange window: publish epilogue + xchg_wait_ack_kernel + xchg_argmin_kernel", exchange), ("ilqr_kernel", ilqr), ("lmpc_kernel", lmpc), ("sysid_kernel", sysid),
                      ("ocp_ipm_kernel<0,3,0> + planner_select_kernel + ocp_ipm_kernel<M,0,0>", planner)):
         report(name, fn)
     print("summary: done")
