@@ -45,6 +45,22 @@ def test_mpccbf_through_the_product_api(emu, oracle):
     assert batch.default_handle().launch_count == 1
 
 
+def test_full_weight_matrix_takes_the_general_instantiation(emu, oracle):
+    """The C-ABI's dispatch (capi.cu): the north-star shape with the reference's diagonal Q runs <3,QDIAG,20>, the same shape with
+    off-diagonal weights the general <3,0,20>; both against the oracle through the product API."""
+    x0, xt, obs, lap_off = scenarios.mpccbf_scenarios(2, N=20, M=3, seed=2)
+    prm = scenarios.default_cbf_params(N=20)
+    Q = np.array(prm["Q"], float)
+    Q[0, 3] = Q[3, 0] = 1.5
+    Q[3, 5] = Q[5, 3] = -2.0
+    for p in (prm, dict(prm, Q=Q)):
+        g = crb.solve_cbf_batch(x0, xt, obs, lap_off, p)
+        r = oracle.solve_cbf_batch(x0, xt, obs, lap_off, p)
+        assert (g["status"] == r["status"]).all() and (g["iters"] == r["iters"]).all()
+        ok = g["status"] == 0
+        assert ok.any() and np.abs(g["u0"] - r["u0"])[ok].max() < 1e-4 and np.abs(g["cost"] - r["cost"])[ok].max() < 1e-5
+
+
 def test_lmpc_against_the_oracle(emu, oracle):
     sc = scenarios.lmpc_scenarios(2, seed=5)
     prm = scenarios.default_lmpc_params()
