@@ -596,7 +596,7 @@ def main():
         t = json.load(open(tp))
         ent = t.get("kernels", {}).get(work.kernel) or (t if work.key == 2 and "dram_bytes_per_launch" in t else None)
         if ent:
-            traffic, traffic_src = ent.get("dram_bytes_per_launch"), "profiles/dram_traffic.json (ncu --set full, one B=%s launch)" % ent.get("batch", "1024")
+            traffic, traffic_src = ent.get("dram_bytes_per_launch"), "profiles/dram_traffic.json (ncu counters dram__bytes_read.sum + dram__bytes_write.sum of one B=%s launch, tools/fp64_counts.py)" % ent.get("batch", "1024")
     cfg = work.config(B, world, D, exchange_name(world, "p2p" if px is not None else px_why), args.l2)
     line = {
         "metric": work.metric, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
